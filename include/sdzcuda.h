@@ -1,0 +1,147 @@
+/*
+ * sdzcuda.h - C ABI of libsdzcuda.so: the B200 (sm_100a) engine behind the public API of
+ * @stardazed/zlib for ONE path: inflate (raw / zlib / gzip, preset dictionary) and the
+ * adler32 / crc32 checksums.  This is the boundary an N-API shim (sd-zlib_b200/ts/), the
+ * Python mirror (sd-zlib_b200/host/sdzlib) and the tests bind to.  Plain pointers and
+ * sizes only; no C++ or torch types; no exceptions; one sdz_ctx per host thread.
+ *
+ * What each entry point replaces in the reference (paths relative to the reference tree):
+ *
+ *   sdz_adler32 / sdz_adler32_chain   adler32(source, seed=1)            src/adler32.ts:17-105
+ *   sdz_crc32   / sdz_crc32_chain     crc32(source, seed=0)              src/crc32.ts:17-106
+ *   sdz_inflate_batch                 new Inflater(opts).append(buf) + finish() per buffer,
+ *                                     and inflate(buf, dict)             src/sd-inflate.ts:54-228
+ *                                     (driving src/inflate.ts:132-503, src/infblocks.ts:123-633,
+ *                                      src/inftree.ts:95-392, src/infcodes.ts:62-676)
+ *   sdz_inflate_sizes                 (new) sizing pass for inflateBatch()'s output arena
+ *   sdz_inflate_batch_device          same as sdz_inflate_batch with every buffer already in HBM
+ *
+ * Results are bit-exact with the reference, including its documented quirks (SURVEY
+ * Appendix A); values that the reference holds as signed int32 JS numbers (checksums,
+ * ISIZE, MTIME) are int32_t here.  There is no CPU fallback: every entry point fails with
+ * SDZ_E_CUDA / SDZ_E_NO_DEVICE when the device is unusable.
+ */
+#ifndef SDZCUDA_H
+#define SDZCUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "sdz_codes.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* error codes (negative); 0 = success */
+enum sdz_err {
+    SDZ_OK = 0,
+    SDZ_E_NO_DEVICE = -1,     /* no CUDA device / wrong architecture                         */
+    SDZ_E_CUDA = -2,          /* a CUDA call failed; sdz_last_error() has the text           */
+    SDZ_E_ARG = -3,           /* bad argument (NULL, misaligned device offset, >= 4 GiB ...) */
+    SDZ_E_NOMEM = -4,         /* host or device allocation failed                            */
+    SDZ_E_OUT_CAP = -5,       /* output arena / slot too small for at least one stream       */
+    SDZ_E_UNSUPPORTED = -6    /* flag or mode not implemented                                */
+};
+
+/* sdz_inflate_batch flags */
+#define SDZ_PARITY_REFERENCE 0u   /* default: identical to @stardazed/zlib, quirks included  */
+#define SDZ_PARITY_SPEC      1u   /* RFC-strict behaviour (not implemented yet)              */
+
+typedef struct sdz_ctx sdz_ctx;
+
+/* Context = one CUDA device + its streams, staging buffers and constant tables. */
+int  sdz_ctx_create(int device, uint32_t flags, sdz_ctx** out);
+void sdz_ctx_destroy(sdz_ctx* ctx);
+const char* sdz_last_error(sdz_ctx* ctx);          /* text of the last failure on this ctx   */
+const char* sdz_version(void);
+/* number of kernel launches issued through this ctx so far (bench.py's gpu_launches) */
+uint64_t sdz_launch_count(sdz_ctx* ctx);
+/* device time of the most recent call's kernels in milliseconds (CUDA events on the ctx
+ * stream), split by phase: [0] inflate kernel, [1] checksum kernel, [2] whole device phase */
+int sdz_last_timing(sdz_ctx* ctx, float ms[3]);
+
+/* Pinned host memory helpers (so that callers can hand over DMA-able buffers). */
+void* sdz_host_alloc(size_t bytes);
+void  sdz_host_free(void* p);
+/* Device memory helpers for callers that keep data resident in HBM. */
+void* sdz_device_alloc(sdz_ctx* ctx, size_t bytes);
+void  sdz_device_free(sdz_ctx* ctx, void* p);
+int   sdz_memcpy_h2d(sdz_ctx* ctx, void* dst, const void* src, size_t bytes);
+int   sdz_memcpy_d2h(sdz_ctx* ctx, void* dst, const void* src, size_t bytes);
+
+/* ---------------------------------------------------------------- checksums
+ * `on_device` != 0: `p` is a device pointer on ctx's device (data already in HBM).
+ * n must be < 4 GiB per call (the reference's crc32 is undefined beyond that).
+ * The value domain is the reference's: signed int32, seed signed or unsigned bit pattern. */
+int sdz_adler32(sdz_ctx* ctx, const uint8_t* p, uint64_t n, int32_t seed, int on_device, int32_t* out);
+int sdz_crc32(sdz_ctx* ctx, const uint8_t* p, uint64_t n, int32_t seed, int on_device, int32_t* out);
+
+/* Seed chaining over consecutive segments of one buffer, evaluated on the device without a
+ * host round trip per segment:  v[0] = f(seg 0, seed), v[i] = f(seg i, v[i-1]).
+ * Exactly what a caller gets from `s = adler32(chunk_i, s)` in a loop (including Q1 for
+ * segments whose length is a non-zero multiple of 5552).  out_values may be NULL except
+ * for the last element, which is always written to *out_last. */
+int sdz_adler32_chain(sdz_ctx* ctx, const uint8_t* p, const uint64_t* seg_len, uint64_t n_seg,
+                      int32_t seed, int on_device, int32_t* out_values, int32_t* out_last);
+int sdz_crc32_chain(sdz_ctx* ctx, const uint8_t* p, const uint64_t* seg_len, uint64_t n_seg,
+                    int32_t seed, int on_device, int32_t* out_values, int32_t* out_last);
+
+/* ---------------------------------------------------------------- batched inflate */
+
+/* one input buffer == one `new Inflater(options)` fed with a single append() */
+typedef struct sdz_in {
+    const uint8_t* data;     /* borrowed for the duration of the call                         */
+    uint64_t len;
+    const uint8_t* dict;     /* options.dictionary, or NULL                                   */
+    uint32_t dict_len;
+    uint8_t  mode;           /* enum sdz_mode                                                 */
+    uint8_t  reserved[3];
+} sdz_in;
+
+/* Decode n independent buffers.  Stream i writes its bytes to
+ * out_arena[out_off[i] .. out_off[i] + out_cap[i]) (host memory; pinned memory from
+ * sdz_host_alloc avoids a staging copy).  results[i] receives the finish() record; a bad
+ * stream never aborts the batch.  Returns SDZ_E_OUT_CAP if some stream needed more than
+ * its slot (that stream's record has out_len = bytes that fit, complete = 0 and
+ * zstatus = SDZ_Z_BUF_ERROR; all others are valid). */
+int sdz_inflate_batch(sdz_ctx* ctx, const sdz_in* in, uint64_t n,
+                      uint8_t* out_arena, const uint64_t* out_off, const uint64_t* out_cap,
+                      sdz_result* results, uint32_t flags);
+
+/* Sizing pass: out_len[i] = number of bytes stream i decodes to (same decode walk, no
+ * stores).  Lets inflateBatch() allocate its output arena exactly. */
+int sdz_inflate_sizes(sdz_ctx* ctx, const sdz_in* in, uint64_t n, uint64_t* out_len, uint32_t flags);
+
+/* Device-resident form: everything below lives in HBM on ctx's device.
+ *   d_in      compressed arena; stream i = d_in[in_off[i] .. in_off[i] + in_len[i]); every
+ *             in_off[i] must be a multiple of 16 and the arena must be readable for
+ *             SDZ_IN_PAD bytes past its last stream (TMA bulk staging reads whole chunks)
+ *   d_dict    dictionary arena (may be NULL); dict_off/dict_len per stream (len 0 = none)
+ *   dict_adler  reference adler32 (src/adler32.ts, incl. Q1) of each WHOLE dictionary
+ *   d_out     output arena; stream i owns d_out[out_off[i] .. out_off[i] + out_cap[i])
+ *   d_results n records
+ * Host arrays: none - every array argument is a device pointer.  Asynchronous on the ctx
+ * stream unless `sync` != 0. */
+#define SDZ_IN_PAD 1024
+typedef struct sdz_batch_dev {
+    const uint8_t*  d_in;
+    const uint64_t* d_in_off;
+    const uint32_t* d_in_len;
+    const uint8_t*  d_mode;        /* enum sdz_mode per stream                              */
+    const uint8_t*  d_dict;        /* may be NULL                                           */
+    const uint64_t* d_dict_off;    /* may be NULL when d_dict is NULL                       */
+    const uint32_t* d_dict_len;
+    const int32_t*  d_dict_adler;
+    uint8_t*        d_out;         /* may be NULL for a sizing pass                         */
+    const uint64_t* d_out_off;
+    const uint32_t* d_out_cap;
+    sdz_result*     d_results;
+    uint64_t        n;
+} sdz_batch_dev;
+int sdz_inflate_batch_device(sdz_ctx* ctx, const sdz_batch_dev* batch, uint32_t flags, int sync);
+int sdz_sync(sdz_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDZCUDA_H */

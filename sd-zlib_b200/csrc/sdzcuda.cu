@@ -1,0 +1,575 @@
+// sdzcuda.cu - host side of libsdzcuda.so (C ABI declared in include/sdzcuda.h).
+// Owns the CUDA context objects, stages batches into HBM, launches the sm_100a kernels and
+// returns the reference-identical records.  There is no CPU decode path in this file.
+#include "../../include/sdzcuda.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "checksum_kernels.cuh"
+#include "inflate_kernel.cuh"
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct sdz_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    std::string err;
+    uint64_t launches = 0;
+    float last_ms[3] = { 0, 0, 0 };
+    // grow-only scratch
+    DevBuf d_in, d_out, d_meta, d_res, d_part, d_misc;
+    void* h_stage = nullptr;           // pinned
+    size_t h_stage_cap = 0;
+    unsigned long long* d_counter = nullptr;
+    int group = 8;                     // lanes per stream
+    int block_threads = 128;
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                         \
+            return SDZ_E_CUDA;                                                                     \
+        }                                                                                          \
+    } while (0)
+
+int grow(sdz_ctx* ctx, DevBuf& b, size_t bytes)
+{
+    if (bytes <= b.cap) return SDZ_OK;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    size_t want = (bytes + (1u << 20)) & ~((size_t(1) << 20) - 1);
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) { ctx->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); b.p = nullptr; return SDZ_E_NOMEM; }
+    b.cap = want;
+    return SDZ_OK;
+}
+
+int grow_stage(sdz_ctx* ctx, size_t bytes)
+{
+    if (bytes <= ctx->h_stage_cap) return SDZ_OK;
+    if (ctx->h_stage) { cudaFreeHost(ctx->h_stage); ctx->h_stage = nullptr; ctx->h_stage_cap = 0; }
+    size_t want = (bytes + (1u << 20)) & ~((size_t(1) << 20) - 1);
+    cudaError_t e = cudaMallocHost(&ctx->h_stage, want);
+    if (e != cudaSuccess) { ctx->err = std::string("cudaMallocHost: ") + cudaGetErrorString(e); return SDZ_E_NOMEM; }
+    ctx->h_stage_cap = want;
+    return SDZ_OK;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- GF(2) helpers on the host (table generation only)
+uint32_t h_mulmod(uint32_t a, uint32_t b)
+{
+    uint32_t p = 0;
+    for (int i = 0; i < 32; i++) {
+        if (a & (0x80000000u >> i)) p ^= b;
+        b = (b & 1u) ? (b >> 1) ^ sdz::CRC_POLY : (b >> 1);
+    }
+    return p;
+}
+
+int upload_tables(sdz_ctx* ctx)
+{
+    static uint32_t tab[4][256], stride[4][256], x2n[32];
+    for (uint32_t n = 0; n < 256; n++) {
+        uint32_t c = n;
+        for (int k = 0; k < 8; k++) c = (c & 1) ? (sdz::CRC_POLY ^ (c >> 1)) : (c >> 1);
+        tab[0][n] = c;
+    }
+    for (uint32_t n = 0; n < 256; n++) {
+        uint32_t c = tab[0][n];
+        for (int k = 1; k < 4; k++) { c = tab[0][c & 0xff] ^ (c >> 8); tab[k][n] = c; }
+    }
+    uint32_t p = 1u << 30;
+    x2n[0] = p;
+    for (int n = 1; n < 32; n++) x2n[n] = p = h_mulmod(p, p);
+    // multiply-by-x^(8*512) per register byte: advance the register over 512 zero bytes
+    for (int j = 0; j < 4; j++)
+        for (uint32_t b = 0; b < 256; b++) {
+            uint32_t c = b << (8 * j);
+            for (uint32_t i = 0; i < sdz::CRC_ROW; i++) c = tab[0][c & 0xff] ^ (c >> 8);
+            stride[j][b] = c;
+        }
+    CK(cudaMemcpyToSymbol(sdz::g_crc_tab, tab, sizeof tab));
+    CK(cudaMemcpyToSymbol(sdz::g_crc_stride_tab, stride, sizeof stride));
+    CK(cudaMemcpyToSymbol(sdz::c_x2n, x2n, sizeof x2n));
+    return SDZ_OK;
+}
+
+template <int G, bool STORE>
+int launch_inflate_t(sdz_ctx* ctx, const sdz::InflateParams& P)
+{
+    const int threads = ctx->block_threads;
+    const int groups = threads / G;
+    const size_t smem = (size_t)groups * sizeof(sdz::GroupSmem);
+    auto kern = sdz::inflate_kernel<G, STORE>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+    if (per_sm < 1) per_sm = 1;
+    unsigned long long want = (P.n + groups - 1) / groups;
+    unsigned long long grid = std::min<unsigned long long>(want, (unsigned long long)ctx->sm_count * per_sm);
+    if (grid == 0) return SDZ_OK;
+    CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), ctx->stream));
+    kern<<<(unsigned)grid, threads, smem, ctx->stream>>>(P);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return SDZ_OK;
+}
+
+template <bool STORE>
+int launch_inflate(sdz_ctx* ctx, const sdz::InflateParams& P)
+{
+    switch (ctx->group) {
+    case 4: return launch_inflate_t<4, STORE>(ctx, P);
+    case 16: return launch_inflate_t<16, STORE>(ctx, P);
+    case 32: return launch_inflate_t<32, STORE>(ctx, P);
+    default: return launch_inflate_t<8, STORE>(ctx, P);
+    }
+}
+
+int launch_finalize(sdz_ctx* ctx, const uint8_t* d_out, sdz_result* d_res, uint64_t n)
+{
+    if (n == 0) return SDZ_OK;
+    CK(cudaMemsetAsync(ctx->d_counter + 1, 0, sizeof(unsigned long long), ctx->stream));
+    unsigned long long warps = n;
+    unsigned grid = (unsigned)std::min<unsigned long long>((warps + 7) / 8, (unsigned long long)ctx->sm_count * 8);
+    sdz::finalize_streams_kernel<<<grid, 256, 0, ctx->stream>>>(d_out, d_res, n, ctx->d_counter + 1);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return SDZ_OK;
+}
+
+int run_batch_device(sdz_ctx* ctx, const sdz_batch_dev* b, bool sizes_only)
+{
+    sdz::InflateParams P;
+    P.in = b->d_in; P.in_off = b->d_in_off; P.in_len = b->d_in_len; P.mode = b->d_mode;
+    P.dict = b->d_dict; P.dict_off = b->d_dict_off; P.dict_len = b->d_dict_len; P.dict_adler = b->d_dict_adler;
+    P.out = sizes_only ? nullptr : b->d_out; P.out_off = b->d_out_off; P.out_cap = b->d_out_cap;
+    P.res = b->d_results; P.n = b->n; P.counter = ctx->d_counter;
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    int rc = sizes_only ? launch_inflate<false>(ctx, P) : launch_inflate<true>(ctx, P);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    if (!sizes_only) {
+        rc = launch_finalize(ctx, b->d_out, b->d_results, b->n);
+        if (rc) return rc;
+    }
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    return SDZ_OK;
+}
+
+void parallel_copy(const std::vector<std::pair<uint8_t*, std::pair<const uint8_t*, size_t>>>& jobs)
+{
+    size_t total = 0;
+    for (auto& j : jobs) total += j.second.second;
+    unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 16u));
+    if (total < (8u << 20) || nt == 1) {
+        for (auto& j : jobs) memcpy(j.first, j.second.first, j.second.second);
+        return;
+    }
+    std::atomic<size_t> next{ 0 };
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++)
+        th.emplace_back([&] {
+            for (;;) {
+                size_t lo = next.fetch_add(256);
+                if (lo >= jobs.size()) break;
+                size_t hi = std::min(jobs.size(), lo + 256);
+                for (size_t i = lo; i < hi; i++) memcpy(jobs[i].first, jobs[i].second.first, jobs[i].second.second);
+            }
+        });
+    for (auto& t : th) t.join();
+}
+
+}  // namespace
+
+// ============================================================================ C ABI
+
+extern "C" {
+
+const char* sdz_version(void) { return "sdzcuda 0.1 (sm_100a)"; }
+
+int sdz_ctx_create(int device, uint32_t flags, sdz_ctx** out)
+{
+    (void)flags;
+    if (!out) return SDZ_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return SDZ_E_NO_DEVICE;
+    if (device < 0 || device >= ndev) return SDZ_E_ARG;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SDZ_E_NO_DEVICE;
+    if (prop.major != 10) return SDZ_E_NO_DEVICE;          // the kernels are built for sm_100a only
+    sdz_ctx* ctx = new sdz_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    auto fail = [&](int rc) { sdz_ctx_destroy(ctx); return rc; };
+    if (cudaSetDevice(device) != cudaSuccess) return fail(SDZ_E_CUDA);
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(SDZ_E_CUDA);
+    for (auto& e : ctx->ev)
+        if (cudaEventCreate(&e) != cudaSuccess) return fail(SDZ_E_CUDA);
+    if (cudaMalloc(&ctx->d_counter, 4 * sizeof(unsigned long long)) != cudaSuccess) return fail(SDZ_E_NOMEM);
+    if (const char* g = getenv("SDZ_GROUP")) { int v = atoi(g); if (v == 4 || v == 8 || v == 16 || v == 32) ctx->group = v; }
+    if (const char* t = getenv("SDZ_BLOCK")) { int v = atoi(t); if (v == 32 || v == 64 || v == 128) ctx->block_threads = v; }
+    if (ctx->block_threads < ctx->group) ctx->block_threads = ctx->group;
+    int rc = upload_tables(ctx);
+    if (rc) return fail(rc);
+    *out = ctx;
+    return SDZ_OK;
+}
+
+void sdz_ctx_destroy(sdz_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (DevBuf* b : { &ctx->d_in, &ctx->d_out, &ctx->d_meta, &ctx->d_res, &ctx->d_part, &ctx->d_misc })
+        if (b->p) cudaFree(b->p);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->d_counter) cudaFree(ctx->d_counter);
+    for (auto& e : ctx->ev)
+        if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* sdz_last_error(sdz_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+uint64_t sdz_launch_count(sdz_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int sdz_last_timing(sdz_ctx* ctx, float ms[3])
+{
+    if (!ctx) return SDZ_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventSynchronize(ctx->ev[2]));
+    CK(cudaEventElapsedTime(&ms[0], ctx->ev[0], ctx->ev[1]));
+    CK(cudaEventElapsedTime(&ms[1], ctx->ev[1], ctx->ev[2]));
+    CK(cudaEventElapsedTime(&ms[2], ctx->ev[0], ctx->ev[2]));
+    return SDZ_OK;
+}
+
+void* sdz_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+void sdz_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+void* sdz_device_alloc(sdz_ctx* ctx, size_t bytes)
+{
+    if (!ctx) return nullptr;
+    void* p = nullptr;
+    cudaSetDevice(ctx->device);
+    if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+void sdz_device_free(sdz_ctx* ctx, void* p) { if (ctx && p) { cudaSetDevice(ctx->device); cudaFree(p); } }
+
+int sdz_memcpy_h2d(sdz_ctx* ctx, void* dst, const void* src, size_t bytes)
+{
+    if (!ctx) return SDZ_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SDZ_OK;
+}
+int sdz_memcpy_d2h(sdz_ctx* ctx, void* dst, const void* src, size_t bytes)
+{
+    if (!ctx) return SDZ_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SDZ_OK;
+}
+int sdz_sync(sdz_ctx* ctx)
+{
+    if (!ctx) return SDZ_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SDZ_OK;
+}
+
+// ---------------------------------------------------------------------------- checksums
+
+static int checksum_chain(sdz_ctx* ctx, bool crc, const uint8_t* p, const uint64_t* seg_len, uint64_t n_seg,
+                          int32_t seed, int on_device, int32_t* out_values, int32_t* out_last)
+{
+    if (!ctx || (!p && n_seg) || !out_last) return SDZ_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (n_seg == 0) { *out_last = seed; return SDZ_OK; }
+    if (n_seg > 0xffffffffull) return SDZ_E_ARG;
+    uint64_t total = 0;
+    for (uint64_t s = 0; s < n_seg; s++) {
+        if (seg_len[s] >= (1ull << 32)) return SDZ_E_ARG;            // reference undefined beyond 4 GiB
+        total += seg_len[s];
+    }
+    const uint8_t* d_p = p;
+    if (!on_device) {
+        int rc = grow(ctx, ctx->d_in, total + 16);
+        if (rc) return rc;
+        if (total) CK(cudaMemcpyAsync(ctx->d_in.p, p, total, cudaMemcpyHostToDevice, ctx->stream));
+        d_p = (const uint8_t*)ctx->d_in.p;
+    }
+    const uint64_t gran = crc ? sdz::CRC_TASK : sdz::ADLER_NMAX;
+    // host-side segment tables: off[n], len[n], base[n+1]
+    std::vector<uint64_t> tbl(3 * n_seg + 1);
+    uint64_t off = 0, base = 0;
+    for (uint64_t s = 0; s < n_seg; s++) {
+        tbl[s] = off; tbl[n_seg + s] = seg_len[s]; tbl[2 * n_seg + s] = base;
+        off += seg_len[s];
+        base += (seg_len[s] + gran - 1) / gran;
+    }
+    tbl[3 * n_seg] = base;
+    const uint64_t n_items = base;
+    size_t meta_bytes = tbl.size() * 8;
+    int rc = grow(ctx, ctx->d_meta, meta_bytes + n_seg * 16 + n_seg * 4 + 64);
+    if (rc) return rc;
+    uint8_t* dm = (uint8_t*)ctx->d_meta.p;
+    CK(cudaMemcpyAsync(dm, tbl.data(), meta_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    uint8_t* d_seginfo = dm + align_up(meta_bytes, 16);
+    int32_t* d_values = (int32_t*)(d_seginfo + n_seg * 16);
+    rc = grow(ctx, ctx->d_part, (n_items + 1) * 12);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (crc) {
+        sdz::CrcTaskTable T{ (const uint64_t*)dm, (const uint64_t*)dm + n_seg, (const uint64_t*)dm + 2 * n_seg, (uint32_t)n_seg };
+        uint32_t* d_partial = (uint32_t*)ctx->d_part.p;
+        if (n_items) {
+            const size_t smem = 4 * 256 * 32 * 4 + 4096;
+            CK(cudaFuncSetAttribute(sdz::crc_tasks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaMemsetAsync(ctx->d_counter + 2, 0, sizeof(unsigned long long), ctx->stream));
+            unsigned grid = (unsigned)std::min<uint64_t>((n_items + 31) / 32, (uint64_t)ctx->sm_count);
+            sdz::crc_tasks_kernel<<<grid, 1024, smem, ctx->stream>>>(d_p, T, n_items, d_partial, ctx->d_counter + 2);
+            ctx->launches++;
+        }
+        sdz::crc_seg_kernel<<<(unsigned)n_seg, 256, 0, ctx->stream>>>(T, d_partial, (uint2*)d_seginfo);
+        sdz::crc_chain_kernel<<<1, 32, 0, ctx->stream>>>((const uint2*)d_seginfo, (uint32_t)n_seg, (uint32_t)seed, d_values);
+        ctx->launches += 2;
+    } else {
+        sdz::SegTable T{ (const uint64_t*)dm, (const uint64_t*)dm + n_seg, (const uint64_t*)dm + 2 * n_seg, (uint32_t)n_seg };
+        uint2* d_partial = (uint2*)ctx->d_part.p;
+        uint32_t* d_pref = (uint32_t*)((uint8_t*)ctx->d_part.p + (n_items + 1) * 8);
+        if (n_items) {
+            unsigned grid = (unsigned)std::min<uint64_t>((n_items + 7) / 8, (uint64_t)ctx->sm_count * 16);
+            sdz::adler_units_kernel<<<grid, 256, 0, ctx->stream>>>(d_p, T, n_items, d_partial);
+            ctx->launches++;
+        }
+        sdz::adler_seg_kernel<<<(unsigned)n_seg, 1024, 0, ctx->stream>>>(T, d_partial, d_pref, (uint4*)d_seginfo);
+        sdz::adler_chain_kernel<<<1, 1024, 0, ctx->stream>>>(T, d_pref, (const uint4*)d_seginfo, (uint32_t)seed, d_values);
+        ctx->launches += 2;
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    std::vector<int32_t> vals(n_seg);
+    CK(cudaMemcpyAsync(vals.data(), d_values, n_seg * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (out_values) memcpy(out_values, vals.data(), n_seg * 4);
+    *out_last = vals[n_seg - 1];
+    return SDZ_OK;
+}
+
+int sdz_adler32_chain(sdz_ctx* ctx, const uint8_t* p, const uint64_t* seg_len, uint64_t n_seg, int32_t seed,
+                      int on_device, int32_t* out_values, int32_t* out_last)
+{
+    return checksum_chain(ctx, false, p, seg_len, n_seg, seed, on_device, out_values, out_last);
+}
+int sdz_crc32_chain(sdz_ctx* ctx, const uint8_t* p, const uint64_t* seg_len, uint64_t n_seg, int32_t seed,
+                    int on_device, int32_t* out_values, int32_t* out_last)
+{
+    return checksum_chain(ctx, true, p, seg_len, n_seg, seed, on_device, out_values, out_last);
+}
+int sdz_adler32(sdz_ctx* ctx, const uint8_t* p, uint64_t n, int32_t seed, int on_device, int32_t* out)
+{
+    return checksum_chain(ctx, false, p, &n, 1, seed, on_device, nullptr, out);
+}
+int sdz_crc32(sdz_ctx* ctx, const uint8_t* p, uint64_t n, int32_t seed, int on_device, int32_t* out)
+{
+    return checksum_chain(ctx, true, p, &n, 1, seed, on_device, nullptr, out);
+}
+
+// ---------------------------------------------------------------------------- batched inflate
+
+int sdz_inflate_batch_device(sdz_ctx* ctx, const sdz_batch_dev* batch, uint32_t flags, int sync)
+{
+    if (!ctx || !batch) return SDZ_E_ARG;
+    if (flags & SDZ_PARITY_SPEC) return SDZ_E_UNSUPPORTED;
+    CK(cudaSetDevice(ctx->device));
+    int rc = run_batch_device(ctx, batch, batch->d_out == nullptr);
+    if (rc) return rc;
+    if (sync) CK(cudaStreamSynchronize(ctx->stream));
+    return SDZ_OK;
+}
+
+// shared host path: stage inputs, run, fetch records (and bytes unless sizes_only)
+static int inflate_host(sdz_ctx* ctx, const sdz_in* in, uint64_t n, uint8_t* out_arena, const uint64_t* out_off,
+                        const uint64_t* out_cap, sdz_result* results, uint64_t* out_len, uint32_t flags, bool sizes_only)
+{
+    if (!ctx || (!in && n)) return SDZ_E_ARG;
+    if (flags & SDZ_PARITY_SPEC) return SDZ_E_UNSUPPORTED;
+    if (!sizes_only && (!results || (n && (!out_arena || !out_off || !out_cap)))) return SDZ_E_ARG;
+    if (n == 0) return SDZ_OK;
+    CK(cudaSetDevice(ctx->device));
+
+    // ---- layout of the compressed arena, the dictionary arena and the per-stream arrays
+    std::vector<uint64_t> in_off(n), dict_off(n), d_out_off(n);
+    std::vector<uint32_t> in_len(n), dict_len(n), d_out_cap(n);
+    std::vector<uint8_t> mode(n);
+    size_t in_bytes = 0, dict_bytes = 0;
+    uint64_t out_lo = ~0ull, out_hi = 0;
+    bool dense = true;
+    for (uint64_t i = 0; i < n; i++) {
+        if (in[i].len >= (1ull << 32) - 64 || (in[i].len && !in[i].data)) return SDZ_E_ARG;
+        if (in[i].mode > SDZ_MODE_RAW) return SDZ_E_ARG;
+        in_off[i] = in_bytes;
+        in_len[i] = (uint32_t)in[i].len;
+        in_bytes += align_up(in[i].len, 16);
+        dict_off[i] = dict_bytes;
+        dict_len[i] = in[i].dict ? in[i].dict_len : 0;
+        dict_bytes += align_up(dict_len[i], 16);
+        mode[i] = (uint8_t)(in[i].mode | (in[i].dict ? 0x80 : 0));
+        if (!sizes_only) {
+            if (out_cap[i] >= (1ull << 32)) return SDZ_E_ARG;
+            out_lo = std::min(out_lo, out_off[i]);
+            out_hi = std::max(out_hi, out_off[i] + out_cap[i]);
+            if (i && out_off[i] != out_off[i - 1] + out_cap[i - 1]) dense = false;
+        }
+    }
+    if (sizes_only) { out_lo = 0; out_hi = 0; }
+    for (uint64_t i = 0; i < n && !sizes_only; i++) { d_out_off[i] = out_off[i] - out_lo; d_out_cap[i] = (uint32_t)out_cap[i]; }
+
+    const size_t in_total = in_bytes + SDZ_IN_PAD;
+    // meta block: in_off, dict_off, out_off (u64) | in_len, dict_len, out_cap, dict_adler (u32) | mode (u8)
+    const size_t meta_bytes = align_up(n * (8 * 3 + 4 * 4 + 1), 16);
+    int rc;
+    if ((rc = grow_stage(ctx, in_total + dict_bytes + 16 + meta_bytes))) return rc;
+    if ((rc = grow(ctx, ctx->d_in, in_total + dict_bytes + 16))) return rc;
+    if ((rc = grow(ctx, ctx->d_meta, meta_bytes))) return rc;
+    if ((rc = grow(ctx, ctx->d_res, n * sizeof(sdz_result)))) return rc;
+    if (!sizes_only && (rc = grow(ctx, ctx->d_out, (out_hi - out_lo) + 64))) return rc;
+
+    uint8_t* hs = (uint8_t*)ctx->h_stage;
+    {
+        std::vector<std::pair<uint8_t*, std::pair<const uint8_t*, size_t>>> jobs;
+        jobs.reserve(n * 2);
+        for (uint64_t i = 0; i < n; i++) {
+            if (in_len[i]) jobs.push_back({ hs + in_off[i], { in[i].data, in_len[i] } });
+            if (dict_len[i]) jobs.push_back({ hs + in_total + dict_off[i], { in[i].dict, dict_len[i] } });
+        }
+        parallel_copy(jobs);
+        memset(hs + in_bytes, 0, SDZ_IN_PAD);
+    }
+    uint8_t* hm = hs + align_up(in_total + dict_bytes, 16);
+    uint64_t* m_in_off = (uint64_t*)hm;
+    uint64_t* m_dict_off = m_in_off + n;
+    uint64_t* m_out_off = m_dict_off + n;
+    uint32_t* m_in_len = (uint32_t*)(m_out_off + n);
+    uint32_t* m_dict_len = m_in_len + n;
+    uint32_t* m_out_cap = m_dict_len + n;
+    int32_t* m_dict_adler = (int32_t*)(m_out_cap + n);
+    uint8_t* m_mode = (uint8_t*)(m_dict_adler + n);
+    memcpy(m_in_off, in_off.data(), n * 8);
+    memcpy(m_dict_off, dict_off.data(), n * 8);
+    memcpy(m_out_off, d_out_off.data(), n * 8);
+    memcpy(m_in_len, in_len.data(), n * 4);
+    memcpy(m_dict_len, dict_len.data(), n * 4);
+    memcpy(m_out_cap, d_out_cap.data(), n * 4);
+    memset(m_dict_adler, 0, n * 4);
+    memcpy(m_mode, mode.data(), n);
+
+    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_in.p, hs, in_total + dict_bytes, cudaMemcpyHostToDevice, ctx->stream));
+
+    // dictionary checksums (reference adler32 incl. Q1) are evaluated on the device, one call each
+    if (dict_bytes) {
+        for (uint64_t i = 0; i < n; i++) {
+            if (!(mode[i] & 0x80)) continue;
+            uint64_t dl = dict_len[i];
+            int32_t v = 1;
+            rc = checksum_chain(ctx, false, (const uint8_t*)ctx->d_in.p + in_total + dict_off[i], &dl, 1, 1, 1, nullptr, &v);
+            if (rc) return rc;
+            m_dict_adler[i] = v;
+        }
+    } else {
+        for (uint64_t i = 0; i < n; i++) if (mode[i] & 0x80) m_dict_adler[i] = 1;   // adler32 of an empty dictionary
+    }
+    CK(cudaMemcpyAsync(ctx->d_meta.p, hm, meta_bytes, cudaMemcpyHostToDevice, ctx->stream));
+
+    uint8_t* dm = (uint8_t*)ctx->d_meta.p;
+    sdz_batch_dev b;
+    b.d_in = (const uint8_t*)ctx->d_in.p;
+    b.d_in_off = (const uint64_t*)dm;
+    b.d_dict_off = b.d_in_off + n;
+    b.d_out_off = b.d_dict_off + n;
+    b.d_in_len = (const uint32_t*)(b.d_out_off + n);
+    b.d_dict_len = b.d_in_len + n;
+    b.d_out_cap = b.d_dict_len + n;
+    b.d_dict_adler = (const int32_t*)(b.d_out_cap + n);
+    b.d_mode = (const uint8_t*)(b.d_dict_adler + n);
+    b.d_dict = (const uint8_t*)ctx->d_in.p + in_total;
+    b.d_out = sizes_only ? nullptr : (uint8_t*)ctx->d_out.p;
+    b.d_results = (sdz_result*)ctx->d_res.p;
+    b.n = n;
+    rc = run_batch_device(ctx, &b, sizes_only);
+    if (rc) return rc;
+
+    std::vector<sdz_result> tmp;
+    sdz_result* rdst = results;
+    if (!rdst) { tmp.resize(n); rdst = tmp.data(); }
+    CK(cudaMemcpyAsync(rdst, ctx->d_res.p, n * sizeof(sdz_result), cudaMemcpyDeviceToHost, ctx->stream));
+    if (!sizes_only) {
+        if (dense) {
+            CK(cudaMemcpyAsync(out_arena + out_lo, ctx->d_out.p, out_hi - out_lo, cudaMemcpyDeviceToHost, ctx->stream));
+        } else {
+            CK(cudaStreamSynchronize(ctx->stream));
+            for (uint64_t i = 0; i < n; i++)
+                if (rdst[i].out_len)
+                    CK(cudaMemcpyAsync(out_arena + out_off[i], (uint8_t*)ctx->d_out.p + d_out_off[i], rdst[i].out_len,
+                                       cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    int ret = SDZ_OK;
+    for (uint64_t i = 0; i < n; i++) {
+        if (!sizes_only) {
+            rdst[i].out_off = out_off[i];
+            if (rdst[i].zstatus == SDZ_Z_BUF_ERROR) ret = SDZ_E_OUT_CAP;    // the kernel ran out of slot
+        }
+        if (out_len) out_len[i] = rdst[i].out_len;
+    }
+    return ret;
+}
+
+int sdz_inflate_batch(sdz_ctx* ctx, const sdz_in* in, uint64_t n, uint8_t* out_arena, const uint64_t* out_off,
+                      const uint64_t* out_cap, sdz_result* results, uint32_t flags)
+{
+    return inflate_host(ctx, in, n, out_arena, out_off, out_cap, results, nullptr, flags, false);
+}
+
+int sdz_inflate_sizes(sdz_ctx* ctx, const sdz_in* in, uint64_t n, uint64_t* out_len, uint32_t flags)
+{
+    if (!out_len && n) return SDZ_E_ARG;
+    return inflate_host(ctx, in, n, nullptr, nullptr, nullptr, nullptr, out_len, flags, true);
+}
+
+}  // extern "C"

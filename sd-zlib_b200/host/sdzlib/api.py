@@ -1,0 +1,243 @@
+"""Reference-shaped API over the C ABI (see package docstring)."""
+import ctypes as C
+import datetime
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _native as N
+
+MODE_SNIFF, MODE_INFLATER, MODE_RAW = 0, 1, 2
+OUTPUT_BUFSIZE = 16384                      # src/zstream.ts:11
+_CHECK = ("unchecked", "match", "mismatch")
+_MSG = [
+    "", "invalid gzip id", "unknown compression method", "invalid window size", "incorrect header check",
+    "need dictionary", "invalid block type", "invalid stored block lengths", "too many length or distance symbols",
+    "invalid bit length repeat", "oversubscribed dynamic bit lengths tree", "incomplete dynamic bit lengths tree",
+    "oversubscribed literal/length tree", "incomplete literal/length tree", "oversubscribed distance tree",
+    "incomplete distance tree", "empty distance tree with lengths", "invalid distance code",
+    "invalid literal/length code",
+]
+_THROWN = [
+    "", "inflate error: bad input", "Custom dictionary is not valid for this data",
+    "Custom dictionary required for this data", "inflate error: ", "inflate error: bad input data",
+    "reference implementation does not terminate on this input (trailing bytes after the stream end)",
+    "data buffer is too small", "Unexpected EOF during decompression", "Data integrity check failed",
+    "Data size check failed", "Decompression error",
+]
+
+
+def _as_u8(source, what):
+    """u8ArrayFromBufferSource (src/common.ts:102-114): bytes-like or any buffer view."""
+    if isinstance(source, np.ndarray):
+        return np.ascontiguousarray(source).view(np.uint8).reshape(-1)
+    try:
+        return np.frombuffer(memoryview(source).cast("B"), dtype=np.uint8)
+    except TypeError:
+        raise TypeError(what)
+
+
+def _i32(v):
+    v = int(v) & 0xFFFFFFFF
+    return v - (1 << 32) if v & 0x80000000 else v
+
+
+# ------------------------------------------------------------------ checksums
+
+def _checksum(fn_name, source, seed, ctx):
+    view = _as_u8(source, "source must be a BufferSource")
+    ctx = ctx or N.default_context()
+    out = C.c_int32()
+    fn = getattr(ctx.lib, fn_name)
+    total = int(view.size)
+    if total < (1 << 32):
+        ctx.check(fn(ctx.h, view.ctypes.data if total else None, total, _i32(seed), 0, C.byref(out)))
+        return out.value
+    raise ValueError("buffers of 4 GiB or more are undefined in the reference (SURVEY Q13)")
+
+
+def adler32(source, seed=1, ctx=None):
+    """adler32(source, seed = 1) -> signed int32, bit-exact with src/adler32.ts (incl. Q1)."""
+    return _checksum("sdz_adler32", source, seed, ctx)
+
+
+def crc32(source, seed=0, ctx=None):
+    """crc32(source, seed = 0) -> signed int32, bit-exact with src/crc32.ts."""
+    return _checksum("sdz_crc32", source, seed, ctx)
+
+
+def _chain(fn_name, source, seg_lens, seed, ctx, device_ptr=None):
+    ctx = ctx or N.default_context()
+    lens = np.ascontiguousarray(seg_lens, dtype=np.uint64)
+    vals = np.zeros(len(lens), dtype=np.int32)
+    last = C.c_int32()
+    if device_ptr is None:
+        view = _as_u8(source, "source must be a BufferSource")
+        ptr, on_dev = view.ctypes.data, 0
+    else:
+        ptr, on_dev = device_ptr, 1
+    ctx.check(getattr(ctx.lib, fn_name)(ctx.h, ptr, lens.ctypes.data, len(lens), _i32(seed), on_dev,
+                                        vals.ctypes.data, C.byref(last)))
+    return vals
+
+
+def adler32_chain(source, seg_lens, seed=1, ctx=None, device_ptr=None):
+    """values[i] of `s = adler32(segment_i, s)` over consecutive segments, one device pass."""
+    return _chain("sdz_adler32_chain", source, seg_lens, seed, ctx, device_ptr)
+
+
+def crc32_chain(source, seg_lens, seed=0, ctx=None, device_ptr=None):
+    return _chain("sdz_crc32_chain", source, seg_lens, seed, ctx, device_ptr)
+
+
+def mergeBuffers(buffers: Sequence[bytes]) -> bytes:
+    """src/common.ts:116-126"""
+    return b"".join(bytes(b) for b in buffers)
+
+
+# ------------------------------------------------------------------ inflate
+
+@dataclass
+class InflateResult:
+    """src/sd-inflate.ts:39-52"""
+    success: bool
+    complete: bool
+    checksum: str
+    fileSize: str
+    fileName: str
+    modDate: Optional[datetime.datetime]
+
+
+def _record_to_result(r, data_view) -> InflateResult:
+    name = bytes(data_view[r.name_off:r.name_off + r.name_len]).decode("latin-1") if r.name_len else ""
+    # `new Date(mtime * 1000)` with a signed int32 mtime
+    mod = None if r.mtime == 0 else datetime.datetime.fromtimestamp(r.mtime, tz=datetime.timezone.utc)
+    return InflateResult(bool(r.success), bool(r.complete), _CHECK[r.checksum_state], _CHECK[r.size_state], name, mod)
+
+
+def _raise_thrown(thrown, msg_id):
+    text = _THROWN[thrown] + (_MSG[msg_id] if thrown == 4 else "")
+    raise ValueError(text) if thrown != 6 else RuntimeError(text)
+
+
+def inflate_batch_raw(views, dictionaries=None, modes=None, caps=None, ctx=None):
+    """One sdz_inflate_batch call.  Returns (out_arena: np.uint8[], out_off, records)."""
+    ctx = ctx or N.default_context()
+    n = len(views)
+    ins = (N.In * max(n, 1))()
+    keep = []
+    for i, v in enumerate(views):
+        ins[i].data = v.ctypes.data if v.size else None
+        ins[i].len = int(v.size)
+        d = None if dictionaries is None else dictionaries[i]
+        if d is not None:
+            dv = _as_u8(d, "options.dictionary must be undefined or a buffer or a buffer view")
+            keep.append(dv)
+            # a zero-length dictionary is still "a dictionary was supplied"
+            ins[i].dict = dv.ctypes.data if dv.size else C.cast(C.create_string_buffer(1), C.c_void_p).value
+            ins[i].dict_len = int(dv.size)
+        ins[i].mode = MODE_SNIFF if modes is None else modes[i]
+    if caps is None:
+        sizes = np.zeros(max(n, 1), dtype=np.uint64)
+        ctx.check(ctx.lib.sdz_inflate_sizes(ctx.h, ins, n, sizes.ctypes.data, 0))
+        caps = sizes[:n]
+    caps = np.ascontiguousarray(caps, dtype=np.uint64)
+    slot = (caps + np.uint64(15)) & ~np.uint64(15)
+    off = np.zeros(n, dtype=np.uint64)
+    if n > 1:
+        off[1:] = np.cumsum(slot[:-1])
+    total = int(slot.sum()) if n else 0
+    arena = np.empty(max(total, 1), dtype=np.uint8)
+    res = (N.Result * max(n, 1))()
+    ctx.check(ctx.lib.sdz_inflate_batch(ctx.h, ins, n, arena.ctypes.data, off.ctypes.data, slot.ctypes.data, res, 0),
+              allow=(N.SDZ_E_OUT_CAP,))
+    return arena, off, res
+
+
+def inflateBatch(buffers, dictionaries=None, raw=None, ctx=None):
+    """inflateBatch(buffers[]) - the one entry point added to the reference API.
+
+    Each buffer is decoded exactly like `inflate(buffer, dictionary)` (container sniffing
+    included) unless raw[i] is given, in which case it behaves like
+    `new Inflater({raw: raw[i], dictionary}).append(buffer); finish()`.  Errors are recorded
+    per stream instead of thrown: returns a list of dicts {data, result, error}.
+    """
+    views = [_as_u8(b, "data must be an ArrayBuffer or buffer view") for b in buffers]
+    modes = None
+    if raw is not None:
+        modes = [MODE_SNIFF if r is None else (MODE_RAW if r else MODE_INFLATER) for r in raw]
+    arena, off, res = inflate_batch_raw(views, dictionaries, modes, None, ctx)
+    out = []
+    for i, v in enumerate(views):
+        r = res[i]
+        err = None
+        sniff = modes is None or modes[i] == MODE_SNIFF
+        thrown = r.thrown_inflate if sniff else r.thrown_append
+        if thrown == 12:
+            err = "options.dictionary cannot be set when options.raw is true"
+        elif thrown:
+            err = _THROWN[thrown] + (_MSG[r.msg_id] if thrown == 4 else "")
+        data = bytes(arena[int(off[i]):int(off[i]) + int(r.out_len)]) if (r.out_len and not r.thrown_append) else b""
+        out.append({"data": data, "result": _record_to_result(r, v), "error": err, "record": r})
+    return out
+
+
+def inflate(data, dictionary=None, ctx=None) -> bytes:
+    """inflate(data, dictionary?) - src/sd-inflate.ts:189-228 (auto-detects the container)."""
+    view = _as_u8(data, "data must be an ArrayBuffer or buffer view")
+    if view.size < 2:
+        raise ValueError("data buffer is too small")
+    arena, off, res = inflate_batch_raw([view], [dictionary], [MODE_SNIFF], None, ctx)
+    r = res[0]
+    if r.thrown_inflate == 12:
+        raise ValueError("options.dictionary cannot be set when options.raw is true")   # RangeError in JS
+    if r.thrown_inflate:
+        _raise_thrown(r.thrown_inflate, r.msg_id)
+    return bytes(arena[:int(r.out_len)])
+
+
+class Inflater:
+    """class Inflater - src/sd-inflate.ts:54-180.
+
+    Round-1 streaming model: every append() re-decodes the bytes received so far on the
+    device and returns the output that is new since the previous call, cut into
+    <= 16 KiB chunks.  finish() reports the record of the whole input.  (The reference's
+    chunk boundaries and its Q2/Q3 mid-block defects across append() calls are not modelled.)
+    """
+
+    def __init__(self, raw=None, dictionary=None, ctx=None):
+        if raw is not None and raw is not True and raw is not False:
+            raise TypeError("options.raw must be undefined or true or false")
+        self._raw = bool(raw)
+        if dictionary is not None:
+            if self._raw:
+                raise ValueError("options.dictionary cannot be set when options.raw is true")   # RangeError
+            _as_u8(dictionary, "options.dictionary must be undefined or a buffer or a buffer view")
+        self._dict = dictionary
+        self._ctx = ctx
+        self._buf = bytearray()
+        self._emitted = 0
+        self._rec = None
+        self._view = np.zeros(0, dtype=np.uint8)
+
+    def append(self, data) -> List[bytes]:
+        chunk = _as_u8(data, "data must be an ArrayBuffer or buffer view")
+        if chunk.size == 0:
+            return []
+        self._buf += chunk.tobytes()
+        view = np.frombuffer(bytes(self._buf), dtype=np.uint8)
+        mode = MODE_RAW if self._raw else MODE_INFLATER
+        arena, off, res = inflate_batch_raw([view], [self._dict], [mode], None, self._ctx)
+        r = res[0]
+        self._rec, self._view = r, view
+        if r.thrown_append:
+            _raise_thrown(r.thrown_append, r.msg_id)
+        new = bytes(arena[self._emitted:int(r.out_len)])
+        self._emitted = int(r.out_len)
+        return [new[i:i + OUTPUT_BUFSIZE] for i in range(0, len(new), OUTPUT_BUFSIZE)]
+
+    def finish(self) -> InflateResult:
+        if self._rec is None:
+            return InflateResult(False, False, "unchecked", "unchecked", "", None)
+        return _record_to_result(self._rec, self._view)

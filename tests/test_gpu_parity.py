@@ -1,0 +1,298 @@
+"""GPU parity tests (run with -m gpu on a B200): every result of the CUDA path, taken
+through the C ABI, is compared bit for bit with the CPU oracle on the same inputs, with the
+reference's fixtures, and through size-independent properties at benchmark sizes."""
+import gzip
+import os
+import random
+import zlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O  # noqa: E402  (checker only)
+from tools import corpus as K  # noqa: E402
+
+import sdzlib  # noqa: E402
+from sdzlib import api as A  # noqa: E402
+
+
+def raw_deflate(data, level=6, wbits=-15, zdict=None):
+    co = zlib.compressobj(level, zlib.DEFLATED, wbits) if zdict is None else zlib.compressobj(level, zlib.DEFLATED, wbits, 8, 0, zdict)
+    return co.compress(data) + co.flush()
+
+
+def run_batch(streams, dicts=None, modes=None, slack=64):
+    """GPU result for each stream: (bytes, record)."""
+    views = [np.frombuffer(bytes(s), dtype=np.uint8) for s in streams]
+    arena, off, res = A.inflate_batch_raw(views, dicts, modes, None)
+    out = []
+    for i in range(len(views)):
+        r = res[i]
+        out.append((bytes(arena[int(off[i]):int(off[i]) + int(r.out_len)]), r))
+    return out
+
+
+def check_against_oracle(streams, dicts=None, modes=None, allow_hang=True):
+    got = run_batch(streams, dicts, modes)
+    for i, s in enumerate(streams):
+        d = None if dicts is None else dicts[i]
+        m = O.MODE_SNIFF if modes is None else modes[i]
+        exp_bytes, exp = O.inflate_oneshot(bytes(s), dictionary=d, mode=m)
+        g_bytes, g = got[i]
+        assert g.observable() == exp.observable(), (i, bytes(s)[:24].hex(), len(s), g.observable(), exp.observable())
+        if not exp.thrown_append:
+            assert g_bytes == exp_bytes, (i, len(g_bytes), len(exp_bytes))
+    return got
+
+
+# ---------------------------------------------------------------- reference fixtures (Appendix B)
+
+def test_fixtures_through_public_api(fx):
+    txt = fx("paradiselost.txt")
+    assert sdzlib.inflate(fx("paradiselost.deflate")) == txt
+    assert sdzlib.inflate(fx("paradiselost.gz")) == txt
+    assert sdzlib.inflate(fx("simple.deflate")) == fx("simple.txt")
+    assert sdzlib.inflate(fx("simple.gz")) == fx("simple.txt")
+    assert sdzlib.inflate(fx("simple.raw")) == fx("simple.txt")
+    v = sdzlib.inflate(fx("vertices.deflate"))
+    assert len(v) == 43440 and zlib.crc32(v) == 0xbf55c371
+
+
+def test_fixture_records(fx):
+    names = ["paradiselost.deflate", "paradiselost.gz", "simple.deflate", "simple.gz", "simple.raw", "vertices.deflate"]
+    got = check_against_oracle([fx(n) for n in names])
+    r = got[1][1]
+    assert (r.success, r.complete, r.checksum_state, r.size_state) == (1, 1, 1, 1)
+    assert r.mtime == 1530824734 and r.stored_checksum == -499006831
+    assert fx("paradiselost.gz")[r.name_off:r.name_off + r.name_len] == b"paradiselost.txt"
+    assert got[0][1].stored_checksum == -1949153550 and got[0][1].n_blocks == 7
+
+
+def test_inflater_class(fx):
+    inf = sdzlib.Inflater()
+    b1 = inf.append(fx("paradiselost.part1.deflate"))
+    b2 = inf.append(fx("paradiselost.part2.deflate"))
+    assert sdzlib.mergeBuffers(b1 + b2) == fx("paradiselost.txt")
+    assert all(len(c) <= 16384 for c in b1 + b2)
+    res = inf.finish()
+    assert (res.success, res.complete, res.checksum, res.fileSize, res.fileName, res.modDate) == (True, True, "match", "unchecked", "", None)
+    inf = sdzlib.Inflater()
+    out = sdzlib.mergeBuffers(inf.append(fx("simple.gz")))
+    res = inf.finish()
+    assert out == fx("simple.txt") and res.success and res.fileName == "simple.txt"
+    assert res.modDate.timestamp() == 1576725008 and res.checksum == "match" and res.fileSize == "match"
+    inf = sdzlib.Inflater(raw=True)
+    assert sdzlib.mergeBuffers(inf.append(fx("simple.raw"))) == fx("simple.txt")
+
+
+def test_inflate_batch_entry_point(fx):
+    bufs = [fx("simple.deflate"), fx("simple.gz"), b"\x78\x01\x07", fx("simple.raw"), fx("paradiselost.gz")[:5000]]
+    out = sdzlib.inflateBatch(bufs)
+    assert out[0]["data"] == fx("simple.txt") and out[0]["error"] is None and out[0]["result"].checksum == "match"
+    assert out[1]["result"].fileName == "simple.txt"
+    assert out[2]["error"] == "inflate error: invalid block type" and out[2]["data"] == b""
+    assert out[3]["data"] == fx("simple.txt")
+    assert out[4]["error"] == "Unexpected EOF during decompression" and not out[4]["result"].complete
+    assert fx("paradiselost.txt").startswith(out[4]["data"]) and len(out[4]["data"]) > 1000
+
+
+# ---------------------------------------------------------------- checksums
+
+def test_checksums_vs_oracle_and_zlib():
+    rnd = random.Random(5)
+    for n in [0, 1, 2, 3, 15, 16, 17, 31, 511, 512, 513, 4095, 5551, 5552, 5553, 11104, 16384, 16656, 65536, 100003,
+              262144, 262145, 1 << 20, (1 << 20) + 5552 * 3 - (1 << 20) % 5552]:
+        b = bytes(rnd.getrandbits(8) for _ in range(n)) if n < 70000 else os.urandom(n)
+        for seed in (None, 0, 1, -1, 0x7fffffff, -2147483648, 0xfff1fff1 - (1 << 32)):
+            a_exp = O.adler32(b) if seed is None else O.adler32(b, seed)
+            c_exp = O.crc32(b) if seed is None else O.crc32(b, seed)
+            a_got = sdzlib.adler32(b) if seed is None else sdzlib.adler32(b, seed)
+            c_got = sdzlib.crc32(b) if seed is None else sdzlib.crc32(b, seed)
+            assert a_got == a_exp, ("adler", n, seed, a_got, a_exp)
+            assert c_got == c_exp, ("crc", n, seed, c_got, c_exp)
+        if n % 5552 or n == 0:
+            assert sdzlib.adler32(b) & 0xFFFFFFFF == zlib.adler32(b)
+        assert sdzlib.crc32(b) & 0xFFFFFFFF == zlib.crc32(b)
+
+
+def test_checksum_unaligned_views():
+    base = np.frombuffer(os.urandom(300000), dtype=np.uint8)
+    for start in (1, 2, 3, 5, 7, 13, 15):
+        for n in (0, 1, 17, 5552, 70001, 262144 + 19):
+            v = base[start:start + n]
+            assert sdzlib.adler32(v) == O.adler32(v.tobytes())
+            assert sdzlib.crc32(v) == O.crc32(v.tobytes())
+
+
+def test_seed_chaining_one_pass():
+    data = os.urandom(3_000_000)
+    lens = [5552 * 4, 1, 0, 700000, 5552, 333333, 11104 * 8, 262144, 5552 * 30]
+    lens.append(len(data) - sum(lens))
+    a_vals = sdzlib.adler32_chain(data, lens)
+    c_vals = sdzlib.crc32_chain(data, lens)
+    a, c, off = 1, 0, 0
+    for i, n in enumerate(lens):
+        a = O.adler32(data[off:off + n], a)
+        c = O.crc32(data[off:off + n], c)
+        off += n
+        assert int(a_vals[i]) == a, ("adler chain", i, n)
+        assert int(c_vals[i]) == c, ("crc chain", i, n)
+    assert int(c_vals[-1]) & 0xFFFFFFFF == zlib.crc32(data)
+
+
+# ---------------------------------------------------------------- generated corpora vs oracle
+
+@pytest.mark.parametrize("level", [1, 6, 9])
+def test_corpora_all_containers(level):
+    streams, plains = [], []
+    for kind, n in ((K.TEXT, 65536), (K.BINARY, 65536), (K.RUNS, 65536), (K.RANDOM, 40000), (K.TINY, 150), (K.TEXT, 300000)):
+        for idx in range(3):
+            plain = K.generate(kind, 100 * level + idx, n)
+            for cont in (K.RAW, K.ZLIB, K.GZIP, K.GZIP_NAME):
+                streams.append(K.compress(plain, level, cont))
+                plains.append(plain.tobytes())
+    got = check_against_oracle(streams)
+    n_complete = 0
+    for (b, r), p in zip(got, plains):
+        assert b == p
+        n_complete += r.complete
+    assert n_complete >= len(streams) * 3 // 4          # some raw streams are incomplete by Q15
+
+
+def test_preset_dictionary_streams():
+    dic = bytes(K.generate(K.TEXT, 999, 470))
+    dictid = O.adler32(dic)
+    streams, dicts = [], []
+    for idx in range(6):
+        plain = K.generate(K.TEXT, 500 + idx, 20000 + 7777 * idx)
+        streams.append(K.compress(plain, 6, K.ZLIB_DICT, dic, dictid)); dicts.append(dic)
+    streams.append(streams[0]); dicts.append(None)                # dictionary required
+    streams.append(streams[0]); dicts.append(dic + b"!")          # wrong dictionary
+    streams.append(K.compress(K.generate(K.TEXT, 1, 5000), 6, K.ZLIB)); dicts.append(dic)   # not needed: ignored
+    big = bytes(K.generate(K.TEXT, 77, 40000))                    # > 32 KiB dictionary: last 32767 bytes are used (Q14)
+    streams.append(K.compress(K.generate(K.TEXT, 78, 30000), 6, K.ZLIB_DICT, big, O.adler32(big))); dicts.append(big)
+    q1 = bytes(K.generate(K.TEXT, 79, 5552))                      # dictionary length hits Q1
+    streams.append(K.compress(K.generate(K.TEXT, 80, 9000), 6, K.ZLIB_DICT, q1, O.adler32(q1))); dicts.append(q1)
+    streams.append(K.compress(K.generate(K.TEXT, 80, 9000), 6, K.ZLIB_DICT, q1, zlib.adler32(q1))); dicts.append(q1)
+    got = check_against_oracle(streams, dicts, [O.MODE_INFLATER] * len(streams))
+    assert got[0][1].success and got[6][1].thrown_append == O.THROW_DICT_REQUIRED
+    assert got[7][1].thrown_append == O.THROW_DICT_INVALID and got[8][1].success
+
+
+# ---------------------------------------------------------------- Appendix A behaviours
+
+def test_divergence_vectors_and_quirks():
+    streams = [
+        bytes.fromhex("030200"),                                   # D1 / Q6 zero fill
+        bytes.fromhex("05c08100000000009056fe2b0000"),             # D2 / Q9 no EOB
+        bytes.fromhex("0dc081080000000020d6fd252e02"),             # D3 / Q9 empty distance tree
+        zlib.compress(b"hello world") + b"\0",                     # Q4 trailing byte
+        zlib.compress(b""),                                        # Q8
+        raw_deflate(b"hello hello hello"),                         # Q15
+        raw_deflate(b"a"), raw_deflate(b"ab"), raw_deflate(b"abc"), raw_deflate(b"abcdefgh"),
+        b"\x78\x02\x03\x00", b"\x79\x9c\x03\x00", b"\x88\x1c\x03\x00", b"\x1f\x8c\x08\x00", b"\x78\x01\x07",
+        b"\x78\x01\x01\x05\x00\x00\x00", b"x", b"", b"\x1f", b"\x78", b"\x1f\x8b", b"\x1f\x8b\x08",
+    ]
+    g = bytearray(gzip.compress(b"hello", mtime=1))                # Q5 FEXTRA
+    g[3] |= 4
+    g[10:10] = b"\x02\x00ab"
+    streams.append(bytes(g))
+    g2 = bytearray(gzip.compress(b"hello comment", mtime=77))      # FCOMMENT + FHCRC are skipped
+    g2[3] |= 16 | 2
+    g2[10:10] = b"a comment\x00\x12\x34"
+    streams.append(bytes(g2))
+    check_against_oracle(streams)
+    check_against_oracle(streams, None, [O.MODE_INFLATER] * len(streams))
+    check_against_oracle(streams, None, [O.MODE_RAW] * len(streams))
+
+
+def test_q1_final_chunk_lengths():
+    """A valid zlib stream whose last 16 KiB chunk is 5552 or 11104 bytes long is reported as a
+    checksum mismatch by the reference (Q1)."""
+    streams = []
+    for total in (5552, 11104, 16384 + 5552, 32768 + 11104, 16384 * 3, 5551, 16384 + 5553):
+        streams.append(K.compress(K.generate(K.TEXT, total, total), 6, K.ZLIB))
+    got = check_against_oracle(streams)
+    assert [r.checksum_state for _, r in got] == [2, 2, 2, 2, 1, 1, 1]
+
+
+def test_q2_stored_blocks():
+    streams = []
+    for n in (1, 100, 16383, 32768, 49151, 49152, 49153, 65535, 65536, 70000, 100000, 131072):
+        streams.append(zlib.compress(os.urandom(n), 6))
+        streams.append(zlib.compress(os.urandom(n), 0))
+    # text, then incompressible, then text: stored blocks in the middle of a stream
+    for k in range(4):
+        plain = K.generate(K.TEXT, k, 30000 + 5000 * k).tobytes() + os.urandom(20000 + 3000 * k) + K.generate(K.TEXT, k + 9, 40000).tobytes()
+        streams.append(zlib.compress(plain, 6))
+    check_against_oracle(streams)
+
+
+def test_truncation_at_every_byte(fx):
+    """Input exhaustion at every position of small streams (incl. mid-header, mid-trailer)."""
+    bases = [fx("simple.deflate"), fx("simple.gz"), fx("simple.raw"),
+             K.compress(K.generate(K.TEXT, 3, 3000), 6, K.ZLIB), K.compress(K.generate(K.BINARY, 3, 2000), 9, K.GZIP_NAME),
+             K.compress(K.generate(K.RANDOM, 3, 600), 6, K.ZLIB), K.compress(K.generate(K.RUNS, 4, 5000), 6, K.RAW)]
+    streams = []
+    for b in bases:
+        step = 1 if len(b) < 400 else 7
+        streams += [b[:k] for k in range(0, len(b), step)]
+    check_against_oracle(streams)
+    check_against_oracle(streams, None, [O.MODE_INFLATER] * len(streams))
+
+
+def test_truncation_large(fx):
+    b = fx("paradiselost.deflate")
+    rnd = random.Random(9)
+    cuts = sorted(rnd.sample(range(2, len(b)), 60)) + [len(b) - 1, len(b) - 2, len(b) - 3, len(b) - 4, len(b) - 5]
+    check_against_oracle([b[:k] for k in cuts])
+    g = fx("paradiselost.gz")
+    check_against_oracle([g[:len(g) - k] for k in range(1, 12)])
+
+
+def test_corrupted_streams():
+    """Random single-byte corruptions: the first event (error, stall or end) must agree."""
+    rnd = random.Random(21)
+    base = [K.compress(K.generate(K.TEXT, 40, 20000), 6, K.ZLIB), K.compress(K.generate(K.BINARY, 41, 9000), 6, K.GZIP),
+            K.compress(K.generate(K.TINY, 42, 120), 6, K.ZLIB), K.compress(K.generate(K.RUNS, 43, 30000), 6, K.RAW)]
+    streams = []
+    for b in base:
+        for _ in range(60):
+            x = bytearray(b)
+            pos = rnd.randrange(len(x)) if rnd.random() < 0.5 else rnd.randrange(min(len(x), 120))
+            x[pos] ^= 1 << rnd.randrange(8)
+            streams.append(bytes(x))
+    got = run_batch(streams)
+    n_hang = 0
+    for s, (gb, gr) in zip(streams, got):
+        eb, er = O.inflate_oneshot(s)
+        if er.thrown_append == O.THROW_HANG and gr.thrown_append != O.THROW_HANG:
+            n_hang += 1                                  # reference never returns here; nothing to compare
+            continue
+        assert gr.observable() == er.observable(), (s[:16].hex(), gr.observable(), er.observable())
+        if not er.thrown_append:
+            assert gb == eb
+    assert n_hang <= len(streams) // 10
+
+
+# ---------------------------------------------------------------- benchmark-size properties
+
+def test_batch_4096_text_streams_roundtrip():
+    n, plen = 4096, 65536
+    comp, stride, clen, plain = K.make_batch(K.TEXT, n, plen, 6, K.ZLIB, keep_plain=True)
+    views = [comp[i * stride:i * stride + int(clen[i])] for i in range(n)]
+    arena, off, res = A.inflate_batch_raw(views, None, None, np.full(n, plen, dtype=np.uint64))
+    assert all(res[i].success and res[i].checksum_state == 1 and res[i].out_len == plen for i in range(n))
+    assert np.array_equal(arena[:n * plen], plain)
+    # checksum of checksums: every running Adler-32 equals zlib's over the plaintext
+    for i in range(0, n, 97):
+        assert res[i].running_checksum & 0xFFFFFFFF == zlib.adler32(plain[i * plen:(i + 1) * plen].tobytes())
+
+
+def test_sizing_pass_matches_decode():
+    streams = [K.compress(K.generate(K.TEXT, i, 1000 + 3571 * i), 6, K.ZLIB) for i in range(20)]
+    views = [np.frombuffer(s, dtype=np.uint8) for s in streams]
+    arena, off, res = A.inflate_batch_raw(views)
+    assert [int(r.out_len) for r in res] == [1000 + 3571 * i for i in range(20)]
