@@ -24,6 +24,7 @@
 #include "sdz_oracle.h"
 
 #include <pthread.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -638,6 +639,7 @@ static int codes_proc(blocks_t* s, zstream* z, int r)
             break;
         case C_WASH:                                                               /* :619-641 */
             if (k > 7) { k -= 8; n++; p--; }
+            if (getenv("SDZO_TRACE")) fprintf(stderr, "  WASH q=%d read=%d ao=%ld total_out=%lld\n", q, s->read, z->avail_out, (long long)z->total_out);
             s->write = q; r = window_flush(s, z, r); q = s->write; m = ROOM(s, q);
             if (s->read != s->write) { SAVE(); return window_flush(s, z, r); }
             cs->mode = C_END;
@@ -692,6 +694,9 @@ static int blocks_proc(blocks_t* s, zstream* z, int r)
             t = (int)(b & 7);
             s->last = t & 1;
             s->n_blocks++;
+            if (getenv("SDZO_TRACE"))
+                fprintf(stderr, "  block %u: type=%d last=%d total_out=%lld read=%d write=%d avail_out=%ld\n", s->n_blocks, t >> 1, t & 1,
+                        (long long)z->total_out, s->read, q, z->avail_out);
             switch (t >> 1) {
             case 0:
                 b >>= 3; k -= 3;
@@ -1146,6 +1151,10 @@ int sdzo_append(sdzo_inflater* I, const uint8_t* data, size_t len, sdzo_chunks* 
         progress_t before = snapshot(I, nomoreinput);
         int err = container_step(&I->inf, z);
         I->last_status = err;
+        if (getenv("SDZO_TRACE"))
+            fprintf(stderr, "call: err=%d total_out=%lld out_idx=%ld avail_in=%ld bmode=%d cmode=%d read=%d write=%d nblocks=%u\n", err,
+                    (long long)z->total_out, z->next_out_index, z->avail_in, I->inf.blocks.mode, I->inf.blocks.codes.mode,
+                    I->inf.blocks.read, I->inf.blocks.write, I->inf.blocks.n_blocks);
 
         if (nomoreinput && err == SDZ_Z_BUF_ERROR) {                               /* :111-115 */
             if (z->avail_in != 0) { out->len = 0; out->n_chunks = 0; return SDZ_THROW_BAD_INPUT; }

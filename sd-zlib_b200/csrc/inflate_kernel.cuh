@@ -150,6 +150,8 @@ struct Decoder {
 
     // reference root widths of the current block's trees (src/inftree.ts:146-165)
     int lbits, dbits, g_l, g_d;
+    int last_klen;                     // length of the code slow_code() decoded last
+    int eob_len;                       // code length of the end-of-block symbol just decoded
 
     // ------------------------------------------------------------------ input staging
     __device__ __forceinline__ void issue_chunk(uint32_t rel)
@@ -234,6 +236,11 @@ struct Decoder {
         uint64_t loaded = wp < end_wp ? (uint64_t)wp * 32 : (uint64_t)in_len * 8;
         return (uint32_t)((loaded - (uint64_t)bc) >> 3);
     }
+    __device__ __forceinline__ uint64_t bit_pos() const
+    {
+        uint64_t loaded = wp < end_wp ? (uint64_t)wp * 32 : (uint64_t)in_len * 8;
+        return loaded - (uint64_t)bc;
+    }
     __device__ __forceinline__ bool ensure(int n) { refill(); return bc >= n; }
     __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)bb & ((1u << n) - 1u); }
     __device__ __forceinline__ void drop(int n) { bb >>= n; bc -= n; }
@@ -314,7 +321,34 @@ struct Decoder {
             }
             fc = (fc + ck) << 1;
         }
-        return 1;
+        return 0;
+    }
+
+    // Number of (exop, bits, base) entries huft_build allocates for this code set
+    // (src/inftree.ts:217-246): the root table plus one sub-table per distinct l-bit
+    // (and, for very long codes, 2l-bit) prefix.  Evaluated by the group's lanes in parallel.
+    __device__ int ref_table_total(const uint32_t* cnt, int g, int pad, int l) const
+    {
+        int total = 1 << l;
+        for (int w = l; w < g; w += l) {
+            // first code longer than w bits -> first prefix that owns a sub-table at this level
+            uint32_t fc = 0, pmin = 1u << w;
+            for (int k = 1; k <= g; k++) {
+                uint32_t ck = cnt[k] + (k == g ? (uint32_t)pad : 0u);
+                if (k > w && ck) { pmin = fc >> (k - w); break; }
+                fc = (fc + ck) << 1;
+            }
+            int part = 0;
+            for (uint32_t P = pmin + (uint32_t)glane; P < (1u << w); P += G) {
+                int j = ref_subtable_width(cnt, g, pad, l, w, P);
+                if (j) part += 1 << j;
+            }
+            #pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) part += __shfl_xor_sync(gmask, part, o, G);
+            total += part;
+            if (total > 4 * 1400) break;
+        }
+        return total;
     }
 
     // Decode one code the slow way (canonical counts), applying the reference's lookahead
@@ -335,6 +369,7 @@ struct Decoder {
         if (g == 1 && ncodes == 1) {                    // the one incomplete set the reference accepts
             if (bb & 1) return R_ERROR;                 // exop 192: invalid code
             drop(1);
+            last_klen = 1;
             *sym_out = sorted[0] & 0xfffu;
             return R_OK;
         }
@@ -352,6 +387,7 @@ struct Decoder {
             }
             index += count; first += count; first <<= 1; code <<= 1;
         }
+        last_klen = klen;
         if (found && klen <= l) { drop(klen); *sym_out = sym; return R_OK; }
         if (!found && A >= g) return R_ERROR;           // every bit of the longest code is there: no such code
         // walk the reference's table levels
@@ -362,7 +398,7 @@ struct Decoder {
             int j = ref_subtable_width(cnt, g, kraft, l, w, prefix);
             if (A - w < j) return R_STALL;
             if (found && klen <= w + j) { drop(klen); *sym_out = sym; return R_OK; }
-            if (!found && w + j >= 15) return R_ERROR;
+            if (j == 0 || (!found && w + j >= 15)) return R_ERROR;
             w += l;
         }
         return R_ERROR;
@@ -392,7 +428,7 @@ struct Decoder {
         int r = slow_code(S->cnt_l, S->sorted_l, lbits, g_l, &sym);
         if (r != R_OK) { if (r == R_ERROR) msg = SDZ_MSG_BAD_LITLEN_CODE; return r; }
         if (sym < 256) return put_literal(sym);
-        if (sym == 256) return R_EOB;
+        if (sym == 256) { eob_len = last_klen; return R_EOB; }
         uint32_t i = sym - 257;
         if (i > 28) { msg = SDZ_MSG_BAD_LITLEN_CODE; return R_ERROR; }
         int xb = i < 8 ? 0 : (i == 28 ? 0 : (int)(i >> 2) - 1);
@@ -411,12 +447,13 @@ struct Decoder {
     // Reference acceptance test for one code-length set (src/inftree.ts:131-178,:298) and the
     // canonical structures (counts, sorted symbols).  Returns 0 ok, 1 oversubscribed,
     // 2 incomplete, 3 empty.  *l_out = reference root width, *g_out = longest code.
-    __device__ int classify(const uint8_t* lens, int n, int want_bits, uint32_t* cnt, int* l_out, int* g_out)
+    __device__ int classify(const uint8_t* lens, int n, int want_bits, uint32_t* cnt, int* l_out, int* g_out, int* pad_out)
     {
         for (int i = glane; i < 16; i += G) cnt[i] = 0;
         __syncwarp(gmask);
         for (int i = glane; i < n; i += G) atomicAdd(&cnt[lens[i]], 1u);
         __syncwarp(gmask);
+        *pad_out = 0;
         if ((int)cnt[0] == n) { *l_out = 0; *g_out = 0; return 3; }
         int j = 1;
         while (j <= 15 && cnt[j] == 0) j++;
@@ -433,6 +470,7 @@ struct Decoder {
         }
         y -= (int)cnt[g];
         if (y < 0) return 1;
+        *pad_out = y;
         return (y != 0 && g != 1) ? 2 : 0;
     }
 
@@ -497,14 +535,21 @@ struct Decoder {
     // messages of inflate_trees_dynamic (src/inftree.ts:333-379).  fixed: skip the checks.
     __device__ int build_tables(int nl, int nd, bool fixed)
     {
-        int st = classify(S->lens, nl, fixed ? 9 : 9, S->cnt_l, &lbits, &g_l);
+        int pad_l = 0, pad_d = 0;
+        int st = classify(S->lens, nl, 9, S->cnt_l, &lbits, &g_l, &pad_l);
+        int used = 0;
         if (!fixed) {
+            // the lit/len and distance tables share an arena of MANY = 1400 entries; running out
+            // of it is reported as DATA_ERROR, i.e. with the "oversubscribed" text
             if (st == 1) { msg = SDZ_MSG_OVERSUB_LITLEN_TREE; return R_ERROR; }
+            if (st != 3) used = ref_table_total(S->cnt_l, g_l, pad_l, lbits);
+            if (used > 1400) { msg = SDZ_MSG_OVERSUB_LITLEN_TREE; return R_ERROR; }
             if (st == 2 || st == 3) { msg = SDZ_MSG_INCOMPLETE_LITLEN_TREE; return R_ERROR; }
         }
-        st = classify(S->lens + nl, nd, fixed ? 5 : 6, S->cnt_d, &dbits, &g_d);
+        st = classify(S->lens + nl, nd, fixed ? 5 : 6, S->cnt_d, &dbits, &g_d, &pad_d);
         if (!fixed) {
             if (st == 1) { msg = SDZ_MSG_OVERSUB_DIST_TREE; return R_ERROR; }
+            if (st != 3 && used + ref_table_total(S->cnt_d, g_d, pad_d, dbits) > 1400) { msg = SDZ_MSG_OVERSUB_DIST_TREE; return R_ERROR; }
             if (st == 2) { msg = SDZ_MSG_INCOMPLETE_DIST_TREE; return R_ERROR; }
             if (st == 3 && nl > 257) { msg = SDZ_MSG_EMPTY_DIST_TREE; return R_ERROR; }
         }
@@ -626,7 +671,7 @@ struct Decoder {
                 pos++;
                 continue;
             }
-            if (p == 256) return R_EOB;
+            if (p == 256) { eob_len = (int)n; return R_EOB; }
             uint32_t xb = (p >> 8) & 7;
             uint32_t len = 3 + (p & 0xff) + ((uint32_t)bb & ((1u << xb) - 1u));
             bb >>= xb; bc -= (int)xb;
@@ -725,8 +770,19 @@ struct Decoder {
             r = decode_codes();
             ring.write(pos - start_pos);
             if (r != R_EOB) { if (r == R_STALL) stall_kind = ST_OTHER; return r; }
-            ring.wash();
-            if (last) return R_EOB;
+            // End of block.  When inflate_fast() decodes the EOB its STREAM_END status leaks through
+            // WASH's early return (src/infcodes.ts:264,:357,:627-638 -> src/infblocks.ts:560-564), so
+            // the block completes after ONE flush attempt; only a slow-path EOB (fewer than 258 bytes
+            // of window room or fewer than 10 unread input bytes, src/infcodes.ts:339) washes the
+            // window completely, returning to append() as often as needed.
+            {
+                uint64_t b_before = bit_pos() - (uint64_t)eob_len;
+                uint32_t kcur = 4u + ((0u - (uint32_t)b_before - 4u) & 7u);     // reference bit-buffer fill (approx.)
+                uint64_t loaded = (b_before + kcur) >> 3;
+                bool fast_eob = ring.room() >= 258 && (uint64_t)in_len >= loaded + 10;
+                if (fast_eob) ring.flush(); else ring.wash();
+            }
+            if (last) { ring.wash(); return R_EOB; }                           // DRY (src/infblocks.ts:579-594)
         }
     }
 };
@@ -886,7 +942,7 @@ __device__ void inflate_stream(Decoder<G, STORE>& d, const InflateParams& P, uns
 finish:
     d.drain();
     __syncwarp(d.gmask);
-    R.out_len = thrown ? 0 : d.pos;
+    R.out_len = (thrown && STORE) ? 0 : d.pos;      // the sizing pass always reports the decoded size
     R.total_in = d.byte_pos();
     R.zstatus = zstatus;
     R.stored_checksum = stored;

@@ -314,7 +314,7 @@ int sdz_sync(sdz_ctx* ctx)
 static int checksum_chain(sdz_ctx* ctx, bool crc, const uint8_t* p, const uint64_t* seg_len, uint64_t n_seg,
                           int32_t seed, int on_device, int32_t* out_values, int32_t* out_last)
 {
-    if (!ctx || (!p && n_seg) || !out_last) return SDZ_E_ARG;
+    if (!ctx || !out_last || (n_seg && !seg_len)) return SDZ_E_ARG;
     CK(cudaSetDevice(ctx->device));
     if (n_seg == 0) { *out_last = seed; return SDZ_OK; }
     if (n_seg > 0xffffffffull) return SDZ_E_ARG;
@@ -323,6 +323,7 @@ static int checksum_chain(sdz_ctx* ctx, bool crc, const uint8_t* p, const uint64
         if (seg_len[s] >= (1ull << 32)) return SDZ_E_ARG;            // reference undefined beyond 4 GiB
         total += seg_len[s];
     }
+    if (total && !p) return SDZ_E_ARG;
     const uint8_t* d_p = p;
     if (!on_device) {
         int rc = grow(ctx, ctx->d_in, total + 16);

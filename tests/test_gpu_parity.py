@@ -36,14 +36,19 @@ def run_batch(streams, dicts=None, modes=None, slack=64):
 
 def check_against_oracle(streams, dicts=None, modes=None, allow_hang=True):
     got = run_batch(streams, dicts, modes)
+    bad = []
     for i, s in enumerate(streams):
         d = None if dicts is None else dicts[i]
         m = O.MODE_SNIFF if modes is None else modes[i]
         exp_bytes, exp = O.inflate_oneshot(bytes(s), dictionary=d, mode=m)
         g_bytes, g = got[i]
-        assert g.observable() == exp.observable(), (i, bytes(s)[:24].hex(), len(s), g.observable(), exp.observable())
-        if not exp.thrown_append:
-            assert g_bytes == exp_bytes, (i, len(g_bytes), len(exp_bytes))
+        go, eo = g.observable(), exp.observable()
+        if go != eo:
+            diff = {k: (go.get(k), eo.get(k)) for k in set(go) | set(eo) if go.get(k) != eo.get(k)}
+            bad.append((i, m, len(s), bytes(s)[:20].hex(), diff))
+        elif not exp.thrown_append and g_bytes != exp_bytes:
+            bad.append((i, m, len(s), "bytes differ", len(g_bytes), len(exp_bytes)))
+    assert not bad, "%d of %d streams differ (got, expected): %s" % (len(bad), len(streams), bad[:12])
     return got
 
 
