@@ -81,7 +81,7 @@ struct RingModel {
     int q, r, ao;                      // write, read, avail_out
     __device__ __forceinline__ void init(int dict_used) { q = r = dict_used; ao = OUTBUF; }
     __device__ __forceinline__ int room() const { return q < r ? r - q - 1 : WSIZE - q; }
-    __device__ void flush()
+    __device__ __forceinline__ void flush()
     {
         int n = (r <= q ? q : WSIZE) - r;
         n = min(n, ao); ao -= n; r += n;
@@ -92,7 +92,7 @@ struct RingModel {
         }
     }
     // the "no room" dance; returns how many times proc() went back to append()
-    __device__ int make_room()
+    __device__ __forceinline__ int make_room()
     {
         int returns = 0;
         for (;;) {
@@ -106,7 +106,7 @@ struct RingModel {
         }
         return returns;
     }
-    __device__ void write(uint32_t n)
+    __device__ __forceinline__ void write(uint32_t n)
     {
         while (n) {
             int m = room();
@@ -116,12 +116,325 @@ struct RingModel {
         }
     }
     // WASH / DRY: everything must leave the window before the block ends (src/infcodes.ts:626-639)
-    __device__ void wash()
+    __device__ __forceinline__ void wash()
     {
         flush();
         while (r != q) { flush(); ao = OUTBUF; flush(); }
     }
 };
+
+
+// ---------------------------------------------------------------------- reference table geometry
+// (pure functions of the code-length counts; kept out of line so that the decoder state
+// stays in registers)
+
+// Width of the sub-table huft_build creates for the codes that share the first `w` bits
+// `prefix` (MSB-first) - src/inftree.ts:217-239.  cnt[] unpadded, `pad` dummy codes at g.
+// Returns 0 when no code has that prefix.
+__device__ __noinline__ int ref_subtable_width(const uint32_t* cnt, int g, int pad, int l, int w, uint32_t prefix)
+{
+    uint32_t fc = 0;
+    for (int k = 1; k <= g; k++) {
+        uint32_t ck = cnt[k] + (k == g ? (uint32_t)pad : 0u);
+        if (k > w) {
+            uint32_t lo = prefix << (k - w), hi = lo + (1u << (k - w));
+            uint32_t a0 = max(lo, fc), a1 = min(hi, fc + ck);
+            if (a0 < a1) {
+                int a = (int)(ck - (a0 - fc)) - 1;
+                int z = min(g - w, l);
+                int j = k - w;
+                int f = 1 << j;
+                if (f > a + 1) {
+                    f -= a + 1;
+                    int xp = k;
+                    if (j < z) {
+                        while (++j < z) {
+                            f <<= 1;
+                            ++xp;
+                            int cx = (int)(cnt[xp] + (xp == g ? (uint32_t)pad : 0u));
+                            if (f <= cx) break;
+                            f -= cx;
+                        }
+                    }
+                }
+                return j;
+            }
+        }
+        fc = (fc + ck) << 1;
+    }
+    return 0;
+}
+
+// Number of (exop, bits, base) entries huft_build allocates for this code set
+// (src/inftree.ts:217-246): the root table plus one sub-table per distinct l-bit (and, for
+// very long codes, 2l-bit) prefix.  Evaluated by the group's lanes in parallel.
+template <int G>
+__device__ __noinline__ int ref_table_total(const uint32_t* cnt, int g, int pad, int l, int glane, unsigned gmask)
+{
+    int total = 1 << l;
+    for (int w = l; w < g; w += l) {
+        uint32_t fc = 0, pmin = 1u << w;
+        for (int k = 1; k <= g; k++) {
+            uint32_t ck = cnt[k] + (k == g ? (uint32_t)pad : 0u);
+            if (k > w && ck) { pmin = fc >> (k - w); break; }
+            fc = (fc + ck) << 1;
+        }
+        int part = 0;
+        for (uint32_t P = pmin + (uint32_t)glane; P < (1u << w); P += G) {
+            int j = ref_subtable_width(cnt, g, pad, l, w, P);
+            if (j) part += 1 << j;
+        }
+        #pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) part += __shfl_xor_sync(gmask, part, o, G);
+        total += part;
+        if (total > 4 * 1400) break;
+    }
+    return total;
+}
+
+// Decode one code the slow way (canonical counts), applying the reference's lookahead rule
+// (SURVEY Q15): a lookup happens only when the table's index width is available.
+// bits = next 32 bits of the stream (LSB first), A = bits left in the input (capped).
+// Returns status << 28 | code_length << 16 | symbol; status = R_OK / R_STALL / R_ERROR.
+__device__ __noinline__ uint32_t slow_lookup(const uint32_t* cnt, const uint16_t* sorted, int l, int g, uint32_t bits, int A)
+{
+    if (A < l) return (uint32_t)R_STALL << 28;
+    int ncodes = 0, y = 1;
+    for (int k = 1; k <= g; k++) { ncodes += (int)cnt[k]; y <<= 1; y -= (int)cnt[k]; }
+    const int pad = y;                                  // unused codes of length g
+    if (g == 1 && ncodes == 1) {                        // the one incomplete set the reference accepts
+        if (bits & 1) return (uint32_t)R_ERROR << 28;   // exop 192: invalid code
+        return (1u << 16) | (sorted[0] & 0xfffu);
+    }
+    int code = 0, first = 0, index = 0, klen = 0;
+    bool found = false;
+    uint32_t sym = 0;
+    int lim = min(A, 15);
+    for (int len = 1; len <= lim; len++) {
+        code |= (int)((bits >> (len - 1)) & 1);
+        int count = len <= g ? (int)cnt[len] : 0;
+        if (code - count < first) {
+            sym = sorted[index + (code - first)] & 0xfffu;
+            klen = len; found = true;
+            break;
+        }
+        index += count; first += count; first <<= 1; code <<= 1;
+    }
+    const uint32_t ok = ((uint32_t)klen << 16) | sym;
+    if (found && klen <= l) return ok;
+    if (!found && A >= g) return (uint32_t)R_ERROR << 28;   // every bit of the longest code is there: no such code
+    // walk the reference's table levels
+    int w = l;
+    for (int level = 0; level < 4; level++) {
+        if (A - w < 1) return (uint32_t)R_STALL << 28;
+        uint32_t prefix = __brev(bits) >> (32 - w);
+        int j = ref_subtable_width(cnt, g, pad, l, w, prefix);
+        if (A - w < j) return (uint32_t)R_STALL << 28;
+        if (found && klen <= w + j) return ok;
+        if (j == 0 || (!found && w + j >= 15)) return (uint32_t)R_ERROR << 28;
+        w += l;
+    }
+    return (uint32_t)R_ERROR << 28;
+}
+
+// first touch of input chunk `rel`: wait for its TMA copy, then reuse the slot of the chunk
+// that was just finished for the next outstanding chunk.  Returns the new `issued` count.
+__device__ __noinline__ uint32_t chunk_cross(GroupSmem* S, const uint8_t* gsrc, uint32_t base_seq, uint32_t rel, uint32_t chunk0,
+                                             uint32_t issued, uint32_t total_chunks, unsigned gmask, int glane)
+{
+    uint32_t seq = base_seq + rel;
+    mbar_wait(&S->mbar[seq % NBUF], (seq / NBUF) & 1);
+    if (rel >= 1 && chunk0 + issued < total_chunks) {
+        __syncwarp(gmask);                              // every lane is done with the slot being recycled
+        if (glane == 0) {
+            uint32_t nseq = base_seq + issued, slot = nseq % NBUF;
+            mbar_arrive_expect_tx(&S->mbar[slot], CH);
+            bulk_copy_g2s(&S->ring[slot * CHW], gsrc + (size_t)(chunk0 + issued) * CH, CH, &S->mbar[slot]);
+        }
+        issued++;
+    }
+    return issued;
+}
+
+
+// ---------------------------------------------------------------------- table construction
+// (out of line: runs once per block; works only on the group's shared memory)
+
+struct TreeInfo {
+    int lbits, dbits, g_l, g_d;        // reference root widths / longest codes (src/inftree.ts:146-165)
+    int msg;
+};
+
+// Reference acceptance test for one code-length set (src/inftree.ts:131-178,:298) and the
+// per-length counts.  Returns 0 ok, 1 oversubscribed, 2 incomplete, 3 empty.
+template <int G>
+__device__ __forceinline__ int classify(const uint8_t* lens, int n, int want_bits, uint32_t* cnt, int* l_out, int* g_out,
+                                        int* pad_out, int glane, unsigned gmask)
+{
+    for (int i = glane; i < 16; i += G) cnt[i] = 0;
+    __syncwarp(gmask);
+    for (int i = glane; i < n; i += G) atomicAdd(&cnt[lens[i]], 1u);
+    __syncwarp(gmask);
+    *pad_out = 0;
+    if ((int)cnt[0] == n) { *l_out = 0; *g_out = 0; return 3; }
+    int j = 1;
+    while (j <= 15 && cnt[j] == 0) j++;
+    int g = 15;
+    while (g > 0 && cnt[g] == 0) g--;
+    int l = want_bits;
+    if (l < j) l = j;
+    if (l > g) l = g;
+    *l_out = l; *g_out = g;
+    int y = 1 << j;
+    for (; j < g; j++, y <<= 1) {
+        y -= (int)cnt[j];
+        if (y < 0) return 1;
+    }
+    y -= (int)cnt[g];
+    if (y < 0) return 1;
+    *pad_out = y;
+    return (y != 0 && g != 1) ? 2 : 0;
+}
+
+// sorted symbols + first codes (aux[16..31]) + end offsets (aux[0..15]), then the root LUT.
+// KIND 0 = literal/length (R = RL), 1 = distance (R = RD).
+template <int G, int KIND, int R>
+__device__ __forceinline__ void make_lut(GroupSmem* S, const uint8_t* lens, int n, const uint32_t* cnt, uint16_t* sorted,
+                                         uint16_t* lut, int glane, unsigned gmask)
+{
+    if (glane == 0) {
+        uint32_t off = 0, code = 0;
+        for (int k = 1; k <= 15; k++) {
+            S->aux[k] = off;
+            S->aux[16 + k] = code;
+            off += cnt[k];
+            code = (code + cnt[k]) << 1;
+        }
+        for (int s = 0; s < n; s++) {
+            uint32_t k = lens[s];
+            if (k) { uint32_t o = S->aux[k]; sorted[o] = (uint16_t)(s | (k << 12)); S->aux[k] = o + 1; }
+        }
+    }
+    uint32_t* lut32 = reinterpret_cast<uint32_t*>(lut);
+    for (int i = glane; i < (1 << R) / 2; i += G) lut32[i] = E_INVALID | (E_INVALID << 16);
+    __syncwarp(gmask);
+    const int ncodes = n - (int)cnt[0];
+    for (int k = glane; k < ncodes; k += G) {
+        uint32_t e = sorted[k];
+        uint32_t sym = e & 0xfff, len = e >> 12;
+        uint32_t idx = (uint32_t)k - (S->aux[len] - cnt[len]);          // aux[len] = one past the last of this length
+        uint32_t code = S->aux[16 + len] + idx;
+        uint32_t rev = __brev(code) >> (32 - len);
+        if (len > (uint32_t)R) { lut[rev & ((1u << R) - 1u)] = (uint16_t)E_LONG; continue; }
+        uint32_t entry;
+        if (KIND == 0) {
+            if (sym < 256) entry = sym;
+            else if (sym == 256) entry = 0x100;
+            else {
+                uint32_t i = sym - 257;
+                if (i > 28) continue;                                   // 286/287: invalid (fixed block only)
+                uint32_t xb = i < 8 ? 0 : (i == 28 ? 0 : (i >> 2) - 1);
+                uint32_t base = i < 8 ? 3 + i : (i == 28 ? 258 : 3 + ((4 + (i & 3)) << xb));
+                entry = 0x800 | (xb << 8) | (base - 3);
+            }
+        } else {
+            if (sym > 29) continue;                                     // 30/31: invalid (fixed block only)
+            uint32_t xb = sym < 4 ? 0 : (sym >> 1) - 1;
+            uint32_t m = sym < 4 ? sym : 2 + (sym & 1);
+            entry = (xb << 8) | m;
+        }
+        entry |= len << 12;
+        for (uint32_t j = rev; j < (1u << R); j += (1u << len)) lut[j] = (uint16_t)entry;
+    }
+    __syncwarp(gmask);
+}
+
+// lit/len + distance tables for lens[0..nl) and lens[nl..nl+nd) with the reference's checks
+// and messages (inflate_trees_dynamic, src/inftree.ts:333-379).  fixed: no checks.
+template <int G>
+__device__ __noinline__ TreeInfo build_tables(GroupSmem* S, int nl, int nd, bool fixed, int glane, unsigned gmask)
+{
+    TreeInfo T;
+    T.msg = SDZ_MSG_NONE; T.lbits = T.dbits = T.g_l = T.g_d = 0;
+    int pad_l = 0, pad_d = 0, used = 0;
+    int st = classify<G>(S->lens, nl, 9, S->cnt_l, &T.lbits, &T.g_l, &pad_l, glane, gmask);
+    if (!fixed) {
+        // the lit/len and distance tables share an arena of MANY = 1400 entries; running out of
+        // it is reported as DATA_ERROR, i.e. with the "oversubscribed" text
+        if (st == 1) { T.msg = SDZ_MSG_OVERSUB_LITLEN_TREE; return T; }
+        if (st != 3) used = ref_table_total<G>(S->cnt_l, T.g_l, pad_l, T.lbits, glane, gmask);
+        if (used > 1400) { T.msg = SDZ_MSG_OVERSUB_LITLEN_TREE; return T; }
+        if (st == 2 || st == 3) { T.msg = SDZ_MSG_INCOMPLETE_LITLEN_TREE; return T; }
+    }
+    st = classify<G>(S->lens + nl, nd, fixed ? 5 : 6, S->cnt_d, &T.dbits, &T.g_d, &pad_d, glane, gmask);
+    if (!fixed) {
+        if (st == 1) { T.msg = SDZ_MSG_OVERSUB_DIST_TREE; return T; }
+        if (st != 3 && used + ref_table_total<G>(S->cnt_d, T.g_d, pad_d, T.dbits, glane, gmask) > 1400) {
+            T.msg = SDZ_MSG_OVERSUB_DIST_TREE; return T;
+        }
+        if (st == 2) { T.msg = SDZ_MSG_INCOMPLETE_DIST_TREE; return T; }
+        if (st == 3 && nl > 257) { T.msg = SDZ_MSG_EMPTY_DIST_TREE; return T; }
+    }
+    make_lut<G, 0, RL>(S, S->lens, nl, S->cnt_l, S->sorted_l, S->lut_l, glane, gmask);
+    make_lut<G, 1, RD>(S, S->lens + nl, nd, S->cnt_d, S->sorted_d, S->lut_d, glane, gmask);
+    if (fixed) { T.lbits = 9; T.dbits = 5; }
+    return T;
+}
+
+// code-length-code LUT for the dynamic header (inflate_trees_bits, src/inftree.ts:313-331).
+// cl[19] are the code-length-code lengths; blut[128] receives sym | len << 5.
+// Returns bb (index width, >= 1) or -msg on error.
+__device__ __noinline__ int build_bits_lut(const uint8_t* cl, uint8_t* blut, uint32_t* cnt, int glane, unsigned gmask)
+{
+    if (glane == 0) {
+        for (int i = 0; i < 16; i++) cnt[i] = 0;
+        for (int i = 0; i < 19; i++) cnt[cl[i]]++;
+    }
+    __syncwarp(gmask);
+    if (cnt[0] == 19) return -SDZ_MSG_INCOMPLETE_BITS_TREE;
+    int j = 1;
+    while (cnt[j] == 0) j++;
+    int g = 7;
+    while (cnt[g] == 0) g--;
+    int l = 7;
+    if (l > g) l = g;
+    int y = 1 << j;
+    for (; j < g; j++, y <<= 1) { y -= (int)cnt[j]; if (y < 0) return -SDZ_MSG_OVERSUB_BITS_TREE; }
+    y -= (int)cnt[g];
+    if (y < 0) return -SDZ_MSG_OVERSUB_BITS_TREE;
+    if (y != 0 && g != 1) return -SDZ_MSG_INCOMPLETE_BITS_TREE;
+    if (glane == 0) {
+        uint32_t code = 0;
+        for (int k = 1; k <= g; k++) {
+            for (int s = 0; s < 19; s++) {
+                if (cl[s] != k) continue;
+                uint32_t rev = __brev(code) >> (32 - k);
+                for (uint32_t q = rev; q < (1u << l); q += (1u << k)) blut[q] = (uint8_t)(s | (k << 5));
+                code++;
+            }
+            code <<= 1;
+        }
+        if (g == 1 && cnt[1] == 1) blut[1] = blut[0];      // a lone 1-bit code answers both patterns (Q11)
+    }
+    __syncwarp(gmask);
+    return l;
+}
+
+// source starts before the output: preset dictionary tail, else the reference's
+// zero-initialised window (src/infcodes.ts:174-193)
+template <int G>
+__device__ __noinline__ void copy_before_start_impl(uint8_t* o, uint32_t p0, uint32_t len, uint32_t dist,
+                                                    const uint8_t* dt, int Dn, int gl)
+{
+    for (uint32_t i = gl; i < len; i += G) {
+        uint32_t k = dist >= len ? i : i % dist;
+        int64_t s = (int64_t)p0 - (int64_t)dist + (int64_t)k;
+        uint8_t v = 0;
+        if (s >= 0) v = o[s];
+        else if (s >= -(int64_t)Dn) v = dt[(int64_t)Dn + s];
+        o[p0 + i] = v;
+    }
+}
 
 template <int G, bool STORE>
 struct Decoder {
@@ -147,43 +460,25 @@ struct Decoder {
     RingModel ring;
     int msg;
     int stall_kind;
-
-    // reference root widths of the current block's trees (src/inftree.ts:146-165)
     int lbits, dbits, g_l, g_d;
-    int last_klen;                     // length of the code slow_code() decoded last
     int eob_len;                       // code length of the end-of-block symbol just decoded
 
     // ------------------------------------------------------------------ input staging
-    __device__ __forceinline__ void issue_chunk(uint32_t rel)
-    {
-        uint32_t seq = base_seq + rel;
-        uint32_t slot = seq % NBUF;
-        if (glane == 0) {
-            mbar_arrive_expect_tx(&S->mbar[slot], CH);
-            bulk_copy_g2s(&S->ring[slot * CHW], gsrc + (size_t)(chunk0 + rel) * CH, CH, &S->mbar[slot]);
-        }
-    }
-
     __device__ __forceinline__ uint32_t load_word(uint32_t w)
     {
         if (w >= end_wp) return 0;
         uint32_t rel = w / CHW - chunk0;
         uint32_t seq = base_seq + rel;
         if (rel >= waited) {
-            mbar_wait(&S->mbar[seq % NBUF], (seq / NBUF) & 1);
+            issued = chunk_cross(S, gsrc, base_seq, rel, chunk0, issued, total_chunks, gmask, glane);
             waited = rel + 1;
-            if (rel >= 1 && chunk0 + issued < total_chunks) {
-                __syncwarp(gmask);      // every lane is done with the slot being recycled
-                issue_chunk(issued);
-                issued++;
-            }
         }
         uint32_t v = S->ring[(seq % NBUF) * CHW + (w % CHW)];
         if (w + 1 == end_wp) v &= tail_mask;
         return v;
     }
 
-    __device__ void drain()
+    __device__ __forceinline__ void drain()
     {
         for (uint32_t rel = waited; rel < issued; rel++) {
             uint32_t seq = base_seq + rel;
@@ -193,7 +488,7 @@ struct Decoder {
     }
 
     // (re)position the reader on a byte boundary of the stream
-    __device__ void seek(uint32_t byte_pos)
+    __device__ __forceinline__ void seek(uint32_t byte_pos)
     {
         drain();
         __syncwarp(gmask);
@@ -203,7 +498,13 @@ struct Decoder {
         chunk0 = w / CHW;
         uint32_t avail_chunks = total_chunks > chunk0 ? total_chunks - chunk0 : 0;
         uint32_t n0 = avail_chunks < (uint32_t)NBUF ? avail_chunks : (uint32_t)NBUF;
-        for (uint32_t i = 0; i < n0; i++) issue_chunk(i);
+        if (glane == 0) {
+            for (uint32_t i = 0; i < n0; i++) {
+                uint32_t slot = (base_seq + i) % NBUF;
+                mbar_arrive_expect_tx(&S->mbar[slot], CH);
+                bulk_copy_g2s(&S->ring[slot * CHW], gsrc + (size_t)(chunk0 + i) * CH, CH, &S->mbar[slot]);
+            }
+        }
         issued = n0;
         wp = w; bb = 0; bc = 0;
         nw = load_word(wp);
@@ -223,37 +524,24 @@ struct Decoder {
         }
     }
 
-    // total bits between the read position and the end of the input
-    __device__ __forceinline__ uint32_t avail_bits() const
+    // total bits between the read position and the end of the input (capped)
+    __device__ __forceinline__ int avail_bits() const
     {
         uint64_t unloaded = wp < end_wp ? (uint64_t)in_len * 8 - (uint64_t)wp * 32 : 0;
         uint64_t a = (uint64_t)bc + unloaded;
-        return a > 4096 ? 4096u : (uint32_t)a;
-    }
-    __device__ __forceinline__ uint32_t byte_pos() const
-    {
-        // bits loaded so far are whole bytes; bc of them are still unread
-        uint64_t loaded = wp < end_wp ? (uint64_t)wp * 32 : (uint64_t)in_len * 8;
-        return (uint32_t)((loaded - (uint64_t)bc) >> 3);
+        return a > 4096 ? 4096 : (int)a;
     }
     __device__ __forceinline__ uint64_t bit_pos() const
     {
         uint64_t loaded = wp < end_wp ? (uint64_t)wp * 32 : (uint64_t)in_len * 8;
         return loaded - (uint64_t)bc;
     }
+    __device__ __forceinline__ uint32_t byte_pos() const { return (uint32_t)(bit_pos() >> 3); }
     __device__ __forceinline__ bool ensure(int n) { refill(); return bc >= n; }
     __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)bb & ((1u << n) - 1u); }
     __device__ __forceinline__ void drop(int n) { bb >>= n; bc -= n; }
 
     // ------------------------------------------------------------------ output
-    __device__ __forceinline__ int put_literal(uint32_t v)
-    {
-        if (pos >= cap) return R_OUTFULL;
-        if (STORE) { if (glane == 0) out[pos] = (uint8_t)v; }
-        pos++;
-        return R_OK;
-    }
-
     __device__ __forceinline__ int copy_match(uint32_t len, uint32_t dist)
     {
         if (len > cap - pos) return R_OUTFULL;
@@ -271,299 +559,21 @@ struct Decoder {
                     for (uint32_t i = glane; i < len; i += G) dst[i] = src[i % dist];
                 }
             } else {
-                // source starts before the output: preset dictionary tail, else the
-                // reference's zero-initialised window (src/infcodes.ts:174-193)
-                for (uint32_t i = glane; i < len; i += G) {
-                    uint32_t k = dist >= len ? i : i % dist;
-                    int64_t s = (int64_t)pos - (int64_t)dist + (int64_t)k;
-                    uint8_t v = 0;
-                    if (s >= 0) v = out[s];
-                    else if (s >= -(int64_t)D) v = dict_tail[(int64_t)D + s];
-                    dst[i] = v;
-                }
+                copy_before_start(len, dist);
             }
         }
         pos += len;
         return R_OK;
     }
 
-    // ------------------------------------------------------------------ reference table geometry
-    // Width of the sub-table huft_build creates for the codes that share the first `w` bits
-    // `prefix` (MSB-first) - src/inftree.ts:217-239.  cnt[] unpadded, `pad` dummy codes at g.
-    __device__ int ref_subtable_width(const uint32_t* cnt, int g, int pad, int l, int w, uint32_t prefix) const
+    __device__ __forceinline__ void copy_before_start(uint32_t len, uint32_t dist)
     {
-        uint32_t fc = 0;
-        for (int k = 1; k <= g; k++) {
-            uint32_t ck = cnt[k] + (k == g ? (uint32_t)pad : 0u);
-            if (k > w) {
-                uint32_t lo = prefix << (k - w), hi = lo + (1u << (k - w));
-                uint32_t a0 = max(lo, fc), a1 = min(hi, fc + ck);
-                if (a0 < a1) {
-                    int a = (int)(ck - (a0 - fc)) - 1;
-                    int z = min(g - w, l);
-                    int j = k - w;
-                    int f = 1 << j;
-                    if (f > a + 1) {
-                        f -= a + 1;
-                        int xp = k;
-                        if (j < z) {
-                            while (++j < z) {
-                                f <<= 1;
-                                ++xp;
-                                int cx = (int)(cnt[xp] + (xp == g ? (uint32_t)pad : 0u));
-                                if (f <= cx) break;
-                                f -= cx;
-                            }
-                        }
-                    }
-                    return j;
-                }
-            }
-            fc = (fc + ck) << 1;
-        }
-        return 0;
-    }
-
-    // Number of (exop, bits, base) entries huft_build allocates for this code set
-    // (src/inftree.ts:217-246): the root table plus one sub-table per distinct l-bit
-    // (and, for very long codes, 2l-bit) prefix.  Evaluated by the group's lanes in parallel.
-    __device__ int ref_table_total(const uint32_t* cnt, int g, int pad, int l) const
-    {
-        int total = 1 << l;
-        for (int w = l; w < g; w += l) {
-            // first code longer than w bits -> first prefix that owns a sub-table at this level
-            uint32_t fc = 0, pmin = 1u << w;
-            for (int k = 1; k <= g; k++) {
-                uint32_t ck = cnt[k] + (k == g ? (uint32_t)pad : 0u);
-                if (k > w && ck) { pmin = fc >> (k - w); break; }
-                fc = (fc + ck) << 1;
-            }
-            int part = 0;
-            for (uint32_t P = pmin + (uint32_t)glane; P < (1u << w); P += G) {
-                int j = ref_subtable_width(cnt, g, pad, l, w, P);
-                if (j) part += 1 << j;
-            }
-            #pragma unroll
-            for (int o = G / 2; o > 0; o >>= 1) part += __shfl_xor_sync(gmask, part, o, G);
-            total += part;
-            if (total > 4 * 1400) break;
-        }
-        return total;
-    }
-
-    // Decode one code the slow way (canonical counts), applying the reference's lookahead
-    // rule: a lookup happens only when the table's index width is available.
-    __device__ __noinline__ int slow_code(const uint32_t* cnt, const uint16_t* sorted, int l, int g, uint32_t* sym_out)
-    {
-        refill();
-        int A = (int)avail_bits();
-        if (A < l) return R_STALL;
-        int ncodes = 0, kraft = 0;
-        for (int k = 1; k <= g; k++) { ncodes += (int)cnt[k]; }
-        kraft = 0;
-        {
-            int y = 1;
-            for (int k = 1; k <= g; k++) { y <<= 1; y -= (int)cnt[k]; }
-            kraft = y;                                  // unused codes of length g
-        }
-        if (g == 1 && ncodes == 1) {                    // the one incomplete set the reference accepts
-            if (bb & 1) return R_ERROR;                 // exop 192: invalid code
-            drop(1);
-            last_klen = 1;
-            *sym_out = sorted[0] & 0xfffu;
-            return R_OK;
-        }
-        int code = 0, first = 0, index = 0, klen = 0;
-        bool found = false;
-        uint32_t sym = 0;
-        int lim = min(A, 15);
-        for (int len = 1; len <= lim; len++) {
-            code |= (int)((bb >> (len - 1)) & 1);
-            int count = len <= g ? (int)cnt[len] : 0;
-            if (code - count < first) {
-                sym = sorted[index + (code - first)] & 0xfffu;
-                klen = len; found = true;
-                break;
-            }
-            index += count; first += count; first <<= 1; code <<= 1;
-        }
-        last_klen = klen;
-        if (found && klen <= l) { drop(klen); *sym_out = sym; return R_OK; }
-        if (!found && A >= g) return R_ERROR;           // every bit of the longest code is there: no such code
-        // walk the reference's table levels
-        int w = l;
-        for (int level = 0; level < 4; level++) {
-            if (A - w < 1) return R_STALL;
-            uint32_t prefix = __brev((uint32_t)bb) >> (32 - w);
-            int j = ref_subtable_width(cnt, g, kraft, l, w, prefix);
-            if (A - w < j) return R_STALL;
-            if (found && klen <= w + j) { drop(klen); *sym_out = sym; return R_OK; }
-            if (j == 0 || (!found && w + j >= 15)) return R_ERROR;
-            w += l;
-        }
-        return R_ERROR;
-    }
-
-    // distance code + extra bits after a length has been consumed
-    __device__ __noinline__ int slow_dist(uint32_t* dist_out)
-    {
-        uint32_t ds;
-        if (g_d == 0) return R_ERROR;                   // no distance codes at all (nl == 257 blocks)
-        int r = slow_code(S->cnt_d, S->sorted_d, dbits, g_d, &ds);
-        if (r != R_OK) { if (r == R_ERROR) msg = SDZ_MSG_BAD_DIST_CODE; return r; }
-        if (ds > 29) { msg = SDZ_MSG_BAD_DIST_CODE; return R_ERROR; }
-        int xb = ds < 4 ? 0 : (int)(ds >> 1) - 1;
-        uint32_t base = ds < 4 ? ds + 1 : 1 + ((2 + (ds & 1)) << xb);
-        refill();
-        if ((int)avail_bits() < xb) return R_STALL;
-        *dist_out = base + peek(xb);
-        drop(xb);
-        return R_OK;
-    }
-
-    // one full symbol (literal, match or EOB) the slow way
-    __device__ __noinline__ int slow_symbol()
-    {
-        uint32_t sym;
-        int r = slow_code(S->cnt_l, S->sorted_l, lbits, g_l, &sym);
-        if (r != R_OK) { if (r == R_ERROR) msg = SDZ_MSG_BAD_LITLEN_CODE; return r; }
-        if (sym < 256) return put_literal(sym);
-        if (sym == 256) { eob_len = last_klen; return R_EOB; }
-        uint32_t i = sym - 257;
-        if (i > 28) { msg = SDZ_MSG_BAD_LITLEN_CODE; return R_ERROR; }
-        int xb = i < 8 ? 0 : (i == 28 ? 0 : (int)(i >> 2) - 1);
-        uint32_t base = i < 8 ? 3 + i : (i == 28 ? 258 : 3 + ((4 + (i & 3)) << xb));
-        refill();
-        if ((int)avail_bits() < xb) return R_STALL;
-        uint32_t len = base + peek(xb);
-        drop(xb);
-        uint32_t dist;
-        r = slow_dist(&dist);
-        if (r != R_OK) return r;
-        return copy_match(len, dist);
-    }
-
-    // ------------------------------------------------------------------ table construction
-    // Reference acceptance test for one code-length set (src/inftree.ts:131-178,:298) and the
-    // canonical structures (counts, sorted symbols).  Returns 0 ok, 1 oversubscribed,
-    // 2 incomplete, 3 empty.  *l_out = reference root width, *g_out = longest code.
-    __device__ int classify(const uint8_t* lens, int n, int want_bits, uint32_t* cnt, int* l_out, int* g_out, int* pad_out)
-    {
-        for (int i = glane; i < 16; i += G) cnt[i] = 0;
-        __syncwarp(gmask);
-        for (int i = glane; i < n; i += G) atomicAdd(&cnt[lens[i]], 1u);
-        __syncwarp(gmask);
-        *pad_out = 0;
-        if ((int)cnt[0] == n) { *l_out = 0; *g_out = 0; return 3; }
-        int j = 1;
-        while (j <= 15 && cnt[j] == 0) j++;
-        int g = 15;
-        while (g > 0 && cnt[g] == 0) g--;
-        int l = want_bits;
-        if (l < j) l = j;
-        if (l > g) l = g;
-        *l_out = l; *g_out = g;
-        int y = 1 << j;
-        for (; j < g; j++, y <<= 1) {
-            y -= (int)cnt[j];
-            if (y < 0) return 1;
-        }
-        y -= (int)cnt[g];
-        if (y < 0) return 1;
-        *pad_out = y;
-        return (y != 0 && g != 1) ? 2 : 0;
-    }
-
-    // sorted symbols + first codes (aux[16..31]) + offsets (aux[0..15])
-    __device__ void canonical(const uint8_t* lens, int n, const uint32_t* cnt, uint16_t* sorted)
-    {
-        if (glane == 0) {
-            uint32_t off = 0, code = 0;
-            for (int k = 1; k <= 15; k++) {
-                S->aux[k] = off;
-                S->aux[16 + k] = code;
-                off += cnt[k];
-                code = (code + cnt[k]) << 1;
-            }
-            for (int s = 0; s < n; s++) {
-                uint32_t k = lens[s];
-                if (k) { uint32_t o = S->aux[k]; sorted[o] = (uint16_t)(s | (k << 12)); S->aux[k] = o + 1; }
-            }
-        }
-        __syncwarp(gmask);
-    }
-
-    // fill one root LUT from the sorted list; KIND 0 = literal/length, 1 = distance
-    template <int KIND, int R>
-    __device__ void fill_lut(uint16_t* lut, const uint16_t* sorted, const uint32_t* cnt, int ncodes)
-    {
-        uint32_t* lut32 = reinterpret_cast<uint32_t*>(lut);
-        for (int i = glane; i < (1 << R) / 2; i += G) lut32[i] = E_INVALID | (E_INVALID << 16);
-        __syncwarp(gmask);
-        for (int k = glane; k < ncodes; k += G) {
-            uint32_t e = sorted[k];
-            uint32_t sym = e & 0xfff, len = e >> 12;
-            // aux[len] now points one past the last symbol of this length
-            uint32_t idx = (uint32_t)k - (S->aux[len] - cnt[len]);
-            uint32_t code = S->aux[16 + len] + idx;
-            uint32_t rev = __brev(code) >> (32 - len);
-            if (len > (uint32_t)R) { lut[rev & ((1u << R) - 1u)] = (uint16_t)E_LONG; continue; }
-            uint32_t entry;
-            if (KIND == 0) {
-                if (sym < 256) entry = sym;
-                else if (sym == 256) entry = 0x100;
-                else {
-                    uint32_t i = sym - 257;
-                    if (i > 28) continue;                               // 286/287: invalid (fixed block only)
-                    uint32_t xb = i < 8 ? 0 : (i == 28 ? 0 : (i >> 2) - 1);
-                    uint32_t base = i < 8 ? 3 + i : (i == 28 ? 258 : 3 + ((4 + (i & 3)) << xb));
-                    entry = 0x800 | (xb << 8) | (base - 3);
-                }
-            } else {
-                if (sym > 29) continue;                                 // 30/31: invalid (fixed block only)
-                uint32_t xb = sym < 4 ? 0 : (sym >> 1) - 1;
-                uint32_t m = sym < 4 ? sym : 2 + (sym & 1);
-                entry = (xb << 8) | m;
-            }
-            entry |= len << 12;
-            for (uint32_t j = rev; j < (1u << R); j += (1u << len)) lut[j] = (uint16_t)entry;
-        }
-        __syncwarp(gmask);
-    }
-
-    // lit/len + distance tables for lens[0..nl) and lens[nl..nl+nd); reference checks and
-    // messages of inflate_trees_dynamic (src/inftree.ts:333-379).  fixed: skip the checks.
-    __device__ int build_tables(int nl, int nd, bool fixed)
-    {
-        int pad_l = 0, pad_d = 0;
-        int st = classify(S->lens, nl, 9, S->cnt_l, &lbits, &g_l, &pad_l);
-        int used = 0;
-        if (!fixed) {
-            // the lit/len and distance tables share an arena of MANY = 1400 entries; running out
-            // of it is reported as DATA_ERROR, i.e. with the "oversubscribed" text
-            if (st == 1) { msg = SDZ_MSG_OVERSUB_LITLEN_TREE; return R_ERROR; }
-            if (st != 3) used = ref_table_total(S->cnt_l, g_l, pad_l, lbits);
-            if (used > 1400) { msg = SDZ_MSG_OVERSUB_LITLEN_TREE; return R_ERROR; }
-            if (st == 2 || st == 3) { msg = SDZ_MSG_INCOMPLETE_LITLEN_TREE; return R_ERROR; }
-        }
-        st = classify(S->lens + nl, nd, fixed ? 5 : 6, S->cnt_d, &dbits, &g_d, &pad_d);
-        if (!fixed) {
-            if (st == 1) { msg = SDZ_MSG_OVERSUB_DIST_TREE; return R_ERROR; }
-            if (st != 3 && used + ref_table_total(S->cnt_d, g_d, pad_d, dbits) > 1400) { msg = SDZ_MSG_OVERSUB_DIST_TREE; return R_ERROR; }
-            if (st == 2) { msg = SDZ_MSG_INCOMPLETE_DIST_TREE; return R_ERROR; }
-            if (st == 3 && nl > 257) { msg = SDZ_MSG_EMPTY_DIST_TREE; return R_ERROR; }
-        }
-        int ncl = nl - (int)S->cnt_l[0], ncd = nd - (int)S->cnt_d[0];
-        canonical(S->lens, nl, S->cnt_l, S->sorted_l);
-        fill_lut<0, RL>(S->lut_l, S->sorted_l, S->cnt_l, ncl);
-        canonical(S->lens + nl, nd, S->cnt_d, S->sorted_d);
-        fill_lut<1, RD>(S->lut_d, S->sorted_d, S->cnt_d, ncd);
-        return R_OK;
+        copy_before_start_impl<G>(out, pos, len, dist, dict_tail, D, glane);
     }
 
     // dynamic block header: HLIT/HDIST/HCLEN, code-length code, RLE-coded lengths
     // (src/infblocks.ts:334-523).  Uses lut_l as scratch for the 7-bit code-length LUT.
-    __device__ int dynamic_header(int* nl_out, int* nd_out)
+    __device__ __forceinline__ int dynamic_header(int* nl_out, int* nd_out)
     {
         if (!ensure(14)) { stall_kind = ST_OTHER; return R_STALL; }
         uint32_t t = peek(14);
@@ -581,46 +591,9 @@ struct Decoder {
             drop(3);
         }
         __syncwarp(gmask);
-        // code-length tree: inflate_trees_bits (src/inftree.ts:313-331), requested root 7
-        int bb_bits, g_b;
-        uint32_t* cnt = S->aux;                         // counts for the 19-symbol set
-        int st;
-        {
-            for (int i = glane; i < 16; i += G) cnt[i] = 0;
-            __syncwarp(gmask);
-            if (glane == 0) for (int i = 0; i < 19; i++) cnt[cl[i]]++;
-            __syncwarp(gmask);
-            if (cnt[0] == 19) { msg = SDZ_MSG_INCOMPLETE_BITS_TREE; return R_ERROR; }
-            int j = 1;
-            while (cnt[j] == 0) j++;
-            int g = 7;
-            while (cnt[g] == 0) g--;
-            int l = 7;
-            if (l > g) l = g;
-            bb_bits = l; g_b = g;
-            int y = 1 << j;
-            st = 0;
-            for (; j < g; j++, y <<= 1) { y -= (int)cnt[j]; if (y < 0) { st = 1; break; } }
-            if (!st) { y -= (int)cnt[g]; if (y < 0) st = 1; else if (y != 0 && g != 1) st = 2; }
-            if (st == 1) { msg = SDZ_MSG_OVERSUB_BITS_TREE; return R_ERROR; }
-            if (st == 2) { msg = SDZ_MSG_INCOMPLETE_BITS_TREE; return R_ERROR; }
-        }
-        // 2^bb_bits-entry LUT: sym | len << 5.  A lone 1-bit code answers both patterns (Q11).
         uint8_t* blut = reinterpret_cast<uint8_t*>(S->lut_l);
-        if (glane == 0) {
-            uint32_t code = 0;
-            for (int k = 1; k <= g_b; k++) {
-                for (int s = 0; s < 19; s++) {
-                    if (cl[s] != k) continue;
-                    uint32_t rev = __brev(code) >> (32 - k);
-                    for (uint32_t j = rev; j < (1u << bb_bits); j += (1u << k)) blut[j] = (uint8_t)(s | (k << 5));
-                    code++;
-                }
-                code <<= 1;
-            }
-            if (g_b == 1 && cnt[1] == 1) blut[1] = blut[0];
-        }
-        __syncwarp(gmask);
+        int bb_bits = build_bits_lut(cl, blut, S->aux, glane, gmask);
+        if (bb_bits < 0) { msg = -bb_bits; return R_ERROR; }
         int index = 0;
         uint32_t prev = 0;
         while (index < total) {
@@ -635,7 +608,7 @@ struct Decoder {
             } else {
                 int i = c == 18 ? 7 : c - 14;
                 int j = c == 18 ? 11 : 3;
-                if (!ensure(tbits + i)) { stall_kind = ST_DYNHDR; return R_STALL; }
+                if (bc < tbits + i) { stall_kind = ST_DYNHDR; return R_STALL; }     // ensure() above left >= 33 bits unless the input ends
                 drop(tbits);
                 j += (int)peek(i);
                 drop(i);
@@ -652,19 +625,32 @@ struct Decoder {
     }
 
     // ------------------------------------------------------------------ symbol loop
-    __device__ int decode_codes()
+    // One loop for the whole block.  `tail` (fewer than five input words left) and root
+    // entries marked long/invalid go through slow_lookup(), which also enforces the
+    // reference's lookahead rule; everything else is one shared-memory LUT read per code.
+    __device__ __forceinline__ int decode_codes()
     {
         for (;;) {
             refill();
+            const bool tail = wp + 5 > end_wp;
             uint32_t e = S->lut_l[(uint32_t)bb & ((1u << RL) - 1u)];
-            uint32_t n = e >> 12;
-            if (wp + 3 > end_wp || n == 0) {           // stream tail or long/invalid code
-                int r = slow_symbol();
-                if (r == R_OK) continue;
-                return r;
+            uint32_t n = e >> 12, p = e & 0xfff;
+            if (tail || n == 0) {
+                uint32_t r = slow_lookup(S->cnt_l, S->sorted_l, lbits, g_l, (uint32_t)bb, avail_bits());
+                uint32_t st = r >> 28;
+                if (st) { if (st == (uint32_t)R_ERROR) msg = SDZ_MSG_BAD_LITLEN_CODE; return (int)st; }
+                n = (r >> 16) & 0xff;
+                uint32_t sym = r & 0xffff;
+                if (sym <= 256) p = sym;
+                else {
+                    uint32_t i = sym - 257;
+                    if (i > 28) { msg = SDZ_MSG_BAD_LITLEN_CODE; return R_ERROR; }
+                    uint32_t xb = i < 8 ? 0 : (i == 28 ? 0 : (i >> 2) - 1);
+                    uint32_t base = i < 8 ? 3 + i : (i == 28 ? 258 : 3 + ((4 + (i & 3)) << xb));
+                    p = 0x800 | (xb << 8) | (base - 3);
+                }
             }
             bb >>= n; bc -= (int)n;
-            uint32_t p = e & 0xfff;
             if (p < 256) {
                 if (pos >= cap) return R_OUTFULL;
                 if (STORE) { if (glane == 0) out[pos] = (uint8_t)p; }
@@ -673,28 +659,34 @@ struct Decoder {
             }
             if (p == 256) { eob_len = (int)n; return R_EOB; }
             uint32_t xb = (p >> 8) & 7;
+            if (tail && avail_bits() < (int)xb) return R_STALL;
             uint32_t len = 3 + (p & 0xff) + ((uint32_t)bb & ((1u << xb) - 1u));
             bb >>= xb; bc -= (int)xb;
             refill();
             uint32_t de = S->lut_d[(uint32_t)bb & ((1u << RD) - 1u)];
             uint32_t dn = de >> 12;
-            uint32_t dist;
-            if (dn == 0) {
-                int r = slow_dist(&dist);
-                if (r != R_OK) return r;
-            } else {
-                bb >>= dn; bc -= (int)dn;
-                uint32_t dx = (de >> 8) & 15;
-                dist = 1 + ((de & 3) << dx) + ((uint32_t)bb & ((1u << dx) - 1u));
-                bb >>= dx; bc -= (int)dx;
+            if (tail || dn == 0) {
+                if (g_d == 0) { msg = SDZ_MSG_BAD_DIST_CODE; return R_ERROR; }
+                uint32_t r = slow_lookup(S->cnt_d, S->sorted_d, dbits, g_d, (uint32_t)bb, avail_bits());
+                uint32_t st = r >> 28;
+                if (st) { if (st == (uint32_t)R_ERROR) msg = SDZ_MSG_BAD_DIST_CODE; return (int)st; }
+                dn = (r >> 16) & 0xff;
+                uint32_t ds = r & 0xffff;
+                if (ds > 29) { msg = SDZ_MSG_BAD_DIST_CODE; return R_ERROR; }
+                de = ((ds < 4 ? 0u : (ds >> 1) - 1u) << 8) | (ds < 4 ? ds : 2u + (ds & 1u));
             }
+            bb >>= dn; bc -= (int)dn;
+            uint32_t dx = (de >> 8) & 15;
+            if (tail && avail_bits() < (int)dx) return R_STALL;
+            uint32_t dist = 1 + ((de & 3) << dx) + ((uint32_t)bb & ((1u << dx) - 1u));
+            bb >>= dx; bc -= (int)dx;
             int r = copy_match(len, dist);
             if (r != R_OK) return r;
         }
     }
 
     // stored block body (src/infblocks.ts:278-333) with the Q2 truncation
-    __device__ int stored_block(uint32_t left)
+    __device__ __forceinline__ int stored_block(uint32_t left)
     {
         uint32_t start = byte_pos();
         uint32_t n_in = in_len - start;
@@ -722,7 +714,7 @@ struct Decoder {
     }
 
     // all deflate blocks; returns R_EOB when the final block completed
-    __device__ int blocks(uint32_t* n_blocks)
+    __device__ __forceinline__ int blocks(uint32_t* n_blocks)
     {
         for (;;) {
             if (!ensure(3)) { stall_kind = ST_OTHER; return R_STALL; }
@@ -732,8 +724,8 @@ struct Decoder {
             (*n_blocks)++;
             uint32_t start_pos = pos;
             int r;
-            switch (t >> 1) {
-            case 0: {
+            uint32_t type = t >> 1;
+            if (type == 0) {
                 drop(bc & 7);
                 if (!ensure(32)) { stall_kind = ST_OTHER; return R_STALL; }
                 uint32_t v = (uint32_t)bb;
@@ -744,29 +736,22 @@ struct Decoder {
                 if (last) { ring.wash(); return R_EOB; }
                 continue;
             }
-            case 1: {
+            if (type == 3) { msg = SDZ_MSG_BAD_BLOCK_TYPE; return R_ERROR; }
+            int nl = 288, nd = 30;
+            if (type == 1) {
                 __syncwarp(gmask);
                 for (int i = glane; i < 320; i += G) {
                     uint8_t v = i < 144 ? 8 : (i < 256 ? 9 : (i < 280 ? 7 : (i < 288 ? 8 : 5)));
                     S->lens[i] = v;
                 }
                 __syncwarp(gmask);
-                build_tables(288, 30, true);
-                lbits = 9; dbits = 5;
-                break;
-            }
-            case 2: {
-                int nl, nd;
+            } else {
                 r = dynamic_header(&nl, &nd);
                 if (r != R_OK) return r;
-                r = build_tables(nl, nd, false);
-                if (r != R_OK) return r;
-                break;
             }
-            default:
-                msg = SDZ_MSG_BAD_BLOCK_TYPE;
-                return R_ERROR;
-            }
+            TreeInfo T = build_tables<G>(S, nl, nd, type == 1, glane, gmask);
+            if (T.msg) { msg = T.msg; return R_ERROR; }
+            lbits = T.lbits; dbits = T.dbits; g_l = T.g_l; g_d = T.g_d;
             r = decode_codes();
             ring.write(pos - start_pos);
             if (r != R_EOB) { if (r == R_STALL) stall_kind = ST_OTHER; return r; }
@@ -789,23 +774,21 @@ struct Decoder {
 
 // ---------------------------------------------------------------------- per-stream driver
 template <int G, bool STORE>
-__device__ void inflate_stream(Decoder<G, STORE>& d, const InflateParams& P, unsigned long long idx)
+__device__ __forceinline__ void inflate_stream(Decoder<G, STORE>& d, const InflateParams& P, unsigned long long idx)
 {
-    sdz_result R;
-    memset(&R, 0, sizeof R);
     const uint32_t in_len = P.in_len[idx];
     const uint8_t mode_raw = P.mode[idx];
     const int mode = mode_raw & 0x7f;
     const bool has_dict = (mode_raw & 0x80) != 0;
     const uint8_t* src = P.in + P.in_off[idx];
-    R.out_off = P.out_off ? P.out_off[idx] : 0;
+    const uint64_t out_off = P.out_off ? P.out_off[idx] : 0;
 
     d.gsrc = src;
     d.in_len = in_len;
     d.end_wp = (in_len + 3) / 4;
     d.tail_mask = (in_len & 3) ? ((1u << ((in_len & 3) * 8)) - 1u) : 0xffffffffu;
     d.total_chunks = (in_len + CH - 1) / CH;
-    d.out = STORE ? P.out + R.out_off : nullptr;
+    d.out = STORE ? P.out + out_off : nullptr;
     d.pos = 0;
     d.cap = (STORE && P.out_cap) ? P.out_cap[idx] : 0xffffffffu;
     d.msg = SDZ_MSG_NONE;
@@ -813,8 +796,10 @@ __device__ void inflate_stream(Decoder<G, STORE>& d, const InflateParams& P, uns
     d.D = 0;
     d.dict_tail = nullptr;
     d.lbits = d.dbits = d.g_l = d.g_d = 0;
+    d.eob_len = 0;
+    d.ring.init(0);
 
-    int thrown = SDZ_THROW_NONE;
+    int thrown = SDZ_THROW_NONE, thrown_inflate = 0;
     int zstatus = SDZ_Z_OK;
     bool done = false;          // Inflate reached Mode.DONE
     bool is_gzip = false;
@@ -822,150 +807,166 @@ __device__ void inflate_stream(Decoder<G, STORE>& d, const InflateParams& P, uns
     uint32_t n_blocks = 0;
     int32_t stored = 0, isize = 0, mtime = 0;
     uint32_t name_off = 0, name_len = 0;
+    uint32_t end_byte = 0;      // bytes consumed (total_in)
+    bool decode = true;
 
     bool raw = mode == SDZ_MODE_RAW;
-    bool skip_all = false;
     if (mode == SDZ_MODE_SNIFF) {
         // inflate(): src/sd-inflate.ts:194-207
-        if (in_len < 2) { R.thrown_inflate = SDZ_THROW_TOO_SMALL; skip_all = true; }
+        if (in_len < 2) { thrown_inflate = SDZ_THROW_TOO_SMALL; decode = false; }
         else {
             uint32_t b0 = src[0], b1 = src[1];
             bool ident = (b0 == 0x78 && (((b0 << 8) + b1) % 31) == 0) || (b0 == 0x1f && b1 == 0x8b);
             raw = !ident;
         }
     }
-    if (!skip_all && raw && has_dict) {                 // RangeError in the constructor (src/sd-inflate.ts:69-71)
-        R.thrown_inflate = SDZ_THROW__COUNT;
-        skip_all = true;
+    if (decode && raw && has_dict) {                    // RangeError in the constructor (src/sd-inflate.ts:69-71)
+        thrown_inflate = SDZ_THROW__COUNT;
+        decode = false;
     }
-    if (skip_all || in_len == 0) {
-        // append() of an empty chunk returns [] (src/sd-inflate.ts:92-94); finish() on a fresh Inflater
-        if (d.glane == 0) P.res[idx] = R;
-        return;
-    }
+    if (in_len == 0) decode = false;                    // append() of an empty chunk returns [] (src/sd-inflate.ts:92-94)
 
-    d.ring.init(0);
-    d.seek(0);
-
-    int r = R_OK;
-    // ---- container header (src/inflate.ts:142-401)
-    if (!raw) {
-        bool ok = true;                                 // false: input ran out (incomplete)
-        #define GETBYTE(v) do { if (!d.ensure(8)) { ok = false; goto hdr_done; } (v) = d.peek(8); d.drop(8); } while (0)
-        uint32_t b;
-        if (!d.ensure(8)) { ok = false; goto hdr_done; }
-        if (d.peek(8) == 0x1f) {
-            d.drop(8);
-            GETBYTE(b);
-            if (b != 0x8b) { d.msg = SDZ_MSG_BAD_GZIP_ID; r = R_ERROR; goto hdr_done; }
-            is_gzip = true;
-        }
-        GETBYTE(b);
-        method = (int)b;
-        if ((method & 0xf) != 8) { d.msg = SDZ_MSG_BAD_METHOD; r = R_ERROR; goto hdr_done; }
-        if ((method >> 4) + 8 > 15) { d.msg = SDZ_MSG_BAD_WINDOW; r = R_ERROR; goto hdr_done; }
-        GETBYTE(b);
-        if (is_gzip) {
-            uint32_t gflags = b;
-            for (int i = 0; i < 4; i++) { GETBYTE(b); mtime = (int32_t)(((uint32_t)mtime >> 8) | (b << 24)); }
-            GETBYTE(b);                                 // XFL
-            GETBYTE(b);                                 // OS
-            if (gflags & 4) {                           // FEXTRA never leaves EXTRA0
-                ok = false;
-                goto hdr_done;
+    // ---- container header, byte by byte as Inflate.inflate does (src/inflate.ts:142-401)
+    uint32_t hp = 0;                                    // header bytes consumed
+    if (decode && !raw) {
+        int err = 0;                                    // sdz_msg of a header error
+        bool ok = false;                                // header complete
+        do {
+            uint32_t b;
+            if (hp >= in_len) break;
+            if (src[hp] == 0x1f) {
+                hp++;
+                if (hp >= in_len) break;
+                b = src[hp++];
+                if (b != 0x8b) { err = SDZ_MSG_BAD_GZIP_ID; break; }
+                is_gzip = true;
             }
-            if (gflags & 8) {
-                name_off = d.byte_pos();
-                for (;;) { GETBYTE(b); if (b == 0) break; name_len++; }
+            if (hp >= in_len) break;
+            method = src[hp++];
+            if ((method & 0xf) != 8) { err = SDZ_MSG_BAD_METHOD; break; }
+            if ((method >> 4) + 8 > 15) { err = SDZ_MSG_BAD_WINDOW; break; }
+            if (hp >= in_len) break;
+            b = src[hp++];
+            if (is_gzip) {
+                const uint32_t gflags = b;
+                bool trunc = false;
+                for (int i = 0; i < 4; i++) {
+                    if (hp >= in_len) { trunc = true; break; }
+                    mtime = (int32_t)(((uint32_t)mtime >> 8) | ((uint32_t)src[hp++] << 24));
+                }
+                if (trunc) break;
+                if (hp + 2 > in_len) { hp = in_len; break; }            // XFL, OS
+                hp += 2;
+                if (gflags & 4) { hp = in_len; break; }                 // FEXTRA never leaves EXTRA0
+                if (gflags & 8) {
+                    name_off = hp;
+                    for (;;) { if (hp >= in_len) { trunc = true; break; } b = src[hp++]; if (b == 0) break; name_len++; }
+                    if (trunc) break;
+                }
+                if (gflags & 16) {
+                    for (;;) { if (hp >= in_len) { trunc = true; break; } b = src[hp++]; if (b == 0) break; }
+                    if (trunc) break;
+                }
+                if (gflags & 2) { if (hp + 2 > in_len) { hp = in_len; break; } hp += 2; }
+            } else {
+                if ((((uint32_t)method << 8) + b) % 31 != 0) { err = SDZ_MSG_BAD_HEADER_CHECK; break; }
+                if (b & 0x20) {
+                    if (hp + 4 > in_len) { hp = in_len; break; }
+                    int32_t dictid = (int32_t)(((uint32_t)src[hp] << 24) | ((uint32_t)src[hp + 1] << 16) | ((uint32_t)src[hp + 2] << 8) | src[hp + 3]);
+                    hp += 4;
+                    // NEED_DICT -> inflateSetDictionary (src/sd-inflate.ts:116-126, src/inflate.ts:475-503)
+                    if (!has_dict) { thrown = SDZ_THROW_DICT_REQUIRED; zstatus = SDZ_Z_NEED_DICT; break; }
+                    if (P.dict_adler[idx] != dictid) { thrown = SDZ_THROW_DICT_INVALID; zstatus = SDZ_Z_NEED_DICT; break; }
+                    uint32_t dl = P.dict_len[idx];
+                    uint32_t used = dl >= (uint32_t)WSIZE ? (uint32_t)WSIZE - 1 : dl;
+                    d.D = (int)used;
+                    d.dict_tail = P.dict + P.dict_off[idx] + (dl - used);
+                    d.ring.init((int)used);
+                }
             }
-            if (gflags & 16) { for (;;) { GETBYTE(b); if (b == 0) break; } }
-            if (gflags & 2) { GETBYTE(b); GETBYTE(b); }
-        } else {
-            if ((((uint32_t)method << 8) + b) % 31 != 0) { d.msg = SDZ_MSG_BAD_HEADER_CHECK; r = R_ERROR; goto hdr_done; }
-            if (b & 0x20) {
-                int32_t dictid = 0;
-                for (int i = 0; i < 4; i++) { uint32_t v; GETBYTE(v); dictid = (int32_t)(((uint32_t)dictid << 8) | v); }
-                // NEED_DICT -> inflateSetDictionary (src/sd-inflate.ts:116-126, src/inflate.ts:475-503)
-                if (!has_dict) { thrown = SDZ_THROW_DICT_REQUIRED; zstatus = SDZ_Z_NEED_DICT; goto finish; }
-                if (P.dict_adler[idx] != dictid) { thrown = SDZ_THROW_DICT_INVALID; zstatus = SDZ_Z_NEED_DICT; goto finish; }
-                uint32_t dl = P.dict_len[idx];
-                uint32_t used = dl >= (uint32_t)WSIZE ? (uint32_t)WSIZE - 1 : dl;
-                d.D = (int)used;
-                d.dict_tail = P.dict + P.dict_off[idx] + (dl - used);
-                d.ring.init((int)used);
-            }
-        }
-    hdr_done:
-        #undef GETBYTE
-        if (r == R_ERROR) { thrown = SDZ_THROW_INFLATE_ERROR; zstatus = SDZ_Z_DATA_ERROR; goto finish; }
-        if (!ok) { zstatus = SDZ_Z_OK; goto finish; }   // truncated header: incomplete, no output
+            ok = true;
+        } while (0);
+        if (err) { d.msg = err; thrown = SDZ_THROW_INFLATE_ERROR; zstatus = SDZ_Z_DATA_ERROR; }
+        if (!ok) { decode = false; end_byte = thrown ? hp : in_len; }
     }
 
     // ---- deflate blocks
-    r = d.blocks(&n_blocks);
-    if (r == R_ERROR) { thrown = SDZ_THROW_INFLATE_ERROR; zstatus = SDZ_Z_DATA_ERROR; goto finish; }
-    if (r == R_OUTFULL) { zstatus = SDZ_Z_BUF_ERROR; goto finish; }
-    if (r == R_STALL) {
-        // input exhausted.  proc() flushes; if that fills the 16 KiB buffer append() calls
-        // again, and BTREE/DTREE cannot be re-entered -> STREAM_ERROR is thrown.
-        if (d.stall_kind == ST_DYNHDR) {
-            d.ring.flush();
-            if (d.ring.ao == 0) { thrown = SDZ_THROW_INFLATE_ERROR; zstatus = SDZ_Z_STREAM_ERROR; d.msg = SDZ_MSG_NONE; }
-        }
-        goto finish;
-    }
-    // ---- final block done: unused whole bytes go back, partial bits are dropped (src/inflate.ts:409-421)
-    d.drop(d.bc & 7);
-    if (raw) {
-        done = true;
-    } else {
-        int nbytes = is_gzip ? 8 : 4;
-        int i = 0;
-        for (; i < nbytes; i++) {
-            if (!d.ensure(8)) break;
-            uint32_t b = d.peek(8);
-            d.drop(8);
-            if (is_gzip) {
-                if (i < 4) stored = (int32_t)(((uint32_t)stored >> 8) | (b << 24));
-                else isize = (int32_t)(((uint32_t)isize >> 8) | (b << 24));
-            } else {
-                stored = (int32_t)(((uint32_t)stored << 8) | b);
+    if (decode) {
+        d.seek(hp);
+        int r = d.blocks(&n_blocks);
+        if (r == R_ERROR) { thrown = SDZ_THROW_INFLATE_ERROR; zstatus = SDZ_Z_DATA_ERROR; }
+        else if (r == R_OUTFULL) { zstatus = SDZ_Z_BUF_ERROR; }
+        else if (r == R_STALL) {
+            // input exhausted.  proc() flushes; if that fills the 16 KiB buffer append() calls
+            // again, and BTREE/DTREE cannot be re-entered -> STREAM_ERROR is thrown.
+            if (d.stall_kind == ST_DYNHDR) {
+                d.ring.flush();
+                if (d.ring.ao == 0) { thrown = SDZ_THROW_INFLATE_ERROR; zstatus = SDZ_Z_STREAM_ERROR; d.msg = SDZ_MSG_NONE; }
             }
+        } else {
+            // final block done: unused whole bytes go back, partial bits are dropped (src/inflate.ts:409-421);
+            // the trailer is read byte by byte (src/inflate.ts:423-463)
+            uint32_t tp = (uint32_t)((d.bit_pos() + 7) >> 3);
+            if (raw) {
+                done = true;
+            } else {
+                const int nbytes = is_gzip ? 8 : 4;
+                int i = 0;
+                for (; i < nbytes && tp < in_len; i++) {
+                    uint32_t b = src[tp++];
+                    if (is_gzip) {
+                        if (i < 4) stored = (int32_t)(((uint32_t)stored >> 8) | (b << 24));
+                        else isize = (int32_t)(((uint32_t)isize >> 8) | (b << 24));
+                    } else {
+                        stored = (int32_t)(((uint32_t)stored << 8) | b);
+                    }
+                }
+                done = i == nbytes;
+            }
+            if (done) {
+                zstatus = SDZ_Z_STREAM_END;
+                if (tp < in_len) thrown = SDZ_THROW_HANG;   // bytes after the end: append() spins
+            }
+            end_byte = tp;
         }
-        done = i == nbytes;
-    }
-    if (done) {
-        zstatus = SDZ_Z_STREAM_END;
-        if (d.byte_pos() < in_len) thrown = SDZ_THROW_HANG;   // bytes after the end: append() spins
+        if (r != R_EOB) end_byte = d.byte_pos();
+        d.drain();
+        __syncwarp(d.gmask);
     }
 
-finish:
-    d.drain();
-    __syncwarp(d.gmask);
-    R.out_len = (thrown && STORE) ? 0 : d.pos;      // the sizing pass always reports the decoded size
-    R.total_in = d.byte_pos();
-    R.zstatus = zstatus;
-    R.stored_checksum = stored;
-    R.stored_isize = isize;
-    R.mtime = mtime;
-    R.name_off = name_len ? name_off : 0;
-    R.name_len = name_len;
-    R.n_blocks = n_blocks;
-    R.msg_id = (uint8_t)d.msg;
-    R.thrown_append = (uint8_t)thrown;
-    R.container = (uint8_t)(is_gzip ? SDZ_GZIP : (method == 0 ? SDZ_RAW : SDZ_ZLIB));
-    R.complete = done ? 1 : 0;
-    if (d.glane == 0) P.res[idx] = R;
+    if (d.glane == 0) {
+        sdz_result R;
+        R.out_off = out_off;
+        R.out_len = (thrown && STORE) ? 0 : d.pos;      // the sizing pass always reports the decoded size
+        R.total_in = end_byte;
+        R.zstatus = zstatus;
+        R.stored_checksum = stored;
+        R.running_checksum = 0;
+        R.stored_isize = isize;
+        R.mtime = mtime;
+        R.name_off = name_len ? name_off : 0;
+        R.name_len = name_len;
+        R.n_blocks = n_blocks;
+        R.msg_id = (uint8_t)d.msg;
+        R.thrown_append = (uint8_t)thrown;
+        R.thrown_inflate = (uint8_t)thrown_inflate;
+        R.container = (uint8_t)(is_gzip ? SDZ_GZIP : (method == 0 ? SDZ_RAW : SDZ_ZLIB));
+        R.complete = done ? 1 : 0;
+        R.checksum_state = R.size_state = R.success = R.have_running = 0;
+        for (int i = 0; i < 7; i++) R.reserved[i] = 0;
+        P.res[idx] = R;
+    }
 }
 
+#ifndef SDZ_MINBLOCKS
+#define SDZ_MINBLOCKS 1
+#endif
 template <int G, bool STORE>
-__global__ void __launch_bounds__(128) inflate_kernel(InflateParams P)
+__global__ void __launch_bounds__(128, SDZ_MINBLOCKS) inflate_kernel(InflateParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int groups = blockDim.x / G;
     const int gid = threadIdx.x / G;
     GroupSmem* S = reinterpret_cast<GroupSmem*>(smem_raw) + gid;
-    (void)groups;
 
     Decoder<G, STORE> d;
     d.S = S;

@@ -37,7 +37,7 @@ struct sdz_ctx {
     void* h_stage = nullptr;           // pinned
     size_t h_stage_cap = 0;
     unsigned long long* d_counter = nullptr;
-    int group = 8;                     // lanes per stream
+    int group = 32;                    // lanes per stream
     int block_threads = 128;
 };
 
@@ -140,10 +140,8 @@ template <bool STORE>
 int launch_inflate(sdz_ctx* ctx, const sdz::InflateParams& P)
 {
     switch (ctx->group) {
-    case 4: return launch_inflate_t<4, STORE>(ctx, P);
     case 16: return launch_inflate_t<16, STORE>(ctx, P);
-    case 32: return launch_inflate_t<32, STORE>(ctx, P);
-    default: return launch_inflate_t<8, STORE>(ctx, P);
+    default: return launch_inflate_t<32, STORE>(ctx, P);
     }
 }
 
@@ -229,7 +227,7 @@ int sdz_ctx_create(int device, uint32_t flags, sdz_ctx** out)
     for (auto& e : ctx->ev)
         if (cudaEventCreate(&e) != cudaSuccess) return fail(SDZ_E_CUDA);
     if (cudaMalloc(&ctx->d_counter, 4 * sizeof(unsigned long long)) != cudaSuccess) return fail(SDZ_E_NOMEM);
-    if (const char* g = getenv("SDZ_GROUP")) { int v = atoi(g); if (v == 4 || v == 8 || v == 16 || v == 32) ctx->group = v; }
+    if (const char* g = getenv("SDZ_GROUP")) { int v = atoi(g); if (v == 16 || v == 32) ctx->group = v; }
     if (const char* t = getenv("SDZ_BLOCK")) { int v = atoi(t); if (v == 32 || v == 64 || v == 128) ctx->block_threads = v; }
     if (ctx->block_threads < ctx->group) ctx->block_threads = ctx->group;
     int rc = upload_tables(ctx);

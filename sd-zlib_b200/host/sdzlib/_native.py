@@ -7,7 +7,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "csrc", "libsdzcuda.so"))
+LIB_PATH = os.environ.get("SDZ_LIB") or os.path.normpath(os.path.join(_HERE, "..", "..", "csrc", "libsdzcuda.so"))
 
 SDZ_OK, SDZ_E_NO_DEVICE, SDZ_E_CUDA, SDZ_E_ARG, SDZ_E_NOMEM, SDZ_E_OUT_CAP, SDZ_E_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 _ERR_NAME = {-1: "no sm_100a CUDA device", -2: "CUDA error", -3: "bad argument", -4: "out of memory",
