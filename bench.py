@@ -362,7 +362,7 @@ def main():
             "config": {"workload": "inflateBatch 65,536 x 64 KiB synthetic-text zlib streams, level 6, per GPU",
                        "streams_per_gpu": n, "distinct_streams_per_gpu": n_distinct, "stream_bytes": STREAM_BYTES,
                        "compressed_bytes_per_gpu": comp_bytes, "l2": "inputs+outputs (%.1f GB) far exceed the 126 MB L2" % ((comp_bytes + out_bytes) / 1e9),
-                       "lanes_per_stream": int(os.environ.get("SDZ_GROUP", "8")), "corpus_gen_s": round(gen_s, 1)},
+                       "lanes_per_stream": int(os.environ.get("SDZ_GROUP", "4")), "corpus_gen_s": round(gen_s, 1)},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": None, "peak_kind": peak_kind,
                          "kernel": "inflate_kernel", "kernel_ms": round(inf_ms, 3), "finalize_ms": round(k_fin / args.steps, 3),

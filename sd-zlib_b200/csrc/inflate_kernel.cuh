@@ -26,10 +26,10 @@
 
 namespace sdz {
 
-constexpr int RL = 10;                 // literal/length LUT root bits
+constexpr int RL = 9;                  // literal/length LUT root bits
 constexpr int RD = 8;                  // distance LUT root bits
 constexpr int CH = 128;                // bytes per TMA bulk copy
-constexpr int NBUF = 4;                // chunks in the per-group input ring
+constexpr int NBUF = 2;                // chunks in the per-group input ring
 constexpr int CHW = CH / 4;
 constexpr int WSIZE = 32768;           // reference window (src/inflate.ts:98)
 constexpr int OUTBUF = 16384;          // reference OUTPUT_BUFSIZE (src/zstream.ts:11)
@@ -38,17 +38,20 @@ constexpr uint32_t E_LONG = 0x0ffe;    // root entry: code longer than the root 
 constexpr uint32_t E_INVALID = 0x0fff; // root entry: no code has this prefix
 
 struct alignas(16) GroupSmem {
-    uint32_t ring[NBUF * CHW];         // 512 B input staging
+    uint32_t ring[NBUF * CHW];         // 256 B input staging (TMA bulk copies)
     uint64_t mbar[NBUF];
     uint16_t lut_l[1 << RL];
     uint16_t lut_d[1 << RD];
-    uint16_t sorted_l[288];            // symbols ordered by (code length, symbol)
-    uint16_t sorted_d[32];
     uint32_t cnt_l[16];                // codes per length (unpadded)
     uint32_t cnt_d[16];
     uint32_t aux[32];                  // build scratch: [0..15] offsets, [16..31] first codes
-    uint8_t lens[320];                 // code lengths of the current block
+    uint32_t stage[8];                 // source bytes of the pending (deferred) match, staged by cp.async
 };
+
+// per-group scratch in global memory: symbols ordered by (code length, symbol) - read by the
+// table build and by the rare canonical (slow) decode - and the block's code-length array
+constexpr int SORTED_L = 288, SORTED_D = 32;
+constexpr int SCRATCH_U16 = SORTED_L + SORTED_D + 160;       // + 320 bytes of code lengths
 
 struct InflateParams {
     const uint8_t* in;
@@ -63,6 +66,7 @@ struct InflateParams {
     const uint64_t* out_off;
     const uint32_t* out_cap;
     sdz_result* res;
+    uint16_t* scratch;                 // SCRATCH_U16 entries per group of the grid
     unsigned long long n;
     unsigned long long* counter;       // dynamic stream scheduler
 };
@@ -237,25 +241,28 @@ __device__ __noinline__ uint32_t slow_lookup(const uint32_t* cnt, const uint16_t
     return (uint32_t)R_ERROR << 28;
 }
 
-// first touch of input chunk `rel`: wait for its TMA copy, then reuse the slot of the chunk
-// that was just finished for the next outstanding chunk.  Returns the new `issued` count.
-__device__ __noinline__ uint32_t chunk_cross(GroupSmem* S, const uint8_t* gsrc, uint32_t base_seq, uint32_t rel, uint32_t chunk0,
-                                             uint32_t issued, uint32_t total_chunks, unsigned gmask, int glane)
+// First touch of input chunk `c` (absolute index in the stream): wait for its TMA copy, then
+// reuse the slot of the chunk that was just finished for the next outstanding chunk.
+// Slot = c % NBUF; `phasebits` holds the mbarrier parity to wait for next on every slot.
+// Returns issued_abs (low 16.. bits are not packed: plain value); phasebits updated by reference
+// would force it to memory, so both come back packed: (issued_abs << 4) | phasebits.
+__device__ __noinline__ uint64_t chunk_cross(GroupSmem* S, const uint8_t* gsrc, uint32_t c, uint32_t chunk0, uint32_t issued_abs,
+                                             uint32_t total_chunks, uint32_t phasebits, unsigned gmask, int glane)
 {
-    uint32_t seq = base_seq + rel;
-    mbar_wait(&S->mbar[seq % NBUF], (seq / NBUF) & 1);
-    if (rel >= 1 && chunk0 + issued < total_chunks) {
+    const uint32_t slot = c % NBUF;
+    mbar_wait(&S->mbar[slot], (phasebits >> slot) & 1u);
+    phasebits ^= 1u << slot;
+    if (c > chunk0 && issued_abs < total_chunks) {
         __syncwarp(gmask);                              // every lane is done with the slot being recycled
         if (glane == 0) {
-            uint32_t nseq = base_seq + issued, slot = nseq % NBUF;
-            mbar_arrive_expect_tx(&S->mbar[slot], CH);
-            bulk_copy_g2s(&S->ring[slot * CHW], gsrc + (size_t)(chunk0 + issued) * CH, CH, &S->mbar[slot]);
+            const uint32_t ns = issued_abs % NBUF;
+            mbar_arrive_expect_tx(&S->mbar[ns], CH);
+            bulk_copy_g2s(&S->ring[ns * CHW], gsrc + (size_t)issued_abs * CH, CH, &S->mbar[ns]);
         }
-        issued++;
+        issued_abs++;
     }
-    return issued;
+    return ((uint64_t)issued_abs << 4) | phasebits;
 }
-
 
 // ---------------------------------------------------------------------- table construction
 // (out of line: runs once per block; works only on the group's shared memory)
@@ -352,12 +359,13 @@ __device__ __forceinline__ void make_lut(GroupSmem* S, const uint8_t* lens, int 
 // lit/len + distance tables for lens[0..nl) and lens[nl..nl+nd) with the reference's checks
 // and messages (inflate_trees_dynamic, src/inftree.ts:333-379).  fixed: no checks.
 template <int G>
-__device__ __noinline__ TreeInfo build_tables(GroupSmem* S, int nl, int nd, bool fixed, int glane, unsigned gmask)
+__device__ __noinline__ TreeInfo build_tables(GroupSmem* S, uint16_t* gsorted, int nl, int nd, bool fixed, int glane, unsigned gmask)
 {
     TreeInfo T;
     T.msg = SDZ_MSG_NONE; T.lbits = T.dbits = T.g_l = T.g_d = 0;
     int pad_l = 0, pad_d = 0, used = 0;
-    int st = classify<G>(S->lens, nl, 9, S->cnt_l, &T.lbits, &T.g_l, &pad_l, glane, gmask);
+    const uint8_t* lens = reinterpret_cast<const uint8_t*>(gsorted + SORTED_L + SORTED_D);
+    int st = classify<G>(lens, nl, 9, S->cnt_l, &T.lbits, &T.g_l, &pad_l, glane, gmask);
     if (!fixed) {
         // the lit/len and distance tables share an arena of MANY = 1400 entries; running out of
         // it is reported as DATA_ERROR, i.e. with the "oversubscribed" text
@@ -366,7 +374,7 @@ __device__ __noinline__ TreeInfo build_tables(GroupSmem* S, int nl, int nd, bool
         if (used > 1400) { T.msg = SDZ_MSG_OVERSUB_LITLEN_TREE; return T; }
         if (st == 2 || st == 3) { T.msg = SDZ_MSG_INCOMPLETE_LITLEN_TREE; return T; }
     }
-    st = classify<G>(S->lens + nl, nd, fixed ? 5 : 6, S->cnt_d, &T.dbits, &T.g_d, &pad_d, glane, gmask);
+    st = classify<G>(lens + nl, nd, fixed ? 5 : 6, S->cnt_d, &T.dbits, &T.g_d, &pad_d, glane, gmask);
     if (!fixed) {
         if (st == 1) { T.msg = SDZ_MSG_OVERSUB_DIST_TREE; return T; }
         if (st != 3 && used + ref_table_total<G>(S->cnt_d, T.g_d, pad_d, T.dbits, glane, gmask) > 1400) {
@@ -375,8 +383,8 @@ __device__ __noinline__ TreeInfo build_tables(GroupSmem* S, int nl, int nd, bool
         if (st == 2) { T.msg = SDZ_MSG_INCOMPLETE_DIST_TREE; return T; }
         if (st == 3 && nl > 257) { T.msg = SDZ_MSG_EMPTY_DIST_TREE; return T; }
     }
-    make_lut<G, 0, RL>(S, S->lens, nl, S->cnt_l, S->sorted_l, S->lut_l, glane, gmask);
-    make_lut<G, 1, RD>(S, S->lens + nl, nd, S->cnt_d, S->sorted_d, S->lut_d, glane, gmask);
+    make_lut<G, 0, RL>(S, lens, nl, S->cnt_l, gsorted, S->lut_l, glane, gmask);
+    make_lut<G, 1, RD>(S, lens + nl, nd, S->cnt_d, gsorted + SORTED_L, S->lut_d, glane, gmask);
     if (fixed) { T.lbits = 9; T.dbits = 5; }
     return T;
 }
@@ -436,9 +444,12 @@ __device__ __noinline__ void copy_before_start_impl(uint8_t* o, uint32_t p0, uin
     }
 }
 
+enum : int { PH_FETCH = 0, PH_BLOCK = 1, PH_CODES = 2, PH_EXIT = 3 };
+
 template <int G, bool STORE>
 struct Decoder {
     GroupSmem* S;
+    uint16_t* gsorted;                 // global scratch: sorted symbols of the current block
     unsigned gmask;
     int glane;
 
@@ -446,10 +457,10 @@ struct Decoder {
     uint64_t bb;
     int bc;
     uint32_t nw;                       // prefetched word `wp`
-    uint32_t wp, end_wp, tail_mask;
+    uint32_t wp, end_wp;
     uint32_t in_len;
     const uint8_t* gsrc;
-    uint32_t chunk0, total_chunks, issued, waited, base_seq;
+    uint32_t chunk0, total_chunks, issued_abs, waited_abs, phasebits;
 
     // ---- output
     uint8_t* out;
@@ -457,34 +468,46 @@ struct Decoder {
     const uint8_t* dict_tail;
     int D;
 
+    // deferred match copy: bytes loaded for the previous short match, stored when the next match
+    // arrives, so that the L2 round trip of a copy overlaps the decode of the following symbols
+    uint32_t pdst, plen, psoff;        // pending destination offset / length (0 = none) / byte offset in stage[]
+
     RingModel ring;
     int msg;
     int stall_kind;
     int lbits, dbits, g_l, g_d;
     int eob_len;                       // code length of the end-of-block symbol just decoded
 
+    // ---- stream / block bookkeeping (phase machine)
+    int phase;
+    unsigned long long idx;
+    uint64_t out_off;
+    uint32_t start_pos, n_blocks, name_off, name_len;
+    int32_t mtime;
+    int last, method;
+    bool raw, is_gzip;
+
     // ------------------------------------------------------------------ input staging
     __device__ __forceinline__ uint32_t load_word(uint32_t w)
     {
-        if (w >= end_wp) return 0;
-        uint32_t rel = w / CHW - chunk0;
-        uint32_t seq = base_seq + rel;
-        if (rel >= waited) {
-            issued = chunk_cross(S, gsrc, base_seq, rel, chunk0, issued, total_chunks, gmask, glane);
-            waited = rel + 1;
+        const uint32_t c = w / CHW;
+        if (c >= waited_abs) {
+            uint64_t r = chunk_cross(S, gsrc, c, chunk0, issued_abs, total_chunks, phasebits, gmask, glane);
+            phasebits = (uint32_t)r & 15u;
+            issued_abs = (uint32_t)(r >> 4);
+            waited_abs = c + 1;
         }
-        uint32_t v = S->ring[(seq % NBUF) * CHW + (w % CHW)];
-        if (w + 1 == end_wp) v &= tail_mask;
-        return v;
+        return S->ring[w % (NBUF * CHW)];
     }
 
     __device__ __forceinline__ void drain()
     {
-        for (uint32_t rel = waited; rel < issued; rel++) {
-            uint32_t seq = base_seq + rel;
-            mbar_wait(&S->mbar[seq % NBUF], (seq / NBUF) & 1);
+        for (uint32_t c = waited_abs; c < issued_abs; c++) {
+            const uint32_t slot = c % NBUF;
+            mbar_wait(&S->mbar[slot], (phasebits >> slot) & 1u);
+            phasebits ^= 1u << slot;
         }
-        waited = issued;
+        waited_abs = issued_abs;
     }
 
     // (re)position the reader on a byte boundary of the stream
@@ -492,35 +515,37 @@ struct Decoder {
     {
         drain();
         __syncwarp(gmask);
-        base_seq += issued;
-        issued = 0; waited = 0;
         uint32_t w = byte_pos >> 2;
         chunk0 = w / CHW;
-        uint32_t avail_chunks = total_chunks > chunk0 ? total_chunks - chunk0 : 0;
-        uint32_t n0 = avail_chunks < (uint32_t)NBUF ? avail_chunks : (uint32_t)NBUF;
+        uint32_t n0 = total_chunks > chunk0 ? total_chunks - chunk0 : 0;
+        if (n0 > (uint32_t)NBUF) n0 = NBUF;
         if (glane == 0) {
             for (uint32_t i = 0; i < n0; i++) {
-                uint32_t slot = (base_seq + i) % NBUF;
+                const uint32_t slot = (chunk0 + i) % NBUF;
                 mbar_arrive_expect_tx(&S->mbar[slot], CH);
                 bulk_copy_g2s(&S->ring[slot * CHW], gsrc + (size_t)(chunk0 + i) * CH, CH, &S->mbar[slot]);
             }
         }
-        issued = n0;
+        waited_abs = chunk0;
+        issued_abs = chunk0 + n0;
         wp = w; bb = 0; bc = 0;
-        nw = load_word(wp);
+        nw = wp < end_wp ? load_word(wp) : 0u;
         refill();
         uint32_t skip = (byte_pos & 3) * 8;
-        if (skip) { uint32_t s = min(skip, (uint32_t)bc); bb >>= s; bc -= (int)s; }
+        if (skip) { uint32_t k = min(skip, (uint32_t)bc); bb >>= k; bc -= (int)k; }
         refill();
     }
 
+    // Bits past the end of the stream that ride along in the last word are never counted in
+    // `bc`; every consumer either checks `bc` / avail_bits() or is far from the end.
     __device__ __forceinline__ void refill()
     {
         if (bc <= 32 && wp < end_wp) {
             bb |= (uint64_t)nw << bc;
-            bc += (wp + 1 < end_wp) ? 32 : (int)((in_len - wp * 4u) * 8u);
+            const uint32_t rem = in_len - wp * 4u;
+            bc += rem >= 4u ? 32 : (int)(rem * 8u);
             wp++;
-            nw = load_word(wp);
+            nw = wp < end_wp ? load_word(wp) : 0u;
         }
     }
 
@@ -542,16 +567,57 @@ struct Decoder {
     __device__ __forceinline__ void drop(int n) { bb >>= n; bc -= n; }
 
     // ------------------------------------------------------------------ output
+    // Deferred match copy.  A short non-overlapping match (<= 16 bytes, the common case) only
+    // ISSUES asynchronous 4-byte copies (cp.async / LDGSTS) of the aligned words that cover its
+    // source into stage[]; the bytes are moved to their destination when the group's next match
+    // (or the end of the stream) arrives, so the L2 / DRAM round trip of the window read overlaps
+    // the decode of the following symbols instead of stalling the lockstep warp.
+    __device__ __forceinline__ void commit_pending()
+    {
+        if (STORE && plen) {
+            cp_async_wait_all();
+            __syncwarp(gmask);                       // words staged by the other lanes are visible
+            const uint8_t* st = reinterpret_cast<const uint8_t*>(S->stage) + psoff;
+            uint8_t* dst = out + pdst;
+            #pragma unroll
+            for (uint32_t k = 0; k < 16 / G + (16 % G ? 1 : 0); k++) {
+                const uint32_t j = glane + k * G;
+                if (j < plen) dst[j] = st[j];
+            }
+        }
+        plen = 0;
+    }
+
     __device__ __forceinline__ int copy_match(uint32_t len, uint32_t dist)
     {
         if (len > cap - pos) return R_OUTFULL;
         if (STORE) {
+            const bool simple = dist >= len && len <= 16u && dist <= pos;
+            commit_pending();                        // previous match: its copies were issued a symbol (or more) ago
             __syncwarp(gmask);                       // earlier stores of this group are visible
             uint8_t* dst = out + pos;
-            if (dist <= pos) {
+            if (simple) {
+                const uint8_t* src = dst - dist;
+                const uint32_t so = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
+                const uint8_t* w0 = src - so;
+                const uint32_t nwords = (so + len + 3u) >> 2;             // <= 5
+                for (uint32_t w = glane; w < nwords; w += G) cp_async4(&S->stage[w], w0 + 4u * w);
+                cp_async_commit();
+                pdst = pos; plen = len; psoff = so;
+            } else if (dist <= pos) {
                 const uint8_t* src = dst - dist;
                 if (dist >= len) {
-                    for (uint32_t i = glane; i < len; i += G) dst[i] = src[i];
+                    for (uint32_t i = glane; i < len; i += 4 * G) {
+                        const bool b1 = i + G < len, b2 = i + 2 * G < len, b3 = i + 3 * G < len;
+                        uint8_t v0 = src[i], v1 = 0, v2 = 0, v3 = 0;
+                        if (b1) v1 = src[i + G];
+                        if (b2) v2 = src[i + 2 * G];
+                        if (b3) v3 = src[i + 3 * G];
+                        dst[i] = v0;
+                        if (b1) dst[i + G] = v1;
+                        if (b2) dst[i + 2 * G] = v2;
+                        if (b3) dst[i + 3 * G] = v3;
+                    }
                 } else if (dist == 1) {
                     uint8_t v = src[0];
                     for (uint32_t i = glane; i < len; i += G) dst[i] = v;
@@ -559,16 +625,11 @@ struct Decoder {
                     for (uint32_t i = glane; i < len; i += G) dst[i] = src[i % dist];
                 }
             } else {
-                copy_before_start(len, dist);
+                copy_before_start_impl<G>(out, pos, len, dist, dict_tail, D, glane);
             }
         }
         pos += len;
         return R_OK;
-    }
-
-    __device__ __forceinline__ void copy_before_start(uint32_t len, uint32_t dist)
-    {
-        copy_before_start_impl<G>(out, pos, len, dist, dict_tail, D, glane);
     }
 
     // dynamic block header: HLIT/HDIST/HCLEN, code-length code, RLE-coded lengths
@@ -581,7 +642,8 @@ struct Decoder {
         drop(14);
         int nl = 257 + (int)(t & 0x1f), nd = 1 + (int)((t >> 5) & 0x1f), ncl = 4 + (int)(t >> 10);
         int total = nl + nd;
-        uint8_t* cl = S->lens + 300;                    // 19 code-length-code lengths (tail of lens[])
+        uint8_t* lens = reinterpret_cast<uint8_t*>(gsorted + SORTED_L + SORTED_D);
+        uint8_t* cl = reinterpret_cast<uint8_t*>(S->lut_d);   // 19 code-length-code lengths (scratch)
         __syncwarp(gmask);
         for (int i = glane; i < 19; i += G) cl[i] = 0;
         __syncwarp(gmask);
@@ -602,7 +664,7 @@ struct Decoder {
             int tbits = (int)(e >> 5), c = (int)(e & 31);
             if (c < 16) {
                 drop(tbits);
-                if (glane == 0) S->lens[index] = (uint8_t)c;
+                if (glane == 0) lens[index] = (uint8_t)c;
                 prev = (uint32_t)c;
                 index++;
             } else {
@@ -615,7 +677,7 @@ struct Decoder {
                 if (index + j > total || (c == 16 && index < 1)) { msg = SDZ_MSG_BAD_REPEAT; return R_ERROR; }
                 uint8_t v = c == 16 ? (uint8_t)prev : (uint8_t)0;
                 prev = v;
-                if (glane == 0) for (int q = 0; q < j; q++) S->lens[index + q] = v;
+                if (glane == 0) for (int q = 0; q < j; q++) lens[index + q] = v;
                 index += j;
             }
         }
@@ -624,65 +686,62 @@ struct Decoder {
         return R_OK;
     }
 
-    // ------------------------------------------------------------------ symbol loop
-    // One loop for the whole block.  `tail` (fewer than five input words left) and root
-    // entries marked long/invalid go through slow_lookup(), which also enforces the
-    // reference's lookahead rule; everything else is one shared-memory LUT read per code.
-    __device__ __forceinline__ int decode_codes()
+    // ------------------------------------------------------------------ one symbol
+    // `tail` (fewer than five input words left) and root entries marked long/invalid go through
+    // slow_lookup(), which also enforces the reference's lookahead rule; everything else is
+    // one shared-memory LUT read per code.
+    __device__ __forceinline__ int step()
     {
-        for (;;) {
-            refill();
-            const bool tail = wp + 5 > end_wp;
-            uint32_t e = S->lut_l[(uint32_t)bb & ((1u << RL) - 1u)];
-            uint32_t n = e >> 12, p = e & 0xfff;
-            if (tail || n == 0) {
-                uint32_t r = slow_lookup(S->cnt_l, S->sorted_l, lbits, g_l, (uint32_t)bb, avail_bits());
-                uint32_t st = r >> 28;
-                if (st) { if (st == (uint32_t)R_ERROR) msg = SDZ_MSG_BAD_LITLEN_CODE; return (int)st; }
-                n = (r >> 16) & 0xff;
-                uint32_t sym = r & 0xffff;
-                if (sym <= 256) p = sym;
-                else {
-                    uint32_t i = sym - 257;
-                    if (i > 28) { msg = SDZ_MSG_BAD_LITLEN_CODE; return R_ERROR; }
-                    uint32_t xb = i < 8 ? 0 : (i == 28 ? 0 : (i >> 2) - 1);
-                    uint32_t base = i < 8 ? 3 + i : (i == 28 ? 258 : 3 + ((4 + (i & 3)) << xb));
-                    p = 0x800 | (xb << 8) | (base - 3);
-                }
+        refill();
+        const bool tail = wp + 5 > end_wp;
+        uint32_t e = S->lut_l[(uint32_t)bb & ((1u << RL) - 1u)];
+        uint32_t n = e >> 12, p = e & 0xfff;
+        if (tail || n == 0) {
+            uint32_t r = slow_lookup(S->cnt_l, gsorted, lbits, g_l, (uint32_t)bb, avail_bits());
+            uint32_t st = r >> 28;
+            if (st) { if (st == (uint32_t)R_ERROR) msg = SDZ_MSG_BAD_LITLEN_CODE; return (int)st; }
+            n = (r >> 16) & 0xff;
+            uint32_t sym = r & 0xffff;
+            if (sym <= 256) p = sym;
+            else {
+                uint32_t i = sym - 257;
+                if (i > 28) { msg = SDZ_MSG_BAD_LITLEN_CODE; return R_ERROR; }
+                uint32_t xb = i < 8 ? 0 : (i == 28 ? 0 : (i >> 2) - 1);
+                uint32_t base = i < 8 ? 3 + i : (i == 28 ? 258 : 3 + ((4 + (i & 3)) << xb));
+                p = 0x800 | (xb << 8) | (base - 3);
             }
-            bb >>= n; bc -= (int)n;
-            if (p < 256) {
-                if (pos >= cap) return R_OUTFULL;
-                if (STORE) { if (glane == 0) out[pos] = (uint8_t)p; }
-                pos++;
-                continue;
-            }
-            if (p == 256) { eob_len = (int)n; return R_EOB; }
-            uint32_t xb = (p >> 8) & 7;
-            if (tail && avail_bits() < (int)xb) return R_STALL;
-            uint32_t len = 3 + (p & 0xff) + ((uint32_t)bb & ((1u << xb) - 1u));
-            bb >>= xb; bc -= (int)xb;
-            refill();
-            uint32_t de = S->lut_d[(uint32_t)bb & ((1u << RD) - 1u)];
-            uint32_t dn = de >> 12;
-            if (tail || dn == 0) {
-                if (g_d == 0) { msg = SDZ_MSG_BAD_DIST_CODE; return R_ERROR; }
-                uint32_t r = slow_lookup(S->cnt_d, S->sorted_d, dbits, g_d, (uint32_t)bb, avail_bits());
-                uint32_t st = r >> 28;
-                if (st) { if (st == (uint32_t)R_ERROR) msg = SDZ_MSG_BAD_DIST_CODE; return (int)st; }
-                dn = (r >> 16) & 0xff;
-                uint32_t ds = r & 0xffff;
-                if (ds > 29) { msg = SDZ_MSG_BAD_DIST_CODE; return R_ERROR; }
-                de = ((ds < 4 ? 0u : (ds >> 1) - 1u) << 8) | (ds < 4 ? ds : 2u + (ds & 1u));
-            }
-            bb >>= dn; bc -= (int)dn;
-            uint32_t dx = (de >> 8) & 15;
-            if (tail && avail_bits() < (int)dx) return R_STALL;
-            uint32_t dist = 1 + ((de & 3) << dx) + ((uint32_t)bb & ((1u << dx) - 1u));
-            bb >>= dx; bc -= (int)dx;
-            int r = copy_match(len, dist);
-            if (r != R_OK) return r;
         }
+        bb >>= n; bc -= (int)n;
+        if (p < 256) {
+            if (pos >= cap) return R_OUTFULL;
+            if (STORE) { if (glane == 0) out[pos] = (uint8_t)p; }
+            pos++;
+            return R_OK;
+        }
+        if (p == 256) { eob_len = (int)n; return R_EOB; }
+        uint32_t xb = (p >> 8) & 7;
+        if (tail && avail_bits() < (int)xb) return R_STALL;
+        uint32_t len = 3 + (p & 0xff) + ((uint32_t)bb & ((1u << xb) - 1u));
+        bb >>= xb; bc -= (int)xb;
+        refill();
+        uint32_t de = S->lut_d[(uint32_t)bb & ((1u << RD) - 1u)];
+        uint32_t dn = de >> 12;
+        if (tail || dn == 0) {
+            if (g_d == 0) { msg = SDZ_MSG_BAD_DIST_CODE; return R_ERROR; }
+            uint32_t r = slow_lookup(S->cnt_d, gsorted + SORTED_L, dbits, g_d, (uint32_t)bb, avail_bits());
+            uint32_t st = r >> 28;
+            if (st) { if (st == (uint32_t)R_ERROR) msg = SDZ_MSG_BAD_DIST_CODE; return (int)st; }
+            dn = (r >> 16) & 0xff;
+            uint32_t ds = r & 0xffff;
+            if (ds > 29) { msg = SDZ_MSG_BAD_DIST_CODE; return R_ERROR; }
+            de = ((ds < 4 ? 0u : (ds >> 1) - 1u) << 8) | (ds < 4 ? ds : 2u + (ds & 1u));
+        }
+        bb >>= dn; bc -= (int)dn;
+        uint32_t dx = (de >> 8) & 15;
+        if (tail && avail_bits() < (int)dx) return R_STALL;
+        uint32_t dist = 1 + ((de & 3) << dx) + ((uint32_t)bb & ((1u << dx) - 1u));
+        bb >>= dx; bc -= (int)dx;
+        return copy_match(len, dist);
     }
 
     // stored block body (src/infblocks.ts:278-333) with the Q2 truncation
@@ -713,215 +772,183 @@ struct Decoder {
         return r;
     }
 
-    // all deflate blocks; returns R_EOB when the final block completed
-    __device__ __forceinline__ int blocks(uint32_t* n_blocks)
+    // ------------------------------------------------------------------ phase machine
+    // PH_FETCH: take the next stream, parse its container header (src/inflate.ts:142-401,
+    // byte by byte from global memory) and position the bit reader on the first block.
+    __device__ __forceinline__ void fetch(const InflateParams& P)
     {
-        for (;;) {
-            if (!ensure(3)) { stall_kind = ST_OTHER; return R_STALL; }
-            uint32_t t = peek(3);
-            drop(3);
-            int last = (int)(t & 1);
-            (*n_blocks)++;
-            uint32_t start_pos = pos;
-            int r;
-            uint32_t type = t >> 1;
-            if (type == 0) {
-                drop(bc & 7);
-                if (!ensure(32)) { stall_kind = ST_OTHER; return R_STALL; }
-                uint32_t v = (uint32_t)bb;
-                if ((((~v) >> 16) & 0xffff) != (v & 0xffff)) { msg = SDZ_MSG_BAD_STORED_LEN; return R_ERROR; }
-                drop(32);
-                r = stored_block(v & 0xffff);
-                if (r != R_OK) return r;
-                if (last) { ring.wash(); return R_EOB; }
-                continue;
+        unsigned long long i = 0;
+        if (glane == 0) i = atomicAdd(P.counter, 1ull);
+        i = __shfl_sync(gmask, i, 0, G);
+        if (i >= P.n) { phase = PH_EXIT; return; }
+        idx = i;
+        in_len = P.in_len[i];
+        const uint8_t mode_raw = P.mode[i];
+        const int mode = mode_raw & 0x7f;
+        const bool has_dict = (mode_raw & 0x80) != 0;
+        const uint8_t* src = P.in + P.in_off[i];
+        out_off = P.out_off ? P.out_off[i] : 0;
+        gsrc = src;
+        end_wp = (in_len + 3) / 4;
+        total_chunks = (in_len + CH - 1) / CH;
+        out = STORE ? P.out + out_off : nullptr;
+        pos = 0;
+        cap = (STORE && P.out_cap) ? P.out_cap[i] : 0xffffffffu;
+        msg = SDZ_MSG_NONE;
+        stall_kind = ST_NONE;
+        D = 0; dict_tail = nullptr;
+        lbits = dbits = g_l = g_d = 0; eob_len = 0;
+        ring.init(0);
+        plen = 0; pdst = 0; psoff = 0;
+        is_gzip = false; method = 0; n_blocks = 0; mtime = 0; name_off = 0; name_len = 0; last = 0;
+
+        int thrown = SDZ_THROW_NONE, thrown_inflate = 0, zstatus = SDZ_Z_OK;
+        bool decode = true;
+        raw = mode == SDZ_MODE_RAW;
+        if (mode == SDZ_MODE_SNIFF) {                                   // inflate(): src/sd-inflate.ts:194-207
+            if (in_len < 2) { thrown_inflate = SDZ_THROW_TOO_SMALL; decode = false; }
+            else {
+                uint32_t b0 = src[0], b1 = src[1];
+                bool ident = (b0 == 0x78 && (((b0 << 8) + b1) % 31) == 0) || (b0 == 0x1f && b1 == 0x8b);
+                raw = !ident;
             }
-            if (type == 3) { msg = SDZ_MSG_BAD_BLOCK_TYPE; return R_ERROR; }
-            int nl = 288, nd = 30;
-            if (type == 1) {
-                __syncwarp(gmask);
-                for (int i = glane; i < 320; i += G) {
-                    uint8_t v = i < 144 ? 8 : (i < 256 ? 9 : (i < 280 ? 7 : (i < 288 ? 8 : 5)));
-                    S->lens[i] = v;
+        }
+        if (decode && raw && has_dict) { thrown_inflate = SDZ_THROW__COUNT; decode = false; }  // RangeError (src/sd-inflate.ts:69-71)
+        if (in_len == 0) decode = false;                                // append() of an empty chunk returns []
+
+        uint32_t hp = 0, end_byte = 0;
+        if (decode && !raw) {
+            int err = 0;
+            bool ok = false;
+            do {
+                uint32_t b;
+                if (hp >= in_len) break;
+                if (src[hp] == 0x1f) {
+                    hp++;
+                    if (hp >= in_len) break;
+                    b = src[hp++];
+                    if (b != 0x8b) { err = SDZ_MSG_BAD_GZIP_ID; break; }
+                    is_gzip = true;
                 }
-                __syncwarp(gmask);
-            } else {
-                r = dynamic_header(&nl, &nd);
-                if (r != R_OK) return r;
-            }
-            TreeInfo T = build_tables<G>(S, nl, nd, type == 1, glane, gmask);
-            if (T.msg) { msg = T.msg; return R_ERROR; }
-            lbits = T.lbits; dbits = T.dbits; g_l = T.g_l; g_d = T.g_d;
-            r = decode_codes();
-            ring.write(pos - start_pos);
-            if (r != R_EOB) { if (r == R_STALL) stall_kind = ST_OTHER; return r; }
-            // End of block.  When inflate_fast() decodes the EOB its STREAM_END status leaks through
-            // WASH's early return (src/infcodes.ts:264,:357,:627-638 -> src/infblocks.ts:560-564), so
-            // the block completes after ONE flush attempt; only a slow-path EOB (fewer than 258 bytes
-            // of window room or fewer than 10 unread input bytes, src/infcodes.ts:339) washes the
-            // window completely, returning to append() as often as needed.
-            {
-                uint64_t b_before = bit_pos() - (uint64_t)eob_len;
-                uint32_t kcur = 4u + ((0u - (uint32_t)b_before - 4u) & 7u);     // reference bit-buffer fill (approx.)
-                uint64_t loaded = (b_before + kcur) >> 3;
-                bool fast_eob = ring.room() >= 258 && (uint64_t)in_len >= loaded + 10;
-                if (fast_eob) ring.flush(); else ring.wash();
-            }
-            if (last) { ring.wash(); return R_EOB; }                           // DRY (src/infblocks.ts:579-594)
-        }
-    }
-};
-
-// ---------------------------------------------------------------------- per-stream driver
-template <int G, bool STORE>
-__device__ __forceinline__ void inflate_stream(Decoder<G, STORE>& d, const InflateParams& P, unsigned long long idx)
-{
-    const uint32_t in_len = P.in_len[idx];
-    const uint8_t mode_raw = P.mode[idx];
-    const int mode = mode_raw & 0x7f;
-    const bool has_dict = (mode_raw & 0x80) != 0;
-    const uint8_t* src = P.in + P.in_off[idx];
-    const uint64_t out_off = P.out_off ? P.out_off[idx] : 0;
-
-    d.gsrc = src;
-    d.in_len = in_len;
-    d.end_wp = (in_len + 3) / 4;
-    d.tail_mask = (in_len & 3) ? ((1u << ((in_len & 3) * 8)) - 1u) : 0xffffffffu;
-    d.total_chunks = (in_len + CH - 1) / CH;
-    d.out = STORE ? P.out + out_off : nullptr;
-    d.pos = 0;
-    d.cap = (STORE && P.out_cap) ? P.out_cap[idx] : 0xffffffffu;
-    d.msg = SDZ_MSG_NONE;
-    d.stall_kind = ST_NONE;
-    d.D = 0;
-    d.dict_tail = nullptr;
-    d.lbits = d.dbits = d.g_l = d.g_d = 0;
-    d.eob_len = 0;
-    d.ring.init(0);
-
-    int thrown = SDZ_THROW_NONE, thrown_inflate = 0;
-    int zstatus = SDZ_Z_OK;
-    bool done = false;          // Inflate reached Mode.DONE
-    bool is_gzip = false;
-    int method = 0;
-    uint32_t n_blocks = 0;
-    int32_t stored = 0, isize = 0, mtime = 0;
-    uint32_t name_off = 0, name_len = 0;
-    uint32_t end_byte = 0;      // bytes consumed (total_in)
-    bool decode = true;
-
-    bool raw = mode == SDZ_MODE_RAW;
-    if (mode == SDZ_MODE_SNIFF) {
-        // inflate(): src/sd-inflate.ts:194-207
-        if (in_len < 2) { thrown_inflate = SDZ_THROW_TOO_SMALL; decode = false; }
-        else {
-            uint32_t b0 = src[0], b1 = src[1];
-            bool ident = (b0 == 0x78 && (((b0 << 8) + b1) % 31) == 0) || (b0 == 0x1f && b1 == 0x8b);
-            raw = !ident;
-        }
-    }
-    if (decode && raw && has_dict) {                    // RangeError in the constructor (src/sd-inflate.ts:69-71)
-        thrown_inflate = SDZ_THROW__COUNT;
-        decode = false;
-    }
-    if (in_len == 0) decode = false;                    // append() of an empty chunk returns [] (src/sd-inflate.ts:92-94)
-
-    // ---- container header, byte by byte as Inflate.inflate does (src/inflate.ts:142-401)
-    uint32_t hp = 0;                                    // header bytes consumed
-    if (decode && !raw) {
-        int err = 0;                                    // sdz_msg of a header error
-        bool ok = false;                                // header complete
-        do {
-            uint32_t b;
-            if (hp >= in_len) break;
-            if (src[hp] == 0x1f) {
-                hp++;
+                if (hp >= in_len) break;
+                method = src[hp++];
+                if ((method & 0xf) != 8) { err = SDZ_MSG_BAD_METHOD; break; }
+                if ((method >> 4) + 8 > 15) { err = SDZ_MSG_BAD_WINDOW; break; }
                 if (hp >= in_len) break;
                 b = src[hp++];
-                if (b != 0x8b) { err = SDZ_MSG_BAD_GZIP_ID; break; }
-                is_gzip = true;
-            }
-            if (hp >= in_len) break;
-            method = src[hp++];
-            if ((method & 0xf) != 8) { err = SDZ_MSG_BAD_METHOD; break; }
-            if ((method >> 4) + 8 > 15) { err = SDZ_MSG_BAD_WINDOW; break; }
-            if (hp >= in_len) break;
-            b = src[hp++];
-            if (is_gzip) {
-                const uint32_t gflags = b;
-                bool trunc = false;
-                for (int i = 0; i < 4; i++) {
-                    if (hp >= in_len) { trunc = true; break; }
-                    mtime = (int32_t)(((uint32_t)mtime >> 8) | ((uint32_t)src[hp++] << 24));
-                }
-                if (trunc) break;
-                if (hp + 2 > in_len) { hp = in_len; break; }            // XFL, OS
-                hp += 2;
-                if (gflags & 4) { hp = in_len; break; }                 // FEXTRA never leaves EXTRA0
-                if (gflags & 8) {
-                    name_off = hp;
-                    for (;;) { if (hp >= in_len) { trunc = true; break; } b = src[hp++]; if (b == 0) break; name_len++; }
+                if (is_gzip) {
+                    const uint32_t gflags = b;
+                    bool trunc = false;
+                    for (int k = 0; k < 4; k++) {
+                        if (hp >= in_len) { trunc = true; break; }
+                        mtime = (int32_t)(((uint32_t)mtime >> 8) | ((uint32_t)src[hp++] << 24));
+                    }
                     if (trunc) break;
+                    if (hp + 2 > in_len) { hp = in_len; break; }        // XFL, OS
+                    hp += 2;
+                    if (gflags & 4) { hp = in_len; break; }             // FEXTRA never leaves EXTRA0
+                    if (gflags & 8) {
+                        name_off = hp;
+                        for (;;) { if (hp >= in_len) { trunc = true; break; } b = src[hp++]; if (b == 0) break; name_len++; }
+                        if (trunc) break;
+                    }
+                    if (gflags & 16) {
+                        for (;;) { if (hp >= in_len) { trunc = true; break; } b = src[hp++]; if (b == 0) break; }
+                        if (trunc) break;
+                    }
+                    if (gflags & 2) { if (hp + 2 > in_len) { hp = in_len; break; } hp += 2; }
+                } else {
+                    if ((((uint32_t)method << 8) + b) % 31 != 0) { err = SDZ_MSG_BAD_HEADER_CHECK; break; }
+                    if (b & 0x20) {
+                        if (hp + 4 > in_len) { hp = in_len; break; }
+                        int32_t dictid = (int32_t)(((uint32_t)src[hp] << 24) | ((uint32_t)src[hp + 1] << 16) |
+                                                   ((uint32_t)src[hp + 2] << 8) | src[hp + 3]);
+                        hp += 4;
+                        // NEED_DICT -> inflateSetDictionary (src/sd-inflate.ts:116-126, src/inflate.ts:475-503)
+                        if (!has_dict) { thrown = SDZ_THROW_DICT_REQUIRED; zstatus = SDZ_Z_NEED_DICT; break; }
+                        if (P.dict_adler[i] != dictid) { thrown = SDZ_THROW_DICT_INVALID; zstatus = SDZ_Z_NEED_DICT; break; }
+                        uint32_t dl = P.dict_len[i];
+                        uint32_t used = dl >= (uint32_t)WSIZE ? (uint32_t)WSIZE - 1 : dl;
+                        D = (int)used;
+                        dict_tail = P.dict + P.dict_off[i] + (dl - used);
+                        ring.init((int)used);
+                    }
                 }
-                if (gflags & 16) {
-                    for (;;) { if (hp >= in_len) { trunc = true; break; } b = src[hp++]; if (b == 0) break; }
-                    if (trunc) break;
-                }
-                if (gflags & 2) { if (hp + 2 > in_len) { hp = in_len; break; } hp += 2; }
-            } else {
-                if ((((uint32_t)method << 8) + b) % 31 != 0) { err = SDZ_MSG_BAD_HEADER_CHECK; break; }
-                if (b & 0x20) {
-                    if (hp + 4 > in_len) { hp = in_len; break; }
-                    int32_t dictid = (int32_t)(((uint32_t)src[hp] << 24) | ((uint32_t)src[hp + 1] << 16) | ((uint32_t)src[hp + 2] << 8) | src[hp + 3]);
-                    hp += 4;
-                    // NEED_DICT -> inflateSetDictionary (src/sd-inflate.ts:116-126, src/inflate.ts:475-503)
-                    if (!has_dict) { thrown = SDZ_THROW_DICT_REQUIRED; zstatus = SDZ_Z_NEED_DICT; break; }
-                    if (P.dict_adler[idx] != dictid) { thrown = SDZ_THROW_DICT_INVALID; zstatus = SDZ_Z_NEED_DICT; break; }
-                    uint32_t dl = P.dict_len[idx];
-                    uint32_t used = dl >= (uint32_t)WSIZE ? (uint32_t)WSIZE - 1 : dl;
-                    d.D = (int)used;
-                    d.dict_tail = P.dict + P.dict_off[idx] + (dl - used);
-                    d.ring.init((int)used);
-                }
-            }
-            ok = true;
-        } while (0);
-        if (err) { d.msg = err; thrown = SDZ_THROW_INFLATE_ERROR; zstatus = SDZ_Z_DATA_ERROR; }
-        if (!ok) { decode = false; end_byte = thrown ? hp : in_len; }
+                ok = true;
+            } while (0);
+            if (err) { msg = err; thrown = SDZ_THROW_INFLATE_ERROR; zstatus = SDZ_Z_DATA_ERROR; }
+            if (!ok) { decode = false; end_byte = thrown ? hp : in_len; }
+        }
+        if (!decode) {
+            write_record(P, thrown, thrown_inflate, zstatus, false, 0, 0, end_byte);
+            return;                                                     // stays in PH_FETCH
+        }
+        seek(hp);
+        phase = PH_BLOCK;
     }
 
-    // ---- deflate blocks
-    if (decode) {
-        d.seek(hp);
-        int r = d.blocks(&n_blocks);
+    __device__ __forceinline__ void write_record(const InflateParams& P, int thrown, int thrown_inflate, int zstatus, bool done,
+                                                 int32_t stored, int32_t isize, uint32_t end_byte)
+    {
+        if (glane == 0) {
+            sdz_result R;
+            R.out_off = out_off;
+            R.out_len = (thrown && STORE) ? 0 : pos;    // the sizing pass always reports the decoded size
+            R.total_in = end_byte;
+            R.zstatus = zstatus;
+            R.stored_checksum = stored;
+            R.running_checksum = 0;
+            R.stored_isize = isize;
+            R.mtime = mtime;
+            R.name_off = name_len ? name_off : 0;
+            R.name_len = name_len;
+            R.n_blocks = n_blocks;
+            R.msg_id = (uint8_t)msg;
+            R.thrown_append = (uint8_t)thrown;
+            R.thrown_inflate = (uint8_t)thrown_inflate;
+            R.container = (uint8_t)(is_gzip ? SDZ_GZIP : (method == 0 ? SDZ_RAW : SDZ_ZLIB));
+            R.complete = done ? 1 : 0;
+            R.checksum_state = R.size_state = R.success = R.have_running = 0;
+            for (int k = 0; k < 7; k++) R.reserved[k] = 0;
+            P.res[idx] = R;
+        }
+    }
+
+    // The stream stops here: r = R_EOB (final block complete), R_STALL, R_ERROR or R_OUTFULL.
+    __device__ __forceinline__ void finish_stream(const InflateParams& P, int r)
+    {
+        int thrown = SDZ_THROW_NONE, zstatus = SDZ_Z_OK;
+        bool done = false;
+        int32_t stored = 0, isize = 0;
+        uint32_t end_byte = byte_pos();
         if (r == R_ERROR) { thrown = SDZ_THROW_INFLATE_ERROR; zstatus = SDZ_Z_DATA_ERROR; }
         else if (r == R_OUTFULL) { zstatus = SDZ_Z_BUF_ERROR; }
         else if (r == R_STALL) {
             // input exhausted.  proc() flushes; if that fills the 16 KiB buffer append() calls
             // again, and BTREE/DTREE cannot be re-entered -> STREAM_ERROR is thrown.
-            if (d.stall_kind == ST_DYNHDR) {
-                d.ring.flush();
-                if (d.ring.ao == 0) { thrown = SDZ_THROW_INFLATE_ERROR; zstatus = SDZ_Z_STREAM_ERROR; d.msg = SDZ_MSG_NONE; }
+            if (stall_kind == ST_DYNHDR) {
+                ring.flush();
+                if (ring.ao == 0) { thrown = SDZ_THROW_INFLATE_ERROR; zstatus = SDZ_Z_STREAM_ERROR; msg = SDZ_MSG_NONE; }
             }
         } else {
             // final block done: unused whole bytes go back, partial bits are dropped (src/inflate.ts:409-421);
             // the trailer is read byte by byte (src/inflate.ts:423-463)
-            uint32_t tp = (uint32_t)((d.bit_pos() + 7) >> 3);
+            uint32_t tp = (uint32_t)((bit_pos() + 7) >> 3);
             if (raw) {
                 done = true;
             } else {
                 const int nbytes = is_gzip ? 8 : 4;
-                int i = 0;
-                for (; i < nbytes && tp < in_len; i++) {
-                    uint32_t b = src[tp++];
+                int k = 0;
+                for (; k < nbytes && tp < in_len; k++) {
+                    uint32_t b = gsrc[tp++];
                     if (is_gzip) {
-                        if (i < 4) stored = (int32_t)(((uint32_t)stored >> 8) | (b << 24));
+                        if (k < 4) stored = (int32_t)(((uint32_t)stored >> 8) | (b << 24));
                         else isize = (int32_t)(((uint32_t)isize >> 8) | (b << 24));
                     } else {
                         stored = (int32_t)(((uint32_t)stored << 8) | b);
                     }
                 }
-                done = i == nbytes;
+                done = k == nbytes;
             }
             if (done) {
                 zstatus = SDZ_Z_STREAM_END;
@@ -929,38 +956,86 @@ __device__ __forceinline__ void inflate_stream(Decoder<G, STORE>& d, const Infla
             }
             end_byte = tp;
         }
-        if (r != R_EOB) end_byte = d.byte_pos();
-        d.drain();
-        __syncwarp(d.gmask);
+        commit_pending();
+        drain();
+        __syncwarp(gmask);
+        write_record(P, thrown, 0, zstatus, done, stored, isize, end_byte);
+        phase = PH_FETCH;
     }
 
-    if (d.glane == 0) {
-        sdz_result R;
-        R.out_off = out_off;
-        R.out_len = (thrown && STORE) ? 0 : d.pos;      // the sizing pass always reports the decoded size
-        R.total_in = end_byte;
-        R.zstatus = zstatus;
-        R.stored_checksum = stored;
-        R.running_checksum = 0;
-        R.stored_isize = isize;
-        R.mtime = mtime;
-        R.name_off = name_len ? name_off : 0;
-        R.name_len = name_len;
-        R.n_blocks = n_blocks;
-        R.msg_id = (uint8_t)d.msg;
-        R.thrown_append = (uint8_t)thrown;
-        R.thrown_inflate = (uint8_t)thrown_inflate;
-        R.container = (uint8_t)(is_gzip ? SDZ_GZIP : (method == 0 ? SDZ_RAW : SDZ_ZLIB));
-        R.complete = done ? 1 : 0;
-        R.checksum_state = R.size_state = R.success = R.have_running = 0;
-        for (int i = 0; i < 7; i++) R.reserved[i] = 0;
-        P.res[idx] = R;
+    // PH_BLOCK: one block header.  Stored blocks are completed here; for fixed / dynamic blocks
+    // the tables are built and the group joins the lockstep symbol loop (PH_CODES).
+    __device__ __forceinline__ void block_begin(const InflateParams& P)
+    {
+        if (!ensure(3)) { stall_kind = ST_OTHER; finish_stream(P, R_STALL); return; }
+        uint32_t t = peek(3);
+        drop(3);
+        last = (int)(t & 1);
+        n_blocks++;
+        start_pos = pos;
+        const uint32_t type = t >> 1;
+        int r;
+        if (type == 0) {
+            drop(bc & 7);
+            if (!ensure(32)) { stall_kind = ST_OTHER; finish_stream(P, R_STALL); return; }
+            uint32_t v = (uint32_t)bb;
+            if ((((~v) >> 16) & 0xffff) != (v & 0xffff)) { msg = SDZ_MSG_BAD_STORED_LEN; finish_stream(P, R_ERROR); return; }
+            drop(32);
+            r = stored_block(v & 0xffff);
+            if (r != R_OK) { finish_stream(P, r); return; }
+            if (last) { ring.wash(); finish_stream(P, R_EOB); }
+            return;                                                     // next block: stays in PH_BLOCK
+        }
+        if (type == 3) { msg = SDZ_MSG_BAD_BLOCK_TYPE; finish_stream(P, R_ERROR); return; }
+        int nl = 288, nd = 30;
+        if (type == 1) {
+            __syncwarp(gmask);
+            uint8_t* lens = reinterpret_cast<uint8_t*>(gsorted + SORTED_L + SORTED_D);
+            for (int k = glane; k < 320; k += G) {
+                uint8_t v = k < 144 ? 8 : (k < 256 ? 9 : (k < 280 ? 7 : (k < 288 ? 8 : 5)));
+                lens[k] = v;
+            }
+            __syncwarp(gmask);
+        } else {
+            r = dynamic_header(&nl, &nd);
+            if (r != R_OK) { finish_stream(P, r); return; }
+        }
+        TreeInfo T = build_tables<G>(S, gsorted, nl, nd, type == 1, glane, gmask);
+        if (T.msg) { msg = T.msg; finish_stream(P, R_ERROR); return; }
+        lbits = T.lbits; dbits = T.dbits; g_l = T.g_l; g_d = T.g_d;
+        phase = PH_CODES;
     }
-}
+
+    // a step() returned something other than R_OK
+    __device__ __forceinline__ void block_end(const InflateParams& P, int r)
+    {
+        ring.write(pos - start_pos);
+        if (r != R_EOB) { if (r == R_STALL) stall_kind = ST_OTHER; finish_stream(P, r); return; }
+        // End of block.  When inflate_fast() decodes the EOB its STREAM_END status leaks through
+        // WASH's early return (src/infcodes.ts:264,:357,:627-638 -> src/infblocks.ts:560-564), so
+        // the block completes after ONE flush attempt; only a slow-path EOB (fewer than 258 bytes
+        // of window room or fewer than 10 unread input bytes, src/infcodes.ts:339) washes the
+        // window completely, returning to append() as often as needed.
+        {
+            uint64_t b_before = bit_pos() - (uint64_t)eob_len;
+            uint32_t kcur = 4u + ((0u - (uint32_t)b_before - 4u) & 7u);     // reference bit-buffer fill (approx.)
+            uint64_t loaded = (b_before + kcur) >> 3;
+            bool fast_eob = ring.room() >= 258 && (uint64_t)in_len >= loaded + 10;
+            if (fast_eob) ring.flush(); else ring.wash();
+        }
+        if (last) { ring.wash(); finish_stream(P, R_EOB); return; }         // DRY (src/infblocks.ts:579-594)
+        phase = PH_BLOCK;
+    }
+};
 
 #ifndef SDZ_MINBLOCKS
 #define SDZ_MINBLOCKS 1
 #endif
+
+// One sub-warp group of G lanes per stream; the 32 / G groups of a warp run the symbol loop in
+// lockstep (they re-converge at the ballot after every symbol), so one instruction stream
+// serves 32 / G streams.  Block headers, table builds and stream changes are serviced between
+// lockstep runs while the other groups of the warp wait.
 template <int G, bool STORE>
 __global__ void __launch_bounds__(128, SDZ_MINBLOCKS) inflate_kernel(InflateParams P)
 {
@@ -970,10 +1045,12 @@ __global__ void __launch_bounds__(128, SDZ_MINBLOCKS) inflate_kernel(InflatePara
 
     Decoder<G, STORE> d;
     d.S = S;
+    d.gsorted = P.scratch + ((size_t)blockIdx.x * (blockDim.x / G) + gid) * SCRATCH_U16;
     d.glane = threadIdx.x % G;
     const int lane = threadIdx.x & 31;
     d.gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - d.glane));
-    d.base_seq = 0; d.issued = 0; d.waited = 0; d.chunk0 = 0;
+    d.issued_abs = 0; d.waited_abs = 0; d.chunk0 = 0; d.phasebits = 0;
+    d.phase = PH_FETCH;
     if (d.glane == 0) {
         for (int i = 0; i < NBUF; i++) mbar_init(&S->mbar[i], 1);
         mbar_fence_init();
@@ -981,11 +1058,18 @@ __global__ void __launch_bounds__(128, SDZ_MINBLOCKS) inflate_kernel(InflatePara
     __syncthreads();
 
     for (;;) {
-        unsigned long long idx = 0;
-        if (d.glane == 0) idx = atomicAdd(P.counter, 1ull);
-        idx = __shfl_sync(d.gmask, idx, 0, G);
-        if (idx >= P.n) break;
-        inflate_stream<G, STORE>(d, P, idx);
+        if (d.phase == PH_FETCH) d.fetch(P);
+        else if (d.phase == PH_BLOCK) d.block_begin(P);
+        __syncwarp();
+        if (__all_sync(0xffffffffu, d.phase == PH_EXIT)) break;
+        // lockstep symbol loop: runs until some group needs a new block or a new stream
+        while (__ballot_sync(0xffffffffu, d.phase == PH_FETCH || d.phase == PH_BLOCK) == 0u) {
+            if (d.phase == PH_CODES) {
+                int r = d.step();
+                if (r != R_OK) d.block_end(P, r);
+            }
+            if (__all_sync(0xffffffffu, d.phase == PH_EXIT)) break;
+        }
     }
 }
 

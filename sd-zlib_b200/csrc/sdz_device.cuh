@@ -55,6 +55,16 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gm
                  : "memory");
 }
 
+// 4-byte asynchronous copy global -> shared (SASS LDGSTS); completion is tracked with
+// commit_group / wait_group, not with a register scoreboard, so the copy can stay in flight
+// across loop iterations.
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src_gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t lane_id()
 {
     uint32_t l;

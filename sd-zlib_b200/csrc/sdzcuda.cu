@@ -37,8 +37,8 @@ struct sdz_ctx {
     void* h_stage = nullptr;           // pinned
     size_t h_stage_cap = 0;
     unsigned long long* d_counter = nullptr;
-    int group = 32;                    // lanes per stream
-    int block_threads = 128;
+    int group = 4;                     // lanes per stream
+    int block_threads = 64;
 };
 
 namespace {
@@ -129,8 +129,14 @@ int launch_inflate_t(sdz_ctx* ctx, const sdz::InflateParams& P)
     unsigned long long want = (P.n + groups - 1) / groups;
     unsigned long long grid = std::min<unsigned long long>(want, (unsigned long long)ctx->sm_count * per_sm);
     if (grid == 0) return SDZ_OK;
+    {
+        int rc = grow(ctx, ctx->d_misc, (size_t)grid * groups * sdz::SCRATCH_U16 * sizeof(uint16_t));
+        if (rc) return rc;
+    }
+    sdz::InflateParams Q = P;
+    Q.scratch = (uint16_t*)ctx->d_misc.p;
     CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), ctx->stream));
-    kern<<<(unsigned)grid, threads, smem, ctx->stream>>>(P);
+    kern<<<(unsigned)grid, threads, smem, ctx->stream>>>(Q);
     ctx->launches++;
     CK(cudaGetLastError());
     return SDZ_OK;
@@ -140,8 +146,10 @@ template <bool STORE>
 int launch_inflate(sdz_ctx* ctx, const sdz::InflateParams& P)
 {
     switch (ctx->group) {
+    case 8: return launch_inflate_t<8, STORE>(ctx, P);
     case 16: return launch_inflate_t<16, STORE>(ctx, P);
-    default: return launch_inflate_t<32, STORE>(ctx, P);
+    case 32: return launch_inflate_t<32, STORE>(ctx, P);
+    default: return launch_inflate_t<4, STORE>(ctx, P);
     }
 }
 
@@ -163,7 +171,7 @@ int run_batch_device(sdz_ctx* ctx, const sdz_batch_dev* b, bool sizes_only)
     P.in = b->d_in; P.in_off = b->d_in_off; P.in_len = b->d_in_len; P.mode = b->d_mode;
     P.dict = b->d_dict; P.dict_off = b->d_dict_off; P.dict_len = b->d_dict_len; P.dict_adler = b->d_dict_adler;
     P.out = sizes_only ? nullptr : b->d_out; P.out_off = b->d_out_off; P.out_cap = b->d_out_cap;
-    P.res = b->d_results; P.n = b->n; P.counter = ctx->d_counter;
+    P.res = b->d_results; P.n = b->n; P.counter = ctx->d_counter; P.scratch = nullptr;
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     int rc = sizes_only ? launch_inflate<false>(ctx, P) : launch_inflate<true>(ctx, P);
     if (rc) return rc;
@@ -227,7 +235,7 @@ int sdz_ctx_create(int device, uint32_t flags, sdz_ctx** out)
     for (auto& e : ctx->ev)
         if (cudaEventCreate(&e) != cudaSuccess) return fail(SDZ_E_CUDA);
     if (cudaMalloc(&ctx->d_counter, 4 * sizeof(unsigned long long)) != cudaSuccess) return fail(SDZ_E_NOMEM);
-    if (const char* g = getenv("SDZ_GROUP")) { int v = atoi(g); if (v == 16 || v == 32) ctx->group = v; }
+    if (const char* g = getenv("SDZ_GROUP")) { int v = atoi(g); if (v == 4 || v == 8 || v == 16 || v == 32) ctx->group = v; }
     if (const char* t = getenv("SDZ_BLOCK")) { int v = atoi(t); if (v == 32 || v == 64 || v == 128) ctx->block_threads = v; }
     if (ctx->block_threads < ctx->group) ctx->block_threads = ctx->group;
     int rc = upload_tables(ctx);
