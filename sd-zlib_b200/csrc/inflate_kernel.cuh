@@ -45,7 +45,7 @@ struct alignas(16) GroupSmem {
     uint32_t cnt_l[16];                // codes per length (unpadded)
     uint32_t cnt_d[16];
     uint32_t aux[32];                  // build scratch: [0..15] offsets, [16..31] first codes
-    uint32_t stage[8];                 // source bytes of the pending (deferred) match, staged by cp.async
+    uint32_t stage[16];                // 8 bytes per lane: source words of the pending (deferred) match (cp.async)
 };
 
 // per-group scratch in global memory: symbols ordered by (code length, symbol) - read by the
@@ -567,41 +567,53 @@ struct Decoder {
     __device__ __forceinline__ void drop(int n) { bb >>= n; bc -= n; }
 
     // ------------------------------------------------------------------ output
-    // Deferred match copy.  A short non-overlapping match (<= 16 bytes, the common case) only
-    // ISSUES asynchronous 4-byte copies (cp.async / LDGSTS) of the aligned words that cover its
-    // source into stage[]; the bytes are moved to their destination when the group's next match
-    // (or the end of the stream) arrives, so the L2 / DRAM round trip of the window read overlaps
-    // the decode of the following symbols instead of stalling the lockstep warp.
+    // Deferred match copy.  A short non-overlapping match (<= 4 G bytes, the common case) only
+    // ISSUES asynchronous copies (cp.async / LDGSTS): lane j stages the two aligned words that
+    // cover source bytes [4j, 4j + 4) into its private 8 bytes of stage[].  The bytes are moved to
+    // their destination when the group's next match (or the end of the stream) arrives, so the
+    // L2 / DRAM round trip of the window read overlaps the decode of the following symbols instead
+    // of stalling the lockstep warp.  Each lane reads back only what it staged itself: no
+    // cross-lane synchronisation is needed at commit time.
     __device__ __forceinline__ void commit_pending()
     {
         if (STORE && plen) {
             cp_async_wait_all();
-            __syncwarp(gmask);                       // words staged by the other lanes are visible
-            const uint8_t* st = reinterpret_cast<const uint8_t*>(S->stage) + psoff;
-            uint8_t* dst = out + pdst;
-            #pragma unroll
-            for (uint32_t k = 0; k < 16 / G + (16 % G ? 1 : 0); k++) {
-                const uint32_t j = glane + k * G;
-                if (j < plen) dst[j] = st[j];
+            const uint32_t j4 = 4u * (uint32_t)glane;
+            if (j4 < plen) {
+                const uint2 w = *reinterpret_cast<const uint2*>(&S->stage[2 * glane]);
+                const uint32_t v = __funnelshift_r(w.x, w.y, psoff * 8u);
+                uint8_t* dst = out + pdst + j4;
+                const uint32_t nb = plen - j4;
+                dst[0] = (uint8_t)v;
+                if (nb > 1) dst[1] = (uint8_t)(v >> 8);
+                if (nb > 2) dst[2] = (uint8_t)(v >> 16);
+                if (nb > 3) dst[3] = (uint8_t)(v >> 24);
             }
         }
         plen = 0;
     }
 
+    // Memory ordering: the lockstep loop executes a full-mask __syncwarp() at the top of every
+    // iteration, so stores of earlier iterations (literals, committed matches) are ordered before
+    // the reads issued here.  Only bytes committed in THIS iteration need an extra group sync.
     __device__ __forceinline__ int copy_match(uint32_t len, uint32_t dist)
     {
         if (len > cap - pos) return R_OUTFULL;
         if (STORE) {
-            const bool simple = dist >= len && len <= 16u && dist <= pos;
+            const bool simple = dist >= len && len <= 4u * G && dist <= pos;
+            const bool hazard = plen != 0 && (!simple || pos - dist + len > pdst);
             commit_pending();                        // previous match: its copies were issued a symbol (or more) ago
-            __syncwarp(gmask);                       // earlier stores of this group are visible
+            if (hazard) __syncwarp(gmask);           // the bytes just committed are (or may be) read below
             uint8_t* dst = out + pos;
             if (simple) {
                 const uint8_t* src = dst - dist;
                 const uint32_t so = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
-                const uint8_t* w0 = src - so;
-                const uint32_t nwords = (so + len + 3u) >> 2;             // <= 5
-                for (uint32_t w = glane; w < nwords; w += G) cp_async4(&S->stage[w], w0 + 4u * w);
+                const uint32_t j4 = 4u * (uint32_t)glane;
+                if (j4 < len) {
+                    const uint8_t* w0 = src - so + j4;
+                    cp_async4(&S->stage[2 * glane], w0);
+                    cp_async4(&S->stage[2 * glane + 1], w0 + 4);
+                }
                 cp_async_commit();
                 pdst = pos; plen = len; psoff = so;
             } else if (dist <= pos) {
@@ -690,7 +702,7 @@ struct Decoder {
     // `tail` (fewer than five input words left) and root entries marked long/invalid go through
     // slow_lookup(), which also enforces the reference's lookahead rule; everything else is
     // one shared-memory LUT read per code.
-    __device__ __forceinline__ int step()
+    __device__ __forceinline__ int step_general()
     {
         refill();
         const bool tail = wp + 5 > end_wp;
@@ -740,6 +752,70 @@ struct Decoder {
         uint32_t dx = (de >> 8) & 15;
         if (tail && avail_bits() < (int)dx) return R_STALL;
         uint32_t dist = 1 + ((de & 3) << dx) + ((uint32_t)bb & ((1u << dx) - 1u));
+        bb >>= dx; bc -= (int)dx;
+        return copy_match(len, dist);
+    }
+
+    // branch-free top-up used by the fast path (at least five whole input words remain):
+    // predicated instructions only, except for the rare hop into the next 128-byte chunk
+    __device__ __forceinline__ void refill_fast()
+    {
+        const bool take = bc <= 32;
+        bb |= take ? ((uint64_t)nw << bc) : 0ull;
+        bc += take ? 32 : 0;
+        wp += take ? 1u : 0u;
+        if (take) {
+            if ((wp % CHW) == 0u && wp / CHW >= waited_abs) {
+                uint64_t r = chunk_cross(S, gsrc, wp / CHW, chunk0, issued_abs, total_chunks, phasebits, gmask, glane);
+                phasebits = (uint32_t)r & 15u;
+                issued_abs = (uint32_t)(r >> 4);
+                waited_abs = wp / CHW + 1;
+            }
+            nw = S->ring[wp % (NBUF * CHW)];
+        }
+    }
+
+    // One symbol on the fast path.  The stream tail and every irregular case (long / invalid
+    // root entry) go through step_general().  (Folding a run of literals into the same lockstep
+    // iteration was measured slower: the warp pays the longest run of its eight groups.)
+    __device__ __forceinline__ int step()
+    {
+        bool slow = wp + 5 > end_wp;
+        uint32_t e = 0;
+        if (!slow) {
+            refill_fast();
+            e = S->lut_l[(uint32_t)bb & ((1u << RL) - 1u)];
+            slow = (e >> 12) == 0;
+        }
+        if (slow) return step_general();
+        const uint32_t n = e >> 12, p = e & 0xfff;
+        bb >>= n; bc -= (int)n;
+        if (p < 256) {
+            if (pos >= cap) return R_OUTFULL;
+            if (STORE) { if (glane == 0) out[pos] = (uint8_t)p; }
+            pos++;
+            return R_OK;
+        }
+        if (p == 256) { eob_len = (int)n; return R_EOB; }
+        const uint32_t xb = (p >> 8) & 7;
+        const uint32_t len = 3 + (p & 0xff) + ((uint32_t)bb & ((1u << xb) - 1u));
+        bb >>= xb; bc -= (int)xb;
+        refill_fast();
+        uint32_t de = S->lut_d[(uint32_t)bb & ((1u << RD) - 1u)];
+        uint32_t dn = de >> 12;
+        if (dn == 0) {
+            if (g_d == 0) { msg = SDZ_MSG_BAD_DIST_CODE; return R_ERROR; }
+            uint32_t r = slow_lookup(S->cnt_d, gsorted + SORTED_L, dbits, g_d, (uint32_t)bb, avail_bits());
+            uint32_t st = r >> 28;
+            if (st) { if (st == (uint32_t)R_ERROR) msg = SDZ_MSG_BAD_DIST_CODE; return (int)st; }
+            dn = (r >> 16) & 0xff;
+            uint32_t ds = r & 0xffff;
+            if (ds > 29) { msg = SDZ_MSG_BAD_DIST_CODE; return R_ERROR; }
+            de = ((ds < 4 ? 0u : (ds >> 1) - 1u) << 8) | (ds < 4 ? ds : 2u + (ds & 1u));
+        }
+        bb >>= dn; bc -= (int)dn;
+        const uint32_t dx = (de >> 8) & 15;
+        const uint32_t dist = 1 + ((de & 3) << dx) + ((uint32_t)bb & ((1u << dx) - 1u));
         bb >>= dx; bc -= (int)dx;
         return copy_match(len, dist);
     }
@@ -1063,12 +1139,16 @@ __global__ void __launch_bounds__(128, SDZ_MINBLOCKS) inflate_kernel(InflatePara
         __syncwarp();
         if (__all_sync(0xffffffffu, d.phase == PH_EXIT)) break;
         // lockstep symbol loop: runs until some group needs a new block or a new stream
-        while (__ballot_sync(0xffffffffu, d.phase == PH_FETCH || d.phase == PH_BLOCK) == 0u) {
+        for (;;) {
+            __syncwarp();                            // re-converge + order the stores of earlier iterations
             if (d.phase == PH_CODES) {
                 int r = d.step();
                 if (r != R_OK) d.block_end(P, r);
             }
-            if (__all_sync(0xffffffffu, d.phase == PH_EXIT)) break;
+            if (__ballot_sync(0xffffffffu, d.phase != PH_CODES) != 0u) {
+                if (__any_sync(0xffffffffu, d.phase == PH_FETCH || d.phase == PH_BLOCK)) break;
+                if (__all_sync(0xffffffffu, d.phase == PH_EXIT)) break;
+            }
         }
     }
 }
