@@ -241,6 +241,23 @@ __device__ __noinline__ uint32_t slow_lookup(const uint32_t* cnt, const uint16_t
     return (uint32_t)R_ERROR << 28;
 }
 
+// Long code (more than R root bits) away from the stream tail: canonical decode that starts at
+// length R + 1.  `start` = state of the canonical walk after R bits, precomputed per block:
+// first code value (<< 1) in the high half, symbol index in the low half.
+// Returns code_length << 16 | symbol, or 0 if no code matches (invalid).
+__device__ __forceinline__ uint32_t canon_long(const uint32_t* cnt, const uint16_t* sorted, int R, int g, uint32_t start, uint32_t bits)
+{
+    int first = (int)(start >> 16), index = (int)(start & 0xffffu);
+    int code = (int)((__brev(bits) >> (32 - R)) << 1);
+    for (int len = R + 1; len <= g; len++) {
+        code |= (int)((bits >> (len - 1)) & 1u);
+        const int count = (int)cnt[len];
+        if (code - count < first) return ((uint32_t)len << 16) | (sorted[index + (code - first)] & 0xfffu);
+        index += count; first += count; first <<= 1; code <<= 1;
+    }
+    return 0u;
+}
+
 // First touch of input chunk `c` (absolute index in the stream): wait for its TMA copy, then
 // reuse the slot of the chunk that was just finished for the next outstanding chunk.
 // Slot = c % NBUF; `phasebits` holds the mbarrier parity to wait for next on every slot.
@@ -326,6 +343,13 @@ __device__ __forceinline__ void make_lut(GroupSmem* S, const uint8_t* lens, int 
     for (int i = glane; i < (1 << R) / 2; i += G) lut32[i] = E_INVALID | (E_INVALID << 16);
     __syncwarp(gmask);
     const int ncodes = n - (int)cnt[0];
+    __syncwarp(gmask);
+    if (glane == 0) {
+        // canonical-walk state after R bits (canon_long): kept in cnt[0], whose zero-length count is not needed any more
+        uint32_t first = 0, index = 0;
+        for (int k = 1; k <= R && k <= 15; k++) { index += cnt[k]; first = (first + cnt[k]) << 1; }
+        S->aux[KIND == 0 ? 0 : 16] = (first << 16) | (index & 0xffffu);
+    }
     for (int k = glane; k < ncodes; k += G) {
         uint32_t e = sorted[k];
         uint32_t sym = e & 0xfff, len = e >> 12;
@@ -576,19 +600,17 @@ struct Decoder {
     // cross-lane synchronisation is needed at commit time.
     __device__ __forceinline__ void commit_pending()
     {
-        if (STORE && plen) {
+        if (STORE) {                                 // straight-line, predicated: nothing happens when plen == 0
             cp_async_wait_all();
             const uint32_t j4 = 4u * (uint32_t)glane;
-            if (j4 < plen) {
-                const uint2 w = *reinterpret_cast<const uint2*>(&S->stage[2 * glane]);
-                const uint32_t v = __funnelshift_r(w.x, w.y, psoff * 8u);
-                uint8_t* dst = out + pdst + j4;
-                const uint32_t nb = plen - j4;
-                dst[0] = (uint8_t)v;
-                if (nb > 1) dst[1] = (uint8_t)(v >> 8);
-                if (nb > 2) dst[2] = (uint8_t)(v >> 16);
-                if (nb > 3) dst[3] = (uint8_t)(v >> 24);
-            }
+            const uint2 w = *reinterpret_cast<const uint2*>(&S->stage[2 * glane]);
+            const uint32_t v = __funnelshift_r(w.x, w.y, psoff * 8u);
+            uint8_t* dst = out + pdst + j4;
+            const uint32_t nb = plen > j4 ? plen - j4 : 0u;
+            st_u8_if(dst, v, nb > 0);
+            st_u8_if(dst + 1, v >> 8, nb > 1);
+            st_u8_if(dst + 2, v >> 16, nb > 2);
+            st_u8_if(dst + 3, v >> 24, nb > 3);
         }
         plen = 0;
     }
@@ -609,11 +631,9 @@ struct Decoder {
                 const uint8_t* src = dst - dist;
                 const uint32_t so = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
                 const uint32_t j4 = 4u * (uint32_t)glane;
-                if (j4 < len) {
-                    const uint8_t* w0 = src - so + j4;
-                    cp_async4(&S->stage[2 * glane], w0);
-                    cp_async4(&S->stage[2 * glane + 1], w0 + 4);
-                }
+                const uint8_t* w0 = src - so + j4;
+                cp_async4_if(&S->stage[2 * glane], w0, j4 < len);
+                cp_async4_if(&S->stage[2 * glane + 1], w0 + 4, j4 < len);
                 cp_async_commit();
                 pdst = pos; plen = len; psoff = so;
             } else if (dist <= pos) {
@@ -764,15 +784,14 @@ struct Decoder {
         bb |= take ? ((uint64_t)nw << bc) : 0ull;
         bc += take ? 32 : 0;
         wp += take ? 1u : 0u;
-        if (take) {
-            if ((wp % CHW) == 0u && wp / CHW >= waited_abs) {
-                uint64_t r = chunk_cross(S, gsrc, wp / CHW, chunk0, issued_abs, total_chunks, phasebits, gmask, glane);
-                phasebits = (uint32_t)r & 15u;
-                issued_abs = (uint32_t)(r >> 4);
-                waited_abs = wp / CHW + 1;
-            }
-            nw = S->ring[wp % (NBUF * CHW)];
+        if (take && (wp % CHW) == 0u && wp / CHW >= waited_abs) {       // rare: first word of the next 128-byte chunk
+            uint64_t r = chunk_cross(S, gsrc, wp / CHW, chunk0, issued_abs, total_chunks, phasebits, gmask, glane);
+            phasebits = (uint32_t)r & 15u;
+            issued_abs = (uint32_t)(r >> 4);
+            waited_abs = wp / CHW + 1;
         }
+        const uint32_t w = S->ring[wp % (NBUF * CHW)];                    // always readable: chunk(wp) has been waited for
+        nw = take ? w : nw;
     }
 
     // One symbol on the fast path.  The stream tail and every irregular case (long / invalid
@@ -785,7 +804,21 @@ struct Decoder {
         if (!slow) {
             refill_fast();
             e = S->lut_l[(uint32_t)bb & ((1u << RL) - 1u)];
-            slow = (e >> 12) == 0;
+            if ((e >> 12) == 0) {                       // code longer than the root (or invalid)
+                slow = true;
+                if (e == E_LONG) {
+                    const uint32_t r = canon_long(S->cnt_l, gsorted, RL, g_l, S->aux[0], (uint32_t)bb);
+                    const uint32_t sym = r & 0xffffu;
+                    if (r != 0 && sym <= 256) { e = ((r >> 16) << 12) | sym; slow = false; }
+                    else if (r != 0 && sym - 257 <= 28) {
+                        const uint32_t i = sym - 257;
+                        const uint32_t xb = i < 8 ? 0 : (i == 28 ? 0 : (i >> 2) - 1);
+                        const uint32_t base = i < 8 ? 3 + i : (i == 28 ? 258 : 3 + ((4 + (i & 3)) << xb));
+                        e = ((r >> 16) << 12) | 0x800 | (xb << 8) | (base - 3);
+                        slow = false;
+                    }
+                }
+            }
         }
         if (slow) return step_general();
         const uint32_t n = e >> 12, p = e & 0xfff;
@@ -804,13 +837,10 @@ struct Decoder {
         uint32_t de = S->lut_d[(uint32_t)bb & ((1u << RD) - 1u)];
         uint32_t dn = de >> 12;
         if (dn == 0) {
-            if (g_d == 0) { msg = SDZ_MSG_BAD_DIST_CODE; return R_ERROR; }
-            uint32_t r = slow_lookup(S->cnt_d, gsorted + SORTED_L, dbits, g_d, (uint32_t)bb, avail_bits());
-            uint32_t st = r >> 28;
-            if (st) { if (st == (uint32_t)R_ERROR) msg = SDZ_MSG_BAD_DIST_CODE; return (int)st; }
-            dn = (r >> 16) & 0xff;
-            uint32_t ds = r & 0xffff;
-            if (ds > 29) { msg = SDZ_MSG_BAD_DIST_CODE; return R_ERROR; }
+            uint32_t r = de == E_LONG ? canon_long(S->cnt_d, gsorted + SORTED_L, RD, g_d, S->aux[16], (uint32_t)bb) : 0u;
+            const uint32_t ds = r & 0xffffu;
+            if (r == 0 || ds > 29) { msg = SDZ_MSG_BAD_DIST_CODE; return R_ERROR; }     // far from the tail: no stall possible
+            dn = r >> 16;
             de = ((ds < 4 ? 0u : (ds >> 1) - 1u) << 8) | (ds < 4 ? ds : 2u + (ds & 1u));
         }
         bb >>= dn; bc -= (int)dn;

@@ -62,6 +62,21 @@ __device__ __forceinline__ void cp_async4(void* dst_smem, const void* src_gmem)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(dst_smem)), "l"(src_gmem) : "memory");
 }
+// predicated forms (no branch, no divergence): the instruction is issued for the whole warp
+__device__ __forceinline__ void cp_async4_if(void* dst_smem, const void* src_gmem, bool pred)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q cp.async.ca.shared.global [%0], [%1], 4;\n\t}" ::"r"(
+                     smem_addr(dst_smem)),
+                 "l"(src_gmem), "r"((uint32_t)pred)
+                 : "memory");
+}
+__device__ __forceinline__ void st_u8_if(uint8_t* p, uint32_t v, bool pred)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.u8 [%0], %1;\n\t}" ::"l"(
+                     __cvta_generic_to_global(p)),
+                 "r"(v), "r"((uint32_t)pred)
+                 : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
