@@ -27,7 +27,7 @@
 namespace sdz {
 
 constexpr int RL = 9;                  // literal/length LUT root bits
-constexpr int RD = 8;                  // distance LUT root bits
+constexpr int RD = 7;                  // distance LUT root bits
 constexpr int CH = 128;                // bytes per TMA bulk copy
 constexpr int NBUF = 2;                // chunks in the per-group input ring
 constexpr int CHW = CH / 4;
@@ -42,16 +42,16 @@ struct alignas(16) GroupSmem {
     uint64_t mbar[NBUF];
     uint16_t lut_l[1 << RL];
     uint16_t lut_d[1 << RD];
-    uint32_t cnt_l[16];                // codes per length (unpadded)
-    uint32_t cnt_d[16];
-    uint32_t aux[32];                  // build scratch: [0..15] offsets, [16..31] first codes
-    uint32_t stage[16];                // 8 bytes per lane: source words of the pending (deferred) match (cp.async)
+    uint32_t cnt_l[16];                // [1..15] codes per length (unpadded); [0] = canonical-walk state after RL bits
+    uint32_t cnt_d[16];                // same for the distance code (state after RD bits)
+    uint32_t stage[8];                 // 8 bytes per lane (G = 4): source words of the pending (deferred) match
 };
+constexpr int MAX_G_DEFERRED = 4;      // groups wider than this use the synchronous copy only
 
 // per-group scratch in global memory: symbols ordered by (code length, symbol) - read by the
 // table build and by the rare canonical (slow) decode - and the block's code-length array
 constexpr int SORTED_L = 288, SORTED_D = 32;
-constexpr int SCRATCH_U16 = SORTED_L + SORTED_D + 160;       // + 320 bytes of code lengths
+constexpr int SCRATCH_U16 = SORTED_L + SORTED_D + 160 + 64;  // + 320 bytes of code lengths + 32 words of build scratch
 
 struct InflateParams {
     const uint8_t* in;
@@ -323,20 +323,20 @@ __device__ __forceinline__ int classify(const uint8_t* lens, int n, int want_bit
 // sorted symbols + first codes (aux[16..31]) + end offsets (aux[0..15]), then the root LUT.
 // KIND 0 = literal/length (R = RL), 1 = distance (R = RD).
 template <int G, int KIND, int R>
-__device__ __forceinline__ void make_lut(GroupSmem* S, const uint8_t* lens, int n, const uint32_t* cnt, uint16_t* sorted,
+__device__ __forceinline__ void make_lut(uint32_t* aux, const uint8_t* lens, int n, uint32_t* cnt, uint16_t* sorted,
                                          uint16_t* lut, int glane, unsigned gmask)
 {
     if (glane == 0) {
         uint32_t off = 0, code = 0;
         for (int k = 1; k <= 15; k++) {
-            S->aux[k] = off;
-            S->aux[16 + k] = code;
+            aux[k] = off;
+            aux[16 + k] = code;
             off += cnt[k];
             code = (code + cnt[k]) << 1;
         }
         for (int s = 0; s < n; s++) {
             uint32_t k = lens[s];
-            if (k) { uint32_t o = S->aux[k]; sorted[o] = (uint16_t)(s | (k << 12)); S->aux[k] = o + 1; }
+            if (k) { uint32_t o = aux[k]; sorted[o] = (uint16_t)(s | (k << 12)); aux[k] = o + 1; }
         }
     }
     uint32_t* lut32 = reinterpret_cast<uint32_t*>(lut);
@@ -348,13 +348,13 @@ __device__ __forceinline__ void make_lut(GroupSmem* S, const uint8_t* lens, int 
         // canonical-walk state after R bits (canon_long): kept in cnt[0], whose zero-length count is not needed any more
         uint32_t first = 0, index = 0;
         for (int k = 1; k <= R && k <= 15; k++) { index += cnt[k]; first = (first + cnt[k]) << 1; }
-        S->aux[KIND == 0 ? 0 : 16] = (first << 16) | (index & 0xffffu);
+        cnt[0] = (first << 16) | (index & 0xffffu);
     }
     for (int k = glane; k < ncodes; k += G) {
         uint32_t e = sorted[k];
         uint32_t sym = e & 0xfff, len = e >> 12;
-        uint32_t idx = (uint32_t)k - (S->aux[len] - cnt[len]);          // aux[len] = one past the last of this length
-        uint32_t code = S->aux[16 + len] + idx;
+        uint32_t idx = (uint32_t)k - (aux[len] - cnt[len]);             // aux[len] = one past the last of this length
+        uint32_t code = aux[16 + len] + idx;
         uint32_t rev = __brev(code) >> (32 - len);
         if (len > (uint32_t)R) { lut[rev & ((1u << R) - 1u)] = (uint16_t)E_LONG; continue; }
         uint32_t entry;
@@ -407,8 +407,9 @@ __device__ __noinline__ TreeInfo build_tables(GroupSmem* S, uint16_t* gsorted, i
         if (st == 2) { T.msg = SDZ_MSG_INCOMPLETE_DIST_TREE; return T; }
         if (st == 3 && nl > 257) { T.msg = SDZ_MSG_EMPTY_DIST_TREE; return T; }
     }
-    make_lut<G, 0, RL>(S, lens, nl, S->cnt_l, gsorted, S->lut_l, glane, gmask);
-    make_lut<G, 1, RD>(S, lens + nl, nd, S->cnt_d, gsorted + SORTED_L, S->lut_d, glane, gmask);
+    uint32_t* aux = reinterpret_cast<uint32_t*>(gsorted + SORTED_L + SORTED_D + 160);
+    make_lut<G, 0, RL>(aux, lens, nl, S->cnt_l, gsorted, S->lut_l, glane, gmask);
+    make_lut<G, 1, RD>(aux, lens + nl, nd, S->cnt_d, gsorted + SORTED_L, S->lut_d, glane, gmask);
     if (fixed) { T.lbits = 9; T.dbits = 5; }
     return T;
 }
@@ -622,7 +623,7 @@ struct Decoder {
     {
         if (len > cap - pos) return R_OUTFULL;
         if (STORE) {
-            const bool simple = dist >= len && len <= 4u * G && dist <= pos;
+            const bool simple = G <= MAX_G_DEFERRED && dist >= len && len <= 4u * G && dist <= pos;
             const bool hazard = plen != 0 && (!simple || pos - dist + len > pdst);
             commit_pending();                        // previous match: its copies were issued a symbol (or more) ago
             if (hazard) __syncwarp(gmask);           // the bytes just committed are (or may be) read below
@@ -686,7 +687,7 @@ struct Decoder {
         }
         __syncwarp(gmask);
         uint8_t* blut = reinterpret_cast<uint8_t*>(S->lut_l);
-        int bb_bits = build_bits_lut(cl, blut, S->aux, glane, gmask);
+        int bb_bits = build_bits_lut(cl, blut, S->cnt_l, glane, gmask);
         if (bb_bits < 0) { msg = -bb_bits; return R_ERROR; }
         int index = 0;
         uint32_t prev = 0;
@@ -807,7 +808,7 @@ struct Decoder {
             if ((e >> 12) == 0) {                       // code longer than the root (or invalid)
                 slow = true;
                 if (e == E_LONG) {
-                    const uint32_t r = canon_long(S->cnt_l, gsorted, RL, g_l, S->aux[0], (uint32_t)bb);
+                    const uint32_t r = canon_long(S->cnt_l, gsorted, RL, g_l, S->cnt_l[0], (uint32_t)bb);
                     const uint32_t sym = r & 0xffffu;
                     if (r != 0 && sym <= 256) { e = ((r >> 16) << 12) | sym; slow = false; }
                     else if (r != 0 && sym - 257 <= 28) {
@@ -837,7 +838,7 @@ struct Decoder {
         uint32_t de = S->lut_d[(uint32_t)bb & ((1u << RD) - 1u)];
         uint32_t dn = de >> 12;
         if (dn == 0) {
-            uint32_t r = de == E_LONG ? canon_long(S->cnt_d, gsorted + SORTED_L, RD, g_d, S->aux[16], (uint32_t)bb) : 0u;
+            uint32_t r = de == E_LONG ? canon_long(S->cnt_d, gsorted + SORTED_L, RD, g_d, S->cnt_d[0], (uint32_t)bb) : 0u;
             const uint32_t ds = r & 0xffffu;
             if (r == 0 || ds > 29) { msg = SDZ_MSG_BAD_DIST_CODE; return R_ERROR; }     // far from the tail: no stall possible
             dn = r >> 16;
