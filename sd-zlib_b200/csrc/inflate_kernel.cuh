@@ -42,11 +42,13 @@ struct alignas(16) GroupSmem {
     uint64_t mbar[NBUF];
     uint16_t lut_l[1 << RL];
     uint16_t lut_d[1 << RD];
-    uint32_t cnt_l[16];                // [1..15] codes per length (unpadded); [0] = canonical-walk state after RL bits
-    uint32_t cnt_d[16];                // same for the distance code (state after RD bits)
-    uint32_t stage[8];                 // 8 bytes per lane (G = 4): source words of the pending (deferred) match
+    uint16_t cnt_l[16];                // [1..15] codes per length (unpadded)
+    uint16_t cnt_d[16];
+    uint16_t start[4];                 // canonical-walk state after the root bits: first_l, index_l, first_d, index_d
+    uint16_t pad_[4];
+    uint32_t stage[16];                // 2 slots x 8 words: source words of the two pending (deferred) matches
 };
-constexpr int MAX_G_DEFERRED = 4;      // groups wider than this use the synchronous copy only
+constexpr int MAX_G_DEFERRED = 4;      // groups wider than this use the synchronous copy only (stage[] holds 8 words)
 
 // per-group scratch in global memory: symbols ordered by (code length, symbol) - read by the
 // table build and by the rare canonical (slow) decode - and the block's code-length array
@@ -135,7 +137,7 @@ struct RingModel {
 // Width of the sub-table huft_build creates for the codes that share the first `w` bits
 // `prefix` (MSB-first) - src/inftree.ts:217-239.  cnt[] unpadded, `pad` dummy codes at g.
 // Returns 0 when no code has that prefix.
-__device__ __noinline__ int ref_subtable_width(const uint32_t* cnt, int g, int pad, int l, int w, uint32_t prefix)
+__device__ __noinline__ int ref_subtable_width(const uint16_t* cnt, int g, int pad, int l, int w, uint32_t prefix)
 {
     uint32_t fc = 0;
     for (int k = 1; k <= g; k++) {
@@ -173,7 +175,7 @@ __device__ __noinline__ int ref_subtable_width(const uint32_t* cnt, int g, int p
 // (src/inftree.ts:217-246): the root table plus one sub-table per distinct l-bit (and, for
 // very long codes, 2l-bit) prefix.  Evaluated by the group's lanes in parallel.
 template <int G>
-__device__ __noinline__ int ref_table_total(const uint32_t* cnt, int g, int pad, int l, int glane, unsigned gmask)
+__device__ __noinline__ int ref_table_total(const uint16_t* cnt, int g, int pad, int l, int glane, unsigned gmask)
 {
     int total = 1 << l;
     for (int w = l; w < g; w += l) {
@@ -200,7 +202,7 @@ __device__ __noinline__ int ref_table_total(const uint32_t* cnt, int g, int pad,
 // (SURVEY Q15): a lookup happens only when the table's index width is available.
 // bits = next 32 bits of the stream (LSB first), A = bits left in the input (capped).
 // Returns status << 28 | code_length << 16 | symbol; status = R_OK / R_STALL / R_ERROR.
-__device__ __noinline__ uint32_t slow_lookup(const uint32_t* cnt, const uint16_t* sorted, int l, int g, uint32_t bits, int A)
+__device__ __noinline__ uint32_t slow_lookup(const uint16_t* cnt, const uint16_t* sorted, int l, int g, uint32_t bits, int A)
 {
     if (A < l) return (uint32_t)R_STALL << 28;
     int ncodes = 0, y = 1;
@@ -243,11 +245,11 @@ __device__ __noinline__ uint32_t slow_lookup(const uint32_t* cnt, const uint16_t
 
 // Long code (more than R root bits) away from the stream tail: canonical decode that starts at
 // length R + 1.  `start` = state of the canonical walk after R bits, precomputed per block:
-// first code value (<< 1) in the high half, symbol index in the low half.
+// { first code value (<< 1), symbol index }.
 // Returns code_length << 16 | symbol, or 0 if no code matches (invalid).
-__device__ __forceinline__ uint32_t canon_long(const uint32_t* cnt, const uint16_t* sorted, int R, int g, uint32_t start, uint32_t bits)
+__device__ __forceinline__ uint32_t canon_long(const uint16_t* cnt, const uint16_t* sorted, int R, int g, const uint16_t* start, uint32_t bits)
 {
-    int first = (int)(start >> 16), index = (int)(start & 0xffffu);
+    int first = (int)start[0], index = (int)start[1];
     int code = (int)((__brev(bits) >> (32 - R)) << 1);
     for (int len = R + 1; len <= g; len++) {
         code |= (int)((bits >> (len - 1)) & 1u);
@@ -292,13 +294,16 @@ struct TreeInfo {
 // Reference acceptance test for one code-length set (src/inftree.ts:131-178,:298) and the
 // per-length counts.  Returns 0 ok, 1 oversubscribed, 2 incomplete, 3 empty.
 template <int G>
-__device__ __forceinline__ int classify(const uint8_t* lens, int n, int want_bits, uint32_t* cnt, int* l_out, int* g_out,
-                                        int* pad_out, int glane, unsigned gmask)
+__device__ __forceinline__ int classify(const uint8_t* lens, int n, int want_bits, uint16_t* cnt, uint32_t* gcount, int* l_out,
+                                        int* g_out, int* pad_out, int* nzero_out, int glane, unsigned gmask)
 {
-    for (int i = glane; i < 16; i += G) cnt[i] = 0;
+    for (int i = glane; i < 16; i += G) gcount[i] = 0;
     __syncwarp(gmask);
-    for (int i = glane; i < n; i += G) atomicAdd(&cnt[lens[i]], 1u);
+    for (int i = glane; i < n; i += G) atomicAdd(&gcount[lens[i]], 1u);
     __syncwarp(gmask);
+    for (int i = glane; i < 16; i += G) cnt[i] = (uint16_t)gcount[i];
+    __syncwarp(gmask);
+    *nzero_out = (int)cnt[0];
     *pad_out = 0;
     if ((int)cnt[0] == n) { *l_out = 0; *g_out = 0; return 3; }
     int j = 1;
@@ -323,8 +328,8 @@ __device__ __forceinline__ int classify(const uint8_t* lens, int n, int want_bit
 // sorted symbols + first codes (aux[16..31]) + end offsets (aux[0..15]), then the root LUT.
 // KIND 0 = literal/length (R = RL), 1 = distance (R = RD).
 template <int G, int KIND, int R>
-__device__ __forceinline__ void make_lut(uint32_t* aux, const uint8_t* lens, int n, uint32_t* cnt, uint16_t* sorted,
-                                         uint16_t* lut, int glane, unsigned gmask)
+__device__ __forceinline__ void make_lut(uint32_t* aux, const uint8_t* lens, int n, int nzero, const uint16_t* cnt, uint16_t* start,
+                                         uint16_t* sorted, uint16_t* lut, int glane, unsigned gmask)
 {
     if (glane == 0) {
         uint32_t off = 0, code = 0;
@@ -342,13 +347,12 @@ __device__ __forceinline__ void make_lut(uint32_t* aux, const uint8_t* lens, int
     uint32_t* lut32 = reinterpret_cast<uint32_t*>(lut);
     for (int i = glane; i < (1 << R) / 2; i += G) lut32[i] = E_INVALID | (E_INVALID << 16);
     __syncwarp(gmask);
-    const int ncodes = n - (int)cnt[0];
-    __syncwarp(gmask);
+    const int ncodes = n - nzero;
     if (glane == 0) {
-        // canonical-walk state after R bits (canon_long): kept in cnt[0], whose zero-length count is not needed any more
+        // canonical-walk state after R bits (canon_long)
         uint32_t first = 0, index = 0;
         for (int k = 1; k <= R && k <= 15; k++) { index += cnt[k]; first = (first + cnt[k]) << 1; }
-        cnt[0] = (first << 16) | (index & 0xffffu);
+        start[0] = (uint16_t)first; start[1] = (uint16_t)index;
     }
     for (int k = glane; k < ncodes; k += G) {
         uint32_t e = sorted[k];
@@ -387,9 +391,10 @@ __device__ __noinline__ TreeInfo build_tables(GroupSmem* S, uint16_t* gsorted, i
 {
     TreeInfo T;
     T.msg = SDZ_MSG_NONE; T.lbits = T.dbits = T.g_l = T.g_d = 0;
-    int pad_l = 0, pad_d = 0, used = 0;
+    int pad_l = 0, pad_d = 0, used = 0, nz_l = 0, nz_d = 0;
     const uint8_t* lens = reinterpret_cast<const uint8_t*>(gsorted + SORTED_L + SORTED_D);
-    int st = classify<G>(lens, nl, 9, S->cnt_l, &T.lbits, &T.g_l, &pad_l, glane, gmask);
+    uint32_t* aux = reinterpret_cast<uint32_t*>(gsorted + SORTED_L + SORTED_D + 160);
+    int st = classify<G>(lens, nl, 9, S->cnt_l, aux, &T.lbits, &T.g_l, &pad_l, &nz_l, glane, gmask);
     if (!fixed) {
         // the lit/len and distance tables share an arena of MANY = 1400 entries; running out of
         // it is reported as DATA_ERROR, i.e. with the "oversubscribed" text
@@ -398,7 +403,7 @@ __device__ __noinline__ TreeInfo build_tables(GroupSmem* S, uint16_t* gsorted, i
         if (used > 1400) { T.msg = SDZ_MSG_OVERSUB_LITLEN_TREE; return T; }
         if (st == 2 || st == 3) { T.msg = SDZ_MSG_INCOMPLETE_LITLEN_TREE; return T; }
     }
-    st = classify<G>(lens + nl, nd, fixed ? 5 : 6, S->cnt_d, &T.dbits, &T.g_d, &pad_d, glane, gmask);
+    st = classify<G>(lens + nl, nd, fixed ? 5 : 6, S->cnt_d, aux, &T.dbits, &T.g_d, &pad_d, &nz_d, glane, gmask);
     if (!fixed) {
         if (st == 1) { T.msg = SDZ_MSG_OVERSUB_DIST_TREE; return T; }
         if (st != 3 && used + ref_table_total<G>(S->cnt_d, T.g_d, pad_d, T.dbits, glane, gmask) > 1400) {
@@ -407,9 +412,8 @@ __device__ __noinline__ TreeInfo build_tables(GroupSmem* S, uint16_t* gsorted, i
         if (st == 2) { T.msg = SDZ_MSG_INCOMPLETE_DIST_TREE; return T; }
         if (st == 3 && nl > 257) { T.msg = SDZ_MSG_EMPTY_DIST_TREE; return T; }
     }
-    uint32_t* aux = reinterpret_cast<uint32_t*>(gsorted + SORTED_L + SORTED_D + 160);
-    make_lut<G, 0, RL>(aux, lens, nl, S->cnt_l, gsorted, S->lut_l, glane, gmask);
-    make_lut<G, 1, RD>(aux, lens + nl, nd, S->cnt_d, gsorted + SORTED_L, S->lut_d, glane, gmask);
+    make_lut<G, 0, RL>(aux, lens, nl, nz_l, S->cnt_l, S->start, gsorted, S->lut_l, glane, gmask);
+    make_lut<G, 1, RD>(aux, lens + nl, nd, nz_d, S->cnt_d, S->start + 2, gsorted + SORTED_L, S->lut_d, glane, gmask);
     if (fixed) { T.lbits = 9; T.dbits = 5; }
     return T;
 }
@@ -417,7 +421,7 @@ __device__ __noinline__ TreeInfo build_tables(GroupSmem* S, uint16_t* gsorted, i
 // code-length-code LUT for the dynamic header (inflate_trees_bits, src/inftree.ts:313-331).
 // cl[19] are the code-length-code lengths; blut[128] receives sym | len << 5.
 // Returns bb (index width, >= 1) or -msg on error.
-__device__ __noinline__ int build_bits_lut(const uint8_t* cl, uint8_t* blut, uint32_t* cnt, int glane, unsigned gmask)
+__device__ __noinline__ int build_bits_lut(const uint8_t* cl, uint8_t* blut, uint16_t* cnt, int glane, unsigned gmask)
 {
     if (glane == 0) {
         for (int i = 0; i < 16; i++) cnt[i] = 0;
@@ -495,7 +499,10 @@ struct Decoder {
 
     // deferred match copy: bytes loaded for the previous short match, stored when the next match
     // arrives, so that the L2 round trip of a copy overlaps the decode of the following symbols
-    uint32_t pdst, plen, psoff;        // pending destination offset / length (0 = none) / byte offset in stage[]
+    // two matches can be pending: `o_` the older one (its copies are complete after wait_group 1),
+    // `n_` the newer one.  len | soff << 8 is packed in *_meta (0 = empty); the older one's words
+    // live in staging slot `ptog`, the newer one's in slot `ptog ^ 1`.
+    uint32_t o_dst, o_meta, n_dst, n_meta, ptog;
 
     RingModel ring;
     int msg;
@@ -592,28 +599,48 @@ struct Decoder {
     __device__ __forceinline__ void drop(int n) { bb >>= n; bc -= n; }
 
     // ------------------------------------------------------------------ output
-    // Deferred match copy.  A short non-overlapping match (<= 4 G bytes, the common case) only
-    // ISSUES asynchronous copies (cp.async / LDGSTS): lane j stages the two aligned words that
-    // cover source bytes [4j, 4j + 4) into its private 8 bytes of stage[].  The bytes are moved to
+    // Deferred match copy.  A short non-overlapping match (<= 16 bytes, the common case) only
+    // ISSUES asynchronous copies (cp.async / LDGSTS): lane j stages the aligned words that cover
+    // its DB = 16 / G source bytes [DB j, DB j + DB) into its private slice of stage[].  The bytes are moved to
     // their destination when the group's next match (or the end of the stream) arrives, so the
     // L2 / DRAM round trip of the window read overlaps the decode of the following symbols instead
     // of stalling the lockstep warp.  Each lane reads back only what it staged itself: no
     // cross-lane synchronisation is needed at commit time.
-    __device__ __forceinline__ void commit_pending()
+    // bytes of a deferred match each lane moves, and the aligned words it stages for them
+    static constexpr int DB = G <= MAX_G_DEFERRED ? 16 / G : 4;
+    static constexpr int DW = DB / 4 + 1;
+
+    // move one pending match from its staging slot to its destination (straight-line, predicated:
+    // nothing happens when meta == 0)
+    __device__ __forceinline__ void commit_slot(uint32_t dst_off, uint32_t meta, uint32_t slot)
     {
-        if (STORE) {                                 // straight-line, predicated: nothing happens when plen == 0
-            cp_async_wait_all();
-            const uint32_t j4 = 4u * (uint32_t)glane;
-            const uint2 w = *reinterpret_cast<const uint2*>(&S->stage[2 * glane]);
-            const uint32_t v = __funnelshift_r(w.x, w.y, psoff * 8u);
-            uint8_t* dst = out + pdst + j4;
-            const uint32_t nb = plen > j4 ? plen - j4 : 0u;
-            st_u8_if(dst, v, nb > 0);
-            st_u8_if(dst + 1, v >> 8, nb > 1);
-            st_u8_if(dst + 2, v >> 16, nb > 2);
-            st_u8_if(dst + 3, v >> 24, nb > 3);
+        const uint32_t plen = meta & 0xffu, soff = meta >> 8;
+        const uint32_t jb = (uint32_t)DB * (uint32_t)glane;
+        const uint32_t* st = &S->stage[8 * slot + DW * glane];
+        uint8_t* dst = out + dst_off + jb;
+        const uint32_t nb = plen > jb ? plen - jb : 0u;
+        uint32_t w[DW];
+        #pragma unroll
+        for (int k = 0; k < DW; k++) w[k] = st[k];
+        #pragma unroll
+        for (int q = 0; q < DB / 4; q++) {
+            const uint32_t v = __funnelshift_r(w[q], w[q + 1], soff * 8u);
+            st_u8_if(dst + 4 * q, v, nb > 4u * q);
+            st_u8_if(dst + 4 * q + 1, v >> 8, nb > 4u * q + 1);
+            st_u8_if(dst + 4 * q + 2, v >> 16, nb > 4u * q + 2);
+            st_u8_if(dst + 4 * q + 3, v >> 24, nb > 4u * q + 3);
         }
-        plen = 0;
+    }
+
+    // complete both pending matches (end of stream, or a copy that may read their bytes)
+    __device__ __forceinline__ void flush_pending()
+    {
+        if (STORE && G <= MAX_G_DEFERRED) {
+            cp_async_wait_all();
+            commit_slot(o_dst, o_meta, ptog);
+            commit_slot(n_dst, n_meta, ptog ^ 1u);
+        }
+        o_meta = 0; n_meta = 0;
     }
 
     // Memory ordering: the lockstep loop executes a full-mask __syncwarp() at the top of every
@@ -623,20 +650,31 @@ struct Decoder {
     {
         if (len > cap - pos) return R_OUTFULL;
         if (STORE) {
-            const bool simple = G <= MAX_G_DEFERRED && dist >= len && len <= 4u * G && dist <= pos;
-            const bool hazard = plen != 0 && (!simple || pos - dist + len > pdst);
-            commit_pending();                        // previous match: its copies were issued a symbol (or more) ago
-            if (hazard) __syncwarp(gmask);           // the bytes just committed are (or may be) read below
+            const bool simple = G <= MAX_G_DEFERRED && dist >= len && len <= 16u && dist <= pos;
+            // the new source must not overlap bytes that are still pending (the older pending match has
+            // the lower destination); copies on the synchronous path read arbitrary earlier bytes
+            const uint32_t first_pending = o_meta ? o_dst : n_dst;
+            const bool any_pending = (o_meta | n_meta) != 0;
+            if (any_pending && (!simple || pos - dist + len > first_pending)) {
+                flush_pending();
+                __syncwarp(gmask);                   // the bytes just committed are (or may be) read below
+            }
             uint8_t* dst = out + pos;
             if (simple) {
+                // the older pending match was issued two matches ago: wait for it (only), store it, and
+                // reuse its staging slot for this match
+                cp_async_wait_but_one();
+                commit_slot(o_dst, o_meta, ptog);
                 const uint8_t* src = dst - dist;
                 const uint32_t so = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
-                const uint32_t j4 = 4u * (uint32_t)glane;
-                const uint8_t* w0 = src - so + j4;
-                cp_async4_if(&S->stage[2 * glane], w0, j4 < len);
-                cp_async4_if(&S->stage[2 * glane + 1], w0 + 4, j4 < len);
+                const uint32_t jb = (uint32_t)DB * (uint32_t)glane;
+                const uint8_t* w0 = src - so + jb;
+                #pragma unroll
+                for (int k = 0; k < DW; k++) cp_async4_if(&S->stage[8 * ptog + DW * glane + k], w0 + 4 * k, jb + 4u * k < len + so);
                 cp_async_commit();
-                pdst = pos; plen = len; psoff = so;
+                o_dst = n_dst; o_meta = n_meta;
+                n_dst = pos; n_meta = len | (so << 8);
+                ptog ^= 1u;
             } else if (dist <= pos) {
                 const uint8_t* src = dst - dist;
                 if (dist >= len) {
@@ -808,7 +846,7 @@ struct Decoder {
             if ((e >> 12) == 0) {                       // code longer than the root (or invalid)
                 slow = true;
                 if (e == E_LONG) {
-                    const uint32_t r = canon_long(S->cnt_l, gsorted, RL, g_l, S->cnt_l[0], (uint32_t)bb);
+                    const uint32_t r = canon_long(S->cnt_l, gsorted, RL, g_l, S->start, (uint32_t)bb);
                     const uint32_t sym = r & 0xffffu;
                     if (r != 0 && sym <= 256) { e = ((r >> 16) << 12) | sym; slow = false; }
                     else if (r != 0 && sym - 257 <= 28) {
@@ -838,7 +876,7 @@ struct Decoder {
         uint32_t de = S->lut_d[(uint32_t)bb & ((1u << RD) - 1u)];
         uint32_t dn = de >> 12;
         if (dn == 0) {
-            uint32_t r = de == E_LONG ? canon_long(S->cnt_d, gsorted + SORTED_L, RD, g_d, S->cnt_d[0], (uint32_t)bb) : 0u;
+            uint32_t r = de == E_LONG ? canon_long(S->cnt_d, gsorted + SORTED_L, RD, g_d, S->start + 2, (uint32_t)bb) : 0u;
             const uint32_t ds = r & 0xffffu;
             if (r == 0 || ds > 29) { msg = SDZ_MSG_BAD_DIST_CODE; return R_ERROR; }     // far from the tail: no stall possible
             dn = r >> 16;
@@ -906,7 +944,7 @@ struct Decoder {
         D = 0; dict_tail = nullptr;
         lbits = dbits = g_l = g_d = 0; eob_len = 0;
         ring.init(0);
-        plen = 0; pdst = 0; psoff = 0;
+        o_dst = o_meta = n_dst = n_meta = 0;
         is_gzip = false; method = 0; n_blocks = 0; mtime = 0; name_off = 0; name_len = 0; last = 0;
 
         int thrown = SDZ_THROW_NONE, thrown_inflate = 0, zstatus = SDZ_Z_OK;
@@ -1063,7 +1101,7 @@ struct Decoder {
             }
             end_byte = tp;
         }
-        commit_pending();
+        flush_pending();
         drain();
         __syncwarp(gmask);
         write_record(P, thrown, 0, zstatus, done, stored, isize, end_byte);
@@ -1157,6 +1195,7 @@ __global__ void __launch_bounds__(128, SDZ_MINBLOCKS) inflate_kernel(InflatePara
     const int lane = threadIdx.x & 31;
     d.gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - d.glane));
     d.issued_abs = 0; d.waited_abs = 0; d.chunk0 = 0; d.phasebits = 0;
+    d.ptog = 0; d.o_dst = d.o_meta = d.n_dst = d.n_meta = 0;
     d.phase = PH_FETCH;
     if (d.glane == 0) {
         for (int i = 0; i < NBUF; i++) mbar_init(&S->mbar[i], 1);

@@ -79,6 +79,8 @@ __device__ __forceinline__ void st_u8_if(uint8_t* p, uint32_t v, bool pred)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// all groups except the most recently committed one are complete
+__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t lane_id()
 {

@@ -146,8 +146,8 @@ template <bool STORE>
 int launch_inflate(sdz_ctx* ctx, const sdz::InflateParams& P)
 {
     switch (ctx->group) {
+    case 2: return launch_inflate_t<2, STORE>(ctx, P);
     case 8: return launch_inflate_t<8, STORE>(ctx, P);
-    case 16: return launch_inflate_t<16, STORE>(ctx, P);
     case 32: return launch_inflate_t<32, STORE>(ctx, P);
     default: return launch_inflate_t<4, STORE>(ctx, P);
     }
@@ -235,7 +235,7 @@ int sdz_ctx_create(int device, uint32_t flags, sdz_ctx** out)
     for (auto& e : ctx->ev)
         if (cudaEventCreate(&e) != cudaSuccess) return fail(SDZ_E_CUDA);
     if (cudaMalloc(&ctx->d_counter, 4 * sizeof(unsigned long long)) != cudaSuccess) return fail(SDZ_E_NOMEM);
-    if (const char* g = getenv("SDZ_GROUP")) { int v = atoi(g); if (v == 4 || v == 8 || v == 16 || v == 32) ctx->group = v; }
+    if (const char* g = getenv("SDZ_GROUP")) { int v = atoi(g); if (v == 2 || v == 4 || v == 8 || v == 32) ctx->group = v; }
     if (const char* t = getenv("SDZ_BLOCK")) { int v = atoi(t); if (v == 32 || v == 64 || v == 128) ctx->block_threads = v; }
     if (ctx->block_threads < ctx->group) ctx->block_threads = ctx->group;
     int rc = upload_tables(ctx);
