@@ -69,6 +69,16 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
 
 
+def measured_traffic(kernel, n_streams):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (full-size run only)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)[kernel]
+        return int(t["dram_bytes_read"] + t["dram_bytes_write"]) if n_streams == N_STREAMS else None
+    except Exception:
+        return None
+
+
 def make_corpus(n_distinct, first_index, threads):
     from tools import corpus as K
     t0 = time.time()
@@ -364,7 +374,7 @@ def main():
                        "compressed_bytes_per_gpu": comp_bytes, "l2": "inputs+outputs (%.1f GB) far exceed the 126 MB L2" % ((comp_bytes + out_bytes) / 1e9),
                        "lanes_per_stream": int(os.environ.get("SDZ_GROUP", "4")), "corpus_gen_s": round(gen_s, 1)},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": None, "peak_kind": peak_kind,
+                         "frac": round(achieved / peak, 4), "traffic": measured_traffic("inflate_kernel", n), "peak_kind": peak_kind,
                          "kernel": "inflate_kernel", "kernel_ms": round(inf_ms, 3), "finalize_ms": round(k_fin / args.steps, 3),
                          "algorithmic_bytes": comp_bytes + out_bytes},
             "cpu_baseline": cpu,
