@@ -27,8 +27,10 @@ struct DevBuf {
 struct sdz_ctx {
     int device = 0;
     int sm_count = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;        // compute stream (kernels; also the timing events)
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;   // copy streams of the pipelined host path
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    std::vector<cudaEvent_t> pipe_ev;    // 2 per sub-batch: input landed, kernels done
     std::string err;
     uint64_t launches = 0;
     float last_ms[3] = { 0, 0, 0 };
@@ -165,22 +167,22 @@ int launch_finalize(sdz_ctx* ctx, const uint8_t* d_out, sdz_result* d_res, uint6
     return SDZ_OK;
 }
 
-int run_batch_device(sdz_ctx* ctx, const sdz_batch_dev* b, bool sizes_only)
+int run_batch_device(sdz_ctx* ctx, const sdz_batch_dev* b, bool sizes_only, bool first = true, bool last = true)
 {
     sdz::InflateParams P;
     P.in = b->d_in; P.in_off = b->d_in_off; P.in_len = b->d_in_len; P.mode = b->d_mode;
     P.dict = b->d_dict; P.dict_off = b->d_dict_off; P.dict_len = b->d_dict_len; P.dict_adler = b->d_dict_adler;
     P.out = sizes_only ? nullptr : b->d_out; P.out_off = b->d_out_off; P.out_cap = b->d_out_cap;
     P.res = b->d_results; P.n = b->n; P.counter = ctx->d_counter; P.scratch = nullptr;
-    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (first) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     int rc = sizes_only ? launch_inflate<false>(ctx, P) : launch_inflate<true>(ctx, P);
     if (rc) return rc;
-    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    if (last) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     if (!sizes_only) {
         rc = launch_finalize(ctx, b->d_out, b->d_results, b->n);
         if (rc) return rc;
     }
-    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    if (last) CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     return SDZ_OK;
 }
 
@@ -232,6 +234,8 @@ int sdz_ctx_create(int device, uint32_t flags, sdz_ctx** out)
     auto fail = [&](int rc) { sdz_ctx_destroy(ctx); return rc; };
     if (cudaSetDevice(device) != cudaSuccess) return fail(SDZ_E_CUDA);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(SDZ_E_CUDA);
+    if (cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking) != cudaSuccess) return fail(SDZ_E_CUDA);
+    if (cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) != cudaSuccess) return fail(SDZ_E_CUDA);
     for (auto& e : ctx->ev)
         if (cudaEventCreate(&e) != cudaSuccess) return fail(SDZ_E_CUDA);
     if (cudaMalloc(&ctx->d_counter, 4 * sizeof(unsigned long long)) != cudaSuccess) return fail(SDZ_E_NOMEM);
@@ -255,6 +259,10 @@ void sdz_ctx_destroy(sdz_ctx* ctx)
     if (ctx->d_counter) cudaFree(ctx->d_counter);
     for (auto& e : ctx->ev)
         if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->pipe_ev)
+        if (e) cudaEventDestroy(e);
+    if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -476,16 +484,6 @@ static int inflate_host(sdz_ctx* ctx, const sdz_in* in, uint64_t n, uint8_t* out
     if (!sizes_only && (rc = grow(ctx, ctx->d_out, (out_hi - out_lo) + 64))) return rc;
 
     uint8_t* hs = (uint8_t*)ctx->h_stage;
-    {
-        std::vector<std::pair<uint8_t*, std::pair<const uint8_t*, size_t>>> jobs;
-        jobs.reserve(n * 2);
-        for (uint64_t i = 0; i < n; i++) {
-            if (in_len[i]) jobs.push_back({ hs + in_off[i], { in[i].data, in_len[i] } });
-            if (dict_len[i]) jobs.push_back({ hs + in_total + dict_off[i], { in[i].dict, dict_len[i] } });
-        }
-        parallel_copy(jobs);
-        memset(hs + in_bytes, 0, SDZ_IN_PAD);
-    }
     uint8_t* hm = hs + align_up(in_total + dict_bytes, 16);
     uint64_t* m_in_off = (uint64_t*)hm;
     uint64_t* m_dict_off = m_in_off + n;
@@ -503,28 +501,29 @@ static int inflate_host(sdz_ctx* ctx, const sdz_in* in, uint64_t n, uint8_t* out
     memcpy(m_out_cap, d_out_cap.data(), n * 4);
     memset(m_dict_adler, 0, n * 4);
     memcpy(m_mode, mode.data(), n);
+    memset(hs + in_bytes, 0, SDZ_IN_PAD);
 
-    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_in.p, hs, in_total + dict_bytes, cudaMemcpyHostToDevice, ctx->stream));
-
-    // dictionary checksums (reference adler32 incl. Q1) are evaluated on the device, one call each
+    uint8_t* d_in = (uint8_t*)ctx->d_in.p;
+    // dictionaries first (small): their reference adler32 (incl. Q1) is evaluated on the device, one call each
     if (dict_bytes) {
+        for (uint64_t i = 0; i < n; i++)
+            if (dict_len[i]) memcpy(hs + in_total + dict_off[i], in[i].dict, dict_len[i]);
+        CK(cudaMemcpyAsync(d_in + in_total, hs + in_total, dict_bytes, cudaMemcpyHostToDevice, ctx->stream));
         for (uint64_t i = 0; i < n; i++) {
             if (!(mode[i] & 0x80)) continue;
             uint64_t dl = dict_len[i];
             int32_t v = 1;
-            rc = checksum_chain(ctx, false, (const uint8_t*)ctx->d_in.p + in_total + dict_off[i], &dl, 1, 1, 1, nullptr, &v);
+            rc = checksum_chain(ctx, false, d_in + in_total + dict_off[i], &dl, 1, 1, 1, nullptr, &v);
             if (rc) return rc;
             m_dict_adler[i] = v;
         }
     } else {
         for (uint64_t i = 0; i < n; i++) if (mode[i] & 0x80) m_dict_adler[i] = 1;   // adler32 of an empty dictionary
     }
-    CK(cudaMemcpyAsync(ctx->d_meta.p, hm, meta_bytes, cudaMemcpyHostToDevice, ctx->stream));
 
     uint8_t* dm = (uint8_t*)ctx->d_meta.p;
     sdz_batch_dev b;
-    b.d_in = (const uint8_t*)ctx->d_in.p;
+    b.d_in = d_in;
     b.d_in_off = (const uint64_t*)dm;
     b.d_dict_off = b.d_in_off + n;
     b.d_out_off = b.d_dict_off + n;
@@ -533,29 +532,80 @@ static int inflate_host(sdz_ctx* ctx, const sdz_in* in, uint64_t n, uint8_t* out
     b.d_out_cap = b.d_dict_len + n;
     b.d_dict_adler = (const int32_t*)(b.d_out_cap + n);
     b.d_mode = (const uint8_t*)(b.d_dict_adler + n);
-    b.d_dict = (const uint8_t*)ctx->d_in.p + in_total;
+    b.d_dict = d_in + in_total;
     b.d_out = sizes_only ? nullptr : (uint8_t*)ctx->d_out.p;
     b.d_results = (sdz_result*)ctx->d_res.p;
     b.n = n;
-    rc = run_batch_device(ctx, &b, sizes_only);
-    if (rc) return rc;
 
     std::vector<sdz_result> tmp;
     sdz_result* rdst = results;
     if (!rdst) { tmp.resize(n); rdst = tmp.data(); }
-    CK(cudaMemcpyAsync(rdst, ctx->d_res.p, n * sizeof(sdz_result), cudaMemcpyDeviceToHost, ctx->stream));
-    if (!sizes_only) {
-        if (dense) {
-            CK(cudaMemcpyAsync(out_arena + out_lo, ctx->d_out.p, out_hi - out_lo, cudaMemcpyDeviceToHost, ctx->stream));
-        } else {
-            CK(cudaStreamSynchronize(ctx->stream));
-            for (uint64_t i = 0; i < n; i++)
-                if (rdst[i].out_len)
-                    CK(cudaMemcpyAsync(out_arena + out_off[i], (uint8_t*)ctx->d_out.p + d_out_off[i], rdst[i].out_len,
-                                       cudaMemcpyDeviceToHost, ctx->stream));
+
+    // ---- pipeline: the batch is cut into sub-batches that still fill the GPU; staging (host
+    // threads) -> H2D (s_h2d) -> kernels (stream) -> D2H (s_d2h) of consecutive sub-batches overlap
+    uint64_t K = n / 16384;
+    if (K < 1) K = 1;
+    if (K > 8) K = 8;
+    if (!sizes_only && !dense) K = 1;
+    while (ctx->pipe_ev.size() < 2 * K) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->pipe_ev.push_back(e);
+    }
+    // zero-copy fast path: the caller's buffers already sit packed (16-byte aligned spacing, the
+    // layout of the device arena) in ONE pinned host region -> DMA straight from it, no staging
+    bool direct = true;
+    const uint8_t* ubase = nullptr;
+    for (uint64_t i = 0; i < n && direct; i++) {
+        if (!in_len[i]) continue;
+        if (!ubase) ubase = in[i].data - in_off[i];
+        if (in[i].data != ubase + in_off[i]) direct = false;
+    }
+    if (direct && ubase) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, ubase) != cudaSuccess || attr.type != cudaMemoryTypeHost) { direct = false; cudaGetLastError(); }
+    } else direct = false;
+    const size_t data_end = in_off[n - 1] + in_len[n - 1];
+
+    CK(cudaMemcpyAsync(ctx->d_meta.p, hm, meta_bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
+    for (uint64_t c = 0; c < K; c++) {
+        const uint64_t lo = n * c / K, hi = n * (c + 1) / K;
+        if (lo == hi) continue;
+        if (!direct) {
+            std::vector<std::pair<uint8_t*, std::pair<const uint8_t*, size_t>>> jobs;
+            jobs.reserve(hi - lo);
+            for (uint64_t i = lo; i < hi; i++)
+                if (in_len[i]) jobs.push_back({ hs + in_off[i], { in[i].data, in_len[i] } });
+            parallel_copy(jobs);
+        }
+        const size_t c_lo = in_off[lo], c_hi = (hi < n ? (size_t)in_off[hi] : (direct ? data_end : in_total));
+        if (c_hi > c_lo)
+            CK(cudaMemcpyAsync(d_in + c_lo, (direct ? ubase : hs) + c_lo, c_hi - c_lo, cudaMemcpyHostToDevice, ctx->s_h2d));
+        CK(cudaEventRecord(ctx->pipe_ev[2 * c], ctx->s_h2d));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->pipe_ev[2 * c], 0));
+        sdz_batch_dev bc = b;
+        bc.d_in_off += lo; bc.d_dict_off += lo; bc.d_out_off += lo; bc.d_in_len += lo; bc.d_dict_len += lo;
+        bc.d_out_cap += lo; bc.d_dict_adler += lo; bc.d_mode += lo; bc.d_results += lo;
+        bc.n = hi - lo;
+        rc = run_batch_device(ctx, &bc, sizes_only, c == 0, c == K - 1);
+        if (rc) return rc;
+        CK(cudaEventRecord(ctx->pipe_ev[2 * c + 1], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->pipe_ev[2 * c + 1], 0));
+        CK(cudaMemcpyAsync(rdst + lo, (sdz_result*)ctx->d_res.p + lo, (hi - lo) * sizeof(sdz_result), cudaMemcpyDeviceToHost, ctx->s_d2h));
+        if (!sizes_only && dense) {
+            const uint64_t o_lo = d_out_off[lo], o_hi = d_out_off[hi - 1] + d_out_cap[hi - 1];
+            CK(cudaMemcpyAsync(out_arena + out_lo + o_lo, (uint8_t*)ctx->d_out.p + o_lo, o_hi - o_lo, cudaMemcpyDeviceToHost, ctx->s_d2h));
         }
     }
+    CK(cudaStreamSynchronize(ctx->s_d2h));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (!sizes_only && !dense) {
+        for (uint64_t i = 0; i < n; i++)
+            if (rdst[i].out_len)
+                CK(cudaMemcpyAsync(out_arena + out_off[i], (uint8_t*)ctx->d_out.p + d_out_off[i], rdst[i].out_len,
+                                   cudaMemcpyDeviceToHost, ctx->s_d2h));
+        CK(cudaStreamSynchronize(ctx->s_d2h));
+    }
     int ret = SDZ_OK;
     for (uint64_t i = 0; i < n; i++) {
         if (!sizes_only) {
