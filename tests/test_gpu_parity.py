@@ -301,3 +301,21 @@ def test_sizing_pass_matches_decode():
     views = [np.frombuffer(s, dtype=np.uint8) for s in streams]
     arena, off, res = A.inflate_batch_raw(views)
     assert [int(r.out_len) for r in res] == [1000 + 3571 * i for i in range(20)]
+
+
+def test_pipelined_host_path_many_small_streams():
+    """n >= 32768 streams makes sdz_inflate_batch cut the batch into sub-batches (pipelined on three
+    CUDA streams); records and bytes must not depend on the cut.  Separate Python buffers force the
+    staging path; test_batch_4096_text_streams_roundtrip covers the packed one."""
+    n = 40000
+    plains = [K.generate(K.TINY if i % 3 else K.TEXT, i, 20 + (i * 37) % 400).tobytes() for i in range(n)]
+    streams = [zlib.compress(p, 6) if i % 2 else gzip.compress(p, 6, mtime=i + 1) for i, p in enumerate(plains)]
+    views = [np.frombuffer(s, dtype=np.uint8) for s in streams]
+    arena, off, res = A.inflate_batch_raw(views)
+    for i in range(n):
+        r = res[i]
+        assert r.success and r.out_len == len(plains[i]), i
+        if i % 997 == 0 or i in (19999, 20000, 39999):
+            assert bytes(arena[int(off[i]):int(off[i]) + int(r.out_len)]) == plains[i]
+            eb, er = O.inflate_oneshot(streams[i])
+            assert r.observable() == er.observable()
