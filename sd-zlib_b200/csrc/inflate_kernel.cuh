@@ -649,7 +649,8 @@ struct Decoder {
     // Memory ordering: the lockstep loop executes a full-mask __syncwarp() at the top of every
     // iteration, so stores of earlier iterations (literals, committed matches) are ordered before
     // the reads issued here.  Only bytes committed in THIS iteration need an extra group sync.
-    __device__ __forceinline__ int copy_match(uint32_t len, uint32_t dist)
+    // `lit_now`: a literal was stored by lane 0 earlier in THIS lockstep iteration (at pos - 1).
+    __device__ __forceinline__ int copy_match(uint32_t len, uint32_t dist, bool lit_now)
     {
         if (len > cap - pos) return R_OUTFULL;
         if (STORE) {
@@ -658,10 +659,11 @@ struct Decoder {
             // the lower destination); copies on the synchronous path read arbitrary earlier bytes
             const uint32_t first_pending = o_meta ? o_dst : n_dst;
             const bool any_pending = (o_meta | n_meta) != 0;
-            if (any_pending && (!simple || pos - dist + len > first_pending)) {
-                flush_pending();
-                __syncwarp(gmask);                   // the bytes just committed are (or may be) read below
-            }
+            const bool hazard = any_pending && (!simple || pos - dist + len > first_pending);
+            if (hazard) flush_pending();
+            // bytes written in this iteration (just-committed matches, the folded literal at pos - 1) are
+            // only ordered before the reads below by a group sync; a deferred match reads pos - 1 iff dist == len
+            if (hazard || !simple || (lit_now && dist == len)) __syncwarp(gmask);
             uint8_t* dst = out + pos;
             if (simple) {
                 // the older pending match was issued two matches ago: wait for it (only), store it, and
@@ -815,7 +817,7 @@ struct Decoder {
         if (tail && avail_bits() < (int)dx) return R_STALL;
         uint32_t dist = 1 + ((de & 3) << dx) + ((uint32_t)bb & ((1u << dx) - 1u));
         bb >>= dx; bc -= (int)dx;
-        return copy_match(len, dist);
+        return copy_match(len, dist, false);
     }
 
     // branch-free top-up used by the fast path (at least five whole input words remain):
@@ -841,6 +843,7 @@ struct Decoder {
     // iteration was measured slower: the warp pays the longest run of its eight groups.)
     __device__ __forceinline__ int step()
     {
+        bool lit_now = false;
 #if SDZ_LIT_RUN > 0
         // leading literals: every lockstep iteration pays for the match path anyway, so plain
         // literals in front of a match are folded into the same iteration
@@ -854,6 +857,7 @@ struct Decoder {
             bb >>= n0; bc -= (int)n0;
             if (STORE) { if (glane == 0) out[pos] = (uint8_t)e0; }
             pos++;
+            lit_now = true;
         }
 #endif
         bool slow = wp + 5 > end_wp;
@@ -904,7 +908,7 @@ struct Decoder {
         const uint32_t dx = (de >> 8) & 15;
         const uint32_t dist = 1 + ((de & 3) << dx) + ((uint32_t)bb & ((1u << dx) - 1u));
         bb >>= dx; bc -= (int)dx;
-        return copy_match(len, dist);
+        return copy_match(len, dist, lit_now);
     }
 
     // stored block body (src/infblocks.ts:278-333) with the Q2 truncation

@@ -41,6 +41,7 @@ struct sdz_ctx {
     unsigned long long* d_counter = nullptr;
     int group = 4;                     // lanes per stream
     int block_threads = 64;
+    bool poison = false;               // SDZ_POISON=1 (tests): fill the device output arena with 0xA5 before every decode
 };
 
 namespace {
@@ -242,6 +243,7 @@ int sdz_ctx_create(int device, uint32_t flags, sdz_ctx** out)
     if (const char* g = getenv("SDZ_GROUP")) { int v = atoi(g); if (v == 2 || v == 4 || v == 8 || v == 32) ctx->group = v; }
     if (const char* t = getenv("SDZ_BLOCK")) { int v = atoi(t); if (v == 32 || v == 64 || v == 128) ctx->block_threads = v; }
     if (ctx->block_threads < ctx->group) ctx->block_threads = ctx->group;
+    if (const char* z = getenv("SDZ_POISON")) ctx->poison = atoi(z) != 0;
     int rc = upload_tables(ctx);
     if (rc) return fail(rc);
     *out = ctx;
@@ -567,6 +569,10 @@ static int inflate_host(sdz_ctx* ctx, const sdz_in* in, uint64_t n, uint8_t* out
     } else direct = false;
     const size_t data_end = in_off[n - 1] + in_len[n - 1];
 
+    if (ctx->poison && !sizes_only) {
+        // stale bytes of an earlier call must never be able to stand in for bytes a kernel failed to write
+        CK(cudaMemsetAsync(ctx->d_out.p, 0xA5, (out_hi - out_lo) + 64, ctx->stream));
+    }
     CK(cudaMemcpyAsync(ctx->d_meta.p, hm, meta_bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
     for (uint64_t c = 0; c < K; c++) {
         const uint64_t lo = n * c / K, hi = n * (c + 1) / K;

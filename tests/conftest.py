@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# poison the device output arena before every decode so that a byte a kernel failed to write (or read too
+# early) can never be masked by stale data of an earlier call
+os.environ.setdefault("SDZ_POISON", "1")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "sd-zlib_b200", "host"))

@@ -319,3 +319,31 @@ def test_pipelined_host_path_many_small_streams():
             assert bytes(arena[int(off[i]):int(off[i]) + int(r.out_len)]) == plains[i]
             eb, er = O.inflate_oneshot(streams[i])
             assert r.observable() == er.observable()
+
+
+def test_cfg4_mixed_container_batch():
+    """BASELINE configs[3] on one GPU: gzip + raw + zlib (+ preset dictionary), levels 1/6/9, text / binary /
+    tiny (fixed blocks) / incompressible <= 49,151 B (stored blocks) / runs - one batch, every finish() record
+    and every byte compared with the oracle."""
+    dic = bytes(K.generate(K.TEXT, 4242, 470))
+    dictid = O.adler32(dic)
+    rnd = random.Random(44)
+    streams, dicts, modes = [], [], []
+    kinds = [(K.TEXT, 65536), (K.BINARY, 65536), (K.TINY, 0), (K.RANDOM, 0), (K.RUNS, 65536), (K.TEXT, 20000)]
+    for i in range(1500):
+        kind, n = kinds[i % len(kinds)]
+        if kind == K.TINY:
+            n = 1 + rnd.randrange(200)
+        elif kind == K.RANDOM:
+            n = 1 + rnd.randrange(49151)
+        plain = K.generate(kind, 7000 + i, n)
+        level = (1, 6, 9)[i % 3]
+        cont = (K.GZIP, K.RAW, K.ZLIB, K.GZIP_NAME, K.ZLIB_DICT)[i % 5]
+        if cont == K.ZLIB_DICT:
+            streams.append(K.compress(plain, level, cont, dic, dictid)); dicts.append(dic); modes.append(O.MODE_INFLATER)
+        else:
+            streams.append(K.compress(plain, level, cont)); dicts.append(None)
+            modes.append(O.MODE_RAW if cont == K.RAW and i % 2 else O.MODE_SNIFF)
+    got = check_against_oracle(streams, dicts, modes)
+    assert sum(1 for _, r in got if r.success) > 1300          # raw streams may be incomplete by Q15
+    assert {r.container for _, r in got} == {0, 1, 2}
