@@ -86,6 +86,14 @@ int sdz_adler32_chain(sdz_ctx* ctx, const uint8_t* p, const uint64_t* seg_len, u
 int sdz_crc32_chain(sdz_ctx* ctx, const uint8_t* p, const uint64_t* seg_len, uint64_t n_seg,
                     int32_t seed, int on_device, int32_t* out_values, int32_t* out_last);
 
+/* Checksums of n independent buffers in one launch (one warp per buffer): out[i] =
+ * adler32(buf_i, seed_i) when kind[i] == 0, crc32(buf_i, seed_i) when kind[i] == 1 - what
+ * Deflater.append() computes over its source data (src/sd-deflate.ts:185-190) and what the gzip /
+ * zlib trailers need.  seeds may be NULL (reference defaults: 1 for adler32, 0 for crc32).  Each
+ * call to the reference is ONE call here, so Q1 applies per buffer. */
+int sdz_checksum_batch(sdz_ctx* ctx, const uint8_t* const* bufs, const uint64_t* lens, const uint8_t* kind,
+                       const int32_t* seeds, uint64_t n, int32_t* out);
+
 /* ---------------------------------------------------------------- batched inflate */
 
 /* one input buffer == one `new Inflater(options)` fed with a single append() */

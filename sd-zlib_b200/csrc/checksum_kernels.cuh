@@ -68,6 +68,29 @@ __global__ void __launch_bounds__(256) finalize_streams_kernel(const uint8_t* ou
     }
 }
 
+// ------------------------------------------------------------------ batched per-buffer checksums
+// one warp per buffer (dynamic scheduling): adler32(buf, seed) or crc32(buf, seed), one reference call each
+__global__ void __launch_bounds__(256) checksum_batch_kernel(const uint8_t* base, const uint64_t* off, const uint64_t* len,
+                                                             const uint8_t* kind, const int32_t* seeds, unsigned long long n,
+                                                             int32_t* out, unsigned long long* counter)
+{
+    __shared__ uint32_t tab[1024];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) tab[i] = (&g_crc_tab[0][0])[i];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31;
+    for (;;) {
+        unsigned long long idx = 0;
+        if (lane == 0) idx = atomicAdd(counter, 1ull);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= n) break;
+        const uint8_t* p = base + off[idx];
+        const bool crc = kind[idx] != 0;
+        const uint32_t seed = seeds ? (uint32_t)seeds[idx] : (crc ? 0u : 1u);
+        const uint32_t v = crc ? crc_call_warp(tab, p, len[idx], seed, lane) : adler_call_warp(p, len[idx], seed, lane);
+        if (lane == 0) out[idx] = (int32_t)v;
+    }
+}
+
 // ------------------------------------------------------------------ large-buffer adler32
 // Segment s = bytes [seg_off[s], seg_off[s] + seg_len[s]) of the buffer; it is cut into
 // units of 5552 bytes (the reference's NMAX blocks); unit_base[s] = first unit of segment s.

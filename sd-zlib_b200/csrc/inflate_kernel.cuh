@@ -766,7 +766,7 @@ struct Decoder {
     // `tail` (fewer than five input words left) and root entries marked long/invalid go through
     // slow_lookup(), which also enforces the reference's lookahead rule; everything else is
     // one shared-memory LUT read per code.
-    __device__ __forceinline__ int step_general()
+    __device__ __forceinline__ int step_general(bool lit_now)
     {
         refill();
         const bool tail = wp + 5 > end_wp;
@@ -817,7 +817,7 @@ struct Decoder {
         if (tail && avail_bits() < (int)dx) return R_STALL;
         uint32_t dist = 1 + ((de & 3) << dx) + ((uint32_t)bb & ((1u << dx) - 1u));
         bb >>= dx; bc -= (int)dx;
-        return copy_match(len, dist, false);
+        return copy_match(len, dist, lit_now);
     }
 
     // branch-free top-up used by the fast path (at least five whole input words remain):
@@ -881,7 +881,7 @@ struct Decoder {
                 }
             }
         }
-        if (slow) return step_general();
+        if (slow) return step_general(lit_now);
         const uint32_t n = e >> 12, p = e & 0xfff;
         bb >>= n; bc -= (int)n;
         if (p < 256) {

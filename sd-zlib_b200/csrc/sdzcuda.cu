@@ -425,6 +425,62 @@ int sdz_crc32(sdz_ctx* ctx, const uint8_t* p, uint64_t n, int32_t seed, int on_d
     return checksum_chain(ctx, true, p, &n, 1, seed, on_device, nullptr, out);
 }
 
+int sdz_checksum_batch(sdz_ctx* ctx, const uint8_t* const* bufs, const uint64_t* lens, const uint8_t* kind,
+                       const int32_t* seeds, uint64_t n, int32_t* out)
+{
+    if (!ctx || (n && (!bufs || !lens || !kind || !out))) return SDZ_E_ARG;
+    if (n == 0) return SDZ_OK;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<uint64_t> off(n);
+    size_t total = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        if (lens[i] >= (1ull << 32) || (lens[i] && !bufs[i])) return SDZ_E_ARG;
+        off[i] = total;
+        total += align_up(lens[i], 16);
+    }
+    const size_t meta = align_up(n * (8 + 8 + 4 + 4 + 1), 16);
+    int rc;
+    if ((rc = grow_stage(ctx, total + 16 + meta))) return rc;
+    if ((rc = grow(ctx, ctx->d_in, total + 16))) return rc;
+    if ((rc = grow(ctx, ctx->d_meta, meta))) return rc;
+    uint8_t* hs = (uint8_t*)ctx->h_stage;
+    {
+        std::vector<std::pair<uint8_t*, std::pair<const uint8_t*, size_t>>> jobs;
+        for (uint64_t i = 0; i < n; i++) if (lens[i]) jobs.push_back({ hs + off[i], { bufs[i], (size_t)lens[i] } });
+        parallel_copy(jobs);
+    }
+    uint8_t* hm = hs + align_up(total + 16, 16);
+    uint64_t* m_off = (uint64_t*)hm;
+    uint64_t* m_len = m_off + n;
+    int32_t* m_seed = (int32_t*)(m_len + n);
+    int32_t* m_out = m_seed + n;
+    uint8_t* m_kind = (uint8_t*)(m_out + n);
+    memcpy(m_off, off.data(), n * 8);
+    memcpy(m_len, lens, n * 8);
+    for (uint64_t i = 0; i < n; i++) m_seed[i] = seeds ? seeds[i] : (kind[i] ? 0 : 1);
+    memcpy(m_kind, kind, n);
+    if (total) CK(cudaMemcpyAsync(ctx->d_in.p, hs, total, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_meta.p, hm, meta, cudaMemcpyHostToDevice, ctx->stream));
+    uint8_t* dm = (uint8_t*)ctx->d_meta.p;
+    const uint64_t* d_off = (const uint64_t*)dm;
+    const uint64_t* d_len = d_off + n;
+    const int32_t* d_seed = (const int32_t*)(d_len + n);
+    int32_t* d_out = (int32_t*)(d_seed + n);
+    const uint8_t* d_kind = (const uint8_t*)(d_out + n);
+    CK(cudaMemsetAsync(ctx->d_counter + 3, 0, sizeof(unsigned long long), ctx->stream));
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    unsigned grid = (unsigned)std::min<uint64_t>((n + 7) / 8, (uint64_t)ctx->sm_count * 8);
+    sdz::checksum_batch_kernel<<<grid, 256, 0, ctx->stream>>>((const uint8_t*)ctx->d_in.p, d_off, d_len, d_kind, d_seed, n, d_out,
+                                                                ctx->d_counter + 3);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    CK(cudaMemcpyAsync(out, d_out, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SDZ_OK;
+}
+
 // ---------------------------------------------------------------------------- batched inflate
 
 int sdz_inflate_batch_device(sdz_ctx* ctx, const sdz_batch_dev* batch, uint32_t flags, int sync)

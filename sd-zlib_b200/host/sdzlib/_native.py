@@ -16,7 +16,7 @@ _ERR_NAME = {-1: "no sm_100a CUDA device", -2: "CUDA error", -3: "bad argument",
 EXPORTS = [
     "sdz_ctx_create", "sdz_ctx_destroy", "sdz_last_error", "sdz_version", "sdz_launch_count", "sdz_last_timing",
     "sdz_host_alloc", "sdz_host_free", "sdz_device_alloc", "sdz_device_free", "sdz_memcpy_h2d", "sdz_memcpy_d2h",
-    "sdz_adler32", "sdz_crc32", "sdz_adler32_chain", "sdz_crc32_chain",
+    "sdz_adler32", "sdz_crc32", "sdz_adler32_chain", "sdz_crc32_chain", "sdz_checksum_batch",
     "sdz_inflate_batch", "sdz_inflate_sizes", "sdz_inflate_batch_device", "sdz_sync",
 ]
 
@@ -100,6 +100,7 @@ def load():
             f.argtypes = [vp, vp, u64, i32, C.c_int, C.POINTER(i32)]
         for f in (L.sdz_adler32_chain, L.sdz_crc32_chain):
             f.argtypes = [vp, vp, vp, u64, i32, C.c_int, vp, C.POINTER(i32)]
+        L.sdz_checksum_batch.argtypes = [vp, vp, vp, vp, vp, u64, vp]
         L.sdz_inflate_batch.argtypes = [vp, vp, u64, vp, vp, vp, vp, u32]
         L.sdz_inflate_sizes.argtypes = [vp, vp, u64, vp, u32]
         L.sdz_inflate_batch_device.argtypes = [vp, C.POINTER(BatchDev), u32, C.c_int]

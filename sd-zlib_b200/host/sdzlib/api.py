@@ -91,6 +91,22 @@ def crc32_chain(source, seg_lens, seed=0, ctx=None, device_ptr=None):
     return _chain("sdz_crc32_chain", source, seg_lens, seed, ctx, device_ptr)
 
 
+def checksum_batch(buffers, kinds, seeds=None, ctx=None):
+    """[adler32(b, seed) if kind == 'adler32' else crc32(b, seed) for b in buffers] in one launch
+    (what Deflater needs for its inputs, src/sd-deflate.ts:185-190)."""
+    ctx = ctx or N.default_context()
+    views = [_as_u8(b, "source must be a BufferSource") for b in buffers]
+    n = len(views)
+    ptrs = (C.c_void_p * max(n, 1))(*[v.ctypes.data if v.size else None for v in views])
+    lens = np.array([v.size for v in views], dtype=np.uint64)
+    kind = np.array([0 if k in (0, "adler32") else 1 for k in kinds], dtype=np.uint8)
+    sd = None if seeds is None else np.array([_i32(s) for s in seeds], dtype=np.int32)
+    out = np.zeros(max(n, 1), dtype=np.int32)
+    ctx.check(ctx.lib.sdz_checksum_batch(ctx.h, ptrs, lens.ctypes.data, kind.ctypes.data,
+                                         None if sd is None else sd.ctypes.data, n, out.ctypes.data))
+    return [int(x) for x in out[:n]]
+
+
 def mergeBuffers(buffers: Sequence[bytes]) -> bytes:
     """src/common.ts:116-126"""
     return b"".join(bytes(b) for b in buffers)

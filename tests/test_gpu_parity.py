@@ -347,3 +347,39 @@ def test_cfg4_mixed_container_batch():
     got = check_against_oracle(streams, dicts, modes)
     assert sum(1 for _, r in got if r.success) > 1300          # raw streams may be incomplete by Q15
     assert {r.container for _, r in got} == {0, 1, 2}
+
+
+def test_checksum_batch():
+    rnd = random.Random(8)
+    sizes = [0, 1, 15, 16, 17, 5551, 5552, 5553, 11104, 16384, 40000, 65536, 100000, 262147]
+    bufs = [os.urandom(n) for n in sizes] * 3
+    kinds = ["adler32" if i % 2 else "crc32" for i in range(len(bufs))]
+    seeds = [rnd.choice([0, 1, -1, 0x12345678, -2147483648]) for _ in bufs]
+    got = sdzlib.checksum_batch(bufs, kinds, seeds)
+    for b, k, s, g in zip(bufs, kinds, seeds, got):
+        exp = O.adler32(b, s) if k == "adler32" else O.crc32(b, s)
+        assert g == exp, (len(b), k, s, g, exp)
+    got = sdzlib.checksum_batch(bufs[:6], kinds[:6])          # reference default seeds
+    for b, k, g in zip(bufs, kinds, got):
+        assert g == (O.adler32(b) if k == "adler32" else O.crc32(b))
+
+
+def test_mixed_kind_stress_roundtrip():
+    """8,192 streams of every corpus kind and several sizes/levels in one batch, decoded into a poisoned
+    arena: bytes must equal the plaintext for every stream (catches intra-warp ordering bugs)."""
+    views, plains = [], []
+    for kind, n, level, cnt in ((K.RUNS, 65536, 6, 2048), (K.TEXT, 30000, 1, 2048), (K.BINARY, 65536, 9, 1024),
+                                (K.RUNS, 9000, 1, 1024), (K.TEXT, 131072, 6, 512), (K.TINY, 180, 6, 1536)):
+        comp, stride, clen, plain = K.make_batch(kind, cnt, n, level, K.ZLIB, first_index=90000 + len(views), keep_plain=True)
+        for i in range(cnt):
+            views.append(comp[i * stride:i * stride + int(clen[i])])
+            plains.append(plain[i * n:(i + 1) * n])
+    order = list(range(len(views)))
+    random.Random(3).shuffle(order)
+    views = [views[i] for i in order]
+    plains = [plains[i] for i in order]
+    arena, off, res = A.inflate_batch_raw(views)
+    for i, p in enumerate(plains):
+        r = res[i]
+        assert r.success and r.out_len == p.size, (i, r.observable())
+        assert np.array_equal(arena[int(off[i]):int(off[i]) + p.size], p), i
