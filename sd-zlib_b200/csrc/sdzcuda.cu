@@ -601,7 +601,7 @@ static int inflate_host(sdz_ctx* ctx, const sdz_in* in, uint64_t n, uint8_t* out
 
     // ---- pipeline: the batch is cut into sub-batches that still fill the GPU; staging (host
     // threads) -> H2D (s_h2d) -> kernels (stream) -> D2H (s_d2h) of consecutive sub-batches overlap
-    uint64_t K = n / 16384;
+    uint64_t K = n / (getenv("SDZ_SUBBATCH") ? (uint64_t)atoll(getenv("SDZ_SUBBATCH")) : 16384ull);
     if (K < 1) K = 1;
     if (K > 8) K = 8;
     if (!sizes_only && !dense) K = 1;
