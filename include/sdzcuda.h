@@ -147,6 +147,18 @@ typedef struct sdz_batch_dev {
     uint64_t        n;
 } sdz_batch_dev;
 int sdz_inflate_batch_device(sdz_ctx* ctx, const sdz_batch_dev* batch, uint32_t flags, int sync);
+
+/* ONE large stream (BASELINE config 5), decoded by all SMs: pass 1 indexes the deflate block boundaries
+ * (speculative header search + per-block extents, chained from the first block), pass 2 decodes every
+ * block in parallel with 16-bit marker symbols for back-references into the unknown 32 KiB window,
+ * propagates the windows in stream order and resolves the markers.  Same record as one
+ * `new Inflater(opts).append(data); finish()` (src/sd-inflate.ts:54-180).  on_device != 0: `data` and
+ * `out` are device pointers (data 4-byte aligned and readable for SDZ_IN_PAD bytes past its end, out
+ * with 64 bytes of slack).  Streams the index cannot handle (preset dictionary, anything that is not a
+ * complete well-formed stream) are handed to the ordinary one-group decoder, which is exact but slow.
+ * Returns SDZ_E_OUT_CAP (res->out_len = needed size) if out_cap is too small. */
+int sdz_inflate_large(sdz_ctx* ctx, const uint8_t* data, uint64_t len, uint8_t mode, int on_device,
+                      uint8_t* out, uint64_t out_cap, sdz_result* res);
 int sdz_sync(sdz_ctx* ctx);
 
 #ifdef __cplusplus

@@ -72,6 +72,11 @@ struct InflateParams {
     const uint32_t* out_cap;
     sdz_result* res;
     uint16_t* scratch;                 // SCRATCH_U16 entries per group of the grid
+    // block-task mode (large single stream, sdz_inflate_large): every work item is ONE deflate block of
+    // stream 0 that starts at bit task_bit[i]; in marker mode its symbols go to out16 + task_out[i]
+    const uint64_t* task_bit;          // nullptr: ordinary stream mode
+    const uint64_t* task_out;          // absolute output offset of each block (marker mode)
+    uint16_t* out16;                   // marker-mode output: byte value, or 256 + index into the 32 KiB window before the block
     unsigned long long n;
     unsigned long long* counter;       // dynamic stream scheduler
 };
@@ -478,7 +483,7 @@ __device__ __noinline__ void copy_before_start_impl(uint8_t* o, uint32_t p0, uin
 
 enum : int { PH_FETCH = 0, PH_BLOCK = 1, PH_CODES = 2, PH_EXIT = 3 };
 
-template <int G, bool STORE>
+template <int G, bool STORE, bool MARK = false>
 struct Decoder {
     GroupSmem* S;
     uint16_t* gsorted;                 // global scratch: sorted symbols of the current block
@@ -496,6 +501,8 @@ struct Decoder {
 
     // ---- output
     uint8_t* out;
+    uint16_t* out16;                   // marker mode
+    uint64_t abs_start;                // marker mode: absolute stream offset of the block being decoded
     uint32_t pos, cap;
     const uint8_t* dict_tail;
     int D;
@@ -609,6 +616,32 @@ struct Decoder {
     // L2 / DRAM round trip of the window read overlaps the decode of the following symbols instead
     // of stalling the lockstep warp.  Each lane reads back only what it staged itself: no
     // cross-lane synchronisation is needed at commit time.
+    __device__ __forceinline__ void store_lit(uint32_t v)
+    {
+        if (STORE) {
+            if (glane == 0) { if (MARK) out16[pos] = (uint16_t)v; else out[pos] = (uint8_t)v; }
+        }
+    }
+
+    // marker mode: the block is decoded without its 32 KiB window.  A source position before the block
+    // start becomes the symbol 256 + (index into the window that ends at the block start); symbols are
+    // copied like bytes otherwise (they may themselves be markers).  Before the start of the whole
+    // stream the reference's window holds zeros.
+    __device__ __forceinline__ void copy_match_marked(uint32_t len, uint32_t dist)
+    {
+        __syncwarp(gmask);
+        uint16_t* dst = out16 + pos;
+        for (uint32_t i = glane; i < len; i += G) {
+            const uint32_t k = dist >= len ? i : i % dist;
+            const int64_t s = (int64_t)pos + (int64_t)k - (int64_t)dist;          // relative to the block start
+            uint16_t v;
+            if (s >= 0) v = out16[s];
+            else if ((int64_t)abs_start + s < 0) v = 0;
+            else v = (uint16_t)(256 + 32768 + s);
+            dst[i] = v;
+        }
+    }
+
     // bytes of a deferred match each lane moves, and the aligned words it stages for them
     static constexpr int DB = G <= MAX_G_DEFERRED ? 16 / G : 4;
     static constexpr int DW = DB / 4 + 1;
@@ -638,7 +671,7 @@ struct Decoder {
     // complete both pending matches (end of stream, or a copy that may read their bytes)
     __device__ __forceinline__ void flush_pending()
     {
-        if (STORE && G <= MAX_G_DEFERRED) {
+        if (STORE && !MARK && G <= MAX_G_DEFERRED) {
             cp_async_wait_all();
             commit_slot(o_dst, o_meta, ptog);
             commit_slot(n_dst, n_meta, ptog ^ 1u);
@@ -653,7 +686,9 @@ struct Decoder {
     __device__ __forceinline__ int copy_match(uint32_t len, uint32_t dist, bool lit_now)
     {
         if (len > cap - pos) return R_OUTFULL;
-        if (STORE) {
+        if (MARK) {
+            copy_match_marked(len, dist);
+        } else if (STORE) {
             const bool simple = G <= MAX_G_DEFERRED && dist >= len && len <= 16u && dist <= pos;
             // the new source must not overlap bytes that are still pending (the older pending match has
             // the lower destination); copies on the synchronous path read arbitrary earlier bytes
@@ -790,7 +825,7 @@ struct Decoder {
         bb >>= n; bc -= (int)n;
         if (p < 256) {
             if (pos >= cap) return R_OUTFULL;
-            if (STORE) { if (glane == 0) out[pos] = (uint8_t)p; }
+            store_lit(p);
             pos++;
             return R_OK;
         }
@@ -855,7 +890,7 @@ struct Decoder {
             if ((e0 >> 12) == 0 || (e0 & 0xfffu) >= 256u) break;
             const uint32_t n0 = e0 >> 12;
             bb >>= n0; bc -= (int)n0;
-            if (STORE) { if (glane == 0) out[pos] = (uint8_t)e0; }
+            store_lit(e0 & 0xffu);
             pos++;
             lit_now = true;
         }
@@ -886,7 +921,7 @@ struct Decoder {
         bb >>= n; bc -= (int)n;
         if (p < 256) {
             if (pos >= cap) return R_OUTFULL;
-            if (STORE) { if (glane == 0) out[pos] = (uint8_t)p; }
+            store_lit(p);
             pos++;
             return R_OK;
         }
@@ -931,8 +966,8 @@ struct Decoder {
         if (copied > cap - pos) return R_OUTFULL;
         if (STORE) {
             const uint8_t* src = gsrc + start;
-            uint8_t* dst = out + pos;
-            for (uint32_t i = glane; i < copied; i += G) dst[i] = src[i];
+            if (MARK) { uint16_t* dst = out16 + pos; for (uint32_t i = glane; i < copied; i += G) dst[i] = src[i]; }
+            else { uint8_t* dst = out + pos; for (uint32_t i = glane; i < copied; i += G) dst[i] = src[i]; }
         }
         pos += copied;
         seek(start + copied);
@@ -942,6 +977,54 @@ struct Decoder {
     // ------------------------------------------------------------------ phase machine
     // PH_FETCH: take the next stream, parse its container header (src/inflate.ts:142-401,
     // byte by byte from global memory) and position the bit reader on the first block.
+    // block-task mode: work item i = the deflate block of stream 0 that starts at bit task_bit[i]
+    __device__ __forceinline__ void fetch_task(const InflateParams& P, unsigned long long i)
+    {
+        in_len = P.in_len[0];
+        gsrc = P.in + P.in_off[0];
+        end_wp = (in_len + 3) / 4;
+        total_chunks = (in_len + CH - 1) / CH;
+        out = nullptr; out_off = 0;
+        abs_start = MARK ? P.task_out[i] : 0;
+        out16 = MARK ? P.out16 + abs_start : nullptr;
+        pos = 0; cap = 0xffffffffu;
+        msg = SDZ_MSG_NONE; stall_kind = ST_NONE;
+        D = 0; dict_tail = nullptr;
+        lbits = dbits = g_l = g_d = 0; eob_len = 0;
+        ring.init(0);
+        o_dst = o_meta = n_dst = n_meta = 0;
+        is_gzip = false; method = 0; n_blocks = 0; mtime = 0; name_off = 0; name_len = 0; last = 0; raw = true;
+        const uint64_t sb = P.task_bit[i];
+        if ((sb >> 3) >= (uint64_t)in_len) { finish_task(P, R_STALL); return; }
+        seek((uint32_t)(sb >> 3));
+        const int skip = (int)(sb & 7);
+        if (bc < skip) { finish_task(P, R_STALL); return; }
+        drop(skip);
+        phase = PH_BLOCK;
+    }
+
+    // record of one block task: out_len = symbols produced, total_in = bit position after the block,
+    // zstatus = R_EOB (block complete) / R_STALL / R_ERROR, n_blocks = BFINAL, container = BTYPE
+    __device__ __forceinline__ void finish_task(const InflateParams& P, int r)
+    {
+        flush_pending();
+        const uint64_t endbit = bit_pos();
+        drain();
+        __syncwarp(gmask);
+        if (glane == 0) {
+            sdz_result R;
+            memset(&R, 0, sizeof R);
+            R.out_len = pos;
+            R.total_in = endbit;
+            R.zstatus = r;
+            R.n_blocks = (uint32_t)last;
+            R.msg_id = (uint8_t)msg;
+            R.container = (uint8_t)method;
+            P.res[idx] = R;
+        }
+        phase = PH_FETCH;
+    }
+
     __device__ __forceinline__ void fetch(const InflateParams& P)
     {
         unsigned long long i = 0;
@@ -949,6 +1032,7 @@ struct Decoder {
         i = __shfl_sync(gmask, i, 0, G);
         if (i >= P.n) { phase = PH_EXIT; return; }
         idx = i;
+        if (P.task_bit) { fetch_task(P, i); return; }
         in_len = P.in_len[i];
         const uint8_t mode_raw = P.mode[i];
         const int mode = mode_raw & 0x7f;
@@ -1084,6 +1168,7 @@ struct Decoder {
     // The stream stops here: r = R_EOB (final block complete), R_STALL, R_ERROR or R_OUTFULL.
     __device__ __forceinline__ void finish_stream(const InflateParams& P, int r)
     {
+        if (P.task_bit) { finish_task(P, r); return; }
         int thrown = SDZ_THROW_NONE, zstatus = SDZ_Z_OK;
         bool done = false;
         int32_t stored = 0, isize = 0;
@@ -1141,6 +1226,7 @@ struct Decoder {
         n_blocks++;
         start_pos = pos;
         const uint32_t type = t >> 1;
+        if (P.task_bit) method = (int)type;                             // block-task records carry BTYPE
         int r;
         if (type == 0) {
             drop(bc & 7);
@@ -1150,6 +1236,7 @@ struct Decoder {
             drop(32);
             r = stored_block(v & 0xffff);
             if (r != R_OK) { finish_stream(P, r); return; }
+            if (P.task_bit) { finish_task(P, R_EOB); return; }
             if (last) { ring.wash(); finish_stream(P, R_EOB); }
             return;                                                     // next block: stays in PH_BLOCK
         }
@@ -1176,6 +1263,7 @@ struct Decoder {
     // a step() returned something other than R_OK
     __device__ __forceinline__ void block_end(const InflateParams& P, int r)
     {
+        if (P.task_bit) { finish_task(P, r); return; }
         ring.write(pos - start_pos);
         if (r != R_EOB) { if (r == R_STALL) stall_kind = ST_OTHER; finish_stream(P, r); return; }
         // End of block.  When inflate_fast() decodes the EOB its STREAM_END status leaks through
@@ -1203,14 +1291,14 @@ struct Decoder {
 // lockstep (they re-converge at the ballot after every symbol), so one instruction stream
 // serves 32 / G streams.  Block headers, table builds and stream changes are serviced between
 // lockstep runs while the other groups of the warp wait.
-template <int G, bool STORE>
+template <int G, bool STORE, bool MARK = false>
 __global__ void __launch_bounds__(128, SDZ_MINBLOCKS) inflate_kernel(InflateParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int gid = threadIdx.x / G;
     GroupSmem* S = reinterpret_cast<GroupSmem*>(smem_raw) + gid;
 
-    Decoder<G, STORE> d;
+    Decoder<G, STORE, MARK> d;
     d.S = S;
     d.gsorted = P.scratch + ((size_t)blockIdx.x * (blockDim.x / G) + gid) * SCRATCH_U16;
     d.glane = threadIdx.x % G;

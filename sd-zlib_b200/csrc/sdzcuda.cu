@@ -14,6 +14,7 @@
 
 #include "checksum_kernels.cuh"
 #include "inflate_kernel.cuh"
+#include "large_kernels.cuh"
 
 namespace {
 
@@ -35,7 +36,7 @@ struct sdz_ctx {
     uint64_t launches = 0;
     float last_ms[3] = { 0, 0, 0 };
     // grow-only scratch
-    DevBuf d_in, d_out, d_meta, d_res, d_part, d_misc;
+    DevBuf d_in, d_out, d_meta, d_res, d_part, d_misc, d_sym, d_task;
     void* h_stage = nullptr;           // pinned
     size_t h_stage_cap = 0;
     unsigned long long* d_counter = nullptr;
@@ -118,13 +119,13 @@ int upload_tables(sdz_ctx* ctx)
     return SDZ_OK;
 }
 
-template <int G, bool STORE>
+template <int G, bool STORE, bool MARK = false>
 int launch_inflate_t(sdz_ctx* ctx, const sdz::InflateParams& P)
 {
     const int threads = ctx->block_threads;
     const int groups = threads / G;
     const size_t smem = (size_t)groups * sizeof(sdz::GroupSmem);
-    auto kern = sdz::inflate_kernel<G, STORE>;
+    auto kern = sdz::inflate_kernel<G, STORE, MARK>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
@@ -175,6 +176,7 @@ int run_batch_device(sdz_ctx* ctx, const sdz_batch_dev* b, bool sizes_only, bool
     P.dict = b->d_dict; P.dict_off = b->d_dict_off; P.dict_len = b->d_dict_len; P.dict_adler = b->d_dict_adler;
     P.out = sizes_only ? nullptr : b->d_out; P.out_off = b->d_out_off; P.out_cap = b->d_out_cap;
     P.res = b->d_results; P.n = b->n; P.counter = ctx->d_counter; P.scratch = nullptr;
+    P.task_bit = nullptr; P.task_out = nullptr; P.out16 = nullptr;
     if (first) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     int rc = sizes_only ? launch_inflate<false>(ctx, P) : launch_inflate<true>(ctx, P);
     if (rc) return rc;
@@ -255,7 +257,7 @@ void sdz_ctx_destroy(sdz_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    for (DevBuf* b : { &ctx->d_in, &ctx->d_out, &ctx->d_meta, &ctx->d_res, &ctx->d_part, &ctx->d_misc })
+    for (DevBuf* b : { &ctx->d_in, &ctx->d_out, &ctx->d_meta, &ctx->d_res, &ctx->d_part, &ctx->d_misc, &ctx->d_sym, &ctx->d_task })
         if (b->p) cudaFree(b->p);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
@@ -692,3 +694,276 @@ int sdz_inflate_sizes(sdz_ctx* ctx, const sdz_in* in, uint64_t n, uint64_t* out_
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------- one large stream
+
+namespace {
+
+// block-task launch: n tasks over stream 0 = [d_src, d_src + len)
+template <bool STORE, bool MARK>
+int launch_tasks(sdz_ctx* ctx, const uint8_t* d_src, uint32_t len, const uint64_t* d_task_bit, const uint64_t* d_task_out,
+                 uint16_t* d_sym, sdz_result* d_res, uint64_t n, const uint64_t* d_zero_off, const uint32_t* d_len0)
+{
+    sdz::InflateParams P;
+    memset(&P, 0, sizeof P);
+    P.in = d_src; P.in_off = d_zero_off; P.in_len = d_len0;
+    P.res = d_res; P.n = n; P.counter = ctx->d_counter;
+    P.task_bit = d_task_bit; P.task_out = d_task_out; P.out16 = d_sym;
+    (void)len;
+    return launch_inflate_t<4, STORE, MARK>(ctx, P);
+}
+
+}  // namespace
+
+extern "C" int sdz_inflate_large(sdz_ctx* ctx, const uint8_t* data, uint64_t len, uint8_t mode, int on_device,
+                                 uint8_t* out, uint64_t out_cap, sdz_result* res)
+{
+    if (!ctx || !res || (len && !data) || mode > SDZ_MODE_RAW) return SDZ_E_ARG;
+    if (len >= (1ull << 32) - 64) return SDZ_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    memset(res, 0, sizeof *res);
+
+    auto fallback = [&]() -> int {
+        // exact but sequential: the ordinary decoder, one group for the whole stream
+        if (on_device) { ctx->err = "sdz_inflate_large: stream needs the sequential decoder; pass host pointers"; return SDZ_E_UNSUPPORTED; }
+        sdz_in in1;
+        memset(&in1, 0, sizeof in1);
+        in1.data = data; in1.len = len; in1.mode = mode;
+        uint64_t need = 0;
+        int rc = inflate_host(ctx, &in1, 1, nullptr, nullptr, nullptr, nullptr, &need, 0, true);
+        if (rc) return rc;
+        if (need > out_cap) { res->out_len = need; return SDZ_E_OUT_CAP; }
+        uint64_t off0 = 0, cap0 = need;
+        return inflate_host(ctx, &in1, 1, out, &off0, &cap0, res, nullptr, 0, false);
+    };
+
+    // ---- container header on the host (a few bytes; src/inflate.ts:142-401)
+    uint8_t head[1024];
+    const size_t hn = (size_t)std::min<uint64_t>(len, sizeof head);
+    if (on_device) CK(cudaMemcpy(head, data, hn, cudaMemcpyDeviceToHost)); else memcpy(head, data, hn);
+    bool raw = mode == SDZ_MODE_RAW, is_gzip = false;
+    int method = 0;
+    int32_t mtime = 0;
+    uint32_t name_off = 0, name_len = 0;
+    size_t hp = 0;
+    if (mode == SDZ_MODE_SNIFF) {
+        if (len < 2) return fallback();
+        const bool ident = (head[0] == 0x78 && (((head[0] << 8) + head[1]) % 31) == 0) || (head[0] == 0x1f && head[1] == 0x8b);
+        raw = !ident;
+    }
+    if (!raw) {
+        if (hn < 2) return fallback();
+        if (head[0] == 0x1f) {
+            if (head[1] != 0x8b || hn < 10 || (head[2] & 0xf) != 8 || (head[2] >> 4) + 8 > 15) return fallback();
+            is_gzip = true; method = head[2];
+            const uint8_t fl = head[3];
+            for (int i = 0; i < 4; i++) mtime = (int32_t)(((uint32_t)mtime >> 8) | ((uint32_t)head[4 + i] << 24));
+            hp = 10;
+            if (fl & 4) return fallback();                                  // FEXTRA
+            if (fl & 8) { name_off = (uint32_t)hp; while (hp < hn && head[hp]) { hp++; name_len++; } if (hp >= hn) return fallback(); hp++; }
+            if (fl & 16) { while (hp < hn && head[hp]) hp++; if (hp >= hn) return fallback(); hp++; }
+            if (fl & 2) hp += 2;
+            if (hp >= hn) return fallback();
+        } else {
+            method = head[0];
+            if ((method & 0xf) != 8 || (method >> 4) + 8 > 15 || ((method << 8) + head[1]) % 31 != 0 || (head[1] & 0x20)) return fallback();
+            hp = 2;
+        }
+    }
+
+    // ---- stage the input
+    int rc;
+    const uint8_t* d_src = data;
+    if (!on_device) {
+        if ((rc = grow(ctx, ctx->d_in, len + SDZ_IN_PAD))) return rc;
+        CK(cudaMemcpyAsync(ctx->d_in.p, data, len, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync((uint8_t*)ctx->d_in.p + len, 0, SDZ_IN_PAD, ctx->stream));
+        d_src = (const uint8_t*)ctx->d_in.p;
+    } else if (reinterpret_cast<uintptr_t>(data) & 15) return SDZ_E_ARG;
+
+    // ---- pass 1a: candidate dynamic-block headers
+    const uint64_t first_bit = (uint64_t)hp * 8, total_bits = len * 8;
+    const uint64_t max_cand = len / 512 + 4096;
+    if ((rc = grow(ctx, ctx->d_task, (max_cand * 2 + 16) * sizeof(uint64_t)))) return rc;
+    uint64_t* d_cand = (uint64_t*)ctx->d_task.p;
+    CK(cudaMemsetAsync(ctx->d_counter + 2, 0, sizeof(unsigned long long), ctx->stream));
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    {
+        const unsigned grid = (unsigned)std::min<uint64_t>(((total_bits - first_bit) + 127) / 128, (uint64_t)ctx->sm_count * 16);
+        sdz::find_dynamic_headers<<<grid, 128, 0, ctx->stream>>>(d_src, first_bit, total_bits, d_cand, ctx->d_counter + 2, max_cand);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    unsigned long long n_cand = 0;
+    CK(cudaMemcpyAsync(&n_cand, ctx->d_counter + 2, sizeof n_cand, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (n_cand > max_cand) return fallback();
+    std::vector<uint64_t> cand(n_cand + 1);
+    if (n_cand) CK(cudaMemcpy(cand.data(), d_cand, n_cand * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    cand[n_cand] = first_bit;                                               // the first block, whatever its type
+    std::sort(cand.begin(), cand.end());
+    cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
+
+    // stream-0 descriptors for the task launches: in_off[0] = 0, in_len[0] = len
+    if ((rc = grow(ctx, ctx->d_meta, 64))) return rc;
+    {
+        uint64_t zero_off = 0;
+        uint32_t len32 = (uint32_t)len;
+        CK(cudaMemcpyAsync(ctx->d_meta.p, &zero_off, 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync((uint8_t*)ctx->d_meta.p + 8, &len32, 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const uint64_t* d_zero_off = (const uint64_t*)ctx->d_meta.p;
+    const uint32_t* d_len0 = (const uint32_t*)((uint8_t*)ctx->d_meta.p + 8);
+
+    // ---- pass 1b: extent of every candidate block (count-only decode of ONE block each)
+    auto extents = [&](const std::vector<uint64_t>& starts, std::vector<sdz_result>& recs) -> int {
+        const uint64_t n = starts.size();
+        int r2;
+        if ((r2 = grow(ctx, ctx->d_task, (n * 2 + 16) * sizeof(uint64_t)))) return r2;
+        if ((r2 = grow(ctx, ctx->d_res, n * sizeof(sdz_result)))) return r2;
+        CK(cudaMemcpyAsync(ctx->d_task.p, starts.data(), n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        r2 = launch_tasks<false, false>(ctx, d_src, (uint32_t)len, (const uint64_t*)ctx->d_task.p, nullptr, nullptr,
+                                        (sdz_result*)ctx->d_res.p, n, d_zero_off, d_len0);
+        if (r2) return r2;
+        recs.resize(n);
+        CK(cudaMemcpyAsync(recs.data(), ctx->d_res.p, n * sizeof(sdz_result), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return SDZ_OK;
+    };
+    std::vector<sdz_result> ext;
+    if ((rc = extents(cand, ext))) return rc;
+
+    // ---- chain of real blocks from the first one
+    std::vector<uint64_t> blk_bit, blk_off;
+    uint64_t cur = first_bit, total_out = 0, end_bit = 0;
+    bool finished = false;
+    for (uint64_t guard = 0; guard < (1ull << 26); guard++) {
+        auto it = std::lower_bound(cand.begin(), cand.end(), cur);
+        sdz_result rec;
+        if (it != cand.end() && *it == cur) rec = ext[it - cand.begin()];
+        else {
+            // a block the header search does not look for (stored / fixed): measure it on its own
+            std::vector<uint64_t> one{ cur };
+            std::vector<sdz_result> r1;
+            if ((rc = extents(one, r1))) return rc;
+            rec = r1[0];
+        }
+        if (rec.zstatus != sdz::R_EOB) return fallback();                   // truncated or damaged: exact sequential path
+        // a stored block's copy depends on where the reference's 16 KiB output chunks fall,
+        // which only the sequential decoder tracks
+        if (rec.container == 0) return fallback();
+        blk_bit.push_back(cur);
+        blk_off.push_back(total_out);
+        total_out += rec.out_len;
+        cur = rec.total_in;
+        if (rec.n_blocks) { finished = true; end_bit = cur; break; }
+    }
+    if (!finished) return fallback();
+    blk_off.push_back(total_out);
+    const uint64_t nb = blk_bit.size();
+    if (total_out > out_cap) { res->out_len = total_out; return SDZ_E_OUT_CAP; }
+
+    // ---- trailer (src/inflate.ts:423-463)
+    uint64_t tp = (end_bit + 7) >> 3;
+    uint8_t tail[8] = { 0 };
+    const int want = raw ? 0 : (is_gzip ? 8 : 4);
+    const int have = (int)std::min<uint64_t>((uint64_t)want, len - std::min(len, tp));
+    if (have) { if (on_device) CK(cudaMemcpy(tail, data + tp, have, cudaMemcpyDeviceToHost)); else memcpy(tail, data + tp, have); }
+    if (have < want || tp + want < len) return fallback();                  // truncated trailer / trailing bytes: exact path
+    int32_t stored = 0, isize = 0;
+    for (int i = 0; i < want; i++) {
+        const uint32_t b = tail[i];
+        if (is_gzip) { if (i < 4) stored = (int32_t)(((uint32_t)stored >> 8) | (b << 24)); else isize = (int32_t)(((uint32_t)isize >> 8) | (b << 24)); }
+        else stored = (int32_t)(((uint32_t)stored << 8) | b);
+    }
+
+    // ---- pass 2a: every block into 16-bit symbols
+    if ((rc = grow(ctx, ctx->d_sym, (total_out + 64) * 2))) return rc;
+    if ((rc = grow(ctx, ctx->d_task, (nb * 2 + 16) * sizeof(uint64_t) + (nb + 1) * 8))) return rc;
+    if ((rc = grow(ctx, ctx->d_res, nb * sizeof(sdz_result)))) return rc;
+    uint64_t* d_tb = (uint64_t*)ctx->d_task.p;
+    uint64_t* d_to = d_tb + nb;
+    CK(cudaMemcpyAsync(d_tb, blk_bit.data(), nb * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_to, blk_off.data(), (nb + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    rc = launch_tasks<true, true>(ctx, d_src, (uint32_t)len, d_tb, d_to, (uint16_t*)ctx->d_sym.p, (sdz_result*)ctx->d_res.p, nb,
+                                  d_zero_off, d_len0);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+
+    // ---- pass 2b / 2c: windows, then everything else
+    uint8_t* d_o = out;
+    if (!on_device) {
+        if ((rc = grow(ctx, ctx->d_out, total_out + 64))) return rc;
+        d_o = (uint8_t*)ctx->d_out.p;
+    }
+    {
+        uint64_t bps = 1;
+        while (bps * bps < nb) bps++;                                       // ~sqrt(nb) blocks per segment
+        const unsigned nseg = (unsigned)((nb + bps - 1) / bps);
+        sdz::propagate_in_segment<<<nseg, 1024, 0, ctx->stream>>>((uint16_t*)ctx->d_sym.p, d_to, nb, bps);
+        sdz::propagate_segments<<<1, 1024, 0, ctx->stream>>>((const uint16_t*)ctx->d_sym.p, d_o, d_to, nb, bps);
+        const unsigned gy = (unsigned)std::min<uint64_t>(nb, 65535);
+        sdz::resolve_markers<<<dim3(8, gy), 256, 0, ctx->stream>>>((const uint16_t*)ctx->d_sym.p, d_o, d_to, nb, bps);
+    }
+    ctx->launches += 3;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+
+    // the marker pass must have reproduced the extents
+    std::vector<sdz_result> chk(nb);
+    CK(cudaMemcpyAsync(chk.data(), ctx->d_res.p, nb * sizeof(sdz_result), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms_keep[3];
+    cudaEventElapsedTime(&ms_keep[0], ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ms_keep[1], ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ms_keep[2], ctx->ev[0], ctx->ev[2]);
+    for (uint64_t b = 0; b < nb; b++)
+        if (chk[b].zstatus != sdz::R_EOB || chk[b].out_len != blk_off[b + 1] - blk_off[b]) return fallback();
+
+    // ---- running checksum as append() computes it over its 16 KiB chunks (src/sd-inflate.ts:133-149)
+    int32_t running = 0;
+    const bool have_running = total_out > 0;
+    if (have_running) {
+        std::vector<uint64_t> segs;
+        uint64_t rem = total_out;
+        const uint64_t last = rem % 16384 ? rem % 16384 : 16384;
+        rem -= last;
+        while (rem >= (1ull << 30)) { segs.push_back(1ull << 30); rem -= 1ull << 30; }        // 2^30 is not a multiple of 5552
+        if (rem) {
+            if ((rem / 16384) % 347 == 0) { segs.push_back(rem - 16384); segs.push_back(16384); }  // never merge into a multiple of 5552 (Q1)
+            else segs.push_back(rem);
+        }
+        segs.push_back(last);
+        segs.erase(std::remove(segs.begin(), segs.end(), 0ull), segs.end());
+        rc = checksum_chain(ctx, is_gzip, d_o, segs.data(), segs.size(), is_gzip ? 0 : 1, 1, nullptr, &running);
+        if (rc) return rc;
+    }
+    ctx->last_ms[0] = ms_keep[0]; ctx->last_ms[1] = ms_keep[1]; ctx->last_ms[2] = ms_keep[2];
+    if (!on_device && total_out) {
+        CK(cudaMemcpyAsync(out, d_o, total_out, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+
+    // ---- finish() record (src/sd-inflate.ts:159-179) and inflate()'s throw mapping (:214-225)
+    res->out_off = 0;
+    res->out_len = total_out;
+    res->total_in = tp + want;
+    res->zstatus = SDZ_Z_STREAM_END;
+    res->stored_checksum = stored;
+    res->running_checksum = have_running ? running : 0;
+    res->have_running = have_running;
+    res->stored_isize = isize;
+    res->mtime = mtime;
+    res->name_off = name_len ? name_off : 0;
+    res->name_len = name_len;
+    res->n_blocks = (uint32_t)nb;
+    res->container = (uint8_t)(is_gzip ? SDZ_GZIP : (method == 0 ? SDZ_RAW : SDZ_ZLIB));
+    res->complete = 1;
+    const int cks = stored == 0 ? SDZ_UNCHECKED : ((have_running && stored == running) ? SDZ_MATCH : SDZ_MISMATCH);
+    const int fsz = isize == 0 ? SDZ_UNCHECKED : (((int64_t)isize == (int64_t)total_out) ? SDZ_MATCH : SDZ_MISMATCH);
+    res->checksum_state = (uint8_t)cks;
+    res->size_state = (uint8_t)fsz;
+    res->success = (uint8_t)(cks != SDZ_MISMATCH && fsz != SDZ_MISMATCH);
+    res->thrown_inflate = (uint8_t)(res->success ? SDZ_THROW_NONE : (cks == SDZ_MISMATCH ? SDZ_THROW_INTEGRITY : SDZ_THROW_SIZE_CHECK));
+    return SDZ_OK;
+}

@@ -16,8 +16,8 @@ mirror is Python.  The TypeScript facade + N-API shim a maintainer would ship ar
 sd-zlib_b200/ts/ and INTEGRATION.md.)
 """
 from .api import (InflateResult, Inflater, adler32, adler32_chain, checksum_batch, crc32, crc32_chain, inflate, inflateBatch,
-                  inflate_batch_raw, mergeBuffers)
+                  inflateLarge, inflate_batch_raw, inflate_large_raw, mergeBuffers)
 from ._native import Context, NativeError, default_context
 
 __all__ = ["adler32", "crc32", "adler32_chain", "crc32_chain", "checksum_batch", "inflate", "Inflater", "InflateResult", "inflateBatch",
-           "inflate_batch_raw", "mergeBuffers", "Context", "NativeError", "default_context"]
+           "inflateLarge", "inflate_batch_raw", "inflate_large_raw", "mergeBuffers", "Context", "NativeError", "default_context"]

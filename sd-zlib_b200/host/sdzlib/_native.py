@@ -17,7 +17,7 @@ EXPORTS = [
     "sdz_ctx_create", "sdz_ctx_destroy", "sdz_last_error", "sdz_version", "sdz_launch_count", "sdz_last_timing",
     "sdz_host_alloc", "sdz_host_free", "sdz_device_alloc", "sdz_device_free", "sdz_memcpy_h2d", "sdz_memcpy_d2h",
     "sdz_adler32", "sdz_crc32", "sdz_adler32_chain", "sdz_crc32_chain", "sdz_checksum_batch",
-    "sdz_inflate_batch", "sdz_inflate_sizes", "sdz_inflate_batch_device", "sdz_sync",
+    "sdz_inflate_batch", "sdz_inflate_sizes", "sdz_inflate_batch_device", "sdz_inflate_large", "sdz_sync",
 ]
 
 
@@ -104,6 +104,7 @@ def load():
         L.sdz_inflate_batch.argtypes = [vp, vp, u64, vp, vp, vp, vp, u32]
         L.sdz_inflate_sizes.argtypes = [vp, vp, u64, vp, u32]
         L.sdz_inflate_batch_device.argtypes = [vp, C.POINTER(BatchDev), u32, C.c_int]
+        L.sdz_inflate_large.argtypes = [vp, vp, u64, C.c_uint8, C.c_int, vp, u64, C.POINTER(Result)]
         _lib = L
         return L
 

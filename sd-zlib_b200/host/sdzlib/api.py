@@ -199,6 +199,37 @@ def inflateBatch(buffers, dictionaries=None, raw=None, ctx=None):
     return out
 
 
+def inflate_large_raw(view, mode=MODE_SNIFF, cap=None, ctx=None):
+    """One sdz_inflate_large call (a single big stream spread over the whole GPU).
+    Returns (out: np.uint8[], record)."""
+    ctx = ctx or N.default_context()
+    res = N.Result()
+    if cap is None:
+        rc = ctx.check(ctx.lib.sdz_inflate_large(ctx.h, view.ctypes.data, int(view.size), mode, 0, None, 0, C.byref(res)),
+                       allow=(N.SDZ_E_OUT_CAP,))
+        if rc == N.SDZ_OK:                      # empty output (or a stream that failed before producing anything)
+            return np.empty(0, dtype=np.uint8), res
+        cap = int(res.out_len)
+    out = np.empty(max(int(cap), 1), dtype=np.uint8)
+    ctx.check(ctx.lib.sdz_inflate_large(ctx.h, view.ctypes.data, int(view.size), mode, 0, out.ctypes.data, int(cap), C.byref(res)),
+              allow=(N.SDZ_E_OUT_CAP,))
+    return out, res
+
+
+def inflateLarge(data, raw=None, ctx=None):
+    """`new Inflater({raw}).append(data); finish()` for ONE large stream, decoded block-parallel.
+    Returns {data, result, error, record} like an element of inflateBatch()."""
+    view = _as_u8(data, "data must be an ArrayBuffer or buffer view")
+    mode = MODE_SNIFF if raw is None else (MODE_RAW if raw else MODE_INFLATER)
+    out, r = inflate_large_raw(view, mode, None, ctx)
+    thrown = r.thrown_inflate if mode == MODE_SNIFF else r.thrown_append
+    err = None
+    if thrown:
+        err = _THROWN[thrown] + (_MSG[r.msg_id] if thrown == 4 else "")
+    body = bytes(out[:int(r.out_len)]) if (r.out_len and not r.thrown_append) else b""
+    return {"data": body, "result": _record_to_result(r, view), "error": err, "record": r}
+
+
 def inflate(data, dictionary=None, ctx=None) -> bytes:
     """inflate(data, dictionary?) - src/sd-inflate.ts:189-228 (auto-detects the container)."""
     view = _as_u8(data, "data must be an ArrayBuffer or buffer view")

@@ -383,3 +383,83 @@ def test_mixed_kind_stress_roundtrip():
         r = res[i]
         assert r.success and r.out_len == p.size, (i, r.observable())
         assert np.array_equal(arena[int(off[i]):int(off[i]) + p.size], p), i
+
+
+# ---------------------------------------------------------------- one large stream (config 5)
+
+def _large_plain(kind, mib, first_index):
+    return np.concatenate([K.generate(kind, first_index + i, 65536) for i in range(mib * 16)])
+
+
+def _check_large(stream, mode, plain=None):
+    view = np.frombuffer(stream, dtype=np.uint8)
+    out, r = A.inflate_large_raw(view, mode)
+    exp_bytes, exp = O.inflate_oneshot(stream, mode=mode)
+    go, eo = r.observable(), exp.observable()
+    assert go == eo, {k: (go.get(k), eo.get(k)) for k in set(go) | set(eo) if go.get(k) != eo.get(k)}
+    if not exp.thrown_append:
+        got = out[:int(r.out_len)]
+        assert got.size == len(exp_bytes)
+        assert np.array_equal(got, np.frombuffer(exp_bytes, dtype=np.uint8))
+    if plain is not None:
+        assert np.array_equal(out[:int(r.out_len)], plain)
+    return r
+
+
+@pytest.mark.parametrize("container", ["gzip", "zlib", "raw"])
+def test_large_stream_block_parallel(container):
+    """One 24 MiB stream (several hundred deflate blocks) through sdz_inflate_large: identical bytes and
+    record to the oracle's one-shot Inflater."""
+    plain = _large_plain(K.TEXT, 24, 7000)
+    if container == "gzip":
+        s = gzip.compress(plain.tobytes(), 6, mtime=1234567)
+        mode = O.MODE_SNIFF
+    elif container == "zlib":
+        s = zlib.compress(plain.tobytes(), 6)
+        mode = O.MODE_INFLATER
+    else:
+        s = raw_deflate(plain.tobytes(), 6)
+        mode = O.MODE_RAW
+    ctx = sdzlib.default_context()
+    before = ctx.launch_count()
+    r = _check_large(s, mode, plain)
+    assert r.n_blocks > 100                      # took the block-parallel path, not the sequential hand-over
+    assert ctx.launch_count() - before >= 6
+
+
+def test_large_stream_kinds_levels_and_flush_points():
+    """Binary / run-heavy data, levels 1 and 9, sync-flush points (empty stored blocks -> sequential
+    hand-over) and a multi-member-looking tail all give the oracle's record."""
+    cases = []
+    cases.append((zlib.compress(_large_plain(K.BINARY, 6, 100).tobytes(), 9), O.MODE_INFLATER))
+    cases.append((zlib.compress(_large_plain(K.RUNS, 8, 200).tobytes(), 1), O.MODE_SNIFF))
+    cases.append((gzip.compress(_large_plain(K.RANDOM, 2, 300).tobytes(), 6, mtime=0), O.MODE_SNIFF))   # stored blocks
+    co = zlib.compressobj(6)
+    p = _large_plain(K.TEXT, 2, 400).tobytes()
+    cases.append((co.compress(p[:700000]) + co.flush(zlib.Z_SYNC_FLUSH) + co.compress(p[700000:]) + co.flush(), O.MODE_SNIFF))
+    cases.append((gzip.compress(p, 6, mtime=5)[:-9], O.MODE_SNIFF))                                    # truncated trailer
+    cases.append((zlib.compress(p, 6)[:300000], O.MODE_SNIFF))                                         # truncated body
+    bad = bytearray(zlib.compress(p, 6))
+    bad[len(bad) // 2] ^= 0x55
+    cases.append((bytes(bad), O.MODE_SNIFF))                                                           # damaged body
+    bad2 = bytearray(gzip.compress(p, 6, mtime=9))
+    bad2[-6] ^= 1
+    cases.append((bytes(bad2), O.MODE_SNIFF))                                                          # wrong CRC
+    for s, m in cases:
+        _check_large(s, m)
+
+
+def test_large_stream_far_references_and_small_blocks():
+    """Windows that span many tiny blocks (Z_FULL_FLUSH is avoided: it emits stored blocks; level-1 output
+    of short period data has long chains of window references across block boundaries)."""
+    rng = np.random.default_rng(11)
+    base = rng.integers(0, 256, 30000, dtype=np.uint8)
+    parts = []
+    for i in range(400):
+        b = base.copy()
+        idx = rng.integers(0, b.size, 40)
+        b[idx] = rng.integers(0, 256, 40, dtype=np.uint8)
+        parts.append(b)
+    plain = np.concatenate(parts)                                   # every byte is (transitively) a ~30 KB-far copy
+    for level in (1, 6):
+        _check_large(zlib.compress(plain.tobytes(), level), O.MODE_SNIFF, plain)
