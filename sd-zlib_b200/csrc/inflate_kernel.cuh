@@ -72,14 +72,33 @@ struct InflateParams {
     const uint32_t* out_cap;
     sdz_result* res;
     uint16_t* scratch;                 // SCRATCH_U16 entries per group of the grid
-    // block-task mode (large single stream, sdz_inflate_large): every work item is ONE deflate block of
-    // stream 0 that starts at bit task_bit[i]; in marker mode its symbols go to out16 + task_out[i]
-    const uint64_t* task_bit;          // nullptr: ordinary stream mode
-    const uint64_t* task_out;          // absolute output offset of each block (marker mode)
-    uint16_t* out16;                   // marker-mode output: byte value, or 256 + index into the 32 KiB window before the block
+    // block-task modes (large single stream, sdz_inflate_large): every work item is (a piece of) ONE
+    // deflate block of stream 0 whose header starts at bit task_bit[i].
+    //   TM_INDEX  count-only walk of the whole block; every `ckpt_step` output bytes a resume point
+    //             (bit position, output position) is appended to ckpt[]
+    //   TM_MARK   decode from the block header (task_resume[i] == 0) or from a resume point, for exactly
+    //             task_limit[i] output symbols, into out16 + task_out[i]
+    const uint64_t* task_bit;
+    const uint64_t* task_resume;       // TM_MARK: bit position to continue at once the block's tables are built (0: none)
+    const uint64_t* task_out;          // TM_MARK: absolute output offset of the piece
+    const uint32_t* task_limit;        // TM_MARK: output symbols of the piece
+    uint16_t* out16;                   // TM_MARK output: byte value, or 256 + index into the 32 KiB window before the piece
+    struct Ckpt* ckpt;                 // TM_INDEX
+    unsigned long long* ckpt_count;
+    unsigned long long ckpt_cap;
+    uint32_t ckpt_step;                // power of two
     unsigned long long n;
     unsigned long long* counter;       // dynamic stream scheduler
 };
+
+// resume point inside a block (TM_INDEX): the symbol at bit `bit` produces output byte `pos` of task `task`
+struct Ckpt {
+    uint64_t bit;
+    uint32_t task;
+    uint32_t pos;
+};
+
+enum { TM_NONE = 0, TM_MARK = 1, TM_INDEX = 2 };
 
 // how a decode step ended
 enum : int { R_OK = 0, R_EOB = 1, R_STALL = 2, R_ERROR = 3, R_OUTFULL = 4 };
@@ -483,8 +502,9 @@ __device__ __noinline__ void copy_before_start_impl(uint8_t* o, uint32_t p0, uin
 
 enum : int { PH_FETCH = 0, PH_BLOCK = 1, PH_CODES = 2, PH_EXIT = 3 };
 
-template <int G, bool STORE, bool MARK = false>
+template <int G, bool STORE, int TM = TM_NONE>
 struct Decoder {
+    static constexpr bool MARK = TM == TM_MARK;
     GroupSmem* S;
     uint16_t* gsorted;                 // global scratch: sorted symbols of the current block
     unsigned gmask;
@@ -502,7 +522,10 @@ struct Decoder {
     // ---- output
     uint8_t* out;
     uint16_t* out16;                   // marker mode
-    uint64_t abs_start;                // marker mode: absolute stream offset of the block being decoded
+    uint64_t abs_start;                // marker mode: absolute stream offset of the piece being decoded
+    uint64_t resume_bit;               // TM_MARK
+    uint32_t limit;                    // TM_MARK: stop after this many symbols
+    uint32_t next_ck;                  // TM_INDEX: output position of the next resume point
     uint32_t pos, cap;
     const uint8_t* dict_tail;
     int D;
@@ -882,8 +905,9 @@ struct Decoder {
 #if SDZ_LIT_RUN > 0
         // leading literals: every lockstep iteration pays for the match path anyway, so plain
         // literals in front of a match are folded into the same iteration
+        // (not in marker mode: a piece must be able to stop after ANY symbol)
         #pragma unroll
-        for (int k = 0; k < SDZ_LIT_RUN; k++) {
+        for (int k = 0; k < (MARK ? 0 : SDZ_LIT_RUN); k++) {
             if (wp + 5 > end_wp || pos >= cap) break;
             refill_fast();
             const uint32_t e0 = S->lut_l[(uint32_t)bb & ((1u << RL) - 1u)];
@@ -987,6 +1011,9 @@ struct Decoder {
         out = nullptr; out_off = 0;
         abs_start = MARK ? P.task_out[i] : 0;
         out16 = MARK ? P.out16 + abs_start : nullptr;
+        resume_bit = MARK ? P.task_resume[i] : 0;
+        limit = MARK ? P.task_limit[i] : 0xffffffffu;
+        next_ck = TM == TM_INDEX ? P.ckpt_step : 0xffffffffu;
         pos = 0; cap = 0xffffffffu;
         msg = SDZ_MSG_NONE; stall_kind = ST_NONE;
         D = 0; dict_tail = nullptr;
@@ -1032,7 +1059,7 @@ struct Decoder {
         i = __shfl_sync(gmask, i, 0, G);
         if (i >= P.n) { phase = PH_EXIT; return; }
         idx = i;
-        if (P.task_bit) { fetch_task(P, i); return; }
+        if (TM != TM_NONE) { fetch_task(P, i); return; }
         in_len = P.in_len[i];
         const uint8_t mode_raw = P.mode[i];
         const int mode = mode_raw & 0x7f;
@@ -1168,7 +1195,7 @@ struct Decoder {
     // The stream stops here: r = R_EOB (final block complete), R_STALL, R_ERROR or R_OUTFULL.
     __device__ __forceinline__ void finish_stream(const InflateParams& P, int r)
     {
-        if (P.task_bit) { finish_task(P, r); return; }
+        if (TM != TM_NONE) { finish_task(P, r); return; }
         int thrown = SDZ_THROW_NONE, zstatus = SDZ_Z_OK;
         bool done = false;
         int32_t stored = 0, isize = 0;
@@ -1226,7 +1253,7 @@ struct Decoder {
         n_blocks++;
         start_pos = pos;
         const uint32_t type = t >> 1;
-        if (P.task_bit) method = (int)type;                             // block-task records carry BTYPE
+        if (TM != TM_NONE) method = (int)type;                           // block-task records carry BTYPE
         int r;
         if (type == 0) {
             drop(bc & 7);
@@ -1236,7 +1263,7 @@ struct Decoder {
             drop(32);
             r = stored_block(v & 0xffff);
             if (r != R_OK) { finish_stream(P, r); return; }
-            if (P.task_bit) { finish_task(P, R_EOB); return; }
+            if (TM != TM_NONE) { finish_task(P, R_EOB); return; }
             if (last) { ring.wash(); finish_stream(P, R_EOB); }
             return;                                                     // next block: stays in PH_BLOCK
         }
@@ -1257,13 +1284,31 @@ struct Decoder {
         TreeInfo T = build_tables<G>(S, gsorted, nl, nd, type == 1, glane, gmask);
         if (T.msg) { msg = T.msg; finish_stream(P, R_ERROR); return; }
         lbits = T.lbits; dbits = T.dbits; g_l = T.g_l; g_d = T.g_d;
+        if (MARK && resume_bit) {                                       // continue in the middle of the block
+            seek((uint32_t)(resume_bit >> 3));
+            const int skip = (int)(resume_bit & 7);
+            if (bc < skip) { finish_task(P, R_STALL); return; }
+            drop(skip);
+        }
         phase = PH_CODES;
+    }
+
+    // TM_INDEX: called at a symbol boundary of the lockstep loop
+    __device__ __forceinline__ void checkpoint(const InflateParams& P)
+    {
+        if (pos >= next_ck) {
+            if (glane == 0) {
+                const unsigned long long slot = atomicAdd(P.ckpt_count, 1ull);
+                if (slot < P.ckpt_cap) { Ckpt c; c.bit = bit_pos(); c.task = (uint32_t)idx; c.pos = pos; P.ckpt[slot] = c; }
+            }
+            next_ck = (pos | (P.ckpt_step - 1u)) + 1u;
+        }
     }
 
     // a step() returned something other than R_OK
     __device__ __forceinline__ void block_end(const InflateParams& P, int r)
     {
-        if (P.task_bit) { finish_task(P, r); return; }
+        if (TM != TM_NONE) { finish_task(P, r); return; }
         ring.write(pos - start_pos);
         if (r != R_EOB) { if (r == R_STALL) stall_kind = ST_OTHER; finish_stream(P, r); return; }
         // End of block.  When inflate_fast() decodes the EOB its STREAM_END status leaks through
@@ -1291,14 +1336,14 @@ struct Decoder {
 // lockstep (they re-converge at the ballot after every symbol), so one instruction stream
 // serves 32 / G streams.  Block headers, table builds and stream changes are serviced between
 // lockstep runs while the other groups of the warp wait.
-template <int G, bool STORE, bool MARK = false>
+template <int G, bool STORE, int TM = TM_NONE>
 __global__ void __launch_bounds__(128, SDZ_MINBLOCKS) inflate_kernel(InflateParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int gid = threadIdx.x / G;
     GroupSmem* S = reinterpret_cast<GroupSmem*>(smem_raw) + gid;
 
-    Decoder<G, STORE, MARK> d;
+    Decoder<G, STORE, TM> d;
     d.S = S;
     d.gsorted = P.scratch + ((size_t)blockIdx.x * (blockDim.x / G) + gid) * SCRATCH_U16;
     d.glane = threadIdx.x % G;
@@ -1322,7 +1367,9 @@ __global__ void __launch_bounds__(128, SDZ_MINBLOCKS) inflate_kernel(InflatePara
         for (;;) {
             __syncwarp();                            // re-converge + order the stores of earlier iterations
             if (d.phase == PH_CODES) {
+                if (TM == TM_INDEX) d.checkpoint(P);
                 int r = d.step();
+                if (TM == TM_MARK && r == R_OK && d.pos >= d.limit) r = R_EOB;     // the piece is complete
                 if (r != R_OK) d.block_end(P, r);
             }
             if (__ballot_sync(0xffffffffu, d.phase != PH_CODES) != 0u) {

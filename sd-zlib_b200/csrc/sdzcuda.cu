@@ -4,6 +4,7 @@
 #include "../../include/sdzcuda.h"
 
 #include <algorithm>
+#include <chrono>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -119,13 +120,13 @@ int upload_tables(sdz_ctx* ctx)
     return SDZ_OK;
 }
 
-template <int G, bool STORE, bool MARK = false>
+template <int G, bool STORE, int TM = sdz::TM_NONE>
 int launch_inflate_t(sdz_ctx* ctx, const sdz::InflateParams& P)
 {
     const int threads = ctx->block_threads;
     const int groups = threads / G;
     const size_t smem = (size_t)groups * sizeof(sdz::GroupSmem);
-    auto kern = sdz::inflate_kernel<G, STORE, MARK>;
+    auto kern = sdz::inflate_kernel<G, STORE, TM>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
@@ -172,11 +173,11 @@ int launch_finalize(sdz_ctx* ctx, const uint8_t* d_out, sdz_result* d_res, uint6
 int run_batch_device(sdz_ctx* ctx, const sdz_batch_dev* b, bool sizes_only, bool first = true, bool last = true)
 {
     sdz::InflateParams P;
+    memset(&P, 0, sizeof P);
     P.in = b->d_in; P.in_off = b->d_in_off; P.in_len = b->d_in_len; P.mode = b->d_mode;
     P.dict = b->d_dict; P.dict_off = b->d_dict_off; P.dict_len = b->d_dict_len; P.dict_adler = b->d_dict_adler;
     P.out = sizes_only ? nullptr : b->d_out; P.out_off = b->d_out_off; P.out_cap = b->d_out_cap;
     P.res = b->d_results; P.n = b->n; P.counter = ctx->d_counter; P.scratch = nullptr;
-    P.task_bit = nullptr; P.task_out = nullptr; P.out16 = nullptr;
     if (first) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     int rc = sizes_only ? launch_inflate<false>(ctx, P) : launch_inflate<true>(ctx, P);
     if (rc) return rc;
@@ -699,18 +700,30 @@ int sdz_inflate_sizes(sdz_ctx* ctx, const sdz_in* in, uint64_t n, uint64_t* out_
 
 namespace {
 
-// block-task launch: n tasks over stream 0 = [d_src, d_src + len)
-template <bool STORE, bool MARK>
-int launch_tasks(sdz_ctx* ctx, const uint8_t* d_src, uint32_t len, const uint64_t* d_task_bit, const uint64_t* d_task_out,
-                 uint16_t* d_sym, sdz_result* d_res, uint64_t n, const uint64_t* d_zero_off, const uint32_t* d_len0)
+struct LargeTasks {
+    const uint64_t* bit = nullptr;      // block header position of every task
+    const uint64_t* resume = nullptr;   // TM_MARK
+    const uint64_t* out = nullptr;      // TM_MARK
+    const uint32_t* limit = nullptr;    // TM_MARK
+    uint16_t* sym = nullptr;            // TM_MARK
+    sdz::Ckpt* ckpt = nullptr;          // TM_INDEX
+    unsigned long long* ckpt_count = nullptr;
+    unsigned long long ckpt_cap = 0;
+    uint32_t ckpt_step = 0;
+};
+
+// block-task launch: n tasks over stream 0 (descriptors d_zero_off / d_len0)
+template <int G, bool STORE, int TM>
+int launch_tasks(sdz_ctx* ctx, const uint8_t* d_src, const LargeTasks& T, sdz_result* d_res, uint64_t n, const uint64_t* d_zero_off,
+                 const uint32_t* d_len0)
 {
     sdz::InflateParams P;
     memset(&P, 0, sizeof P);
     P.in = d_src; P.in_off = d_zero_off; P.in_len = d_len0;
     P.res = d_res; P.n = n; P.counter = ctx->d_counter;
-    P.task_bit = d_task_bit; P.task_out = d_task_out; P.out16 = d_sym;
-    (void)len;
-    return launch_inflate_t<4, STORE, MARK>(ctx, P);
+    P.task_bit = T.bit; P.task_resume = T.resume; P.task_out = T.out; P.task_limit = T.limit; P.out16 = T.sym;
+    P.ckpt = T.ckpt; P.ckpt_count = T.ckpt_count; P.ckpt_cap = T.ckpt_cap; P.ckpt_step = T.ckpt_step;
+    return launch_inflate_t<G, STORE, TM>(ctx, P);
 }
 
 }  // namespace
@@ -722,6 +735,16 @@ extern "C" int sdz_inflate_large(sdz_ctx* ctx, const uint8_t* data, uint64_t len
     if (len >= (1ull << 32) - 64) return SDZ_E_ARG;
     CK(cudaSetDevice(ctx->device));
     memset(res, 0, sizeof *res);
+    // SDZ_TRACE_LARGE=1: wall-clock of every phase on stderr (the phases are separated by host syncs)
+    static const bool trace = getenv("SDZ_TRACE_LARGE") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!trace) return;
+        cudaStreamSynchronize(ctx->stream);
+        const auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[sdz_inflate_large] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_last).count());
+        t_last = t;
+    };
 
     auto fallback = [&]() -> int {
         // exact but sequential: the ordinary decoder, one group for the whole stream
@@ -781,23 +804,31 @@ extern "C" int sdz_inflate_large(sdz_ctx* ctx, const uint8_t* data, uint64_t len
         d_src = (const uint8_t*)ctx->d_in.p;
     } else if (reinterpret_cast<uintptr_t>(data) & 15) return SDZ_E_ARG;
 
+    lap("header + input staging");
     // ---- pass 1a: candidate dynamic-block headers
     const uint64_t first_bit = (uint64_t)hp * 8, total_bits = len * 8;
-    const uint64_t max_cand = len / 512 + 4096;
-    if ((rc = grow(ctx, ctx->d_task, (max_cand * 2 + 16) * sizeof(uint64_t)))) return rc;
+    const uint64_t max_cand = len / 512 + 4096, max_surv = total_bits / 32 + 4096;
+    if ((rc = grow(ctx, ctx->d_task, (max_cand + 16) * sizeof(uint64_t)))) return rc;
+    if ((rc = grow(ctx, ctx->d_part, max_surv * sizeof(uint64_t)))) return rc;
     uint64_t* d_cand = (uint64_t*)ctx->d_task.p;
-    CK(cudaMemsetAsync(ctx->d_counter + 2, 0, sizeof(unsigned long long), ctx->stream));
+    unsigned long long* d_ncand = ctx->d_counter + 2;                        // [2] candidates, [3] survivors / resume points
+    CK(cudaMemsetAsync(d_ncand, 0, 2 * sizeof(unsigned long long), ctx->stream));
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     {
-        const unsigned grid = (unsigned)std::min<uint64_t>(((total_bits - first_bit) + 127) / 128, (uint64_t)ctx->sm_count * 16);
-        sdz::find_dynamic_headers<<<grid, 128, 0, ctx->stream>>>(d_src, first_bit, total_bits, d_cand, ctx->d_counter + 2, max_cand);
-        ctx->launches++;
+        const uint64_t tiles = (total_bits - first_bit + sdz::PF_TILE - 1) / sdz::PF_TILE;
+        const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((tiles + 7) / 8, (uint64_t)ctx->sm_count * 8));
+        sdz::prefilter_headers<<<grid, 256, 0, ctx->stream>>>(d_src, first_bit, total_bits, (uint64_t*)ctx->d_part.p, d_ncand + 1, max_surv);
+        lap("1a prefilter");
+        sdz::verify_headers<<<ctx->sm_count * 16, 128, 0, ctx->stream>>>(d_src, total_bits, (const uint64_t*)ctx->d_part.p, d_ncand + 1, max_surv,
+                                                                     d_cand, d_ncand, max_cand);
+        ctx->launches += 2;
         CK(cudaGetLastError());
     }
-    unsigned long long n_cand = 0;
-    CK(cudaMemcpyAsync(&n_cand, ctx->d_counter + 2, sizeof n_cand, cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned long long counts[2] = { 0, 0 };
+    CK(cudaMemcpyAsync(counts, d_ncand, sizeof counts, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (n_cand > max_cand) return fallback();
+    const unsigned long long n_cand = counts[0];
+    if (n_cand > max_cand || counts[1] > max_surv) return fallback();
     std::vector<uint64_t> cand(n_cand + 1);
     if (n_cand) CK(cudaMemcpy(cand.data(), d_cand, n_cand * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     cand[n_cand] = first_bit;                                               // the first block, whatever its type
@@ -815,52 +846,108 @@ extern "C" int sdz_inflate_large(sdz_ctx* ctx, const uint8_t* data, uint64_t len
     const uint64_t* d_zero_off = (const uint64_t*)ctx->d_meta.p;
     const uint32_t* d_len0 = (const uint32_t*)((uint8_t*)ctx->d_meta.p + 8);
 
-    // ---- pass 1b: extent of every candidate block (count-only decode of ONE block each)
-    auto extents = [&](const std::vector<uint64_t>& starts, std::vector<sdz_result>& recs) -> int {
+    // ---- pass 1b: extent and resume points of every candidate block (count-only walk of ONE block each)
+    static const uint32_t ck_step = [] {
+        const char* e = getenv("SDZ_LARGE_STEP");
+        uint32_t v = e ? (uint32_t)atoi(e) : 16384u;
+        uint32_t p2 = 1024;
+        while (p2 < v && p2 < (1u << 24)) p2 <<= 1;
+        return p2;
+    }();
+    auto extents = [&](const std::vector<uint64_t>& starts, std::vector<sdz_result>& recs, std::vector<sdz::Ckpt>& cks) -> int {
         const uint64_t n = starts.size();
         int r2;
-        if ((r2 = grow(ctx, ctx->d_task, (n * 2 + 16) * sizeof(uint64_t)))) return r2;
+        if ((r2 = grow(ctx, ctx->d_task, (n + 16) * sizeof(uint64_t)))) return r2;
         if ((r2 = grow(ctx, ctx->d_res, n * sizeof(sdz_result)))) return r2;
         CK(cudaMemcpyAsync(ctx->d_task.p, starts.data(), n * 8, cudaMemcpyHostToDevice, ctx->stream));
-        r2 = launch_tasks<false, false>(ctx, d_src, (uint32_t)len, (const uint64_t*)ctx->d_task.p, nullptr, nullptr,
-                                        (sdz_result*)ctx->d_res.p, n, d_zero_off, d_len0);
-        if (r2) return r2;
+        unsigned long long cap = n == 1 ? 65536 : len / 64 + 65536, got = 0;
+        for (int attempt = 0; attempt < 2; attempt++) {
+            if ((r2 = grow(ctx, ctx->d_part, cap * sizeof(sdz::Ckpt)))) return r2;
+            CK(cudaMemsetAsync(d_ncand + 1, 0, sizeof(unsigned long long), ctx->stream));
+            LargeTasks T;
+            T.bit = (const uint64_t*)ctx->d_task.p;
+            T.ckpt = (sdz::Ckpt*)ctx->d_part.p; T.ckpt_count = d_ncand + 1; T.ckpt_cap = cap; T.ckpt_step = ck_step;
+            static const int index_g = getenv("SDZ_INDEX_G") ? atoi(getenv("SDZ_INDEX_G")) : 4;
+            if (index_g == 8) r2 = launch_tasks<8, false, sdz::TM_INDEX>(ctx, d_src, T, (sdz_result*)ctx->d_res.p, n, d_zero_off, d_len0);
+            else if (index_g == 32) r2 = launch_tasks<32, false, sdz::TM_INDEX>(ctx, d_src, T, (sdz_result*)ctx->d_res.p, n, d_zero_off, d_len0);
+            else r2 = launch_tasks<4, false, sdz::TM_INDEX>(ctx, d_src, T, (sdz_result*)ctx->d_res.p, n, d_zero_off, d_len0);
+            if (r2) return r2;
+            CK(cudaMemcpyAsync(&got, d_ncand + 1, sizeof got, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (got <= cap) break;
+            cap = got + 1024;                                               // extremely compressible data: once more with room
+        }
         recs.resize(n);
+        cks.resize(got);
         CK(cudaMemcpyAsync(recs.data(), ctx->d_res.p, n * sizeof(sdz_result), cudaMemcpyDeviceToHost, ctx->stream));
+        if (got) CK(cudaMemcpyAsync(cks.data(), ctx->d_part.p, got * sizeof(sdz::Ckpt), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        std::sort(cks.begin(), cks.end(), [](const sdz::Ckpt& a, const sdz::Ckpt& b) { return a.task != b.task ? a.task < b.task : a.pos < b.pos; });
         return SDZ_OK;
     };
+    lap("1a header search");
     std::vector<sdz_result> ext;
-    if ((rc = extents(cand, ext))) return rc;
+    std::vector<sdz::Ckpt> ckpts;
+    if ((rc = extents(cand, ext, ckpts))) return rc;
+    lap("1b block extents");
 
-    // ---- chain of real blocks from the first one
-    std::vector<uint64_t> blk_bit, blk_off;
-    uint64_t cur = first_bit, total_out = 0, end_bit = 0;
+    // ---- chain of real blocks from the first one, cut into pieces at the resume points
+    std::vector<uint64_t> t_bit, t_resume, t_off;
+    std::vector<uint32_t> t_limit;
+    uint64_t cur = first_bit, total_out = 0, end_bit = 0, nb = 0, n_single = 0;
     bool finished = false;
+    auto add_pieces = [&](uint64_t block_bit, uint64_t block_len, const sdz::Ckpt* c, size_t nc) {
+        uint64_t from = 0, resume = 0;
+        for (size_t k = 0; k <= nc; k++) {
+            const uint64_t to = k < nc ? c[k].pos : block_len;
+            if (to > from) {
+                t_bit.push_back(block_bit); t_resume.push_back(resume); t_off.push_back(total_out + from);
+                t_limit.push_back((uint32_t)(to - from));
+            }
+            if (k < nc) { from = to; resume = c[k].bit; }
+        }
+    };
     for (uint64_t guard = 0; guard < (1ull << 26); guard++) {
         auto it = std::lower_bound(cand.begin(), cand.end(), cur);
         sdz_result rec;
-        if (it != cand.end() && *it == cur) rec = ext[it - cand.begin()];
-        else {
+        std::vector<sdz::Ckpt> own;
+        const sdz::Ckpt* c = nullptr;
+        size_t nc = 0;
+        if (it != cand.end() && *it == cur) {
+            const uint32_t ti = (uint32_t)(it - cand.begin());
+            rec = ext[ti];
+            auto lo = std::lower_bound(ckpts.begin(), ckpts.end(), ti, [](const sdz::Ckpt& a, uint32_t t) { return a.task < t; });
+            auto hi = std::upper_bound(lo, ckpts.end(), ti, [](uint32_t t, const sdz::Ckpt& a) { return t < a.task; });
+            c = ckpts.data() + (lo - ckpts.begin());
+            nc = (size_t)(hi - lo);
+        } else {
             // a block the header search does not look for (stored / fixed): measure it on its own
             std::vector<uint64_t> one{ cur };
+            n_single++;
             std::vector<sdz_result> r1;
-            if ((rc = extents(one, r1))) return rc;
+            if ((rc = extents(one, r1, own))) return rc;
             rec = r1[0];
+            c = own.data();
+            nc = own.size();
         }
         if (rec.zstatus != sdz::R_EOB) return fallback();                   // truncated or damaged: exact sequential path
         // a stored block's copy depends on where the reference's 16 KiB output chunks fall,
         // which only the sequential decoder tracks
         if (rec.container == 0) return fallback();
-        blk_bit.push_back(cur);
-        blk_off.push_back(total_out);
+        if (rec.out_len >= (1ull << 32)) return fallback();
+        add_pieces(cur, rec.out_len, c, nc);
+        nb++;
         total_out += rec.out_len;
         cur = rec.total_in;
         if (rec.n_blocks) { finished = true; end_bit = cur; break; }
     }
     if (!finished) return fallback();
-    blk_off.push_back(total_out);
-    const uint64_t nb = blk_bit.size();
+    t_off.push_back(total_out);
+    const uint64_t nt = t_bit.size();
+    lap("chain walk");
+    if (trace) fprintf(stderr, "[sdz_inflate_large] %llu survivors, %llu candidates, %llu blocks (%llu measured singly), %llu pieces, %llu -> %llu bytes\n",
+                       counts[1], (unsigned long long)cand.size(), (unsigned long long)nb, (unsigned long long)n_single, (unsigned long long)nt,
+                       (unsigned long long)len, (unsigned long long)total_out);
     if (total_out > out_cap) { res->out_len = total_out; return SDZ_E_OUT_CAP; }
 
     // ---- trailer (src/inflate.ts:423-463)
@@ -877,18 +964,28 @@ extern "C" int sdz_inflate_large(sdz_ctx* ctx, const uint8_t* data, uint64_t len
         else stored = (int32_t)(((uint32_t)stored << 8) | b);
     }
 
-    // ---- pass 2a: every block into 16-bit symbols
-    if ((rc = grow(ctx, ctx->d_sym, (total_out + 64) * 2))) return rc;
-    if ((rc = grow(ctx, ctx->d_task, (nb * 2 + 16) * sizeof(uint64_t) + (nb + 1) * 8))) return rc;
-    if ((rc = grow(ctx, ctx->d_res, nb * sizeof(sdz_result)))) return rc;
-    uint64_t* d_tb = (uint64_t*)ctx->d_task.p;
-    uint64_t* d_to = d_tb + nb;
-    CK(cudaMemcpyAsync(d_tb, blk_bit.data(), nb * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(d_to, blk_off.data(), (nb + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    rc = launch_tasks<true, true>(ctx, d_src, (uint32_t)len, d_tb, d_to, (uint16_t*)ctx->d_sym.p, (sdz_result*)ctx->d_res.p, nb,
-                                  d_zero_off, d_len0);
-    if (rc) return rc;
+    // ---- pass 2a: every piece into 16-bit symbols
+    uint64_t* d_tb = nullptr;
+    uint64_t* d_to = nullptr;
+    if (nt) {
+        if ((rc = grow(ctx, ctx->d_sym, (total_out + 64) * 2))) return rc;
+        if ((rc = grow(ctx, ctx->d_task, (nt * 3 + 1) * 8 + nt * 4 + 64))) return rc;
+        if ((rc = grow(ctx, ctx->d_res, nt * sizeof(sdz_result)))) return rc;
+        d_tb = (uint64_t*)ctx->d_task.p;
+        uint64_t* d_tr = d_tb + nt;
+        d_to = d_tr + nt;
+        uint32_t* d_tl = (uint32_t*)(d_to + nt + 1);
+        CK(cudaMemcpyAsync(d_tb, t_bit.data(), nt * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d_tr, t_resume.data(), nt * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d_to, t_off.data(), (nt + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d_tl, t_limit.data(), nt * 4, cudaMemcpyHostToDevice, ctx->stream));
+        LargeTasks T;
+        T.bit = d_tb; T.resume = d_tr; T.out = d_to; T.limit = d_tl; T.sym = (uint16_t*)ctx->d_sym.p;
+        rc = launch_tasks<4, true, sdz::TM_MARK>(ctx, d_src, T, (sdz_result*)ctx->d_res.p, nt, d_zero_off, d_len0);
+        if (rc) return rc;
+    }
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    lap("2a marker decode");
 
     // ---- pass 2b / 2c: windows, then everything else
     uint8_t* d_o = out;
@@ -896,29 +993,33 @@ extern "C" int sdz_inflate_large(sdz_ctx* ctx, const uint8_t* data, uint64_t len
         if ((rc = grow(ctx, ctx->d_out, total_out + 64))) return rc;
         d_o = (uint8_t*)ctx->d_out.p;
     }
-    {
+    if (nt) {
         uint64_t bps = 1;
-        while (bps * bps < nb) bps++;                                       // ~sqrt(nb) blocks per segment
-        const unsigned nseg = (unsigned)((nb + bps - 1) / bps);
-        sdz::propagate_in_segment<<<nseg, 1024, 0, ctx->stream>>>((uint16_t*)ctx->d_sym.p, d_to, nb, bps);
-        sdz::propagate_segments<<<1, 1024, 0, ctx->stream>>>((const uint16_t*)ctx->d_sym.p, d_o, d_to, nb, bps);
-        const unsigned gy = (unsigned)std::min<uint64_t>(nb, 65535);
-        sdz::resolve_markers<<<dim3(8, gy), 256, 0, ctx->stream>>>((const uint16_t*)ctx->d_sym.p, d_o, d_to, nb, bps);
+        while (bps * bps < nt) bps++;                                       // ~sqrt(nt) pieces per segment
+        const unsigned nseg = (unsigned)((nt + bps - 1) / bps);
+        sdz::propagate_in_segment<<<nseg, 1024, 0, ctx->stream>>>((uint16_t*)ctx->d_sym.p, d_to, nt, bps);
+        sdz::propagate_segments<<<1, 1024, 0, ctx->stream>>>((const uint16_t*)ctx->d_sym.p, d_o, d_to, nt, bps);
+        const unsigned gy = (unsigned)std::min<uint64_t>(nt, 65535);
+        sdz::resolve_markers<<<dim3(4, gy), 256, 0, ctx->stream>>>((const uint16_t*)ctx->d_sym.p, d_o, d_to, nt, bps);
+        ctx->launches += 3;
     }
-    ctx->launches += 3;
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
 
+    lap("2b-d windows + markers");
     // the marker pass must have reproduced the extents
-    std::vector<sdz_result> chk(nb);
-    CK(cudaMemcpyAsync(chk.data(), ctx->d_res.p, nb * sizeof(sdz_result), cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<sdz_result> chk(nt);
+    if (nt) CK(cudaMemcpyAsync(chk.data(), ctx->d_res.p, nt * sizeof(sdz_result), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     float ms_keep[3];
     cudaEventElapsedTime(&ms_keep[0], ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&ms_keep[1], ctx->ev[1], ctx->ev[2]);
     cudaEventElapsedTime(&ms_keep[2], ctx->ev[0], ctx->ev[2]);
-    for (uint64_t b = 0; b < nb; b++)
-        if (chk[b].zstatus != sdz::R_EOB || chk[b].out_len != blk_off[b + 1] - blk_off[b]) return fallback();
+    for (uint64_t t = 0; t < nt; t++) {
+        if (chk[t].zstatus != sdz::R_EOB || chk[t].out_len != t_limit[t]) return fallback();
+        // a piece that is followed by another piece of the same block must end exactly on that piece's resume point
+        if (t + 1 < nt && t_bit[t + 1] == t_bit[t] && chk[t].total_in != t_resume[t + 1]) return fallback();
+    }
 
     // ---- running checksum as append() computes it over its 16 KiB chunks (src/sd-inflate.ts:133-149)
     int32_t running = 0;
@@ -938,12 +1039,14 @@ extern "C" int sdz_inflate_large(sdz_ctx* ctx, const uint8_t* data, uint64_t len
         rc = checksum_chain(ctx, is_gzip, d_o, segs.data(), segs.size(), is_gzip ? 0 : 1, 1, nullptr, &running);
         if (rc) return rc;
     }
+    lap("checksum");
     ctx->last_ms[0] = ms_keep[0]; ctx->last_ms[1] = ms_keep[1]; ctx->last_ms[2] = ms_keep[2];
     if (!on_device && total_out) {
         CK(cudaMemcpyAsync(out, d_o, total_out, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
 
+    lap("output copy");
     // ---- finish() record (src/sd-inflate.ts:159-179) and inflate()'s throw mapping (:214-225)
     res->out_off = 0;
     res->out_len = total_out;
