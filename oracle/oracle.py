@@ -187,6 +187,17 @@ def inflate_oneshot(data, dictionary=None, mode=MODE_SNIFF, out_cap=None):
         cap = r.out_len
 
 
+def inflate_oneshot_np(data, out, mode=MODE_SNIFF):
+    """Same call on numpy uint8 arrays without any Python-side copy (bench.py's CPU baseline leg for one
+    large stream).  Returns the Result; `out` must be large enough."""
+    r = Result()
+    rc = lib().sdzo_inflate_oneshot(data.ctypes.data_as(C.POINTER(C.c_uint8)), data.size, None, 0, mode,
+                                    out.ctypes.data_as(C.POINTER(C.c_uint8)), out.size, C.byref(r))
+    if rc != 0:
+        raise ValueError("output buffer too small: need %d" % r.out_len)
+    return r
+
+
 def inflate_batch_mt(in_arena, in_off, in_len, out_off, out_cap, n_threads, modes=None, out_arena=None):
     """Threaded batch of one-shots over numpy arrays (CPU baseline).  Returns (out_arena, results)."""
     import numpy as np

@@ -886,7 +886,8 @@ struct Decoder {
         bb |= take ? ((uint64_t)nw << bc) : 0ull;
         bc += take ? 32 : 0;
         wp += take ? 1u : 0u;
-        if (take && (wp % CHW) == 0u && wp / CHW >= waited_abs) {       // rare: first word of the next 128-byte chunk
+        // chunk(wp) had been waited for, so wp < waited_abs * CHW held before the increment
+        if (take && wp == waited_abs * CHW) {                             // rare: first word of the next 128-byte chunk
             uint64_t r = chunk_cross(S, gsrc, wp / CHW, chunk0, issued_abs, total_chunks, phasebits, gmask, glane);
             phasebits = (uint32_t)r & 15u;
             issued_abs = (uint32_t)(r >> 4);
@@ -901,58 +902,56 @@ struct Decoder {
     // iteration was measured slower: the warp pays the longest run of its eight groups.)
     __device__ __forceinline__ int step()
     {
+        // stream tail: the two refills below need whole words, and only step_general() knows the stall rules
+        if (wp + 5 > end_wp) return step_general(false);
+        // ONE top-up serves a folded literal (<= RL bits) and the literal/length code with its extra bits
+        // (<= 15 + 5): at least 33 bits are valid afterwards
+        refill_fast();
         bool lit_now = false;
+        uint32_t e = S->lut_l[(uint32_t)bb & ((1u << RL) - 1u)];
 #if SDZ_LIT_RUN > 0
-        // leading literals: every lockstep iteration pays for the match path anyway, so plain
-        // literals in front of a match are folded into the same iteration
+        // leading literal: every lockstep iteration pays for the match path anyway, so a plain literal in
+        // front of a match is folded into the same iteration
         // (not in marker mode: a piece must be able to stop after ANY symbol)
-        #pragma unroll
-        for (int k = 0; k < (MARK ? 0 : SDZ_LIT_RUN); k++) {
-            if (wp + 5 > end_wp || pos >= cap) break;
-            refill_fast();
-            const uint32_t e0 = S->lut_l[(uint32_t)bb & ((1u << RL) - 1u)];
-            if ((e0 >> 12) == 0 || (e0 & 0xfffu) >= 256u) break;
-            const uint32_t n0 = e0 >> 12;
+        if (!MARK && e >= 0x1000u && (e & 0xf00u) == 0u && pos < cap) {
+            const uint32_t n0 = e >> 12;
             bb >>= n0; bc -= (int)n0;
-            store_lit(e0 & 0xffu);
+            store_lit(e & 0xffu);
             pos++;
             lit_now = true;
+            e = S->lut_l[(uint32_t)bb & ((1u << RL) - 1u)];
         }
 #endif
-        bool slow = wp + 5 > end_wp;
-        uint32_t e = 0;
-        if (!slow) {
-            refill_fast();
-            e = S->lut_l[(uint32_t)bb & ((1u << RL) - 1u)];
-            if ((e >> 12) == 0) {                       // code longer than the root (or invalid)
-                slow = true;
-                if (e == E_LONG) {
-                    const uint32_t r = canon_long(S->cnt_l, gsorted, RL, g_l, S->start, (uint32_t)bb);
-                    const uint32_t sym = r & 0xffffu;
-                    if (r != 0 && sym <= 256) { e = ((r >> 16) << 12) | sym; slow = false; }
-                    else if (r != 0 && sym - 257 <= 28) {
-                        const uint32_t i = sym - 257;
-                        const uint32_t xb = i < 8 ? 0 : (i == 28 ? 0 : (i >> 2) - 1);
-                        const uint32_t base = i < 8 ? 3 + i : (i == 28 ? 258 : 3 + ((4 + (i & 3)) << xb));
-                        e = ((r >> 16) << 12) | 0x800 | (xb << 8) | (base - 3);
-                        slow = false;
-                    }
+        bool slow = false;
+        if ((e >> 12) == 0) {                           // code longer than the root (or invalid)
+            slow = true;
+            if (e == E_LONG) {
+                const uint32_t r = canon_long(S->cnt_l, gsorted, RL, g_l, S->start, (uint32_t)bb);
+                const uint32_t sym = r & 0xffffu;
+                if (r != 0 && sym <= 256) { e = ((r >> 16) << 12) | sym; slow = false; }
+                else if (r != 0 && sym - 257 <= 28) {
+                    const uint32_t i = sym - 257;
+                    const uint32_t xb = i < 8 ? 0 : (i == 28 ? 0 : (i >> 2) - 1);
+                    const uint32_t base = i < 8 ? 3 + i : (i == 28 ? 258 : 3 + ((4 + (i & 3)) << xb));
+                    e = ((r >> 16) << 12) | 0x800 | (xb << 8) | (base - 3);
+                    slow = false;
                 }
             }
         }
         if (slow) return step_general(lit_now);
         const uint32_t n = e >> 12, p = e & 0xfff;
-        bb >>= n; bc -= (int)n;
         if (p < 256) {
             if (pos >= cap) return R_OUTFULL;
+            bb >>= n; bc -= (int)n;
             store_lit(p);
             pos++;
             return R_OK;
         }
-        if (p == 256) { eob_len = (int)n; return R_EOB; }
+        if (p == 256) { bb >>= n; bc -= (int)n; eob_len = (int)n; return R_EOB; }
+        // code and extra bits leave the bit buffer in one shift (n + xb <= 20)
         const uint32_t xb = (p >> 8) & 7;
-        const uint32_t len = 3 + (p & 0xff) + ((uint32_t)bb & ((1u << xb) - 1u));
-        bb >>= xb; bc -= (int)xb;
+        const uint32_t len = 3 + (p & 0xff) + (((uint32_t)bb >> n) & ((1u << xb) - 1u));
+        bb >>= (n + xb); bc -= (int)(n + xb);
         refill_fast();
         uint32_t de = S->lut_d[(uint32_t)bb & ((1u << RD) - 1u)];
         uint32_t dn = de >> 12;
@@ -963,10 +962,9 @@ struct Decoder {
             dn = r >> 16;
             de = ((ds < 4 ? 0u : (ds >> 1) - 1u) << 8) | (ds < 4 ? ds : 2u + (ds & 1u));
         }
-        bb >>= dn; bc -= (int)dn;
         const uint32_t dx = (de >> 8) & 15;
-        const uint32_t dist = 1 + ((de & 3) << dx) + ((uint32_t)bb & ((1u << dx) - 1u));
-        bb >>= dx; bc -= (int)dx;
+        const uint32_t dist = 1 + ((de & 3) << dx) + (((uint32_t)bb >> dn) & ((1u << dx) - 1u));     // dn + dx <= 28
+        bb >>= (dn + dx); bc -= (int)(dn + dx);
         return copy_match(len, dist, lit_now);
     }
 

@@ -91,10 +91,12 @@ def main():
     sample = zlib.compressobj(a.level, zlib.DEFLATED, 31)
     sp = b"".join(K.generate(K.TEXT, 500000 + i, 65536).tobytes() for i in range(cm * 16))
     ss = sample.compress(sp) + sample.flush()
+    ss_np = np.frombuffer(ss, dtype=np.uint8)
+    ob = np.empty(len(sp) + 64, dtype=np.uint8)
     t = time.perf_counter()
-    ob, orec = O.inflate_oneshot(ss)
+    orec = O.inflate_oneshot_np(ss_np, ob)
     cpu_dt = time.perf_counter() - t
-    assert orec.success and len(ob) == len(sp)
+    assert orec.success and orec.out_len == len(sp)
 
     best = min(times)
     k = times.index(best)
