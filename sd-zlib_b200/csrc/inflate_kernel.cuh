@@ -717,7 +717,9 @@ struct Decoder {
             // the lower destination); copies on the synchronous path read arbitrary earlier bytes
             const uint32_t first_pending = o_meta ? o_dst : n_dst;
             const bool any_pending = (o_meta | n_meta) != 0;
-            const bool hazard = any_pending && (!simple || pos - dist + len > first_pending);
+            // (a copy on the synchronous path whose source lies entirely below the pending destinations can
+            // overtake them: its own destination is disjoint from theirs)
+            const bool hazard = any_pending && (dist > pos || pos - dist + len > first_pending);
             if (hazard) flush_pending();
             // bytes written in this iteration (just-committed matches, the folded literal at pos - 1) are
             // only ordered before the reads below by a group sync; a deferred match reads pos - 1 iff dist == len
@@ -741,16 +743,13 @@ struct Decoder {
             } else if (dist <= pos) {
                 const uint8_t* src = dst - dist;
                 if (dist >= len) {
-                    for (uint32_t i = glane; i < len; i += 4 * G) {
-                        const bool b1 = i + G < len, b2 = i + 2 * G < len, b3 = i + 3 * G < len;
-                        uint8_t v0 = src[i], v1 = 0, v2 = 0, v3 = 0;
-                        if (b1) v1 = src[i + G];
-                        if (b2) v2 = src[i + 2 * G];
-                        if (b3) v3 = src[i + 3 * G];
-                        dst[i] = v0;
-                        if (b1) dst[i + G] = v1;
-                        if (b2) dst[i + 2 * G] = v2;
-                        if (b3) dst[i + 3 * G] = v3;
+                    // eight loads in flight per lane: one memory round trip for matches up to 8 G bytes
+                    for (uint32_t i = glane; i < len; i += 8 * G) {
+                        uint8_t v[8];
+                        #pragma unroll
+                        for (int k = 0; k < 8; k++) v[k] = i + k * G < len ? src[i + k * G] : (uint8_t)0;
+                        #pragma unroll
+                        for (int k = 0; k < 8; k++) if (i + k * G < len) dst[i + k * G] = v[k];
                     }
                 } else if (dist == 1) {
                     uint8_t v = src[0];

@@ -40,7 +40,15 @@ struct sdz_ctx {
     DevBuf d_in, d_out, d_meta, d_res, d_part, d_misc, d_sym, d_task;
     void* h_stage = nullptr;           // pinned
     size_t h_stage_cap = 0;
-    unsigned long long* d_counter = nullptr;
+    void* h_res = nullptr;             // pinned landing zone of the result records (a copy into the caller's pageable
+    size_t h_res_cap = 0;              // array would block the host thread and serialise the pipeline)
+    unsigned long long* d_counter = nullptr;   // [0..3] lane 0 / checksums / large-stream path, [4 + 2 l ..] lane l
+    // compute lanes of the pipelined host path: sub-batch kernels of different lanes may run concurrently,
+    // so each lane has its own stream, work counters and table scratch (lane 0 = stream / d_misc)
+    static constexpr int N_LANES = 3;
+    cudaStream_t lane_stream[N_LANES] = { nullptr, nullptr, nullptr };
+    DevBuf lane_scratch[N_LANES];
+    int cur_lane = 0;
     int group = 4;                     // lanes per stream
     int block_threads = 64;
     bool poison = false;               // SDZ_POISON=1 (tests): fill the device output arena with 0xA5 before every decode
@@ -76,6 +84,17 @@ int grow_stage(sdz_ctx* ctx, size_t bytes)
     cudaError_t e = cudaMallocHost(&ctx->h_stage, want);
     if (e != cudaSuccess) { ctx->err = std::string("cudaMallocHost: ") + cudaGetErrorString(e); return SDZ_E_NOMEM; }
     ctx->h_stage_cap = want;
+    return SDZ_OK;
+}
+
+int grow_res(sdz_ctx* ctx, size_t bytes)
+{
+    if (bytes <= ctx->h_res_cap) return SDZ_OK;
+    if (ctx->h_res) { cudaFreeHost(ctx->h_res); ctx->h_res = nullptr; ctx->h_res_cap = 0; }
+    size_t want = (bytes + (1u << 20)) & ~((size_t(1) << 20) - 1);
+    cudaError_t e = cudaMallocHost(&ctx->h_res, want);
+    if (e != cudaSuccess) { ctx->err = std::string("cudaMallocHost: ") + cudaGetErrorString(e); return SDZ_E_NOMEM; }
+    ctx->h_res_cap = want;
     return SDZ_OK;
 }
 
@@ -134,14 +153,18 @@ int launch_inflate_t(sdz_ctx* ctx, const sdz::InflateParams& P)
     unsigned long long want = (P.n + groups - 1) / groups;
     unsigned long long grid = std::min<unsigned long long>(want, (unsigned long long)ctx->sm_count * per_sm);
     if (grid == 0) return SDZ_OK;
+    const int lane = ctx->cur_lane;
+    DevBuf& scratch = lane ? ctx->lane_scratch[lane] : ctx->d_misc;
+    cudaStream_t st = ctx->lane_stream[lane];
     {
-        int rc = grow(ctx, ctx->d_misc, (size_t)grid * groups * sdz::SCRATCH_U16 * sizeof(uint16_t));
+        int rc = grow(ctx, scratch, (size_t)grid * groups * sdz::SCRATCH_U16 * sizeof(uint16_t));
         if (rc) return rc;
     }
     sdz::InflateParams Q = P;
-    Q.scratch = (uint16_t*)ctx->d_misc.p;
-    CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), ctx->stream));
-    kern<<<(unsigned)grid, threads, smem, ctx->stream>>>(Q);
+    Q.scratch = (uint16_t*)scratch.p;
+    Q.counter = lane ? ctx->d_counter + 4 + 2 * lane : ctx->d_counter;
+    CK(cudaMemsetAsync(Q.counter, 0, sizeof(unsigned long long), st));
+    kern<<<(unsigned)grid, threads, smem, st>>>(Q);
     ctx->launches++;
     CK(cudaGetLastError());
     return SDZ_OK;
@@ -161,10 +184,13 @@ int launch_inflate(sdz_ctx* ctx, const sdz::InflateParams& P)
 int launch_finalize(sdz_ctx* ctx, const uint8_t* d_out, sdz_result* d_res, uint64_t n)
 {
     if (n == 0) return SDZ_OK;
-    CK(cudaMemsetAsync(ctx->d_counter + 1, 0, sizeof(unsigned long long), ctx->stream));
+    const int lane = ctx->cur_lane;
+    unsigned long long* counter = lane ? ctx->d_counter + 4 + 2 * lane + 1 : ctx->d_counter + 1;
+    cudaStream_t st = ctx->lane_stream[lane];
+    CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
     unsigned long long warps = n;
     unsigned grid = (unsigned)std::min<unsigned long long>((warps + 7) / 8, (unsigned long long)ctx->sm_count * 8);
-    sdz::finalize_streams_kernel<<<grid, 256, 0, ctx->stream>>>(d_out, d_res, n, ctx->d_counter + 1);
+    sdz::finalize_streams_kernel<<<grid, 256, 0, st>>>(d_out, d_res, n, counter);
     ctx->launches++;
     CK(cudaGetLastError());
     return SDZ_OK;
@@ -178,15 +204,16 @@ int run_batch_device(sdz_ctx* ctx, const sdz_batch_dev* b, bool sizes_only, bool
     P.dict = b->d_dict; P.dict_off = b->d_dict_off; P.dict_len = b->d_dict_len; P.dict_adler = b->d_dict_adler;
     P.out = sizes_only ? nullptr : b->d_out; P.out_off = b->d_out_off; P.out_cap = b->d_out_cap;
     P.res = b->d_results; P.n = b->n; P.counter = ctx->d_counter; P.scratch = nullptr;
-    if (first) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    cudaStream_t st = ctx->lane_stream[ctx->cur_lane];
+    if (first) CK(cudaEventRecord(ctx->ev[0], st));
     int rc = sizes_only ? launch_inflate<false>(ctx, P) : launch_inflate<true>(ctx, P);
     if (rc) return rc;
-    if (last) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    if (last) CK(cudaEventRecord(ctx->ev[1], st));
     if (!sizes_only) {
         rc = launch_finalize(ctx, b->d_out, b->d_results, b->n);
         if (rc) return rc;
     }
-    if (last) CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    if (last) CK(cudaEventRecord(ctx->ev[2], st));
     return SDZ_OK;
 }
 
@@ -242,7 +269,10 @@ int sdz_ctx_create(int device, uint32_t flags, sdz_ctx** out)
     if (cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) != cudaSuccess) return fail(SDZ_E_CUDA);
     for (auto& e : ctx->ev)
         if (cudaEventCreate(&e) != cudaSuccess) return fail(SDZ_E_CUDA);
-    if (cudaMalloc(&ctx->d_counter, 4 * sizeof(unsigned long long)) != cudaSuccess) return fail(SDZ_E_NOMEM);
+    if (cudaMalloc(&ctx->d_counter, (4 + 2 * sdz_ctx::N_LANES) * sizeof(unsigned long long)) != cudaSuccess) return fail(SDZ_E_NOMEM);
+    ctx->lane_stream[0] = ctx->stream;
+    for (int l = 1; l < sdz_ctx::N_LANES; l++)
+        if (cudaStreamCreateWithFlags(&ctx->lane_stream[l], cudaStreamNonBlocking) != cudaSuccess) return fail(SDZ_E_CUDA);
     if (const char* g = getenv("SDZ_GROUP")) { int v = atoi(g); if (v == 2 || v == 4 || v == 8 || v == 32) ctx->group = v; }
     if (const char* t = getenv("SDZ_BLOCK")) { int v = atoi(t); if (v == 32 || v == 64 || v == 128) ctx->block_threads = v; }
     if (ctx->block_threads < ctx->group) ctx->block_threads = ctx->group;
@@ -260,7 +290,12 @@ void sdz_ctx_destroy(sdz_ctx* ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (DevBuf* b : { &ctx->d_in, &ctx->d_out, &ctx->d_meta, &ctx->d_res, &ctx->d_part, &ctx->d_misc, &ctx->d_sym, &ctx->d_task })
         if (b->p) cudaFree(b->p);
+    for (int l = 1; l < sdz_ctx::N_LANES; l++) {
+        if (ctx->lane_stream[l]) { cudaStreamSynchronize(ctx->lane_stream[l]); cudaStreamDestroy(ctx->lane_stream[l]); }
+        if (ctx->lane_scratch[l].p) cudaFree(ctx->lane_scratch[l].p);
+    }
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->h_res) cudaFreeHost(ctx->h_res);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
     for (auto& e : ctx->ev)
         if (e) cudaEventDestroy(e);
@@ -598,16 +633,19 @@ static int inflate_host(sdz_ctx* ctx, const sdz_in* in, uint64_t n, uint8_t* out
     b.d_results = (sdz_result*)ctx->d_res.p;
     b.n = n;
 
-    std::vector<sdz_result> tmp;
-    sdz_result* rdst = results;
-    if (!rdst) { tmp.resize(n); rdst = tmp.data(); }
+    if ((rc = grow_res(ctx, n * sizeof(sdz_result)))) return rc;
+    sdz_result* rdst = (sdz_result*)ctx->h_res;
 
     // ---- pipeline: the batch is cut into sub-batches that still fill the GPU; staging (host
     // threads) -> H2D (s_h2d) -> kernels (stream) -> D2H (s_d2h) of consecutive sub-batches overlap
-    uint64_t K = n / (getenv("SDZ_SUBBATCH") ? (uint64_t)atoll(getenv("SDZ_SUBBATCH")) : 16384ull);
+    // Sub-batches are small (the device -> host copy of the first one starts early and the copy engine never
+    // waits for a big kernel); kernels of consecutive sub-batches go to different compute lanes, so together
+    // they still fill the GPU.
+    uint64_t K = n / (getenv("SDZ_SUBBATCH") ? (uint64_t)atoll(getenv("SDZ_SUBBATCH")) : 4096ull);
     if (K < 1) K = 1;
-    if (K > 8) K = 8;
+    if (K > 32) K = 32;
     if (!sizes_only && !dense) K = 1;
+    const int n_lanes = K > 1 ? sdz_ctx::N_LANES : 1;
     while (ctx->pipe_ev.size() < 2 * K) {
         cudaEvent_t e;
         CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -632,6 +670,16 @@ static int inflate_host(sdz_ctx* ctx, const sdz_in* in, uint64_t n, uint8_t* out
         // stale bytes of an earlier call must never be able to stand in for bytes a kernel failed to write
         CK(cudaMemsetAsync(ctx->d_out.p, 0xA5, (out_hi - out_lo) + 64, ctx->stream));
     }
+    CK(cudaStreamSynchronize(ctx->stream));              // dictionaries / poison are in place before any lane starts
+    // SDZ_TRACE_PIPE=1: device timeline of every sub-batch on stderr
+    static const bool trace_pipe = getenv("SDZ_TRACE_PIPE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    if (trace_pipe) {
+        tev.resize(3 * K + 1);
+        for (auto& e : tev) cudaEventCreate(&e);
+        cudaEventRecord(tev[3 * K], ctx->s_h2d);
+    }
+    const auto t_host0 = std::chrono::steady_clock::now();
     CK(cudaMemcpyAsync(ctx->d_meta.p, hm, meta_bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
     for (uint64_t c = 0; c < K; c++) {
         const uint64_t lo = n * c / K, hi = n * (c + 1) / K;
@@ -647,23 +695,41 @@ static int inflate_host(sdz_ctx* ctx, const sdz_in* in, uint64_t n, uint8_t* out
         if (c_hi > c_lo)
             CK(cudaMemcpyAsync(d_in + c_lo, (direct ? ubase : hs) + c_lo, c_hi - c_lo, cudaMemcpyHostToDevice, ctx->s_h2d));
         CK(cudaEventRecord(ctx->pipe_ev[2 * c], ctx->s_h2d));
-        CK(cudaStreamWaitEvent(ctx->stream, ctx->pipe_ev[2 * c], 0));
+        if (trace_pipe) cudaEventRecord(tev[3 * c], ctx->s_h2d);
+        ctx->cur_lane = (int)(c % n_lanes);
+        cudaStream_t lane_st = ctx->lane_stream[ctx->cur_lane];
+        CK(cudaStreamWaitEvent(lane_st, ctx->pipe_ev[2 * c], 0));
         sdz_batch_dev bc = b;
         bc.d_in_off += lo; bc.d_dict_off += lo; bc.d_out_off += lo; bc.d_in_len += lo; bc.d_dict_len += lo;
         bc.d_out_cap += lo; bc.d_dict_adler += lo; bc.d_mode += lo; bc.d_results += lo;
         bc.n = hi - lo;
         rc = run_batch_device(ctx, &bc, sizes_only, c == 0, c == K - 1);
+        ctx->cur_lane = 0;
         if (rc) return rc;
-        CK(cudaEventRecord(ctx->pipe_ev[2 * c + 1], ctx->stream));
+        CK(cudaEventRecord(ctx->pipe_ev[2 * c + 1], lane_st));
+        if (trace_pipe) cudaEventRecord(tev[3 * c + 1], lane_st);
         CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->pipe_ev[2 * c + 1], 0));
         CK(cudaMemcpyAsync(rdst + lo, (sdz_result*)ctx->d_res.p + lo, (hi - lo) * sizeof(sdz_result), cudaMemcpyDeviceToHost, ctx->s_d2h));
         if (!sizes_only && dense) {
             const uint64_t o_lo = d_out_off[lo], o_hi = d_out_off[hi - 1] + d_out_cap[hi - 1];
             CK(cudaMemcpyAsync(out_arena + out_lo + o_lo, (uint8_t*)ctx->d_out.p + o_lo, o_hi - o_lo, cudaMemcpyDeviceToHost, ctx->s_d2h));
         }
+        if (trace_pipe) cudaEventRecord(tev[3 * c + 2], ctx->s_d2h);
     }
+    const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
     CK(cudaStreamSynchronize(ctx->s_d2h));
-    CK(cudaStreamSynchronize(ctx->stream));
+    for (int l = 0; l < n_lanes; l++) CK(cudaStreamSynchronize(ctx->lane_stream[l]));
+    if (trace_pipe) {
+        fprintf(stderr, "[sdz pipe] %llu sub-batches, host enqueue %.2f ms\n", (unsigned long long)K, host_ms);
+        for (uint64_t c = 0; c < K; c++) {
+            float a = 0, b2 = 0, d = 0;
+            cudaEventElapsedTime(&a, tev[3 * K], tev[3 * c]);
+            cudaEventElapsedTime(&b2, tev[3 * K], tev[3 * c + 1]);
+            cudaEventElapsedTime(&d, tev[3 * K], tev[3 * c + 2]);
+            fprintf(stderr, "[sdz pipe] %2llu: input landed %7.2f  kernels done %7.2f  output landed %7.2f ms\n", (unsigned long long)c, a, b2, d);
+        }
+        for (auto& e : tev) cudaEventDestroy(e);
+    }
     if (!sizes_only && !dense) {
         for (uint64_t i = 0; i < n; i++)
             if (rdst[i].out_len)
@@ -679,6 +745,7 @@ static int inflate_host(sdz_ctx* ctx, const sdz_in* in, uint64_t n, uint8_t* out
         }
         if (out_len) out_len[i] = rdst[i].out_len;
     }
+    if (results) memcpy(results, rdst, n * sizeof(sdz_result));
     return ret;
 }
 
