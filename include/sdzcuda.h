@@ -159,6 +159,41 @@ int sdz_inflate_batch_device(sdz_ctx* ctx, const sdz_batch_dev* batch, uint32_t 
  * Returns SDZ_E_OUT_CAP (res->out_len = needed size) if out_cap is too small. */
 int sdz_inflate_large(sdz_ctx* ctx, const uint8_t* data, uint64_t len, uint8_t mode, int on_device,
                       uint8_t* out, uint64_t out_cap, sdz_result* res);
+
+/* The same path as phases of a session, for a stream spread over several GPUs (one process per GPU, every
+ * rank holding the whole compressed stream).  Rank r of n:
+ *   sdz_large_open; sdz_large_index(r, n) -> all-gather the block / resume-point records -> sdz_large_plan on
+ *   every rank (identical result); sdz_large_range(r, n) = its slice of the output; sdz_large_decode(r, n, d_out);
+ *   receive the final 32 KiB before its slice from rank r-1 into d_out - 32768 (rank 0: nothing);
+ *   sdz_large_windows; send the last 32 KiB of its slice to rank r+1; sdz_large_resolve; sdz_crc32 of the slice;
+ *   sdz_crc32_combine in rank order; sdz_large_finish with the combined value.
+ * sdz_inflate_large is exactly this sequence for r = 0, n = 1.  SDZ_E_UNSUPPORTED from any phase = the stream needs
+ * the sequential decoder (sdz_inflate_batch). */
+typedef struct sdz_large sdz_large;
+typedef struct sdz_large_block {      /* one candidate deflate block                                          */
+    uint64_t bit, end_bit;            /* bit position of its header / of the first bit after it               */
+    uint64_t out_len;                 /* bytes it decodes to                                                  */
+    uint8_t  last, btype, ok;         /* BFINAL, BTYPE, 1 = walked to its end-of-block code                   */
+    uint8_t  reserved[5];
+} sdz_large_block;
+typedef struct sdz_large_ckpt {       /* resume point inside a block: the symbol at `bit` produces byte `pos` */
+    uint64_t block_bit, bit;
+    uint32_t pos, reserved;
+} sdz_large_ckpt;
+int  sdz_large_open(sdz_ctx* ctx, const uint8_t* data, uint64_t len, uint8_t mode, int on_device, sdz_large** out);
+void sdz_large_close(sdz_large* L);
+int  sdz_large_index(sdz_large* L, uint32_t part, uint32_t n_parts, const sdz_large_block** blocks, uint64_t* n_blocks,
+                     const sdz_large_ckpt** ckpts, uint64_t* n_ckpts);      /* arrays owned by the session */
+int  sdz_large_plan(sdz_large* L, const sdz_large_block* blocks, uint64_t n_blocks, const sdz_large_ckpt* ckpts, uint64_t n_ckpts,
+                    uint64_t* total_out, uint64_t* n_pieces);
+int  sdz_large_range(sdz_large* L, uint32_t part, uint32_t n_parts, uint64_t* off_lo, uint64_t* off_hi);
+int  sdz_large_decode(sdz_large* L, uint32_t part, uint32_t n_parts, uint8_t* d_out);
+int  sdz_large_windows(sdz_large* L);
+int  sdz_large_resolve(sdz_large* L);
+int  sdz_large_finish(sdz_large* L, int32_t running_checksum, sdz_result* res);
+int  sdz_large_is_gzip(sdz_large* L);
+/* crc32(A || B) from crc32(A), crc32(B), len(B) - host arithmetic, no device needed */
+int32_t sdz_crc32_combine(int32_t crc_a, int32_t crc_b, uint64_t len_b);
 int sdz_sync(sdz_ctx* ctx);
 
 #ifdef __cplusplus

@@ -165,14 +165,14 @@ __device__ __forceinline__ bool precode_plausible(const uint32_t* src32, uint64_
 // pass are queued per warp so that the Kraft test runs on full warps; its survivors (a fraction of a
 // per cent) go to surv[] for stage 2.
 constexpr int PF_TILE = 4096;
-__global__ void __launch_bounds__(256) prefilter_headers(const uint8_t* src, uint64_t first_bit, uint64_t total_bits, uint64_t* surv,
-                                                         unsigned long long* n_surv, unsigned long long cap)
+__global__ void __launch_bounds__(256) prefilter_headers(const uint8_t* src, uint64_t first_bit, uint64_t end_bit, uint64_t total_bits,
+                                                         uint64_t* surv, unsigned long long* n_surv, unsigned long long cap)
 {
     __shared__ uint32_t queue_all[8][64];
     const uint32_t* src32 = reinterpret_cast<const uint32_t*>(src);
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint32_t* q = queue_all[warp];
-    const uint64_t n_pos = total_bits - first_bit;
+    const uint64_t n_pos = end_bit - first_bit;                      // positions [first_bit, end_bit) are tested
     const uint64_t warps_total = (uint64_t)gridDim.x * 8u;
     auto kraft = [&](uint64_t p) {
         const uint32_t h = bits32_at(src32, p);
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(256) prefilter_headers(const uint8_t* src, uin
         uint32_t qn = 0;
         for (uint32_t r = 0; r < PF_TILE / 32; r++) {
             const uint64_t p = base + r * 32u + lane;
-            bool ok = p + 17 + 12 <= total_bits;
+            bool ok = p < end_bit && p + 17 + 12 <= total_bits;
             if (ok) {
                 const uint32_t h = bits32_at(src32, p);
                 ok = ((h >> 1) & 3u) == 2u && ((h >> 3) & 31u) <= 29u && ((h >> 8) & 31u) <= 29u;

@@ -764,6 +764,11 @@ int sdz_inflate_sizes(sdz_ctx* ctx, const sdz_in* in, uint64_t n, uint64_t* out_
 }  // extern "C"
 
 // ---------------------------------------------------------------------------- one large stream
+//
+// The work is organised as phases of a session (sdz_large_*), so that the SAME code serves one GPU
+// (sdz_inflate_large drives all phases for part 0 of 1) and a stream spread over several GPUs, one
+// process each (every rank drives the phases for its part and exchanges three small things with the
+// others: the block index, the 32 KiB window at its left edge, and its partial CRC).
 
 namespace {
 
@@ -793,7 +798,513 @@ int launch_tasks(sdz_ctx* ctx, const uint8_t* d_src, const LargeTasks& T, sdz_re
     return launch_inflate_t<G, STORE, TM>(ctx, P);
 }
 
+uint32_t large_ckpt_step()
+{
+    static const uint32_t step = [] {
+        const char* e = getenv("SDZ_LARGE_STEP");
+        uint32_t v = e ? (uint32_t)atoi(e) : 16384u;
+        uint32_t p2 = 1024;
+        while (p2 < v && p2 < (1u << 24)) p2 <<= 1;
+        return p2;
+    }();
+    return step;
+}
+
 }  // namespace
+
+struct sdz_large {
+    sdz_ctx* ctx = nullptr;
+    const uint8_t* data = nullptr;      // as given by the caller (host or device)
+    uint64_t len = 0;
+    uint8_t mode = 0;
+    int on_device = 0;
+    const uint8_t* d_src = nullptr;     // the stream in HBM
+    // container header (src/inflate.ts:142-401)
+    bool raw = false, is_gzip = false;
+    int method = 0;
+    int32_t mtime = 0;
+    uint32_t name_off = 0, name_len = 0;
+    uint64_t first_bit = 0, total_bits = 0;
+    const uint64_t* d_zero_off = nullptr;
+    const uint32_t* d_len0 = nullptr;
+    // index of the part this session was asked for (handed to the caller)
+    std::vector<sdz_large_block> blocks;
+    std::vector<sdz_large_ckpt> ckpts;
+    // plan: the chain of real blocks cut into pieces
+    std::vector<uint64_t> t_bit, t_resume, t_off;
+    std::vector<uint32_t> t_limit;
+    uint64_t total_out = 0, end_bit = 0, n_blocks = 0;
+    bool planned = false;
+    int32_t stored = 0, isize = 0;
+    uint64_t total_in = 0;
+    // the part being decoded
+    uint64_t p_lo = 0, p_hi = 0, bps = 1;
+    uint8_t* d_out = nullptr;           // device address of output byte off_lo()
+    DevBuf d_sym, d_tasks, d_desc;
+    uint64_t* d_to = nullptr;           // absolute output offsets of the part's pieces (+ end)
+    uint64_t off_lo() const { return t_off[p_lo]; }
+    uint64_t off_hi() const { return t_off[p_hi]; }
+    // trace
+    bool trace = false;
+    std::chrono::steady_clock::time_point t_last;
+    void lap(const char* what)
+    {
+        if (!trace) return;
+        cudaStreamSynchronize(ctx->stream);
+        const auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[sdz_large] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_last).count());
+        t_last = t;
+    }
+};
+
+namespace {
+
+// extent + resume points of the blocks whose headers start at `starts` (count-only walk of ONE block each)
+int large_extents(sdz_large* L, const std::vector<uint64_t>& starts, std::vector<sdz_result>& recs, std::vector<sdz::Ckpt>& cks)
+{
+    sdz_ctx* ctx = L->ctx;
+    const uint64_t n = starts.size();
+    recs.clear(); cks.clear();
+    if (!n) return SDZ_OK;
+    int r2;
+    unsigned long long* d_count = ctx->d_counter + 3;
+    if ((r2 = grow(ctx, ctx->d_task, (n + 16) * sizeof(uint64_t)))) return r2;
+    if ((r2 = grow(ctx, ctx->d_res, n * sizeof(sdz_result)))) return r2;
+    CK(cudaMemcpyAsync(ctx->d_task.p, starts.data(), n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    unsigned long long cap = n == 1 ? 65536 : L->len / 64 + 65536, got = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if ((r2 = grow(ctx, ctx->d_part, cap * sizeof(sdz::Ckpt)))) return r2;
+        CK(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), ctx->stream));
+        LargeTasks T;
+        T.bit = (const uint64_t*)ctx->d_task.p;
+        T.ckpt = (sdz::Ckpt*)ctx->d_part.p; T.ckpt_count = d_count; T.ckpt_cap = cap; T.ckpt_step = large_ckpt_step();
+        r2 = launch_tasks<4, false, sdz::TM_INDEX>(ctx, L->d_src, T, (sdz_result*)ctx->d_res.p, n, L->d_zero_off, L->d_len0);
+        if (r2) return r2;
+        CK(cudaMemcpyAsync(&got, d_count, sizeof got, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (got <= cap) break;
+        cap = got + 1024;                                                   // extremely compressible data: once more with room
+    }
+    recs.resize(n);
+    cks.resize(got);
+    CK(cudaMemcpyAsync(recs.data(), ctx->d_res.p, n * sizeof(sdz_result), cudaMemcpyDeviceToHost, ctx->stream));
+    if (got) CK(cudaMemcpyAsync(cks.data(), ctx->d_part.p, got * sizeof(sdz::Ckpt), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::sort(cks.begin(), cks.end(), [](const sdz::Ckpt& a, const sdz::Ckpt& b) { return a.task != b.task ? a.task < b.task : a.pos < b.pos; });
+    return SDZ_OK;
+}
+
+void large_records(const std::vector<uint64_t>& starts, const std::vector<sdz_result>& recs, const std::vector<sdz::Ckpt>& cks,
+                   std::vector<sdz_large_block>& blocks, std::vector<sdz_large_ckpt>& ckpts)
+{
+    for (size_t i = 0; i < starts.size(); i++) {
+        sdz_large_block b;
+        memset(&b, 0, sizeof b);
+        b.bit = starts[i]; b.end_bit = recs[i].total_in; b.out_len = recs[i].out_len;
+        b.last = (uint8_t)(recs[i].n_blocks != 0); b.btype = recs[i].container; b.ok = (uint8_t)(recs[i].zstatus == sdz::R_EOB);
+        blocks.push_back(b);
+    }
+    for (const sdz::Ckpt& c : cks) {
+        sdz_large_ckpt k;
+        k.block_bit = starts[c.task]; k.bit = c.bit; k.pos = c.pos; k.reserved = 0;
+        ckpts.push_back(k);
+    }
+}
+
+}  // namespace
+
+extern "C" int sdz_large_open(sdz_ctx* ctx, const uint8_t* data, uint64_t len, uint8_t mode, int on_device, sdz_large** out)
+{
+    if (!ctx || !out || (len && !data) || mode > SDZ_MODE_RAW) return SDZ_E_ARG;
+    if (len >= (1ull << 32) - 64) return SDZ_E_ARG;
+    *out = nullptr;
+    CK(cudaSetDevice(ctx->device));
+    // ---- container header on the host (a few bytes; src/inflate.ts:142-401).  Anything but a plain, complete
+    // header goes to the sequential decoder, which knows every corner of the reference's state machine.
+    uint8_t head[1024];
+    const size_t hn = (size_t)std::min<uint64_t>(len, sizeof head);
+    if (on_device) CK(cudaMemcpy(head, data, hn, cudaMemcpyDeviceToHost)); else if (hn) memcpy(head, data, hn);
+    bool raw = mode == SDZ_MODE_RAW, is_gzip = false;
+    int method = 0;
+    int32_t mtime = 0;
+    uint32_t name_off = 0, name_len = 0;
+    size_t hp = 0;
+    auto seq = [&]() { ctx->err = "stream needs the sequential decoder"; return SDZ_E_UNSUPPORTED; };
+    if (mode == SDZ_MODE_SNIFF) {
+        if (len < 2) return seq();
+        const bool ident = (head[0] == 0x78 && (((head[0] << 8) + head[1]) % 31) == 0) || (head[0] == 0x1f && head[1] == 0x8b);
+        raw = !ident;
+    }
+    if (!raw) {
+        if (hn < 2) return seq();
+        if (head[0] == 0x1f) {
+            if (head[1] != 0x8b || hn < 10 || (head[2] & 0xf) != 8 || (head[2] >> 4) + 8 > 15) return seq();
+            is_gzip = true; method = head[2];
+            const uint8_t fl = head[3];
+            for (int i = 0; i < 4; i++) mtime = (int32_t)(((uint32_t)mtime >> 8) | ((uint32_t)head[4 + i] << 24));
+            hp = 10;
+            if (fl & 4) return seq();                                       // FEXTRA
+            if (fl & 8) { name_off = (uint32_t)hp; while (hp < hn && head[hp]) { hp++; name_len++; } if (hp >= hn) return seq(); hp++; }
+            if (fl & 16) { while (hp < hn && head[hp]) hp++; if (hp >= hn) return seq(); hp++; }
+            if (fl & 2) hp += 2;
+            if (hp >= hn) return seq();
+        } else {
+            method = head[0];
+            if ((method & 0xf) != 8 || (method >> 4) + 8 > 15 || ((method << 8) + head[1]) % 31 != 0 || (head[1] & 0x20)) return seq();
+            hp = 2;
+        }
+    }
+    if (len < hp + 1) return seq();
+
+    sdz_large* L = new sdz_large();
+    L->ctx = ctx; L->data = data; L->len = len; L->mode = mode; L->on_device = on_device;
+    L->raw = raw; L->is_gzip = is_gzip; L->method = method; L->mtime = mtime; L->name_off = name_off; L->name_len = name_len;
+    L->first_bit = (uint64_t)hp * 8; L->total_bits = len * 8;
+    L->trace = getenv("SDZ_TRACE_LARGE") != nullptr;
+    L->t_last = std::chrono::steady_clock::now();
+    auto fail = [&](int rc) { delete L; return rc; };
+    // ---- the stream in HBM
+    int rc;
+    L->d_src = data;
+    if (!on_device) {
+        if ((rc = grow(ctx, ctx->d_in, len + SDZ_IN_PAD))) return fail(rc);
+        if (cudaMemcpyAsync(ctx->d_in.p, data, len, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+            cudaMemsetAsync((uint8_t*)ctx->d_in.p + len, 0, SDZ_IN_PAD, ctx->stream) != cudaSuccess) { ctx->err = "staging the stream failed"; return fail(SDZ_E_CUDA); }
+        L->d_src = (const uint8_t*)ctx->d_in.p;
+    } else if (reinterpret_cast<uintptr_t>(data) & 15) return fail(SDZ_E_ARG);
+    // stream-0 descriptors for the task launches: in_off[0] = 0, in_len[0] = len
+    // (owned by the session: the context's scratch is reused by every other call, e.g. the checksum of a slice)
+    if ((rc = grow(ctx, L->d_desc, 64))) return fail(rc);
+    {
+        uint64_t zero_off = 0;
+        uint32_t len32 = (uint32_t)len;
+        if (cudaMemcpyAsync(L->d_desc.p, &zero_off, 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+            cudaMemcpyAsync((uint8_t*)L->d_desc.p + 8, &len32, 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = "staging the stream failed"; cudaFree(L->d_desc.p); return fail(SDZ_E_CUDA); }
+    }
+    L->d_zero_off = (const uint64_t*)L->d_desc.p;
+    L->d_len0 = (const uint32_t*)((uint8_t*)L->d_desc.p + 8);
+    L->lap("header + input staging");
+    *out = L;
+    return SDZ_OK;
+}
+
+extern "C" void sdz_large_close(sdz_large* L)
+{
+    if (!L) return;
+    cudaSetDevice(L->ctx->device);
+    cudaStreamSynchronize(L->ctx->stream);
+    if (L->d_sym.p) cudaFree(L->d_sym.p);
+    if (L->d_tasks.p) cudaFree(L->d_tasks.p);
+    if (L->d_desc.p) cudaFree(L->d_desc.p);
+    delete L;
+}
+
+// pass 1 for part `part` of `n_parts`: candidate headers in that slice of the payload bits (+ the first block of the
+// stream in part 0), their extents and resume points
+extern "C" int sdz_large_index(sdz_large* L, uint32_t part, uint32_t n_parts, const sdz_large_block** blocks, uint64_t* n_blocks,
+                               const sdz_large_ckpt** ckpts, uint64_t* n_ckpts)
+{
+    if (!L || !n_parts || part >= n_parts || !blocks || !n_blocks || !ckpts || !n_ckpts) return SDZ_E_ARG;
+    sdz_ctx* ctx = L->ctx;
+    CK(cudaSetDevice(ctx->device));
+    L->blocks.clear(); L->ckpts.clear();
+    const uint64_t span_all = L->total_bits - L->first_bit;
+    uint64_t lo = L->first_bit + span_all / n_parts * part, hi = part + 1 == n_parts ? L->total_bits : L->first_bit + span_all / n_parts * (part + 1);
+    const uint64_t span = hi - lo;
+    const uint64_t max_cand = span / 4096 + 4096, max_surv = span / 32 + 4096;
+    int rc;
+    if ((rc = grow(ctx, ctx->d_task, (max_cand + 16) * sizeof(uint64_t)))) return rc;
+    if ((rc = grow(ctx, ctx->d_part, max_surv * sizeof(uint64_t)))) return rc;
+    uint64_t* d_cand = (uint64_t*)ctx->d_task.p;
+    unsigned long long* d_ncand = ctx->d_counter + 2;                        // [2] candidates, [3] survivors / resume points
+    CK(cudaMemsetAsync(d_ncand, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (span) {
+        const uint64_t tiles = (span + sdz::PF_TILE - 1) / sdz::PF_TILE;
+        const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((tiles + 7) / 8, (uint64_t)ctx->sm_count * 8));
+        sdz::prefilter_headers<<<grid, 256, 0, ctx->stream>>>(L->d_src, lo, hi, L->total_bits, (uint64_t*)ctx->d_part.p, d_ncand + 1, max_surv);
+        L->lap("1a prefilter");
+        sdz::verify_headers<<<ctx->sm_count * 16, 128, 0, ctx->stream>>>(L->d_src, L->total_bits, (const uint64_t*)ctx->d_part.p, d_ncand + 1, max_surv,
+                                                                     d_cand, d_ncand, max_cand);
+        ctx->launches += 2;
+        CK(cudaGetLastError());
+    }
+    unsigned long long counts[2] = { 0, 0 };
+    CK(cudaMemcpyAsync(counts, d_ncand, sizeof counts, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (counts[0] > max_cand || counts[1] > max_surv) { ctx->err = "stream needs the sequential decoder"; return SDZ_E_UNSUPPORTED; }
+    std::vector<uint64_t> cand(counts[0]);
+    if (counts[0]) CK(cudaMemcpy(cand.data(), d_cand, counts[0] * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (part == 0) cand.push_back(L->first_bit);                            // the first block, whatever its type
+    std::sort(cand.begin(), cand.end());
+    cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
+    L->lap("1a header search");
+    std::vector<sdz_result> recs;
+    std::vector<sdz::Ckpt> cks;
+    if ((rc = large_extents(L, cand, recs, cks))) return rc;
+    large_records(cand, recs, cks, L->blocks, L->ckpts);
+    L->lap("1b block extents");
+    if (L->trace) fprintf(stderr, "[sdz_large] part %u/%u: %llu survivors, %llu candidates, %llu resume points\n", part, n_parts, counts[1],
+                          (unsigned long long)cand.size(), (unsigned long long)cks.size());
+    *blocks = L->blocks.data(); *n_blocks = L->blocks.size();
+    *ckpts = L->ckpts.data(); *n_ckpts = L->ckpts.size();
+    return SDZ_OK;
+}
+
+// The chain of real blocks from the first one (false candidates are never reached), cut into pieces at the resume
+// points.  `blocks` / `ckpts`: the index of ALL parts, in any order.
+extern "C" int sdz_large_plan(sdz_large* L, const sdz_large_block* blocks, uint64_t n_blocks, const sdz_large_ckpt* ckpts, uint64_t n_ckpts,
+                              uint64_t* total_out, uint64_t* n_pieces)
+{
+    if (!L || (n_blocks && !blocks) || (n_ckpts && !ckpts)) return SDZ_E_ARG;
+    sdz_ctx* ctx = L->ctx;
+    CK(cudaSetDevice(ctx->device));
+    auto seq = [&]() { ctx->err = "stream needs the sequential decoder"; return SDZ_E_UNSUPPORTED; };
+    std::vector<sdz_large_block> B(blocks, blocks + n_blocks);
+    std::vector<sdz_large_ckpt> C(ckpts, ckpts + n_ckpts);
+    std::sort(B.begin(), B.end(), [](const sdz_large_block& a, const sdz_large_block& b) { return a.bit < b.bit; });
+    std::sort(C.begin(), C.end(), [](const sdz_large_ckpt& a, const sdz_large_ckpt& b) { return a.block_bit != b.block_bit ? a.block_bit < b.block_bit : a.pos < b.pos; });
+    L->t_bit.clear(); L->t_resume.clear(); L->t_off.clear(); L->t_limit.clear();
+    uint64_t cur = L->first_bit, total = 0, nb = 0, n_single = 0;
+    bool finished = false;
+    int rc;
+    for (uint64_t guard = 0; guard < (1ull << 26); guard++) {
+        auto it = std::lower_bound(B.begin(), B.end(), cur, [](const sdz_large_block& a, uint64_t v) { return a.bit < v; });
+        sdz_large_block blk;
+        std::vector<sdz_large_ckpt> own;
+        const sdz_large_ckpt* c = nullptr;
+        size_t nc = 0;
+        if (it != B.end() && it->bit == cur) {
+            blk = *it;
+            auto lo = std::lower_bound(C.begin(), C.end(), cur, [](const sdz_large_ckpt& a, uint64_t v) { return a.block_bit < v; });
+            auto hi = std::upper_bound(lo, C.end(), cur, [](uint64_t v, const sdz_large_ckpt& a) { return v < a.block_bit; });
+            c = C.data() + (lo - C.begin());
+            nc = (size_t)(hi - lo);
+        } else {
+            // a block the header search does not look for (stored / fixed): measure it on its own
+            std::vector<uint64_t> one{ cur };
+            std::vector<sdz_result> r1;
+            std::vector<sdz::Ckpt> k1;
+            std::vector<sdz_large_block> b1;
+            n_single++;
+            if ((rc = large_extents(L, one, r1, k1))) return rc;
+            large_records(one, r1, k1, b1, own);
+            blk = b1[0];
+            c = own.data();
+            nc = own.size();
+        }
+        if (!blk.ok) return seq();                                          // truncated or damaged: exact sequential path
+        // a stored block's copy depends on where the reference's 16 KiB output chunks fall (SURVEY Q2),
+        // which only the sequential decoder tracks
+        if (blk.btype == 0) return seq();
+        if (blk.out_len >= (1ull << 32)) return seq();
+        uint64_t from = 0, resume = 0;
+        for (size_t k = 0; k <= nc; k++) {
+            const uint64_t to = k < nc ? c[k].pos : blk.out_len;
+            if (to > from) {
+                L->t_bit.push_back(cur); L->t_resume.push_back(resume); L->t_off.push_back(total + from);
+                L->t_limit.push_back((uint32_t)(to - from));
+            }
+            if (k < nc) { from = to; resume = c[k].bit; }
+        }
+        nb++;
+        total += blk.out_len;
+        cur = blk.end_bit;
+        if (blk.last) { finished = true; break; }
+    }
+    if (!finished) return seq();
+    L->t_off.push_back(total);
+    L->total_out = total; L->end_bit = cur; L->n_blocks = nb;
+    // ---- trailer (src/inflate.ts:423-463)
+    const uint64_t tp = (L->end_bit + 7) >> 3;
+    uint8_t tail[8] = { 0 };
+    const int want = L->raw ? 0 : (L->is_gzip ? 8 : 4);
+    const int have = (int)std::min<uint64_t>((uint64_t)want, L->len - std::min(L->len, tp));
+    if (have) { if (L->on_device) CK(cudaMemcpy(tail, L->data + tp, have, cudaMemcpyDeviceToHost)); else memcpy(tail, L->data + tp, have); }
+    if (have < want || tp + want < L->len) return seq();                    // truncated trailer / trailing bytes: exact path
+    L->stored = 0; L->isize = 0;
+    for (int i = 0; i < want; i++) {
+        const uint32_t b = tail[i];
+        if (L->is_gzip) { if (i < 4) L->stored = (int32_t)(((uint32_t)L->stored >> 8) | (b << 24)); else L->isize = (int32_t)(((uint32_t)L->isize >> 8) | (b << 24)); }
+        else L->stored = (int32_t)(((uint32_t)L->stored << 8) | b);
+    }
+    L->total_in = tp + want;
+    L->planned = true;
+    L->lap("chain walk");
+    if (L->trace) fprintf(stderr, "[sdz_large] %llu candidates, %llu blocks (%llu measured singly), %llu pieces, %llu -> %llu bytes\n",
+                          (unsigned long long)n_blocks, (unsigned long long)nb, (unsigned long long)n_single, (unsigned long long)L->t_bit.size(),
+                          (unsigned long long)L->len, (unsigned long long)total);
+    if (total_out) *total_out = total;
+    if (n_pieces) *n_pieces = L->t_bit.size();
+    return SDZ_OK;
+}
+
+// output bytes [*off_lo, *off_hi) belong to part `part` of `n_parts` (cut at piece boundaries, balanced on bytes)
+extern "C" int sdz_large_range(sdz_large* L, uint32_t part, uint32_t n_parts, uint64_t* off_lo, uint64_t* off_hi)
+{
+    if (!L || !L->planned || !n_parts || part >= n_parts || !off_lo || !off_hi) return SDZ_E_ARG;
+    auto cut = [&](uint32_t k) -> uint64_t {
+        if (k == 0) return 0;
+        if (k >= n_parts) return L->t_bit.size();
+        const uint64_t target = L->total_out / n_parts * k;
+        return (uint64_t)(std::lower_bound(L->t_off.begin(), L->t_off.end() - 1, target) - L->t_off.begin());
+    };
+    *off_lo = L->t_off[cut(part)];
+    *off_hi = L->t_off[cut(part + 1)];
+    return SDZ_OK;
+}
+
+// pass 2a + 2b for this part: its pieces into 16-bit symbols, then the windows inside the part are composed.
+// d_out: device address of output byte off_lo; 32 KiB BELOW it must be addressable when part > 0 (the window that
+// arrives from the part before) and 64 bytes above off_hi.
+extern "C" int sdz_large_decode(sdz_large* L, uint32_t part, uint32_t n_parts, uint8_t* d_out)
+{
+    if (!L || !L->planned || !n_parts || part >= n_parts) return SDZ_E_ARG;
+    sdz_ctx* ctx = L->ctx;
+    CK(cudaSetDevice(ctx->device));
+    uint64_t lo, hi;
+    sdz_large_range(L, part, n_parts, &lo, &hi);
+    L->p_lo = (uint64_t)(std::lower_bound(L->t_off.begin(), L->t_off.end() - 1, lo) - L->t_off.begin());
+    L->p_hi = hi == L->total_out ? L->t_bit.size() : (uint64_t)(std::lower_bound(L->t_off.begin(), L->t_off.end() - 1, hi) - L->t_off.begin());
+    L->d_out = d_out;
+    const uint64_t nt = L->p_hi - L->p_lo;
+    if (!nt) { CK(cudaEventRecord(ctx->ev[1], ctx->stream)); return SDZ_OK; }
+    if (!d_out) return SDZ_E_ARG;
+    int rc;
+    if ((rc = grow(ctx, L->d_sym, (hi - lo + 64) * 2))) return rc;
+    if ((rc = grow(ctx, L->d_tasks, (nt * 3 + 1) * 8 + nt * 4 + 64))) return rc;
+    if ((rc = grow(ctx, ctx->d_res, nt * sizeof(sdz_result)))) return rc;
+    uint64_t* d_tb = (uint64_t*)L->d_tasks.p;
+    uint64_t* d_tr = d_tb + nt;
+    L->d_to = d_tr + nt;
+    uint32_t* d_tl = (uint32_t*)(L->d_to + nt + 1);
+    CK(cudaMemcpyAsync(d_tb, L->t_bit.data() + L->p_lo, nt * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_tr, L->t_resume.data() + L->p_lo, nt * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(L->d_to, L->t_off.data() + L->p_lo, (nt + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_tl, L->t_limit.data() + L->p_lo, nt * 4, cudaMemcpyHostToDevice, ctx->stream));
+    // the kernels address symbols and bytes by ABSOLUTE output offset: hand them the address offset 0 would have
+    uint16_t* sym0 = (uint16_t*)L->d_sym.p - lo;
+    LargeTasks T;
+    T.bit = d_tb; T.resume = d_tr; T.out = L->d_to; T.limit = d_tl; T.sym = sym0;
+    rc = launch_tasks<4, true, sdz::TM_MARK>(ctx, L->d_src, T, (sdz_result*)ctx->d_res.p, nt, L->d_zero_off, L->d_len0);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    L->lap("2a marker decode");
+    L->bps = 1;
+    while (L->bps * L->bps < nt) L->bps++;                                  // ~sqrt(nt) pieces per segment
+    const unsigned nseg = (unsigned)((nt + L->bps - 1) / L->bps);
+    sdz::propagate_in_segment<<<nseg, 1024, 0, ctx->stream>>>(sym0, L->d_to, nt, L->bps);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    // the marker pass must have reproduced the extents
+    std::vector<sdz_result> chk(nt);
+    CK(cudaMemcpyAsync(chk.data(), ctx->d_res.p, nt * sizeof(sdz_result), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (uint64_t t = 0; t < nt; t++) {
+        const uint64_t g = L->p_lo + t;
+        bool bad = chk[t].zstatus != sdz::R_EOB || chk[t].out_len != L->t_limit[g];
+        // a piece that is followed by another piece of the same block must end exactly on that piece's resume point
+        if (g + 1 < L->t_bit.size() && L->t_bit[g + 1] == L->t_bit[g] && chk[t].total_in != L->t_resume[g + 1]) bad = true;
+        if (bad) {
+            if (L->trace)
+                fprintf(stderr, "[sdz_large] piece %llu (part %u/%u, block bit %llu, resume %llu, limit %u): status %d, out_len %llu, end bit %llu, next resume %llu\n",
+                        (unsigned long long)g, part, n_parts, (unsigned long long)L->t_bit[g], (unsigned long long)L->t_resume[g], L->t_limit[g],
+                        chk[t].zstatus, (unsigned long long)chk[t].out_len, (unsigned long long)chk[t].total_in,
+                        (unsigned long long)(g + 1 < L->t_bit.size() ? L->t_resume[g + 1] : 0));
+            ctx->err = "stream needs the sequential decoder";
+            return SDZ_E_UNSUPPORTED;
+        }
+    }
+    L->lap("2b windows inside segments");
+    return SDZ_OK;
+}
+
+// pass 2c: with the final 32 KiB before off_lo in place (at d_out - 32768; not needed for the part that starts the
+// stream), the last 32 KiB of every segment of this part become final - in particular the last 32 KiB of the part,
+// which is the window the next part is waiting for.
+extern "C" int sdz_large_windows(sdz_large* L)
+{
+    if (!L || !L->planned) return SDZ_E_ARG;
+    sdz_ctx* ctx = L->ctx;
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t nt = L->p_hi - L->p_lo;
+    if (!nt) return SDZ_OK;
+    const uint64_t lo = L->off_lo();
+    sdz::propagate_segments<<<1, 1024, 0, ctx->stream>>>((const uint16_t*)L->d_sym.p - lo, L->d_out - lo, L->d_to, nt, L->bps);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    L->lap("2c windows across segments");
+    return SDZ_OK;
+}
+
+// pass 2d: every remaining symbol of the part
+extern "C" int sdz_large_resolve(sdz_large* L)
+{
+    if (!L || !L->planned) return SDZ_E_ARG;
+    sdz_ctx* ctx = L->ctx;
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t nt = L->p_hi - L->p_lo;
+    if (nt) {
+        const uint64_t lo = L->off_lo();
+        const unsigned gy = (unsigned)std::min<uint64_t>(nt, 65535);
+        sdz::resolve_markers<<<dim3(4, gy), 256, 0, ctx->stream>>>((const uint16_t*)L->d_sym.p - lo, L->d_out - lo, L->d_to, nt, L->bps);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    L->lap("2d markers");
+    return SDZ_OK;
+}
+
+// finish() record of the whole stream (src/sd-inflate.ts:159-179) and inflate()'s throw mapping (:214-225), given the
+// running checksum of ALL output bytes (crc32 for gzip, the chunked adler32 otherwise)
+extern "C" int sdz_large_finish(sdz_large* L, int32_t running, sdz_result* res)
+{
+    if (!L || !L->planned || !res) return SDZ_E_ARG;
+    memset(res, 0, sizeof *res);
+    const bool have_running = L->total_out > 0;
+    res->out_off = 0;
+    res->out_len = L->total_out;
+    res->total_in = L->total_in;
+    res->zstatus = SDZ_Z_STREAM_END;
+    res->stored_checksum = L->stored;
+    res->running_checksum = have_running ? running : 0;
+    res->have_running = have_running;
+    res->stored_isize = L->isize;
+    res->mtime = L->mtime;
+    res->name_off = L->name_len ? L->name_off : 0;
+    res->name_len = L->name_len;
+    res->n_blocks = (uint32_t)L->n_blocks;
+    res->container = (uint8_t)(L->is_gzip ? SDZ_GZIP : (L->method == 0 ? SDZ_RAW : SDZ_ZLIB));
+    res->complete = 1;
+    const int cks = L->stored == 0 ? SDZ_UNCHECKED : ((have_running && L->stored == running) ? SDZ_MATCH : SDZ_MISMATCH);
+    const int fsz = L->isize == 0 ? SDZ_UNCHECKED : (((int64_t)L->isize == (int64_t)L->total_out) ? SDZ_MATCH : SDZ_MISMATCH);
+    res->checksum_state = (uint8_t)cks;
+    res->size_state = (uint8_t)fsz;
+    res->success = (uint8_t)(cks != SDZ_MISMATCH && fsz != SDZ_MISMATCH);
+    res->thrown_inflate = (uint8_t)(res->success ? SDZ_THROW_NONE : (cks == SDZ_MISMATCH ? SDZ_THROW_INTEGRITY : SDZ_THROW_SIZE_CHECK));
+    return SDZ_OK;
+}
+
+extern "C" int sdz_large_is_gzip(sdz_large* L) { return L && L->is_gzip; }
+
+// crc32(A || B) from crc32(A), crc32(B) and len(B): multiplication by x^(8 len2) modulo the CRC polynomial
+// (reflected), the same GF(2) arithmetic the device kernels use for their partials.  Pure host code.
+extern "C" int32_t sdz_crc32_combine(int32_t crc1, int32_t crc2, uint64_t len2)
+{
+    // x^(8 * len2) by square-and-multiply over the bits of len2 (x2n[k] = x^(2^k), k >= 3 for bytes)
+    uint32_t p = 1u << 31;                                                  // the polynomial "1"
+    uint32_t sq = 1u << 30;                                                 // x^1
+    for (int i = 0; i < 3; i++) sq = h_mulmod(sq, sq);                      // x^8
+    for (uint64_t n = len2; n; n >>= 1) {
+        if (n & 1) p = h_mulmod(p, sq);
+        sq = h_mulmod(sq, sq);
+    }
+    return (int32_t)(h_mulmod(p, (uint32_t)crc1) ^ (uint32_t)crc2);
+}
 
 extern "C" int sdz_inflate_large(sdz_ctx* ctx, const uint8_t* data, uint64_t len, uint8_t mode, int on_device,
                                  uint8_t* out, uint64_t out_cap, sdz_result* res)
@@ -802,19 +1313,10 @@ extern "C" int sdz_inflate_large(sdz_ctx* ctx, const uint8_t* data, uint64_t len
     if (len >= (1ull << 32) - 64) return SDZ_E_ARG;
     CK(cudaSetDevice(ctx->device));
     memset(res, 0, sizeof *res);
-    // SDZ_TRACE_LARGE=1: wall-clock of every phase on stderr (the phases are separated by host syncs)
-    static const bool trace = getenv("SDZ_TRACE_LARGE") != nullptr;
-    auto t_last = std::chrono::steady_clock::now();
-    auto lap = [&](const char* what) {
-        if (!trace) return;
-        cudaStreamSynchronize(ctx->stream);
-        const auto t = std::chrono::steady_clock::now();
-        fprintf(stderr, "[sdz_inflate_large] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_last).count());
-        t_last = t;
-    };
-
+    sdz_large* L = nullptr;
     auto fallback = [&]() -> int {
         // exact but sequential: the ordinary decoder, one group for the whole stream
+        if (L) { sdz_large_close(L); L = nullptr; }
         if (on_device) { ctx->err = "sdz_inflate_large: stream needs the sequential decoder; pass host pointers"; return SDZ_E_UNSUPPORTED; }
         sdz_in in1;
         memset(&in1, 0, sizeof in1);
@@ -826,272 +1328,38 @@ extern "C" int sdz_inflate_large(sdz_ctx* ctx, const uint8_t* data, uint64_t len
         uint64_t off0 = 0, cap0 = need;
         return inflate_host(ctx, &in1, 1, out, &off0, &cap0, res, nullptr, 0, false);
     };
-
-    // ---- container header on the host (a few bytes; src/inflate.ts:142-401)
-    uint8_t head[1024];
-    const size_t hn = (size_t)std::min<uint64_t>(len, sizeof head);
-    if (on_device) CK(cudaMemcpy(head, data, hn, cudaMemcpyDeviceToHost)); else memcpy(head, data, hn);
-    bool raw = mode == SDZ_MODE_RAW, is_gzip = false;
-    int method = 0;
-    int32_t mtime = 0;
-    uint32_t name_off = 0, name_len = 0;
-    size_t hp = 0;
-    if (mode == SDZ_MODE_SNIFF) {
-        if (len < 2) return fallback();
-        const bool ident = (head[0] == 0x78 && (((head[0] << 8) + head[1]) % 31) == 0) || (head[0] == 0x1f && head[1] == 0x8b);
-        raw = !ident;
-    }
-    if (!raw) {
-        if (hn < 2) return fallback();
-        if (head[0] == 0x1f) {
-            if (head[1] != 0x8b || hn < 10 || (head[2] & 0xf) != 8 || (head[2] >> 4) + 8 > 15) return fallback();
-            is_gzip = true; method = head[2];
-            const uint8_t fl = head[3];
-            for (int i = 0; i < 4; i++) mtime = (int32_t)(((uint32_t)mtime >> 8) | ((uint32_t)head[4 + i] << 24));
-            hp = 10;
-            if (fl & 4) return fallback();                                  // FEXTRA
-            if (fl & 8) { name_off = (uint32_t)hp; while (hp < hn && head[hp]) { hp++; name_len++; } if (hp >= hn) return fallback(); hp++; }
-            if (fl & 16) { while (hp < hn && head[hp]) hp++; if (hp >= hn) return fallback(); hp++; }
-            if (fl & 2) hp += 2;
-            if (hp >= hn) return fallback();
-        } else {
-            method = head[0];
-            if ((method & 0xf) != 8 || (method >> 4) + 8 > 15 || ((method << 8) + head[1]) % 31 != 0 || (head[1] & 0x20)) return fallback();
-            hp = 2;
-        }
-    }
-
-    // ---- stage the input
-    int rc;
-    const uint8_t* d_src = data;
-    if (!on_device) {
-        if ((rc = grow(ctx, ctx->d_in, len + SDZ_IN_PAD))) return rc;
-        CK(cudaMemcpyAsync(ctx->d_in.p, data, len, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemsetAsync((uint8_t*)ctx->d_in.p + len, 0, SDZ_IN_PAD, ctx->stream));
-        d_src = (const uint8_t*)ctx->d_in.p;
-    } else if (reinterpret_cast<uintptr_t>(data) & 15) return SDZ_E_ARG;
-
-    lap("header + input staging");
-    // ---- pass 1a: candidate dynamic-block headers
-    const uint64_t first_bit = (uint64_t)hp * 8, total_bits = len * 8;
-    const uint64_t max_cand = len / 512 + 4096, max_surv = total_bits / 32 + 4096;
-    if ((rc = grow(ctx, ctx->d_task, (max_cand + 16) * sizeof(uint64_t)))) return rc;
-    if ((rc = grow(ctx, ctx->d_part, max_surv * sizeof(uint64_t)))) return rc;
-    uint64_t* d_cand = (uint64_t*)ctx->d_task.p;
-    unsigned long long* d_ncand = ctx->d_counter + 2;                        // [2] candidates, [3] survivors / resume points
-    CK(cudaMemsetAsync(d_ncand, 0, 2 * sizeof(unsigned long long), ctx->stream));
-    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    {
-        const uint64_t tiles = (total_bits - first_bit + sdz::PF_TILE - 1) / sdz::PF_TILE;
-        const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((tiles + 7) / 8, (uint64_t)ctx->sm_count * 8));
-        sdz::prefilter_headers<<<grid, 256, 0, ctx->stream>>>(d_src, first_bit, total_bits, (uint64_t*)ctx->d_part.p, d_ncand + 1, max_surv);
-        lap("1a prefilter");
-        sdz::verify_headers<<<ctx->sm_count * 16, 128, 0, ctx->stream>>>(d_src, total_bits, (const uint64_t*)ctx->d_part.p, d_ncand + 1, max_surv,
-                                                                     d_cand, d_ncand, max_cand);
-        ctx->launches += 2;
-        CK(cudaGetLastError());
-    }
-    unsigned long long counts[2] = { 0, 0 };
-    CK(cudaMemcpyAsync(counts, d_ncand, sizeof counts, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    const unsigned long long n_cand = counts[0];
-    if (n_cand > max_cand || counts[1] > max_surv) return fallback();
-    std::vector<uint64_t> cand(n_cand + 1);
-    if (n_cand) CK(cudaMemcpy(cand.data(), d_cand, n_cand * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-    cand[n_cand] = first_bit;                                               // the first block, whatever its type
-    std::sort(cand.begin(), cand.end());
-    cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
-
-    // stream-0 descriptors for the task launches: in_off[0] = 0, in_len[0] = len
-    if ((rc = grow(ctx, ctx->d_meta, 64))) return rc;
-    {
-        uint64_t zero_off = 0;
-        uint32_t len32 = (uint32_t)len;
-        CK(cudaMemcpyAsync(ctx->d_meta.p, &zero_off, 8, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync((uint8_t*)ctx->d_meta.p + 8, &len32, 4, cudaMemcpyHostToDevice, ctx->stream));
-    }
-    const uint64_t* d_zero_off = (const uint64_t*)ctx->d_meta.p;
-    const uint32_t* d_len0 = (const uint32_t*)((uint8_t*)ctx->d_meta.p + 8);
-
-    // ---- pass 1b: extent and resume points of every candidate block (count-only walk of ONE block each)
-    static const uint32_t ck_step = [] {
-        const char* e = getenv("SDZ_LARGE_STEP");
-        uint32_t v = e ? (uint32_t)atoi(e) : 16384u;
-        uint32_t p2 = 1024;
-        while (p2 < v && p2 < (1u << 24)) p2 <<= 1;
-        return p2;
-    }();
-    auto extents = [&](const std::vector<uint64_t>& starts, std::vector<sdz_result>& recs, std::vector<sdz::Ckpt>& cks) -> int {
-        const uint64_t n = starts.size();
-        int r2;
-        if ((r2 = grow(ctx, ctx->d_task, (n + 16) * sizeof(uint64_t)))) return r2;
-        if ((r2 = grow(ctx, ctx->d_res, n * sizeof(sdz_result)))) return r2;
-        CK(cudaMemcpyAsync(ctx->d_task.p, starts.data(), n * 8, cudaMemcpyHostToDevice, ctx->stream));
-        unsigned long long cap = n == 1 ? 65536 : len / 64 + 65536, got = 0;
-        for (int attempt = 0; attempt < 2; attempt++) {
-            if ((r2 = grow(ctx, ctx->d_part, cap * sizeof(sdz::Ckpt)))) return r2;
-            CK(cudaMemsetAsync(d_ncand + 1, 0, sizeof(unsigned long long), ctx->stream));
-            LargeTasks T;
-            T.bit = (const uint64_t*)ctx->d_task.p;
-            T.ckpt = (sdz::Ckpt*)ctx->d_part.p; T.ckpt_count = d_ncand + 1; T.ckpt_cap = cap; T.ckpt_step = ck_step;
-            static const int index_g = getenv("SDZ_INDEX_G") ? atoi(getenv("SDZ_INDEX_G")) : 4;
-            if (index_g == 8) r2 = launch_tasks<8, false, sdz::TM_INDEX>(ctx, d_src, T, (sdz_result*)ctx->d_res.p, n, d_zero_off, d_len0);
-            else if (index_g == 32) r2 = launch_tasks<32, false, sdz::TM_INDEX>(ctx, d_src, T, (sdz_result*)ctx->d_res.p, n, d_zero_off, d_len0);
-            else r2 = launch_tasks<4, false, sdz::TM_INDEX>(ctx, d_src, T, (sdz_result*)ctx->d_res.p, n, d_zero_off, d_len0);
-            if (r2) return r2;
-            CK(cudaMemcpyAsync(&got, d_ncand + 1, sizeof got, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
-            if (got <= cap) break;
-            cap = got + 1024;                                               // extremely compressible data: once more with room
-        }
-        recs.resize(n);
-        cks.resize(got);
-        CK(cudaMemcpyAsync(recs.data(), ctx->d_res.p, n * sizeof(sdz_result), cudaMemcpyDeviceToHost, ctx->stream));
-        if (got) CK(cudaMemcpyAsync(cks.data(), ctx->d_part.p, got * sizeof(sdz::Ckpt), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        std::sort(cks.begin(), cks.end(), [](const sdz::Ckpt& a, const sdz::Ckpt& b) { return a.task != b.task ? a.task < b.task : a.pos < b.pos; });
-        return SDZ_OK;
-    };
-    lap("1a header search");
-    std::vector<sdz_result> ext;
-    std::vector<sdz::Ckpt> ckpts;
-    if ((rc = extents(cand, ext, ckpts))) return rc;
-    lap("1b block extents");
-
-    // ---- chain of real blocks from the first one, cut into pieces at the resume points
-    std::vector<uint64_t> t_bit, t_resume, t_off;
-    std::vector<uint32_t> t_limit;
-    uint64_t cur = first_bit, total_out = 0, end_bit = 0, nb = 0, n_single = 0;
-    bool finished = false;
-    auto add_pieces = [&](uint64_t block_bit, uint64_t block_len, const sdz::Ckpt* c, size_t nc) {
-        uint64_t from = 0, resume = 0;
-        for (size_t k = 0; k <= nc; k++) {
-            const uint64_t to = k < nc ? c[k].pos : block_len;
-            if (to > from) {
-                t_bit.push_back(block_bit); t_resume.push_back(resume); t_off.push_back(total_out + from);
-                t_limit.push_back((uint32_t)(to - from));
-            }
-            if (k < nc) { from = to; resume = c[k].bit; }
-        }
-    };
-    for (uint64_t guard = 0; guard < (1ull << 26); guard++) {
-        auto it = std::lower_bound(cand.begin(), cand.end(), cur);
-        sdz_result rec;
-        std::vector<sdz::Ckpt> own;
-        const sdz::Ckpt* c = nullptr;
-        size_t nc = 0;
-        if (it != cand.end() && *it == cur) {
-            const uint32_t ti = (uint32_t)(it - cand.begin());
-            rec = ext[ti];
-            auto lo = std::lower_bound(ckpts.begin(), ckpts.end(), ti, [](const sdz::Ckpt& a, uint32_t t) { return a.task < t; });
-            auto hi = std::upper_bound(lo, ckpts.end(), ti, [](uint32_t t, const sdz::Ckpt& a) { return t < a.task; });
-            c = ckpts.data() + (lo - ckpts.begin());
-            nc = (size_t)(hi - lo);
-        } else {
-            // a block the header search does not look for (stored / fixed): measure it on its own
-            std::vector<uint64_t> one{ cur };
-            n_single++;
-            std::vector<sdz_result> r1;
-            if ((rc = extents(one, r1, own))) return rc;
-            rec = r1[0];
-            c = own.data();
-            nc = own.size();
-        }
-        if (rec.zstatus != sdz::R_EOB) return fallback();                   // truncated or damaged: exact sequential path
-        // a stored block's copy depends on where the reference's 16 KiB output chunks fall (SURVEY Q2),
-        // which only the sequential decoder tracks
-        if (rec.container == 0) return fallback();
-        if (rec.out_len >= (1ull << 32)) return fallback();
-        add_pieces(cur, rec.out_len, c, nc);
-        nb++;
-        total_out += rec.out_len;
-        cur = rec.total_in;
-        if (rec.n_blocks) { finished = true; end_bit = cur; break; }
-    }
-    if (!finished) return fallback();
-    t_off.push_back(total_out);
-    const uint64_t nt = t_bit.size();
-    lap("chain walk");
-    if (trace) fprintf(stderr, "[sdz_inflate_large] %llu survivors, %llu candidates, %llu blocks (%llu measured singly), %llu pieces, %llu -> %llu bytes\n",
-                       counts[1], (unsigned long long)cand.size(), (unsigned long long)nb, (unsigned long long)n_single, (unsigned long long)nt,
-                       (unsigned long long)len, (unsigned long long)total_out);
-    if (total_out > out_cap) { res->out_len = total_out; return SDZ_E_OUT_CAP; }
-
-    // ---- trailer (src/inflate.ts:423-463)
-    uint64_t tp = (end_bit + 7) >> 3;
-    uint8_t tail[8] = { 0 };
-    const int want = raw ? 0 : (is_gzip ? 8 : 4);
-    const int have = (int)std::min<uint64_t>((uint64_t)want, len - std::min(len, tp));
-    if (have) { if (on_device) CK(cudaMemcpy(tail, data + tp, have, cudaMemcpyDeviceToHost)); else memcpy(tail, data + tp, have); }
-    if (have < want || tp + want < len) return fallback();                  // truncated trailer / trailing bytes: exact path
-    int32_t stored = 0, isize = 0;
-    for (int i = 0; i < want; i++) {
-        const uint32_t b = tail[i];
-        if (is_gzip) { if (i < 4) stored = (int32_t)(((uint32_t)stored >> 8) | (b << 24)); else isize = (int32_t)(((uint32_t)isize >> 8) | (b << 24)); }
-        else stored = (int32_t)(((uint32_t)stored << 8) | b);
-    }
-
-    // ---- pass 2a: every piece into 16-bit symbols
-    uint64_t* d_tb = nullptr;
-    uint64_t* d_to = nullptr;
-    if (nt) {
-        if ((rc = grow(ctx, ctx->d_sym, (total_out + 64) * 2))) return rc;
-        if ((rc = grow(ctx, ctx->d_task, (nt * 3 + 1) * 8 + nt * 4 + 64))) return rc;
-        if ((rc = grow(ctx, ctx->d_res, nt * sizeof(sdz_result)))) return rc;
-        d_tb = (uint64_t*)ctx->d_task.p;
-        uint64_t* d_tr = d_tb + nt;
-        d_to = d_tr + nt;
-        uint32_t* d_tl = (uint32_t*)(d_to + nt + 1);
-        CK(cudaMemcpyAsync(d_tb, t_bit.data(), nt * 8, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(d_tr, t_resume.data(), nt * 8, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(d_to, t_off.data(), (nt + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(d_tl, t_limit.data(), nt * 4, cudaMemcpyHostToDevice, ctx->stream));
-        LargeTasks T;
-        T.bit = d_tb; T.resume = d_tr; T.out = d_to; T.limit = d_tl; T.sym = (uint16_t*)ctx->d_sym.p;
-        rc = launch_tasks<4, true, sdz::TM_MARK>(ctx, d_src, T, (sdz_result*)ctx->d_res.p, nt, d_zero_off, d_len0);
-        if (rc) return rc;
-    }
-    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-    lap("2a marker decode");
-
-    // ---- pass 2b / 2c: windows, then everything else
+    auto done = [&](int rc) { if (L) sdz_large_close(L); return rc; };
+#define LARGE_STEP(call)                                          \
+    do {                                                          \
+        int rc_ = (call);                                         \
+        if (rc_ == SDZ_E_UNSUPPORTED) return fallback();          \
+        if (rc_) return done(rc_);                                \
+    } while (0)
+    LARGE_STEP(sdz_large_open(ctx, data, len, mode, on_device, &L));
+    const sdz_large_block* blocks = nullptr;
+    const sdz_large_ckpt* ckpts = nullptr;
+    uint64_t nb = 0, nc = 0, total_out = 0, nt = 0;
+    LARGE_STEP(sdz_large_index(L, 0, 1, &blocks, &nb, &ckpts, &nc));
+    LARGE_STEP(sdz_large_plan(L, blocks, nb, ckpts, nc, &total_out, &nt));
+    if (total_out > out_cap) { res->out_len = total_out; return done(SDZ_E_OUT_CAP); }
     uint8_t* d_o = out;
     if (!on_device) {
-        if ((rc = grow(ctx, ctx->d_out, total_out + 64))) return rc;
+        int rc = grow(ctx, ctx->d_out, total_out + 64);
+        if (rc) return done(rc);
         d_o = (uint8_t*)ctx->d_out.p;
     }
-    if (nt) {
-        uint64_t bps = 1;
-        while (bps * bps < nt) bps++;                                       // ~sqrt(nt) pieces per segment
-        const unsigned nseg = (unsigned)((nt + bps - 1) / bps);
-        sdz::propagate_in_segment<<<nseg, 1024, 0, ctx->stream>>>((uint16_t*)ctx->d_sym.p, d_to, nt, bps);
-        sdz::propagate_segments<<<1, 1024, 0, ctx->stream>>>((const uint16_t*)ctx->d_sym.p, d_o, d_to, nt, bps);
-        const unsigned gy = (unsigned)std::min<uint64_t>(nt, 65535);
-        sdz::resolve_markers<<<dim3(4, gy), 256, 0, ctx->stream>>>((const uint16_t*)ctx->d_sym.p, d_o, d_to, nt, bps);
-        ctx->launches += 3;
-    }
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-
-    lap("2b-d windows + markers");
-    // the marker pass must have reproduced the extents
-    std::vector<sdz_result> chk(nt);
-    if (nt) CK(cudaMemcpyAsync(chk.data(), ctx->d_res.p, nt * sizeof(sdz_result), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    LARGE_STEP(sdz_large_decode(L, 0, 1, d_o));
+    LARGE_STEP(sdz_large_windows(L));
+    LARGE_STEP(sdz_large_resolve(L));
+#undef LARGE_STEP
     float ms_keep[3];
     cudaEventElapsedTime(&ms_keep[0], ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&ms_keep[1], ctx->ev[1], ctx->ev[2]);
     cudaEventElapsedTime(&ms_keep[2], ctx->ev[0], ctx->ev[2]);
-    for (uint64_t t = 0; t < nt; t++) {
-        if (chk[t].zstatus != sdz::R_EOB || chk[t].out_len != t_limit[t]) return fallback();
-        // a piece that is followed by another piece of the same block must end exactly on that piece's resume point
-        if (t + 1 < nt && t_bit[t + 1] == t_bit[t] && chk[t].total_in != t_resume[t + 1]) return fallback();
-    }
 
     // ---- running checksum as append() computes it over its 16 KiB chunks (src/sd-inflate.ts:133-149)
     int32_t running = 0;
-    const bool have_running = total_out > 0;
-    if (have_running) {
+    if (total_out > 0) {
         std::vector<uint64_t> segs;
         uint64_t rem = total_out;
         const uint64_t last = rem % 16384 ? rem % 16384 : 16384;
@@ -1103,37 +1371,16 @@ extern "C" int sdz_inflate_large(sdz_ctx* ctx, const uint8_t* data, uint64_t len
         }
         segs.push_back(last);
         segs.erase(std::remove(segs.begin(), segs.end(), 0ull), segs.end());
-        rc = checksum_chain(ctx, is_gzip, d_o, segs.data(), segs.size(), is_gzip ? 0 : 1, 1, nullptr, &running);
-        if (rc) return rc;
+        int rc = checksum_chain(ctx, L->is_gzip, d_o, segs.data(), segs.size(), L->is_gzip ? 0 : 1, 1, nullptr, &running);
+        if (rc) return done(rc);
     }
-    lap("checksum");
+    L->lap("checksum");
     ctx->last_ms[0] = ms_keep[0]; ctx->last_ms[1] = ms_keep[1]; ctx->last_ms[2] = ms_keep[2];
     if (!on_device && total_out) {
         CK(cudaMemcpyAsync(out, d_o, total_out, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
-
-    lap("output copy");
-    // ---- finish() record (src/sd-inflate.ts:159-179) and inflate()'s throw mapping (:214-225)
-    res->out_off = 0;
-    res->out_len = total_out;
-    res->total_in = tp + want;
-    res->zstatus = SDZ_Z_STREAM_END;
-    res->stored_checksum = stored;
-    res->running_checksum = have_running ? running : 0;
-    res->have_running = have_running;
-    res->stored_isize = isize;
-    res->mtime = mtime;
-    res->name_off = name_len ? name_off : 0;
-    res->name_len = name_len;
-    res->n_blocks = (uint32_t)nb;
-    res->container = (uint8_t)(is_gzip ? SDZ_GZIP : (method == 0 ? SDZ_RAW : SDZ_ZLIB));
-    res->complete = 1;
-    const int cks = stored == 0 ? SDZ_UNCHECKED : ((have_running && stored == running) ? SDZ_MATCH : SDZ_MISMATCH);
-    const int fsz = isize == 0 ? SDZ_UNCHECKED : (((int64_t)isize == (int64_t)total_out) ? SDZ_MATCH : SDZ_MISMATCH);
-    res->checksum_state = (uint8_t)cks;
-    res->size_state = (uint8_t)fsz;
-    res->success = (uint8_t)(cks != SDZ_MISMATCH && fsz != SDZ_MISMATCH);
-    res->thrown_inflate = (uint8_t)(res->success ? SDZ_THROW_NONE : (cks == SDZ_MISMATCH ? SDZ_THROW_INTEGRITY : SDZ_THROW_SIZE_CHECK));
-    return SDZ_OK;
+    L->lap("output copy");
+    int rc = sdz_large_finish(L, running, res);
+    return done(rc);
 }

@@ -18,6 +18,8 @@ EXPORTS = [
     "sdz_host_alloc", "sdz_host_free", "sdz_device_alloc", "sdz_device_free", "sdz_memcpy_h2d", "sdz_memcpy_d2h",
     "sdz_adler32", "sdz_crc32", "sdz_adler32_chain", "sdz_crc32_chain", "sdz_checksum_batch",
     "sdz_inflate_batch", "sdz_inflate_sizes", "sdz_inflate_batch_device", "sdz_inflate_large", "sdz_sync",
+    "sdz_large_open", "sdz_large_close", "sdz_large_index", "sdz_large_plan", "sdz_large_range", "sdz_large_decode",
+    "sdz_large_windows", "sdz_large_resolve", "sdz_large_finish", "sdz_large_is_gzip", "sdz_crc32_combine",
 ]
 
 
@@ -105,6 +107,19 @@ def load():
         L.sdz_inflate_sizes.argtypes = [vp, vp, u64, vp, u32]
         L.sdz_inflate_batch_device.argtypes = [vp, C.POINTER(BatchDev), u32, C.c_int]
         L.sdz_inflate_large.argtypes = [vp, vp, u64, C.c_uint8, C.c_int, vp, u64, C.POINTER(Result)]
+        L.sdz_large_open.argtypes = [vp, vp, u64, C.c_uint8, C.c_int, C.POINTER(vp)]
+        L.sdz_large_close.argtypes = [vp]
+        L.sdz_large_close.restype = None
+        L.sdz_large_index.argtypes = [vp, u32, u32, C.POINTER(vp), C.POINTER(u64), C.POINTER(vp), C.POINTER(u64)]
+        L.sdz_large_plan.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64), C.POINTER(u64)]
+        L.sdz_large_range.argtypes = [vp, u32, u32, C.POINTER(u64), C.POINTER(u64)]
+        L.sdz_large_decode.argtypes = [vp, u32, u32, vp]
+        L.sdz_large_windows.argtypes = [vp]
+        L.sdz_large_resolve.argtypes = [vp]
+        L.sdz_large_finish.argtypes = [vp, i32, C.POINTER(Result)]
+        L.sdz_large_is_gzip.argtypes = [vp]
+        L.sdz_crc32_combine.argtypes = [i32, i32, u64]
+        L.sdz_crc32_combine.restype = i32
         _lib = L
         return L
 

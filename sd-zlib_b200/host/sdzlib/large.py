@@ -1,0 +1,266 @@
+"""One large stream spread over several parts (GPUs): host-side driver of the sdz_large_* phases.
+
+The reference decodes a stream strictly sequentially through one 32 KiB window (src/sd-inflate.ts:87-153);
+nothing in it corresponds to this file.  What is reproduced is its RESULT: the bytes and the finish() record
+(src/sd-inflate.ts:159-179).
+
+Protocol for rank r of n (every rank holds the whole compressed stream):
+
+    index(r, n)                      candidate blocks + resume points found in slice r of the compressed bits
+    all-gather of those records      (the only variable-size exchange; a few hundred KB for a 1 GiB stream)
+    plan(all records)                identical on every rank: the chain of real blocks, cut into pieces
+    range(r, n)                      the slice [lo, hi) of the OUTPUT that rank r produces
+    decode(r, n, out)                pieces -> marker symbols, windows composed inside the slice
+    recv 32 KiB from r - 1           the final window before `lo`   (rank 0: nothing to wait for)
+    windows()                        the last 32 KiB of the slice become final
+    send 32 KiB to r + 1
+    resolve()                        every remaining marker of the slice
+    crc32(slice), all-gather (crc, length), combine in rank order -> finish() record on every rank
+
+`Backend` is what a rank does locally (CudaBackend binds libsdzcuda.so; tests substitute a CPU stand-in for the
+message flow), `Comm` is how ranks talk (TorchComm = torch.distributed, NCCL on GPUs / gloo on CPUs; LoopComm runs all
+"ranks" in one process, which is also how several parts are exercised on a single GPU).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+
+WIN = 32768
+MODE_SNIFF, MODE_INFLATER, MODE_RAW = 0, 1, 2
+
+BLOCK_DT = np.dtype([("bit", "<u8"), ("end_bit", "<u8"), ("out_len", "<u8"), ("last", "u1"), ("btype", "u1"), ("ok", "u1"),
+                     ("reserved", "u1", (5,))])
+CKPT_DT = np.dtype([("block_bit", "<u8"), ("bit", "<u8"), ("pos", "<u4"), ("reserved", "<u4")])
+assert BLOCK_DT.itemsize == 32 and CKPT_DT.itemsize == 24
+
+
+class NeedsSequentialDecoder(Exception):
+    """The stream is not one the block-parallel path handles (stored blocks, preset dictionary, truncated or damaged
+    data, trailing bytes): decode it with inflateBatch / inflate instead."""
+
+
+def crc32_combine(crc_a, crc_b, len_b):
+    """crc32(A || B) from the parts (signed int32 in and out, like the reference's values)."""
+    return int(N.load().sdz_crc32_combine(int(crc_a), int(crc_b), int(len_b)))
+
+
+class CudaBackend:
+    """The phases of one rank, on one device, through the C ABI.  `stream_ptr` is a DEVICE pointer to the whole
+    compressed stream (16-byte aligned, readable for 1 KiB past its end)."""
+
+    def __init__(self, ctx, stream_ptr, length, mode=MODE_SNIFF):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        h = C.c_void_p()
+        rc = self.lib.sdz_large_open(ctx.h, stream_ptr, int(length), mode, 1, C.byref(h))
+        self._check(rc)
+        self.h = h
+
+    def _check(self, rc):
+        if rc == N.SDZ_E_UNSUPPORTED:
+            raise NeedsSequentialDecoder()
+        self.ctx.check(rc)
+
+    def index(self, part, n_parts):
+        bp, cp = C.c_void_p(), C.c_void_p()
+        nb, nc = C.c_uint64(), C.c_uint64()
+        self._check(self.lib.sdz_large_index(self.h, part, n_parts, C.byref(bp), C.byref(nb), C.byref(cp), C.byref(nc)))
+        blocks = np.empty(nb.value, dtype=BLOCK_DT)
+        ckpts = np.empty(nc.value, dtype=CKPT_DT)
+        if nb.value:
+            C.memmove(blocks.ctypes.data, bp.value, blocks.nbytes)
+        if nc.value:
+            C.memmove(ckpts.ctypes.data, cp.value, ckpts.nbytes)
+        return blocks, ckpts
+
+    def plan(self, blocks, ckpts):
+        blocks = np.ascontiguousarray(blocks, dtype=BLOCK_DT)
+        ckpts = np.ascontiguousarray(ckpts, dtype=CKPT_DT)
+        total, pieces = C.c_uint64(), C.c_uint64()
+        self._check(self.lib.sdz_large_plan(self.h, blocks.ctypes.data, blocks.size, ckpts.ctypes.data, ckpts.size,
+                                            C.byref(total), C.byref(pieces)))
+        return total.value, pieces.value
+
+    def range(self, part, n_parts):
+        lo, hi = C.c_uint64(), C.c_uint64()
+        self._check(self.lib.sdz_large_range(self.h, part, n_parts, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def decode(self, part, n_parts, out_ptr):
+        self._check(self.lib.sdz_large_decode(self.h, part, n_parts, out_ptr))
+
+    def windows(self):
+        self._check(self.lib.sdz_large_windows(self.h))
+
+    def resolve(self):
+        self._check(self.lib.sdz_large_resolve(self.h))
+
+    def is_gzip(self):
+        return bool(self.lib.sdz_large_is_gzip(self.h))
+
+    def crc32(self, ptr, n):
+        out = C.c_int32()
+        self.ctx.check(self.lib.sdz_crc32(self.ctx.h, ptr, int(n), 0, 1, C.byref(out)))
+        return out.value
+
+    def finish(self, running):
+        r = N.Result()
+        self._check(self.lib.sdz_large_finish(self.h, int(running), C.byref(r)))
+        return r
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sdz_large_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def merge_index(parts):
+    """parts: [(blocks, ckpts)] of every rank -> the concatenated index plan() takes."""
+    blocks = np.concatenate([np.asarray(b, dtype=BLOCK_DT) for b, _ in parts]) if parts else np.empty(0, BLOCK_DT)
+    ckpts = np.concatenate([np.asarray(c, dtype=CKPT_DT) for _, c in parts]) if parts else np.empty(0, CKPT_DT)
+    return blocks, ckpts
+
+
+def combine_crcs(parts):
+    """parts: [(crc32 of the slice, slice length)] in rank order -> crc32 of the whole output (0 for no output)."""
+    crc = 0
+    for c, n in parts:
+        if n:
+            crc = crc32_combine(crc, c, n)
+    return crc
+
+
+def run_rank(backend, comm, rank, world, alloc):
+    """The protocol above for one rank.  `alloc(nbytes)` returns (object to keep alive, device/host pointer) for
+    the rank's output slice with WIN bytes of headroom BEFORE and 64 bytes after it.
+    Returns (keepalive, pointer to the slice, lo, hi, finish() record)."""
+    if not backend.is_gzip():
+        # the running adler32 of zlib / raw streams is chained over the reference's 16 KiB chunks; only the
+        # single-GPU path reproduces that chain
+        raise NeedsSequentialDecoder()
+    mine = backend.index(rank, world)
+    everyone = comm.allgather_index(mine)
+    backend.plan(*merge_index(everyone))
+    lo, hi = backend.range(rank, world)
+    keep, base = alloc(WIN + (hi - lo) + 64)
+    out_ptr = base + WIN
+    backend.decode(rank, world, out_ptr)
+    if rank > 0:
+        comm.recv_window(rank - 1, keep, base)              # lands in the headroom: the 32 KiB before `lo`
+    backend.windows()
+    if rank + 1 < world:
+        # the last 32 KiB before `hi`; a slice shorter than the window forwards part of what it received
+        comm.send_window(rank + 1, keep, out_ptr + (hi - lo) - WIN)
+    backend.resolve()
+    crc = backend.crc32(out_ptr, hi - lo) if hi > lo else 0
+    parts = comm.allgather_crc((crc, hi - lo))
+    rec = backend.finish(combine_crcs(parts))
+    return keep, out_ptr, lo, hi, rec
+
+
+class TorchComm:
+    """torch.distributed plumbing: NCCL with CUDA tensors, gloo with CPU tensors."""
+
+    def __init__(self, device, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.device, self.group = torch, dist, device, group
+
+    def _allgather_bytes(self, payload):
+        torch, dist = self.torch, self.dist
+        world = dist.get_world_size(self.group)
+        n = torch.tensor([payload.size], dtype=torch.int64, device=self.device)
+        sizes = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(sizes, n, group=self.group)
+        sizes = [int(s.item()) for s in sizes]
+        cap = max(max(sizes), 1)
+        mine = torch.zeros(cap, dtype=torch.uint8, device=self.device)
+        if payload.size:
+            mine[:payload.size] = torch.from_numpy(payload).to(self.device)
+        bufs = [torch.empty(cap, dtype=torch.uint8, device=self.device) for _ in range(world)]
+        dist.all_gather(bufs, mine, group=self.group)
+        return [b[:s].cpu().numpy() for b, s in zip(bufs, sizes)]
+
+    def allgather_index(self, mine):
+        blocks, ckpts = mine
+        b = self._allgather_bytes(np.frombuffer(blocks.tobytes(), dtype=np.uint8))
+        c = self._allgather_bytes(np.frombuffer(ckpts.tobytes(), dtype=np.uint8))
+        return [(np.frombuffer(x.tobytes(), dtype=BLOCK_DT), np.frombuffer(y.tobytes(), dtype=CKPT_DT)) for x, y in zip(b, c)]
+
+    def allgather_crc(self, mine):
+        arr = np.array([mine[0], mine[1]], dtype=np.int64)
+        got = self._allgather_bytes(np.frombuffer(arr.tobytes(), dtype=np.uint8))
+        return [tuple(int(v) for v in np.frombuffer(g.tobytes(), dtype=np.int64)) for g in got]
+
+    def _window(self, keep, ptr):
+        # `keep` is the torch uint8 tensor that owns the rank's buffer; ptr is an address inside it
+        off = ptr - keep.data_ptr()
+        return keep[off:off + WIN]
+
+    def recv_window(self, src, keep, ptr):
+        self.dist.recv(self._window(keep, ptr), src=src, group=self.group)
+
+    def send_window(self, dst, keep, ptr):
+        self.dist.send(self._window(keep, ptr), dst=dst, group=self.group)
+
+
+def torch_alloc(device):
+    import torch
+
+    def alloc(nbytes):
+        t = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+        return t, t.data_ptr()
+    return alloc
+
+
+def inflate_large_parts(view, n_parts, mode=MODE_SNIFF, ctx=None):
+    """All `n_parts` ranks of the protocol on ONE GPU, one after the other (the windows travel through the host).
+    Exercises every multi-part code path without a second device.  Returns (bytes as np.uint8, finish() record)."""
+    ctx = ctx or N.default_context()
+    lib = ctx.lib
+    n = int(view.size)
+    d_in = lib.sdz_device_alloc(ctx.h, n + 1024)
+    pad = np.zeros(n + 1024, dtype=np.uint8)
+    pad[:n] = view
+    ctx.check(lib.sdz_memcpy_h2d(ctx.h, d_in, pad.ctypes.data, pad.size))
+    ranks, bufs = [], []
+    try:
+        ranks = [CudaBackend(ctx, d_in, n, mode) for _ in range(n_parts)]
+        if not ranks[0].is_gzip():
+            raise NeedsSequentialDecoder()
+        merged = merge_index([r.index(p, n_parts) for p, r in enumerate(ranks)])
+        total = 0
+        for r in ranks:
+            total, _ = r.plan(*merged)
+        out = np.empty(total, dtype=np.uint8)
+        window = np.zeros(WIN, dtype=np.uint8)
+        crcs = []
+        for p, r in enumerate(ranks):
+            lo, hi = r.range(p, n_parts)
+            base = lib.sdz_device_alloc(ctx.h, WIN + (hi - lo) + 64)
+            bufs.append(base)
+            r.decode(p, n_parts, base + WIN)
+            if p > 0:
+                ctx.check(lib.sdz_memcpy_h2d(ctx.h, base, window.ctypes.data, WIN))
+            r.windows()
+            ctx.check(lib.sdz_memcpy_d2h(ctx.h, window.ctypes.data, base + (hi - lo), WIN))    # [hi - WIN, hi) of this slice
+            r.resolve()
+            if hi > lo:
+                ctx.check(lib.sdz_memcpy_d2h(ctx.h, out[lo:hi].ctypes.data, base + WIN, hi - lo))
+            crcs.append((r.crc32(base + WIN, hi - lo) if hi > lo else 0, hi - lo))
+        rec = ranks[0].finish(combine_crcs(crcs))
+        return out, rec
+    finally:
+        for r in ranks:
+            r.close()
+        for b in bufs:
+            lib.sdz_device_free(ctx.h, b)
+        lib.sdz_device_free(ctx.h, d_in)

@@ -68,3 +68,18 @@ def test_argument_errors_like_reference():
         sdzlib.adler32(None)
     assert sdzlib.Inflater().append(b"") == []
     assert sdzlib.mergeBuffers([b"ab", b"", b"c"]) == b"abc"
+
+
+def test_crc32_combine_is_host_arithmetic():
+    """sdz_crc32_combine needs no device: crc(A || B) from the parts, against zlib, in the reference's signed domain."""
+    import zlib
+    import numpy as np
+    from sdzlib import large as LG
+    rng = np.random.default_rng(2)
+    sgn = lambda v: v - (1 << 32) if v & 0x80000000 else v
+    for la, lb in ((0, 0), (1, 0), (0, 1), (5, 7), (4096, 1), (70001, 123457), (3, 1 << 20)):
+        a = rng.integers(0, 256, la, dtype=np.uint8).tobytes()
+        b = rng.integers(0, 256, lb, dtype=np.uint8).tobytes()
+        assert LG.crc32_combine(sgn(zlib.crc32(a)), sgn(zlib.crc32(b)), lb) == sgn(zlib.crc32(a + b)), (la, lb)
+    parts = [rng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in (10, 0, 33000, 1)]
+    assert LG.combine_crcs([(sgn(zlib.crc32(p)), len(p)) for p in parts]) == sgn(zlib.crc32(b"".join(parts)))

@@ -463,3 +463,30 @@ def test_large_stream_far_references_and_small_blocks():
     plain = np.concatenate(parts)                                   # every byte is (transitively) a ~30 KB-far copy
     for level in (1, 6):
         _check_large(zlib.compress(plain.tobytes(), level), O.MODE_SNIFF, plain)
+
+
+@pytest.mark.parametrize("n_parts,mib", [(2, 8), (3, 24), (7, 3)])
+def test_large_stream_multi_part_protocol_on_one_gpu(n_parts, mib):
+    """The multi-GPU protocol (index slices, merged plan, output slices, 32 KiB window relay, CRC combine) with all
+    ranks played by one device: identical bytes and record to the oracle."""
+    from sdzlib import large as LG
+    plain = _large_plain(K.TEXT, mib, 9100 + mib)
+    s = gzip.compress(plain.tobytes(), 6, mtime=77)
+    out, r = LG.inflate_large_parts(np.frombuffer(s, dtype=np.uint8), n_parts)
+    assert np.array_equal(out, plain)
+    _, exp = O.inflate_oneshot(s)
+    assert r.observable() == exp.observable()
+
+
+def test_large_stream_slices_shorter_than_the_window():
+    """100 KB of output over 6 parts: every slice is shorter than 32 KiB, so windows span several slices."""
+    from sdzlib import large as LG
+    rng = np.random.default_rng(4)
+    base = rng.integers(97, 123, 9000, dtype=np.uint8)
+    plain = np.concatenate([np.roll(base, i * 17) for i in range(11)])[:100000]
+    s = gzip.compress(plain.tobytes(), 6, mtime=1)
+    out, r = LG.inflate_large_parts(np.frombuffer(s, dtype=np.uint8), 6)
+    assert np.array_equal(out, plain)
+    assert r.success and r.checksum_state == 1 and r.size_state == 1
+    with pytest.raises(LG.NeedsSequentialDecoder):
+        LG.inflate_large_parts(np.frombuffer(zlib.compress(plain.tobytes(), 6), dtype=np.uint8), 2)   # zlib: single-GPU path only

@@ -81,3 +81,106 @@ def test_two_rank_sharding_and_record_gather():
         lo, hi = shard(n_streams, r, world)
         covered += list(range(lo, hi))
     assert covered == list(range(n_streams))
+
+
+# ---------------------------------------------------------------- one large stream over several ranks
+
+class _StandInBackend:
+    """CPU stand-in for sdzlib.large.CudaBackend: same methods, numpy instead of kernels.  Every rank 'finds' a few
+    records in its slice of the compressed bits; decode() refuses to produce the right bytes unless the protocol
+    delivered the full index, and windows() checks that the 32 KiB before the slice arrived from the left."""
+
+    def __init__(self, plain, rank, world):
+        self.plain, self.rank, self.world = plain, rank, world
+
+    def is_gzip(self):
+        return True
+
+    def index(self, part, n_parts):
+        from sdzlib import large as LG
+        b = np.zeros(3 + part, dtype=LG.BLOCK_DT)
+        b["bit"] = 1000 * part + np.arange(b.size)
+        b["ok"] = 1
+        c = np.zeros(2 * part + 1, dtype=LG.CKPT_DT)
+        c["block_bit"] = 1000 * part
+        c["pos"] = np.arange(c.size)
+        return b, c
+
+    def plan(self, blocks, ckpts):
+        exp_b = sorted(1000 * p + i for p in range(self.world) for i in range(3 + p))
+        assert sorted(int(v) for v in blocks["bit"]) == exp_b
+        assert ckpts.size == sum(2 * p + 1 for p in range(self.world))
+        return self.plain.size, 0
+
+    def range(self, part, n_parts):
+        n = self.plain.size
+        return n * part // n_parts, n * (part + 1) // n_parts
+
+    def decode(self, part, n_parts, out_ptr):
+        self.lo, self.hi = self.range(part, n_parts)
+        self.out_ptr = out_ptr
+        seg = np.ascontiguousarray(self.plain[self.lo:self.hi])
+        C.memmove(out_ptr, seg.ctypes.data, seg.size)
+
+    def windows(self):
+        if self.rank > 0:
+            from sdzlib import large as LG
+            got = np.empty(LG.WIN, dtype=np.uint8)
+            C.memmove(got.ctypes.data, self.out_ptr - LG.WIN, LG.WIN)
+            w0 = self.lo - LG.WIN
+            exp = self.plain[max(w0, 0):self.lo]
+            assert np.array_equal(got[LG.WIN - exp.size:], exp), "left window did not arrive intact"
+
+    def resolve(self):
+        pass
+
+    def crc32(self, ptr, n):
+        import zlib
+        buf = np.empty(n, dtype=np.uint8)
+        C.memmove(buf.ctypes.data, ptr, n)
+        v = zlib.crc32(buf.tobytes())
+        return v - (1 << 32) if v & 0x80000000 else v
+
+    def finish(self, running):
+        return running
+
+
+def _large_worker(rank, world, port, n_bytes, out_q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "sd-zlib_b200", "host"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sdzlib import large as LG
+    plain = np.random.default_rng(5).integers(0, 256, n_bytes, dtype=np.uint8)
+    comm = LG.TorchComm(torch.device("cpu"))
+    keep, ptr, lo, hi, rec = LG.run_rank(_StandInBackend(plain, rank, world), comm, rank, world, LG.torch_alloc(torch.device("cpu")))
+    got = np.empty(hi - lo, dtype=np.uint8)
+    C.memmove(got.ctypes.data, ptr, hi - lo)
+    assert np.array_equal(got, plain[lo:hi])
+    out_q.put((rank, lo, hi, int(rec)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_bytes", [(2, 300000), (3, 70000)])      # 70000 / 3 < 32 KiB: windows span two slices
+def test_large_stream_rank_protocol(world, n_bytes):
+    import zlib
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_large_worker, args=(r, world, port, n_bytes, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    plain = np.random.default_rng(5).integers(0, 256, n_bytes, dtype=np.uint8)
+    exp = zlib.crc32(plain.tobytes())
+    exp = exp - (1 << 32) if exp & 0x80000000 else exp
+    assert [g[1] for g in got] == [n_bytes * r // world for r in range(world)]
+    assert got[-1][2] == n_bytes
+    assert all(g[3] == exp for g in got)                                  # every rank assembled the whole-stream CRC
