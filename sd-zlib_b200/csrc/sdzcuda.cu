@@ -38,6 +38,10 @@ struct sdz_ctx {
     float last_ms[3] = { 0, 0, 0 };
     // grow-only scratch
     DevBuf d_in, d_out, d_meta, d_res, d_part, d_misc, d_sym, d_task;
+    // buffers of the last closed large-stream session (symbols, task arrays, descriptors): the next session takes them
+    // over instead of paying cudaMalloc / cudaFree of gigabytes per call
+    DevBuf large_cache[3];
+    bool large_cache_full = false;
     void* h_stage = nullptr;           // pinned
     size_t h_stage_cap = 0;
     void* h_res = nullptr;             // pinned landing zone of the result records (a copy into the caller's pageable
@@ -288,7 +292,8 @@ void sdz_ctx_destroy(sdz_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    for (DevBuf* b : { &ctx->d_in, &ctx->d_out, &ctx->d_meta, &ctx->d_res, &ctx->d_part, &ctx->d_misc, &ctx->d_sym, &ctx->d_task })
+    for (DevBuf* b : { &ctx->d_in, &ctx->d_out, &ctx->d_meta, &ctx->d_res, &ctx->d_part, &ctx->d_misc, &ctx->d_sym, &ctx->d_task,
+                       &ctx->large_cache[0], &ctx->large_cache[1], &ctx->large_cache[2] })
         if (b->p) cudaFree(b->p);
     for (int l = 1; l < sdz_ctx::N_LANES; l++) {
         if (ctx->lane_stream[l]) { cudaStreamSynchronize(ctx->lane_stream[l]); cudaStreamDestroy(ctx->lane_stream[l]); }
@@ -798,16 +803,20 @@ int launch_tasks(sdz_ctx* ctx, const uint8_t* d_src, const LargeTasks& T, sdz_re
     return launch_inflate_t<G, STORE, TM>(ctx, P);
 }
 
-uint32_t large_ckpt_step()
+// output bytes per piece (power of two): 16 KiB keeps one wave of pieces in flight for streams of a few hundred MB;
+// larger streams have pieces to spare and save table rebuilds and window steps with 32 KiB (measured at 1 GiB: 8 KiB
+// 80.6 ms, 16 KiB 74.3 ms, 32 KiB 70.5 ms).  SDZ_LARGE_STEP overrides.
+uint32_t large_ckpt_step(uint64_t compressed_len)
 {
-    static const uint32_t step = [] {
+    static const uint32_t forced = [] {
         const char* e = getenv("SDZ_LARGE_STEP");
-        uint32_t v = e ? (uint32_t)atoi(e) : 16384u;
-        uint32_t p2 = 1024;
+        if (!e) return 0u;
+        uint32_t v = (uint32_t)atoi(e), p2 = 1024;
         while (p2 < v && p2 < (1u << 24)) p2 <<= 1;
         return p2;
     }();
-    return step;
+    if (forced) return forced;
+    return compressed_len >= (160ull << 20) ? 32768u : 16384u;
 }
 
 }  // namespace
@@ -877,7 +886,7 @@ int large_extents(sdz_large* L, const std::vector<uint64_t>& starts, std::vector
         CK(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), ctx->stream));
         LargeTasks T;
         T.bit = (const uint64_t*)ctx->d_task.p;
-        T.ckpt = (sdz::Ckpt*)ctx->d_part.p; T.ckpt_count = d_count; T.ckpt_cap = cap; T.ckpt_step = large_ckpt_step();
+        T.ckpt = (sdz::Ckpt*)ctx->d_part.p; T.ckpt_count = d_count; T.ckpt_cap = cap; T.ckpt_step = large_ckpt_step(L->len);
         r2 = launch_tasks<4, false, sdz::TM_INDEX>(ctx, L->d_src, T, (sdz_result*)ctx->d_res.p, n, L->d_zero_off, L->d_len0);
         if (r2) return r2;
         CK(cudaMemcpyAsync(&got, d_count, sizeof got, cudaMemcpyDeviceToHost, ctx->stream));
@@ -890,7 +899,19 @@ int large_extents(sdz_large* L, const std::vector<uint64_t>& starts, std::vector
     CK(cudaMemcpyAsync(recs.data(), ctx->d_res.p, n * sizeof(sdz_result), cudaMemcpyDeviceToHost, ctx->stream));
     if (got) CK(cudaMemcpyAsync(cks.data(), ctx->d_part.p, got * sizeof(sdz::Ckpt), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    std::sort(cks.begin(), cks.end(), [](const sdz::Ckpt& a, const sdz::Ckpt& b) { return a.task != b.task ? a.task < b.task : a.pos < b.pos; });
+    // order by (task, pos): the kernel appends in completion order.  Counting sort on the task, then the handful of
+    // resume points of each block by position.
+    if (got) {
+        std::vector<uint32_t> first(n + 1, 0);
+        for (const sdz::Ckpt& c : cks) first[c.task + 1]++;
+        for (uint64_t i = 0; i < n; i++) first[i + 1] += first[i];
+        std::vector<sdz::Ckpt> sorted(got);
+        std::vector<uint32_t> fill(first.begin(), first.end() - 1);
+        for (const sdz::Ckpt& c : cks) sorted[fill[c.task]++] = c;
+        for (uint64_t i = 0; i < n; i++)
+            std::sort(sorted.begin() + first[i], sorted.begin() + first[i + 1], [](const sdz::Ckpt& a, const sdz::Ckpt& b) { return a.pos < b.pos; });
+        cks.swap(sorted);
+    }
     return SDZ_OK;
 }
 
@@ -962,7 +983,12 @@ extern "C" int sdz_large_open(sdz_ctx* ctx, const uint8_t* data, uint64_t len, u
     L->first_bit = (uint64_t)hp * 8; L->total_bits = len * 8;
     L->trace = getenv("SDZ_TRACE_LARGE") != nullptr;
     L->t_last = std::chrono::steady_clock::now();
-    auto fail = [&](int rc) { delete L; return rc; };
+    if (ctx->large_cache_full) {
+        L->d_sym = ctx->large_cache[0]; L->d_tasks = ctx->large_cache[1]; L->d_desc = ctx->large_cache[2];
+        for (auto& b : ctx->large_cache) b = DevBuf();
+        ctx->large_cache_full = false;
+    }
+    auto fail = [&](int rc) { sdz_large_close(L); return rc; };
     // ---- the stream in HBM
     int rc;
     L->d_src = data;
@@ -980,7 +1006,7 @@ extern "C" int sdz_large_open(sdz_ctx* ctx, const uint8_t* data, uint64_t len, u
         uint32_t len32 = (uint32_t)len;
         if (cudaMemcpyAsync(L->d_desc.p, &zero_off, 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
             cudaMemcpyAsync((uint8_t*)L->d_desc.p + 8, &len32, 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
-            cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = "staging the stream failed"; cudaFree(L->d_desc.p); return fail(SDZ_E_CUDA); }
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = "staging the stream failed"; return fail(SDZ_E_CUDA); }
     }
     L->d_zero_off = (const uint64_t*)L->d_desc.p;
     L->d_len0 = (const uint32_t*)((uint8_t*)L->d_desc.p + 8);
@@ -994,9 +1020,15 @@ extern "C" void sdz_large_close(sdz_large* L)
     if (!L) return;
     cudaSetDevice(L->ctx->device);
     cudaStreamSynchronize(L->ctx->stream);
-    if (L->d_sym.p) cudaFree(L->d_sym.p);
-    if (L->d_tasks.p) cudaFree(L->d_tasks.p);
-    if (L->d_desc.p) cudaFree(L->d_desc.p);
+    sdz_ctx* ctx = L->ctx;
+    if (!ctx->large_cache_full) {
+        ctx->large_cache[0] = L->d_sym; ctx->large_cache[1] = L->d_tasks; ctx->large_cache[2] = L->d_desc;
+        ctx->large_cache_full = true;
+    } else {
+        if (L->d_sym.p) cudaFree(L->d_sym.p);
+        if (L->d_tasks.p) cudaFree(L->d_tasks.p);
+        if (L->d_desc.p) cudaFree(L->d_desc.p);
+    }
     delete L;
 }
 
@@ -1063,8 +1095,11 @@ extern "C" int sdz_large_plan(sdz_large* L, const sdz_large_block* blocks, uint6
     auto seq = [&]() { ctx->err = "stream needs the sequential decoder"; return SDZ_E_UNSUPPORTED; };
     std::vector<sdz_large_block> B(blocks, blocks + n_blocks);
     std::vector<sdz_large_ckpt> C(ckpts, ckpts + n_ckpts);
-    std::sort(B.begin(), B.end(), [](const sdz_large_block& a, const sdz_large_block& b) { return a.bit < b.bit; });
-    std::sort(C.begin(), C.end(), [](const sdz_large_ckpt& a, const sdz_large_ckpt& b) { return a.block_bit != b.block_bit ? a.block_bit < b.block_bit : a.pos < b.pos; });
+    // (the parts concatenated in rank order are already sorted)
+    auto b_less = [](const sdz_large_block& a, const sdz_large_block& b) { return a.bit < b.bit; };
+    auto c_less = [](const sdz_large_ckpt& a, const sdz_large_ckpt& b) { return a.block_bit != b.block_bit ? a.block_bit < b.block_bit : a.pos < b.pos; };
+    if (!std::is_sorted(B.begin(), B.end(), b_less)) std::sort(B.begin(), B.end(), b_less);
+    if (!std::is_sorted(C.begin(), C.end(), c_less)) std::sort(C.begin(), C.end(), c_less);
     L->t_bit.clear(); L->t_resume.clear(); L->t_off.clear(); L->t_limit.clear();
     uint64_t cur = L->first_bit, total = 0, nb = 0, n_single = 0;
     bool finished = false;
@@ -1191,8 +1226,10 @@ extern "C" int sdz_large_decode(sdz_large* L, uint32_t part, uint32_t n_parts, u
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     L->lap("2a marker decode");
+    // ~sqrt(pieces of the WHOLE stream) per segment: pass 2b walks the pieces of a segment in order, pass 2c walks
+    // the segments of ALL parts in order (rank after rank), so this balances the two serial chains
     L->bps = 1;
-    while (L->bps * L->bps < nt) L->bps++;                                  // ~sqrt(nt) pieces per segment
+    while (L->bps * L->bps < L->t_bit.size()) L->bps++;
     const unsigned nseg = (unsigned)((nt + L->bps - 1) / L->bps);
     sdz::propagate_in_segment<<<nseg, 1024, 0, ctx->stream>>>(sym0, L->d_to, nt, L->bps);
     ctx->launches++;

@@ -191,9 +191,15 @@ class TorchComm:
 
     def allgather_index(self, mine):
         blocks, ckpts = mine
-        b = self._allgather_bytes(np.frombuffer(blocks.tobytes(), dtype=np.uint8))
-        c = self._allgather_bytes(np.frombuffer(ckpts.tobytes(), dtype=np.uint8))
-        return [(np.frombuffer(x.tobytes(), dtype=BLOCK_DT), np.frombuffer(y.tobytes(), dtype=CKPT_DT)) for x, y in zip(b, c)]
+        head = np.array([blocks.size, ckpts.size], dtype=np.uint64)
+        payload = np.frombuffer(head.tobytes() + blocks.tobytes() + ckpts.tobytes(), dtype=np.uint8)      # one exchange
+        out = []
+        for g in self._allgather_bytes(payload):
+            raw = g.tobytes()
+            nb, nc = (int(v) for v in np.frombuffer(raw[:16], dtype=np.uint64))
+            b_end = 16 + nb * BLOCK_DT.itemsize
+            out.append((np.frombuffer(raw[16:b_end], dtype=BLOCK_DT), np.frombuffer(raw[b_end:b_end + nc * CKPT_DT.itemsize], dtype=CKPT_DT)))
+        return out
 
     def allgather_crc(self, mine):
         arr = np.array([mine[0], mine[1]], dtype=np.int64)
@@ -206,10 +212,17 @@ class TorchComm:
         return keep[off:off + WIN]
 
     def recv_window(self, src, keep, ptr):
-        self.dist.recv(self._window(keep, ptr), src=src, group=self.group)
+        w = self._window(keep, ptr)
+        self.dist.recv(w, src=src, group=self.group)
+        if w.is_cuda:
+            # NCCL only enqueues the receive; the next phase runs on the library's own stream
+            self.torch.cuda.current_stream(w.device).synchronize()
 
     def send_window(self, dst, keep, ptr):
-        self.dist.send(self._window(keep, ptr), dst=dst, group=self.group)
+        w = self._window(keep, ptr)
+        self.dist.send(w, dst=dst, group=self.group)
+        if w.is_cuda:
+            self.torch.cuda.current_stream(w.device).synchronize()
 
 
 def torch_alloc(device):
