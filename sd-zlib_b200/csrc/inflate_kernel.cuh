@@ -694,7 +694,7 @@ struct Decoder {
     // complete both pending matches (end of stream, or a copy that may read their bytes)
     __device__ __forceinline__ void flush_pending()
     {
-        if (STORE && !MARK && G <= MAX_G_DEFERRED) {
+        if (STORE && G <= MAX_G_DEFERRED) {
             cp_async_wait_all();
             commit_slot(o_dst, o_meta, ptog);
             commit_slot(n_dst, n_meta, ptog ^ 1u);
@@ -709,56 +709,62 @@ struct Decoder {
     __device__ __forceinline__ int copy_match(uint32_t len, uint32_t dist, bool lit_now)
     {
         if (len > cap - pos) return R_OUTFULL;
-        if (MARK) {
+        if (MARK && dist > pos) {
+            // reaches before the piece: those symbols become markers (synchronous; group sync inside)
+            if ((o_meta | n_meta) != 0u) flush_pending();
             copy_match_marked(len, dist);
         } else if (STORE) {
-            const bool simple = G <= MAX_G_DEFERRED && dist >= len && len <= 16u && dist <= pos;
+            // Marker mode: a symbol is two bytes, and a copy that stays inside the piece is an ordinary copy of
+            // 2 len bytes at distance 2 dist in the symbol buffer - everything below runs in BYTE units.
+            constexpr uint32_t E = MARK ? 2u : 1u;
+            const uint32_t bpos = pos * E, blen = len * E, bdist = dist * E;
+            const bool simple = G <= MAX_G_DEFERRED && bdist >= blen && blen <= 16u && bdist <= bpos;
             // the new source must not overlap bytes that are still pending (the older pending match has
             // the lower destination); copies on the synchronous path read arbitrary earlier bytes
             const uint32_t first_pending = o_meta ? o_dst : n_dst;
             const bool any_pending = (o_meta | n_meta) != 0;
             // (a copy on the synchronous path whose source lies entirely below the pending destinations can
             // overtake them: its own destination is disjoint from theirs)
-            const bool hazard = any_pending && (dist > pos || pos - dist + len > first_pending);
+            const bool hazard = any_pending && (bdist > bpos || bpos - bdist + blen > first_pending);
             if (hazard) flush_pending();
             // bytes written in this iteration (just-committed matches, the folded literal at pos - 1) are
             // only ordered before the reads below by a group sync; a deferred match reads pos - 1 iff dist == len
-            if (hazard || !simple || (lit_now && dist == len)) __syncwarp(gmask);
-            uint8_t* dst = out + pos;
+            if (hazard || !simple || (lit_now && bdist == blen)) __syncwarp(gmask);
+            uint8_t* dst = out + bpos;
             if (simple) {
                 // the older pending match was issued two matches ago: wait for it (only), store it, and
                 // reuse its staging slot for this match
                 cp_async_wait_but_one();
                 commit_slot(o_dst, o_meta, ptog);
-                const uint8_t* src = dst - dist;
+                const uint8_t* src = dst - bdist;
                 const uint32_t so = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
                 const uint32_t jb = (uint32_t)DB * (uint32_t)glane;
                 const uint8_t* w0 = src - so + jb;
                 #pragma unroll
-                for (int k = 0; k < DW; k++) cp_async4_if(&S->stage[8 * ptog + DW * glane + k], w0 + 4 * k, jb + 4u * k < len + so);
+                for (int k = 0; k < DW; k++) cp_async4_if(&S->stage[8 * ptog + DW * glane + k], w0 + 4 * k, jb + 4u * k < blen + so);
                 cp_async_commit();
                 o_dst = n_dst; o_meta = n_meta;
-                n_dst = pos; n_meta = len | (so << 8);
+                n_dst = bpos; n_meta = blen | (so << 8);
                 ptog ^= 1u;
-            } else if (dist <= pos) {
-                const uint8_t* src = dst - dist;
-                if (dist >= len) {
+            } else if (bdist <= bpos) {
+                const uint8_t* src = dst - bdist;
+                if (bdist >= blen) {
                     // eight loads in flight per lane: one memory round trip for matches up to 8 G bytes
-                    for (uint32_t i = glane; i < len; i += 8 * G) {
+                    for (uint32_t i = glane; i < blen; i += 8 * G) {
                         uint8_t v[8];
                         #pragma unroll
-                        for (int k = 0; k < 8; k++) v[k] = i + k * G < len ? src[i + k * G] : (uint8_t)0;
+                        for (int k = 0; k < 8; k++) v[k] = i + k * G < blen ? src[i + k * G] : (uint8_t)0;
                         #pragma unroll
-                        for (int k = 0; k < 8; k++) if (i + k * G < len) dst[i + k * G] = v[k];
+                        for (int k = 0; k < 8; k++) if (i + k * G < blen) dst[i + k * G] = v[k];
                     }
-                } else if (dist == 1) {
+                } else if (bdist == 1) {
                     uint8_t v = src[0];
-                    for (uint32_t i = glane; i < len; i += G) dst[i] = v;
+                    for (uint32_t i = glane; i < blen; i += G) dst[i] = v;
                 } else {                             // lane-strided replicate of the period
-                    for (uint32_t i = glane; i < len; i += G) dst[i] = src[i % dist];
+                    for (uint32_t i = glane; i < blen; i += G) dst[i] = src[i % bdist];
                 }
             } else {
-                copy_before_start_impl<G>(out, pos, len, dist, dict_tail, D, glane);
+                copy_before_start_impl<G>(out, pos, len, dist, dict_tail, D, glane);     // byte mode only (bdist > bpos)
             }
         }
         pos += len;
@@ -911,8 +917,8 @@ struct Decoder {
 #if SDZ_LIT_RUN > 0
         // leading literal: every lockstep iteration pays for the match path anyway, so a plain literal in
         // front of a match is folded into the same iteration
-        // (not in marker mode: a piece must be able to stop after ANY symbol)
-        if (!MARK && e >= 0x1000u && (e & 0xf00u) == 0u && pos < cap) {
+        // (marker mode: never the last symbol of the piece, so that the piece still ends on a symbol boundary)
+        if (e >= 0x1000u && (e & 0xf00u) == 0u && pos < cap && (!MARK || pos + 1u < limit)) {
             const uint32_t n0 = e >> 12;
             bb >>= n0; bc -= (int)n0;
             store_lit(e & 0xffu);
@@ -1005,9 +1011,10 @@ struct Decoder {
         gsrc = P.in + P.in_off[0];
         end_wp = (in_len + 3) / 4;
         total_chunks = (in_len + CH - 1) / CH;
-        out = nullptr; out_off = 0;
+        out_off = 0;
         abs_start = MARK ? P.task_out[i] : 0;
         out16 = MARK ? P.out16 + abs_start : nullptr;
+        out = reinterpret_cast<uint8_t*>(out16);                    // byte view of the symbols (copy_match)
         resume_bit = MARK ? P.task_resume[i] : 0;
         limit = MARK ? P.task_limit[i] : 0xffffffffu;
         next_ck = TM == TM_INDEX ? P.ckpt_step : 0xffffffffu;
