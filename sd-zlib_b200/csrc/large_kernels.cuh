@@ -28,114 +28,17 @@ __device__ __forceinline__ uint32_t bits32_at(const uint32_t* src32, uint64_t p)
     return __funnelshift_r(lo, hi, (uint32_t)(p & 31));
 }
 
-__device__ __constant__ uint8_t c_border_l[19] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 };
-
 // reference acceptance of one code-length set given its per-length counts (src/inftree.ts:131-178,:298):
 // 0 ok, 1 oversubscribed, 2 incomplete, 3 empty
-__device__ __forceinline__ int classify_counts(const uint16_t* cnt, int max_len)
+// reference acceptance of one code-length set (src/inftree.ts:131-178,:298) from its Kraft sum `kr` (in units of
+// 2^-15, exact for lengths <= 15) and its longest code: 0 ok, 1 oversubscribed, 2 incomplete, 3 empty.
+// (huft_build's level-by-level "y < 0" test fires iff the total exceeds 1; "y != 0 && g != 1" is "not complete,
+// unless all codes have length 1".)
+__device__ __forceinline__ int classify_kraft(uint32_t kr, uint32_t max_len)
 {
-    int j = 1;
-    while (j <= max_len && cnt[j] == 0) j++;
-    if (j > max_len) return 3;
-    int g = max_len;
-    while (cnt[g] == 0) g--;
-    int y = 1 << j;
-    for (; j < g; j++, y <<= 1) { y -= cnt[j]; if (y < 0) return 1; }
-    y -= cnt[g];
-    if (y < 0) return 1;
-    return (y != 0 && g != 1) ? 2 : 0;
-}
-
-// Does the reference accept a dynamic block header at bit p?  (src/infblocks.ts:334-523 with the tree rules of
-// src/inftree.ts:131-178,:298-379.)  lut: 128 bytes of scratch private to the thread.
-__device__ bool is_dynamic_header(const uint32_t* src32, uint64_t p, uint64_t total_bits, uint8_t* lut)
-{
-    if (p + 17 + 12 > total_bits) return false;
-    const uint32_t h = bits32_at(src32, p);
-    if (((h >> 1) & 3u) != 2u) return false;                              // BTYPE = dynamic
-    const uint32_t hlit = (h >> 3) & 31u, hdist = (h >> 8) & 31u, hclen = (h >> 13) & 15u;
-    if (hlit > 29u || hdist > 29u) return false;                          // src/infblocks.ts:355
-    const int ncl = 4 + (int)hclen, nl = 257 + (int)hlit, nd = 1 + (int)hdist;
-    uint64_t q = p + 17;
-    if (q + 3ull * ncl > total_bits) return false;
-    // code-length-code lengths and their tree (inflate_trees_bits)
-    uint8_t cl[19];
-    #pragma unroll
-    for (int i = 0; i < 19; i++) cl[i] = 0;
-    uint16_t cnt[16];
-    #pragma unroll
-    for (int i = 0; i < 16; i++) cnt[i] = 0;
-    {
-        uint32_t w = bits32_at(src32, q);
-        int have = 32;
-        for (int i = 0; i < ncl; i++) {
-            if (have < 3) { w = bits32_at(src32, q); have = 32; }
-            const uint32_t v = w & 7u;
-            w >>= 3; have -= 3; q += 3;
-            cl[c_border_l[i]] = (uint8_t)v;
-            cnt[v]++;
-        }
-    }
-    {
-        const int st = classify_counts(cnt, 7);
-        if (st != 0) return false;
-    }
-    int g = 7;
-    while (cnt[g] == 0) g--;
-    const int l = g;                                                  // root width = min(7, g)
-    // 2^l-entry LUT: symbol | length << 5
-    {
-        uint32_t code = 0;
-        for (int k = 1; k <= g; k++) {
-            for (int s = 0; s < 19; s++) {
-                if (cl[s] != k) continue;
-                const uint32_t rev = __brev(code) >> (32 - k);
-                for (uint32_t t = rev; t < (1u << l); t += (1u << k)) lut[t] = (uint8_t)(s | (k << 5));
-                code++;
-            }
-            code <<= 1;
-        }
-        if (g == 1 && cnt[1] == 1) lut[1] = lut[0];
-    }
-    // the nl + nd code lengths (run-length coded); only their per-length counts are needed
-    uint16_t cL[16], cD[16];
-    #pragma unroll
-    for (int i = 0; i < 16; i++) { cL[i] = 0; cD[i] = 0; }
-    const int total = nl + nd;
-    int index = 0;
-    uint32_t prev = 0;
-    bool ok = true;
-    while (index < total) {
-        if (q + 14 > total_bits) { ok = false; break; }
-        const uint32_t w = bits32_at(src32, q);
-        const uint32_t e = lut[w & ((1u << l) - 1u)];
-        const int tb = (int)(e >> 5), c = (int)(e & 31u);
-        if (c < 16) {
-            q += tb;
-            if (index < nl) cL[c]++; else cD[c]++;
-            prev = (uint32_t)c;
-            index++;
-        } else {
-            const int xb = c == 18 ? 7 : c - 14;
-            int rep = (c == 18 ? 11 : 3) + (int)((w >> tb) & ((1u << xb) - 1u));
-            q += tb + xb;
-            if (index + rep > total || (c == 16 && index < 1)) { ok = false; break; }
-            const uint32_t v = c == 16 ? prev : 0u;
-            prev = v;
-            while (rep--) { if (index < nl) cL[v]++; else cD[v]++; index++; }
-        }
-    }
-    if (!ok) return false;
-    // literal/length and distance trees (inflate_trees_dynamic); the MANY arena limit is ignored here:
-    // a block rejected only by that rule is still a block boundary for the index
-    {
-        const int sl = classify_counts(cL, 15);
-        if (sl != 0) return false;
-        const int sd = classify_counts(cD, 15);
-        if (sd == 1 || sd == 2) return false;
-        if (sd == 3 && nl > 257) return false;
-    }
-    return true;
+    if (kr == 0u) return 3;
+    if (kr > 32768u) return 1;
+    return (kr != 32768u && max_len != 1u) ? 2 : 0;
 }
 
 __device__ __forceinline__ uint64_t bits64_at(const uint32_t* src32, uint64_t p)
@@ -146,32 +49,137 @@ __device__ __forceinline__ uint64_t bits64_at(const uint32_t* src32, uint64_t p)
     return (uint64_t)__funnelshift_r(a, b, sh) | ((uint64_t)__funnelshift_r(b, c, sh) << 32);
 }
 
+// Does the reference accept a dynamic block header at bit p?  (src/infblocks.ts:334-523 with the tree rules of
+// src/inftree.ts:131-178,:298-379.)  Registers only and no data-dependent branches inside a step, so the 32 candidates of
+// a warp stay converged: the code-length code is decoded canonically (per-length symbol masks + find-nth-set-bit)
+// instead of through a per-thread table, and the two big trees are judged by their Kraft sums, so no per-length
+// counters are kept.  A false candidate is random data: its lengths oversubscribe a tree within a few dozen symbols
+// and the walk stops there.
+__device__ bool is_dynamic_header(const uint32_t* src32, uint64_t p, uint64_t total_bits)
+{
+    if (p + 17 + 12 > total_bits) return false;
+    const uint32_t h = bits32_at(src32, p);
+    if (((h >> 1) & 3u) != 2u) return false;                              // BTYPE = dynamic
+    const uint32_t hlit = (h >> 3) & 31u, hdist = (h >> 8) & 31u, hclen = (h >> 13) & 15u;
+    if (hlit > 29u || hdist > 29u) return false;                          // src/infblocks.ts:355
+    const uint32_t ncl = 4u + hclen;
+    const int nl = 257 + (int)hlit, nd = 1 + (int)hdist;
+    uint64_t q = p + 17;
+    if (q + 3ull * ncl > total_bits) return false;
+    // the 3-bit lengths in transmission order (fields 0..9 in x0, 10..18 in x1) -> symbol order (y0: symbols 0..9, y1: 10..18)
+    const uint64_t v = bits64_at(src32, q) & ((1ull << (3u * ncl)) - 1ull);
+    q += 3ull * ncl;
+    const uint32_t x0 = (uint32_t)v & 0x3fffffffu, x1 = (uint32_t)(v >> 30);
+    uint32_t y0 = 0, y1 = 0;
+    {
+        constexpr int border[19] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 };
+        #pragma unroll
+        for (int i = 0; i < 19; i++) {
+            const uint32_t f = ((i < 10 ? x0 : x1) >> (3 * (i % 10))) & 7u;
+            const int sy = border[i];
+            if (sy < 10) y0 |= f << (3 * sy); else y1 |= f << (3 * (sy - 10));
+        }
+    }
+    // per-length symbol masks (bit 3 s of m0 / bit 3 (s - 10) of m1), counts and first canonical codes
+    constexpr uint32_t M = 0x09249249u;
+    const uint32_t a0 = y0 & M, a1 = (y0 >> 1) & M, a2 = (y0 >> 2) & M, c0 = y1 & M, c1 = (y1 >> 1) & M, c2 = (y1 >> 2) & M;
+    uint32_t m0[8], m1[8], cnt[8], first[8];
+    #pragma unroll
+    for (int L = 1; L <= 7; L++) {
+        m0[L] = ((L & 1) ? a0 : (a0 ^ M)) & ((L & 2) ? a1 : (a1 ^ M)) & ((L & 4) ? a2 : (a2 ^ M));
+        m1[L] = ((L & 1) ? c0 : (c0 ^ M)) & ((L & 2) ? c1 : (c1 ^ M)) & ((L & 4) ? c2 : (c2 ^ M));
+        cnt[L] = (uint32_t)(__popc(m0[L]) + __popc(m1[L]));
+    }
+    uint32_t kraft = 0, n_codes = 0, code = 0;
+    #pragma unroll
+    for (int L = 1; L <= 7; L++) {
+        kraft += cnt[L] << (7 - L);
+        n_codes += cnt[L];
+        first[L] = code;
+        code = (code + cnt[L]) << 1;
+    }
+    const bool single = n_codes == 1u && cnt[1] == 1u;                    // one code of length 1: both bit values decode to it (Q11)
+    if (kraft != 128u && !single) return false;
+    // the nl + nd code lengths (run-length coded)
+    const int total = nl + nd;
+    int index = 0;
+    uint32_t prev = 0, krL = 0, krD = 0, maxL = 0, maxD = 0;
+    while (index < total) {
+        if (q + 14 > total_bits) return false;
+        const uint32_t w = bits32_at(src32, q);
+        const uint32_t x = __brev(w) >> 25;                               // the next 7 bits, first bit most significant
+        uint32_t tb = 1, j = 0, s0 = m0[1], s1 = m1[1];
+        bool found = single;
+        #pragma unroll
+        for (int L = 1; L <= 7; L++) {
+            const uint32_t d = (x >> (7 - L)) - first[L];
+            const bool hit = !found && d < cnt[L];
+            if (hit) { tb = L; j = d; s0 = m0[L]; s1 = m1[L]; }
+            found = found || hit;
+        }
+        if (!found) return false;                                         // (not reachable for a complete code)
+        const uint32_t in0 = (uint32_t)__popc(s0);
+        const uint32_t bitpos = j < in0 ? __fns(s0, 0, (int)j + 1) : __fns(s1, 0, (int)(j - in0) + 1);
+        const uint32_t c = bitpos / 3u + (j < in0 ? 0u : 10u);            // the symbol: 0..18
+        uint32_t rep = 1, val = c;
+        if (c >= 16u) {
+            const uint32_t xb = c == 18u ? 7u : c - 14u;
+            rep = (c == 18u ? 11u : 3u) + ((w >> tb) & ((1u << xb) - 1u));
+            tb += xb;
+            if ((c == 16u && index < 1) || index + (int)rep > total) return false;
+            val = c == 16u ? prev : 0u;
+        }
+        q += tb;
+        prev = val;
+        const uint32_t toL = index < nl ? min(rep, (uint32_t)(nl - index)) : 0u, toD = rep - toL;
+        const uint32_t kr = val ? (32768u >> val) : 0u;
+        krL += toL * kr; krD += toD * kr;
+        if (toL && val > maxL) maxL = val;
+        if (toD && val > maxD) maxD = val;
+        index += (int)rep;
+        if (krL > 32768u || krD > 32768u) return false;                   // oversubscribed: src/inftree.ts:146-166
+    }
+    // literal/length and distance trees (inflate_trees_dynamic); the MANY arena limit is ignored here: a block rejected
+    // only by that rule is still a block boundary for the index
+    if (classify_kraft(krL, maxL) != 0) return false;
+    const int sd = classify_kraft(krD, maxD);
+    if (sd == 1 || sd == 2) return false;
+    if (sd == 3 && nl > 257) return false;
+    return true;
+}
+
 // Necessary condition, in registers only: the 4 + HCLEN code-length-code lengths form a complete code
-// (Kraft sum exactly 1) or the one-code special case.
+// (Kraft sum exactly 1) or the one-code special case.  The 3-bit fields are counted per value with bit planes and
+// population counts instead of nineteen extract-shift-add steps.
 __device__ __forceinline__ bool precode_plausible(const uint32_t* src32, uint64_t p, uint32_t h)
 {
     const uint32_t ncl = 4u + ((h >> 13) & 15u);
     const uint64_t v = bits64_at(src32, p + 17) & ((1ull << (3u * ncl)) - 1ull);
-    uint32_t x0 = (uint32_t)v & 0x3fffffffu, x1 = (uint32_t)(v >> 30);
+    constexpr uint64_t M = 0x1249249249249249ull;                      // bit 0 of every 3-bit field
+    const uint64_t b0 = v & M, b1 = (v >> 1) & M, b2 = (v >> 2) & M;
+    const uint64_t n0 = b0 ^ M, n1 = b1 ^ M, n2 = b2 ^ M;
     uint32_t k = 0;
-    #pragma unroll
-    for (int i = 0; i < 10; i++) { k += (128u >> (x0 & 7u)) & 0x7fu; x0 >>= 3; }
-    #pragma unroll
-    for (int i = 0; i < 9; i++) { k += (128u >> (x1 & 7u)) & 0x7fu; x1 >>= 3; }
+    k += (uint32_t)__popcll(b0 & n1 & n2) << 6;                         // length 1: 2^-1 of 128
+    k += (uint32_t)__popcll(n0 & b1 & n2) << 5;
+    k += (uint32_t)__popcll(b0 & b1 & n2) << 4;
+    k += (uint32_t)__popcll(n0 & n1 & b2) << 3;
+    k += (uint32_t)__popcll(b0 & n1 & b2) << 2;
+    k += (uint32_t)__popcll(n0 & b1 & b2) << 1;
+    k += (uint32_t)__popcll(b0 & b1 & b2);
     return k == 128u || k == 64u;
 }
 
-// pass 1a, stage 1: every bit position is tested for BTYPE / HLIT / HDIST (22 % pass); the positions that
-// pass are queued per warp so that the Kraft test runs on full warps; its survivors (a fraction of a
-// per cent) go to surv[] for stage 2.
-constexpr int PF_TILE = 4096;
+// pass 1a, stage 1.  Every lane tests 32 consecutive bit positions at once with shifted copies of a 64-bit window:
+// BTYPE = 10b, HLIT <= 29, HDIST <= 29 (22 % pass).  The positions that pass are queued per warp so that the Kraft test
+// runs on full warps; its survivors (0.14 %) go to surv[] for stage 2.
+constexpr int PF_TILE = 4096;                                          // positions per warp and tile (4 rounds of 1024)
 __global__ void __launch_bounds__(256) prefilter_headers(const uint8_t* src, uint64_t first_bit, uint64_t end_bit, uint64_t total_bits,
                                                          uint64_t* surv, unsigned long long* n_surv, unsigned long long cap)
 {
-    __shared__ uint32_t queue_all[8][64];
+    __shared__ uint16_t queue_all[8][1024 + 32];
     const uint32_t* src32 = reinterpret_cast<const uint32_t*>(src);
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    uint32_t* q = queue_all[warp];
+    uint16_t* q = queue_all[warp];
     const uint64_t n_pos = end_bit - first_bit;                      // positions [first_bit, end_bit) are tested
     const uint64_t warps_total = (uint64_t)gridDim.x * 8u;
     auto kraft = [&](uint64_t p) {
@@ -184,22 +192,41 @@ __global__ void __launch_bounds__(256) prefilter_headers(const uint8_t* src, uin
     for (uint64_t tile = (uint64_t)blockIdx.x * 8u + warp; tile * PF_TILE < n_pos; tile += warps_total) {
         const uint64_t base = first_bit + tile * PF_TILE;
         uint32_t qn = 0;
-        for (uint32_t r = 0; r < PF_TILE / 32; r++) {
-            const uint64_t p = base + r * 32u + lane;
-            bool ok = p < end_bit && p + 17 + 12 <= total_bits;
-            if (ok) {
-                const uint32_t h = bits32_at(src32, p);
-                ok = ((h >> 1) & 3u) == 2u && ((h >> 3) & 31u) <= 29u && ((h >> 8) & 31u) <= 29u;
+        for (uint32_t r = 0; r < PF_TILE / 1024; r++) {
+            const uint32_t rel0 = r * 1024u + lane * 32u;
+            const uint64_t p0 = base + rel0;
+            uint32_t m = 0;
+            if (p0 < end_bit && p0 + 17 + 12 <= total_bits) {
+                const uint64_t w = bits64_at(src32, p0);
+                const uint64_t t = ~(w >> 1) & (w >> 2)                                       // BTYPE: low bit 0, high bit 1
+                                   & ~((w >> 4) & (w >> 5) & (w >> 6) & (w >> 7))             // HLIT  < 30
+                                   & ~((w >> 9) & (w >> 10) & (w >> 11) & (w >> 12));         // HDIST < 30
+                m = (uint32_t)t;
+                // positions of this lane beyond the scan range or too close to the end of the stream
+                const uint64_t lim = end_bit < total_bits - 28 ? end_bit : total_bits - 28;   // p + 29 <= total_bits
+                if (p0 + 32 > lim) m = lim > p0 ? m & (uint32_t)((1ull << (lim - p0)) - 1ull) : 0u;
             }
-            const uint32_t m = __ballot_sync(0xffffffffu, ok);
-            if (ok) q[qn + __popc(m & ((1u << lane) - 1u))] = r * 32u + lane;
-            qn += __popc(m);
+            // warp-wide exclusive prefix of the per-lane counts
+            const uint32_t c = (uint32_t)__popc(m);
+            uint32_t inc = c;
+            #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= (uint32_t)d) inc += up;
+            }
+            uint32_t at = qn + inc - c;
+            while (m) {
+                const uint32_t i = (uint32_t)__ffs((int)m) - 1u;
+                m &= m - 1u;
+                q[at++] = (uint16_t)(rel0 + i);
+            }
+            qn += __shfl_sync(0xffffffffu, inc, 31);
             __syncwarp();
-            if (qn >= 32u) {
+            while (qn >= 32u) {
                 qn -= 32u;
                 kraft(base + q[qn + lane]);
-                __syncwarp();
             }
+            __syncwarp();
         }
         if (lane < qn) kraft(base + q[lane]);
         __syncwarp();
@@ -211,13 +238,11 @@ __global__ void __launch_bounds__(128) verify_headers(const uint8_t* src, uint64
                                                       const unsigned long long* n_surv, unsigned long long cap, uint64_t* cand,
                                                       unsigned long long* n_cand, unsigned long long max_cand)
 {
-    __shared__ uint8_t lut_all[128 * 128];
-    uint8_t* lut = lut_all + threadIdx.x * 128;
     const uint32_t* src32 = reinterpret_cast<const uint32_t*>(src);
     const unsigned long long n = *n_surv < cap ? *n_surv : cap;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
         const uint64_t p = surv[i];
-        if (is_dynamic_header(src32, p, total_bits, lut)) {
+        if (is_dynamic_header(src32, p, total_bits)) {
             const unsigned long long slot = atomicAdd(n_cand, 1ull);
             if (slot < max_cand) cand[slot] = p;
         }
