@@ -1228,8 +1228,10 @@ extern "C" int sdz_large_decode(sdz_large* L, uint32_t part, uint32_t n_parts, u
     L->lap("2a marker decode");
     // ~sqrt(pieces of the WHOLE stream) per segment: pass 2b walks the pieces of a segment in order, pass 2c walks
     // the segments of ALL parts in order (rank after rank), so this balances the two serial chains
+    // ... and never more segments than SMs: pass 2b runs one 1,024-thread CTA per segment, one CTA per SM
     L->bps = 1;
     while (L->bps * L->bps < L->t_bit.size()) L->bps++;
+    L->bps = std::max<uint64_t>(L->bps, (nt + ctx->sm_count - 1) / ctx->sm_count);
     const unsigned nseg = (unsigned)((nt + L->bps - 1) / L->bps);
     sdz::propagate_in_segment<<<nseg, 1024, 0, ctx->stream>>>(sym0, L->d_to, nt, L->bps);
     ctx->launches++;
