@@ -82,7 +82,14 @@ def measured_traffic(kernel, n_streams):
 def make_corpus(n_distinct, first_index, threads):
     from tools import corpus as K
     t0 = time.time()
+    cache = os.environ.get("SDZ_CORPUS_CACHE")      # tools/bench_variants.py: several runs on one box share the corpus
+    path = "%s.%d.%d.npz" % (cache, n_distinct, first_index) if cache else None
+    if path and os.path.exists(path):
+        z = np.load(path)
+        return z["comp"], int(z["stride"]), z["clen"], time.time() - t0
     comp, stride, clen, _ = K.make_batch(K.TEXT, n_distinct, STREAM_BYTES, LEVEL, K.ZLIB, first_index=first_index, threads=threads)
+    if path:
+        np.savez(path, comp=comp, stride=np.int64(stride), clen=clen)
     return comp, stride, clen, time.time() - t0
 
 
@@ -346,7 +353,7 @@ def main():
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on a bounded sample
     cpu = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and args.cpu_sample > 0:
         ns = min(args.cpu_sample, n)
         o_off = np.arange(ns, dtype=np.uint64) * np.uint64(STREAM_BYTES)
         o_cap = np.full(ns, STREAM_BYTES, dtype=np.uint64)

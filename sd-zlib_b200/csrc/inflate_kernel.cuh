@@ -29,6 +29,15 @@ namespace sdz {
 #ifndef SDZ_LIT_RUN
 #define SDZ_LIT_RUN 1                  // plain literals folded in front of every lockstep symbol (measured: 0 -> 90, 1 -> 99, 2 -> 97 GB/s)
 #endif
+#ifndef SDZ_CHUNKED
+#define SDZ_CHUNKED 0                  // 1: long far matches are issued as 16-byte deferred pieces, one per lockstep iteration
+                                       // (measured slower, 104.3 vs 107.0 GB/s: the extra iterations cost more issue slots than the
+                                       // load-to-store round trip of the synchronous copy, which only idles one warp)
+#endif
+#ifndef SDZ_LONG_SMEM
+#define SDZ_LONG_SMEM 32               // literal/length symbols with codes longer than the root kept in shared memory (0 or 32):
+                                       // 8 blocks x (16 x 1,760 B + 1 KiB) = exactly the 228 KiB of one SM (+1.5 %)
+#endif
 constexpr int RL = 9;                  // literal/length LUT root bits
 constexpr int RD = 7;                  // distance LUT root bits
 constexpr int CH = 128;                // bytes per TMA bulk copy
@@ -50,6 +59,9 @@ struct alignas(16) GroupSmem {
     uint16_t start[4];                 // canonical-walk state after the root bits: first_l, index_l, first_d, index_d
     uint16_t pad_[4];
     uint32_t stage[16];                // 2 slots x 8 words: source words of the two pending (deferred) matches
+#if SDZ_LONG_SMEM > 0
+    uint16_t long_l[SDZ_LONG_SMEM];    // first symbols (canonical order) whose literal/length code is longer than RL bits
+#endif
 };
 constexpr int MAX_G_DEFERRED = 4;      // groups wider than this use the synchronous copy only (stage[] holds 8 words)
 
@@ -274,14 +286,21 @@ __device__ __noinline__ uint32_t slow_lookup(const uint16_t* cnt, const uint16_t
 // length R + 1.  `start` = state of the canonical walk after R bits, precomputed per block:
 // { first code value (<< 1), symbol index }.
 // Returns code_length << 16 | symbol, or 0 if no code matches (invalid).
-__device__ __forceinline__ uint32_t canon_long(const uint16_t* cnt, const uint16_t* sorted, int R, int g, const uint16_t* start, uint32_t bits)
+// `near` (optional): shared-memory copy of sorted[start[1] .. start[1] + n_near).
+__device__ __forceinline__ uint32_t canon_long(const uint16_t* cnt, const uint16_t* sorted, int R, int g, const uint16_t* start, uint32_t bits,
+                                               const uint16_t* near = nullptr, int n_near = 0)
 {
     int first = (int)start[0], index = (int)start[1];
+    const int index0 = index;
     int code = (int)((__brev(bits) >> (32 - R)) << 1);
     for (int len = R + 1; len <= g; len++) {
         code |= (int)((bits >> (len - 1)) & 1u);
         const int count = (int)cnt[len];
-        if (code - count < first) return ((uint32_t)len << 16) | (sorted[index + (code - first)] & 0xfffu);
+        if (code - count < first) {
+            const int at = index + (code - first);
+            const uint32_t sym = (near != nullptr && at - index0 < n_near) ? near[at - index0] : sorted[at];
+            return ((uint32_t)len << 16) | (sym & 0xfffu);
+        }
         index += count; first += count; first <<= 1; code <<= 1;
     }
     return 0u;
@@ -440,6 +459,13 @@ __device__ __noinline__ TreeInfo build_tables(GroupSmem* S, uint16_t* gsorted, i
         if (st == 3 && nl > 257) { T.msg = SDZ_MSG_EMPTY_DIST_TREE; return T; }
     }
     make_lut<G, 0, RL>(aux, lens, nl, nz_l, S->cnt_l, S->start, gsorted, S->lut_l, glane, gmask);
+#if SDZ_LONG_SMEM > 0
+    {
+        const int i0 = (int)S->start[1], nc = nl - nz_l;
+        for (int j = glane; j < SDZ_LONG_SMEM; j += G) S->long_l[j] = i0 + j < nc ? gsorted[i0 + j] : (uint16_t)0;
+        __syncwarp(gmask);
+    }
+#endif
     make_lut<G, 1, RD>(aux, lens + nl, nd, nz_d, S->cnt_d, S->start + 2, gsorted + SORTED_L, S->lut_d, glane, gmask);
     if (fixed) { T.lbits = 9; T.dbits = 5; }
     return T;
@@ -536,6 +562,8 @@ struct Decoder {
     // `n_` the newer one.  len | soff << 8 is packed in *_meta (0 = empty); the older one's words
     // live in staging slot `ptog`, the newer one's in slot `ptog ^ 1`.
     uint32_t o_dst, o_meta, n_dst, n_meta, ptog;
+    // rest of a long match that is being issued piecewise: (symbols left) | distance << 9, 0 = none
+    uint32_t rem;
 
     RingModel ring;
     int msg;
@@ -905,15 +933,43 @@ struct Decoder {
     // One symbol on the fast path.  The stream tail and every irregular case (long / invalid
     // root entry) go through step_general().  (Folding a run of literals into the same lockstep
     // iteration was measured slower: the warp pays the longest run of its eight groups.)
+    // A long match whose source lies well before the pending copies (distance >= 64 bytes) is not copied
+    // synchronously: it is cut into pieces of 16 bytes that go through the deferred path, one piece per
+    // lockstep iteration (the group decodes nothing while pieces are left).  The copy instructions are
+    // executed by the warp in every iteration anyway, so the pieces cost no extra issue slots and no
+    // load-to-store round trip.  Returns the length of the piece to copy now.
+    static constexpr uint32_t PIECE = (MARK ? 8u : 16u);               // symbols per piece (16 bytes)
+    __device__ __forceinline__ uint32_t first_piece(uint32_t len, uint32_t dist)
+    {
+#if SDZ_CHUNKED
+        if (STORE && G <= MAX_G_DEFERRED && TM != TM_INDEX && len > PIECE && dist >= 4u * PIECE && dist <= pos && len <= cap - pos) {
+            rem = (len - PIECE) | (dist << 9);
+            return PIECE;
+        }
+#endif
+        return len;
+    }
+
     __device__ __forceinline__ int step()
     {
+#if SDZ_CHUNKED
+        if (STORE && rem != 0u) {                       // next piece of a long match
+            const uint32_t left = rem & 0x1ffu, dist = rem >> 9;
+            const uint32_t now = left > PIECE ? PIECE : left;
+            rem = left > PIECE ? rem - PIECE : 0u;
+            return copy_match(now, dist, false);
+        }
+#endif
         // stream tail: the two refills below need whole words, and only step_general() knows the stall rules
-        if (wp + 5 > end_wp) return step_general(false);
+        // (one call site for step_general(): it is inlined once)
+        bool slow = wp + 5 > end_wp;
+        bool lit_now = false;
+        uint32_t e = 0;
+        if (!slow) {
         // ONE top-up serves a folded literal (<= RL bits) and the literal/length code with its extra bits
         // (<= 15 + 5): at least 33 bits are valid afterwards
         refill_fast();
-        bool lit_now = false;
-        uint32_t e = S->lut_l[(uint32_t)bb & ((1u << RL) - 1u)];
+        e = S->lut_l[(uint32_t)bb & ((1u << RL) - 1u)];
 #if SDZ_LIT_RUN > 0
         // leading literal: every lockstep iteration pays for the match path anyway, so a plain literal in
         // front of a match is folded into the same iteration
@@ -927,11 +983,14 @@ struct Decoder {
             e = S->lut_l[(uint32_t)bb & ((1u << RL) - 1u)];
         }
 #endif
-        bool slow = false;
         if ((e >> 12) == 0) {                           // code longer than the root (or invalid)
             slow = true;
             if (e == E_LONG) {
+#if SDZ_LONG_SMEM > 0
+                const uint32_t r = canon_long(S->cnt_l, gsorted, RL, g_l, S->start, (uint32_t)bb, S->long_l, SDZ_LONG_SMEM);
+#else
                 const uint32_t r = canon_long(S->cnt_l, gsorted, RL, g_l, S->start, (uint32_t)bb);
+#endif
                 const uint32_t sym = r & 0xffffu;
                 if (r != 0 && sym <= 256) { e = ((r >> 16) << 12) | sym; slow = false; }
                 else if (r != 0 && sym - 257 <= 28) {
@@ -942,6 +1001,7 @@ struct Decoder {
                     slow = false;
                 }
             }
+        }
         }
         if (slow) return step_general(lit_now);
         const uint32_t n = e >> 12, p = e & 0xfff;
@@ -970,7 +1030,7 @@ struct Decoder {
         const uint32_t dx = (de >> 8) & 15;
         const uint32_t dist = 1 + ((de & 3) << dx) + (((uint32_t)bb >> dn) & ((1u << dx) - 1u));     // dn + dx <= 28
         bb >>= (dn + dx); bc -= (int)(dn + dx);
-        return copy_match(len, dist, lit_now);
+        return copy_match(first_piece(len, dist), dist, lit_now);
     }
 
     // stored block body (src/infblocks.ts:278-333) with the Q2 truncation
@@ -1023,7 +1083,7 @@ struct Decoder {
         D = 0; dict_tail = nullptr;
         lbits = dbits = g_l = g_d = 0; eob_len = 0;
         ring.init(0);
-        o_dst = o_meta = n_dst = n_meta = 0;
+        o_dst = o_meta = n_dst = n_meta = 0; rem = 0;
         is_gzip = false; method = 0; n_blocks = 0; mtime = 0; name_off = 0; name_len = 0; last = 0; raw = true;
         const uint64_t sb = P.task_bit[i];
         if ((sb >> 3) >= (uint64_t)in_len) { finish_task(P, R_STALL); return; }
@@ -1081,7 +1141,7 @@ struct Decoder {
         D = 0; dict_tail = nullptr;
         lbits = dbits = g_l = g_d = 0; eob_len = 0;
         ring.init(0);
-        o_dst = o_meta = n_dst = n_meta = 0;
+        o_dst = o_meta = n_dst = n_meta = 0; rem = 0;
         is_gzip = false; method = 0; n_blocks = 0; mtime = 0; name_off = 0; name_len = 0; last = 0;
 
         int thrown = SDZ_THROW_NONE, thrown_inflate = 0, zstatus = SDZ_Z_OK;
@@ -1333,7 +1393,7 @@ struct Decoder {
 };
 
 #ifndef SDZ_MINBLOCKS
-#define SDZ_MINBLOCKS 1
+#define SDZ_MINBLOCKS 4                // 128 registers: eight 64-thread blocks per SM
 #endif
 
 // One sub-warp group of G lanes per stream; the 32 / G groups of a warp run the symbol loop in
@@ -1354,7 +1414,7 @@ __global__ void __launch_bounds__(128, SDZ_MINBLOCKS) inflate_kernel(InflatePara
     const int lane = threadIdx.x & 31;
     d.gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - d.glane));
     d.issued_abs = 0; d.waited_abs = 0; d.chunk0 = 0; d.phasebits = 0;
-    d.ptog = 0; d.o_dst = d.o_meta = d.n_dst = d.n_meta = 0;
+    d.ptog = 0; d.o_dst = d.o_meta = d.n_dst = d.n_meta = 0; d.rem = 0;
     d.phase = PH_FETCH;
     if (d.glane == 0) {
         for (int i = 0; i < NBUF; i++) mbar_init(&S->mbar[i], 1);
