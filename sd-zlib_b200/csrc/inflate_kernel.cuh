@@ -29,6 +29,9 @@ namespace sdz {
 #ifndef SDZ_LIT_RUN
 #define SDZ_LIT_RUN 1                  // plain literals folded in front of every lockstep symbol (measured: 0 -> 90, 1 -> 99, 2 -> 97 GB/s)
 #endif
+#ifndef SDZ_FLAT
+#define SDZ_FLAT 1                     // straight-line (predicated) lockstep iteration, see step_flat()
+#endif
 #ifndef SDZ_CHUNKED
 #define SDZ_CHUNKED 0                  // 1: long far matches are issued as 16-byte deferred pieces, one per lockstep iteration
                                        // (measured slower, 104.3 vs 107.0 GB/s: the extra iterations cost more issue slots than the
@@ -1033,6 +1036,104 @@ struct Decoder {
         return copy_match(first_piece(len, dist), dist, lit_now);
     }
 
+
+    // One lockstep iteration as straight-line code.  The warp executes the match path in practically every
+    // iteration (one of its eight groups almost always has a match), so literal groups run it too, with
+    // every side effect predicated off: no divergence between literal and match groups, no reconvergence
+    // points, one branch for everything rare (long / invalid code, end of block), one for copies that are
+    // not plain deferred copies.  The stream tail and the last 260 bytes of the output slot go through
+    // step_general(), which has all the checks.
+    __device__ __forceinline__ int step_flat()
+    {
+        constexpr uint32_t LMASK = (1u << RL) - 1u, DMASK = (1u << RD) - 1u;
+        bool general = wp + 5 > end_wp || cap - pos < 260u;     // (one call site for step_general(): it is inlined once)
+        bool fold = false;
+        uint32_t e = 0;
+        if (!general) {
+        refill_fast();
+        e = S->lut_l[(uint32_t)bb & LMASK];
+        // leading plain literal (marker mode: never the last symbol of the piece)
+        fold = SDZ_LIT_RUN > 0 && e >= 0x1000u && (e & 0xf00u) == 0u && (!MARK || pos + 1u < limit);
+        {
+            const uint32_t n0 = fold ? e >> 12 : 0u;
+            if (STORE) { if (MARK) st_u16_if(out16 + pos, e & 0xffu, fold && glane == 0); else st_u8_if(out + pos, e & 0xffu, fold && glane == 0); }
+            pos += fold ? 1u : 0u;
+            bb >>= n0; bc -= (int)n0;
+            e = S->lut_l[(uint32_t)bb & LMASK];          // the same entry again when nothing was folded
+        }
+        if ((e >> 12) == 0u || (e & 0xfffu) == 0x100u) {    // rare: code longer than the root, invalid code, end of block
+            bool ok = false;
+            if (e == E_LONG) {
+#if SDZ_LONG_SMEM > 0
+                const uint32_t r = canon_long(S->cnt_l, gsorted, RL, g_l, S->start, (uint32_t)bb, S->long_l, SDZ_LONG_SMEM);
+#else
+                const uint32_t r = canon_long(S->cnt_l, gsorted, RL, g_l, S->start, (uint32_t)bb);
+#endif
+                const uint32_t sym = r & 0xffffu;
+                if (r != 0u && sym <= 256u) { e = ((r >> 16) << 12) | sym; ok = true; }
+                else if (r != 0u && sym - 257u <= 28u) {
+                    const uint32_t i = sym - 257u;
+                    const uint32_t xb = i < 8 ? 0 : (i == 28 ? 0 : (i >> 2) - 1);
+                    const uint32_t base = i < 8 ? 3 + i : (i == 28 ? 258 : 3 + ((4 + (i & 3)) << xb));
+                    e = ((r >> 16) << 12) | 0x800u | (xb << 8) | (base - 3u);
+                    ok = true;
+                }
+            } else if ((e >> 12) != 0u) ok = true;          // end of block with a root-table code
+            if (!ok) general = true;
+            else if ((e & 0xfffu) == 0x100u) { const uint32_t n = e >> 12; bb >>= n; bc -= (int)n; eob_len = (int)n; return R_EOB; }
+        }
+        }
+        if (general) return step_general(fold);
+        const uint32_t n = e >> 12, p = e & 0xfffu;
+        const bool ismatch = p >= 256u;
+        if (STORE) { if (MARK) st_u16_if(out16 + pos, p, !ismatch && glane == 0); else st_u8_if(out + pos, p, !ismatch && glane == 0); }
+        // a literal is a "match" of length 1 without extra bits: one consume and one `pos +=` serve both
+        const uint32_t xb = ismatch ? (p >> 8) & 7u : 0u;
+        const uint32_t len = ismatch ? 3u + (p & 0xffu) + (((uint32_t)bb >> n) & ((1u << xb) - 1u)) : 1u;
+        bb >>= (n + xb); bc -= (int)(n + xb);
+        refill_fast();                                     // harmless for literal groups: at least five whole words remain
+        uint32_t de = S->lut_d[(uint32_t)bb & DMASK];
+        uint32_t dn = de >> 12;
+        if (ismatch && dn == 0u) {                         // rare: distance code longer than the root, or invalid
+            const uint32_t r = de == E_LONG ? canon_long(S->cnt_d, gsorted + SORTED_L, RD, g_d, S->start + 2, (uint32_t)bb) : 0u;
+            const uint32_t ds = r & 0xffffu;
+            if (r == 0u || ds > 29u) { msg = SDZ_MSG_BAD_DIST_CODE; return R_ERROR; }     // far from the tail: no stall possible
+            dn = r >> 16;
+            de = ((ds < 4 ? 0u : (ds >> 1) - 1u) << 8) | (ds < 4 ? ds : 2u + (ds & 1u));
+        }
+        const uint32_t dx = (de >> 8) & 15u;
+        const uint32_t dist = 1u + ((de & 3u) << dx) + (((uint32_t)bb >> dn) & ((1u << dx) - 1u));
+        const uint32_t dcons = ismatch ? dn + dx : 0u;
+        bb >>= dcons; bc -= (int)dcons;
+        if (!STORE) { pos += len; return R_OK; }
+        // ---- copy (byte units; a marker symbol is two bytes)
+        constexpr uint32_t E = MARK ? 2u : 1u;
+        const uint32_t bpos = pos * E, blen = len * E, bdist = dist * E;
+        const bool simple = G <= MAX_G_DEFERRED && ismatch && bdist >= blen && blen <= 16u && bdist <= bpos && !(fold && bdist == blen);
+        const uint32_t first_pending = o_meta ? o_dst : n_dst;
+        const bool hazard = (o_meta | n_meta) != 0u && (bdist > bpos || bpos - bdist + blen > first_pending);
+        if (ismatch && (!simple || hazard)) return copy_match(len, dist, fold);     // long / overlapping / marker / early source, pending bytes
+        // plain deferred copy, predicated on `simple` (nothing happens for a literal)
+        if constexpr (G <= MAX_G_DEFERRED) {
+        cp_async_wait_but_one();
+        commit_slot(o_dst, simple ? o_meta : 0u, ptog);
+        {
+            const uint8_t* src = out + bpos - bdist;
+            const uint32_t so = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
+            const uint32_t jb = (uint32_t)DB * (uint32_t)glane;
+            const uint8_t* w0 = src - so + jb;
+            #pragma unroll
+            for (int k = 0; k < DW; k++) cp_async4_if(&S->stage[8 * ptog + DW * glane + k], w0 + 4 * k, simple && jb + 4u * k < blen + so);
+            cp_async_commit();
+            o_dst = simple ? n_dst : o_dst; o_meta = simple ? n_meta : o_meta;
+            n_dst = simple ? bpos : n_dst; n_meta = simple ? (blen | (so << 8)) : n_meta;
+            ptog ^= simple ? 1u : 0u;
+        }
+        }
+        pos += len;
+        return R_OK;
+    }
+
     // stored block body (src/infblocks.ts:278-333) with the Q2 truncation
     __device__ __forceinline__ int stored_block(uint32_t left)
     {
@@ -1432,7 +1533,11 @@ __global__ void __launch_bounds__(128, SDZ_MINBLOCKS) inflate_kernel(InflatePara
             __syncwarp();                            // re-converge + order the stores of earlier iterations
             if (d.phase == PH_CODES) {
                 if (TM == TM_INDEX) d.checkpoint(P);
+#if SDZ_FLAT
+                int r = d.step_flat();
+#else
                 int r = d.step();
+#endif
                 if (TM == TM_MARK && r == R_OK && d.pos >= d.limit) r = R_EOB;     // the piece is complete
                 if (r != R_OK) d.block_end(P, r);
             }

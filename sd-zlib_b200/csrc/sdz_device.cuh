@@ -77,6 +77,13 @@ __device__ __forceinline__ void st_u8_if(uint8_t* p, uint32_t v, bool pred)
                  "r"(v), "r"((uint32_t)pred)
                  : "memory");
 }
+__device__ __forceinline__ void st_u16_if(uint16_t* p, uint32_t v, bool pred)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.u16 [%0], %1;\n\t}" ::"l"(
+                     __cvta_generic_to_global(p)),
+                 "h"((uint16_t)v), "r"((uint32_t)pred)
+                 : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 // all groups except the most recently committed one are complete
