@@ -32,6 +32,15 @@ namespace sdz {
 #ifndef SDZ_FLAT
 #define SDZ_FLAT 1                     // straight-line (predicated) lockstep iteration, see step_flat()
 #endif
+#ifndef SDZ_CONT
+#define SDZ_CONT 0                     // 1: step_flat() issues a long far match as 16-byte deferred pieces, one per iteration, as
+                                       // predicated straight-line code (the group decodes nothing while pieces are left).
+                                       // Measured slower (112.8 vs 122.8 GB/s): the synchronous copy of the 3 % long matches is
+                                       // cheaper than the iterations their groups lose
+#endif
+#ifndef SDZ_CAPMARGIN
+#define SDZ_CAPMARGIN 2                // step_flat(): output room below which step_general() takes over (2: fold + literal)
+#endif
 #ifndef SDZ_CHUNKED
 #define SDZ_CHUNKED 0                  // 1: long far matches are issued as 16-byte deferred pieces, one per lockstep iteration
                                        // (measured slower, 104.3 vs 107.0 GB/s: the extra iterations cost more issue slots than the
@@ -916,9 +925,9 @@ struct Decoder {
 
     // branch-free top-up used by the fast path (at least five whole input words remain):
     // predicated instructions only, except for the rare hop into the next 128-byte chunk
-    __device__ __forceinline__ void refill_fast()
+    __device__ __forceinline__ void refill_fast(bool enable = true)
     {
-        const bool take = bc <= 32;
+        const bool take = enable && bc <= 32;
         bb |= take ? ((uint64_t)nw << bc) : 0ull;
         bc += take ? 32 : 0;
         wp += take ? 1u : 0u;
@@ -1046,14 +1055,16 @@ struct Decoder {
     __device__ __forceinline__ int step_flat()
     {
         constexpr uint32_t LMASK = (1u << RL) - 1u, DMASK = (1u << RD) - 1u;
-        bool general = wp + 5 > end_wp || cap - pos < 260u;     // (one call site for step_general(): it is inlined once)
+        // `cont`: pieces of a long match are left; the group neither reads nor consumes input in this iteration
+        const bool cont = SDZ_CONT && STORE && G <= MAX_G_DEFERRED && rem != 0u;
+        bool general = !cont && (wp + 5 > end_wp || cap - pos < (uint32_t)SDZ_CAPMARGIN);     // (one call site for step_general(): it is inlined once)
         bool fold = false;
         uint32_t e = 0;
         if (!general) {
-        refill_fast();
+        refill_fast(!cont);
         e = S->lut_l[(uint32_t)bb & LMASK];
         // leading plain literal (marker mode: never the last symbol of the piece)
-        fold = SDZ_LIT_RUN > 0 && e >= 0x1000u && (e & 0xf00u) == 0u && (!MARK || pos + 1u < limit);
+        fold = SDZ_LIT_RUN > 0 && !cont && e >= 0x1000u && (e & 0xf00u) == 0u && (!MARK || pos + 1u < limit);
         {
             const uint32_t n0 = fold ? e >> 12 : 0u;
             if (STORE) { if (MARK) st_u16_if(out16 + pos, e & 0xffu, fold && glane == 0); else st_u8_if(out + pos, e & 0xffu, fold && glane == 0); }
@@ -1061,7 +1072,7 @@ struct Decoder {
             bb >>= n0; bc -= (int)n0;
             e = S->lut_l[(uint32_t)bb & LMASK];          // the same entry again when nothing was folded
         }
-        if ((e >> 12) == 0u || (e & 0xfffu) == 0x100u) {    // rare: code longer than the root, invalid code, end of block
+        if (!cont && ((e >> 12) == 0u || (e & 0xfffu) == 0x100u)) {    // rare: code longer than the root, invalid code, end of block
             bool ok = false;
             if (e == E_LONG) {
 #if SDZ_LONG_SMEM > 0
@@ -1084,17 +1095,17 @@ struct Decoder {
         }
         }
         if (general) return step_general(fold);
-        const uint32_t n = e >> 12, p = e & 0xfffu;
-        const bool ismatch = p >= 256u;
+        const uint32_t n = cont ? 0u : e >> 12, p = e & 0xfffu;
+        const bool ismatch = cont || p >= 256u;
         if (STORE) { if (MARK) st_u16_if(out16 + pos, p, !ismatch && glane == 0); else st_u8_if(out + pos, p, !ismatch && glane == 0); }
         // a literal is a "match" of length 1 without extra bits: one consume and one `pos +=` serve both
-        const uint32_t xb = ismatch ? (p >> 8) & 7u : 0u;
-        const uint32_t len = ismatch ? 3u + (p & 0xffu) + (((uint32_t)bb >> n) & ((1u << xb) - 1u)) : 1u;
+        const uint32_t xb = (ismatch && !cont) ? (p >> 8) & 7u : 0u;
+        uint32_t len = ismatch ? 3u + (p & 0xffu) + (((uint32_t)bb >> n) & ((1u << xb) - 1u)) : 1u;
         bb >>= (n + xb); bc -= (int)(n + xb);
-        refill_fast();                                     // harmless for literal groups: at least five whole words remain
+        refill_fast(!cont);                                // harmless for literal groups: at least five whole words remain
         uint32_t de = S->lut_d[(uint32_t)bb & DMASK];
         uint32_t dn = de >> 12;
-        if (ismatch && dn == 0u) {                         // rare: distance code longer than the root, or invalid
+        if (ismatch && !cont && dn == 0u) {                // rare: distance code longer than the root, or invalid
             const uint32_t r = de == E_LONG ? canon_long(S->cnt_d, gsorted + SORTED_L, RD, g_d, S->start + 2, (uint32_t)bb) : 0u;
             const uint32_t ds = r & 0xffffu;
             if (r == 0u || ds > 29u) { msg = SDZ_MSG_BAD_DIST_CODE; return R_ERROR; }     // far from the tail: no stall possible
@@ -1102,14 +1113,24 @@ struct Decoder {
             de = ((ds < 4 ? 0u : (ds >> 1) - 1u) << 8) | (ds < 4 ? ds : 2u + (ds & 1u));
         }
         const uint32_t dx = (de >> 8) & 15u;
-        const uint32_t dist = 1u + ((de & 3u) << dx) + (((uint32_t)bb >> dn) & ((1u << dx) - 1u));
-        const uint32_t dcons = ismatch ? dn + dx : 0u;
+        uint32_t dist = 1u + ((de & 3u) << dx) + (((uint32_t)bb >> dn) & ((1u << dx) - 1u));
+        const uint32_t dcons = (ismatch && !cont) ? dn + dx : 0u;
         bb >>= dcons; bc -= (int)dcons;
         if (!STORE) { pos += len; return R_OK; }
         // ---- copy (byte units; a marker symbol is two bytes)
         constexpr uint32_t E = MARK ? 2u : 1u;
+        if (SDZ_CONT && G <= MAX_G_DEFERRED) {
+            // next piece of the match in progress, or the first piece of a long match whose source is far enough
+            // behind that the pieces never read pending bytes (64 bytes; the whole match must fit the output slot)
+            const uint32_t left = cont ? rem & 0x1ffu : len;
+            dist = cont ? rem >> 9 : dist;
+            const bool far = cont || (ismatch && left > PIECE && dist >= 4u * PIECE && dist <= pos && left <= cap - pos);
+            len = (far && left > PIECE) ? PIECE : left;
+            rem = (far && left > PIECE) ? ((left - PIECE) | (dist << 9)) : 0u;
+        }
         const uint32_t bpos = pos * E, blen = len * E, bdist = dist * E;
-        const bool simple = G <= MAX_G_DEFERRED && ismatch && bdist >= blen && blen <= 16u && bdist <= bpos && !(fold && bdist == blen);
+        const bool simple = G <= MAX_G_DEFERRED && ismatch && bdist >= blen && blen <= 16u && bdist <= bpos && !(fold && bdist == blen) &&
+                            len <= cap - pos;
         const uint32_t first_pending = o_meta ? o_dst : n_dst;
         const bool hazard = (o_meta | n_meta) != 0u && (bdist > bpos || bpos - bdist + blen > first_pending);
         if (ismatch && (!simple || hazard)) return copy_match(len, dist, fold);     // long / overlapping / marker / early source, pending bytes
