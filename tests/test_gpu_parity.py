@@ -490,3 +490,40 @@ def test_large_stream_slices_shorter_than_the_window():
     assert r.success and r.checksum_state == 1 and r.size_state == 1
     with pytest.raises(LG.NeedsSequentialDecoder):
         LG.inflate_large_parts(np.frombuffer(zlib.compress(plain.tobytes(), 6), dtype=np.uint8), 2)   # zlib: single-GPU path only
+
+
+@pytest.mark.gpu
+def test_inflater_append_split_points():
+    """Inflater.append() over 2-4 chunks cut at random byte positions.  Wherever the reference
+    itself survives the split (the oracle twin of class Inflater does not throw), the device path returns the same
+    <= 16 KiB chunk shapes per append(), the same bytes and the same finish() record.  Splits that land in one of the
+    reference's non-resumable states (inside a dynamic block header, Q3, and the cases that follow from it) make the
+    reference throw or spin; the device path re-decodes the bytes received so far and is not affected - those
+    splits are counted, not compared (documented divergence)."""
+    import random
+    rnd = random.Random(7)
+    cases = []
+    for kind, n, cont in ((K.TEXT, 40000, K.ZLIB), (K.TEXT, 70000, K.GZIP_NAME), (K.BINARY, 50000, K.RAW), (K.RUNS, 60000, K.ZLIB),
+                          (K.RANDOM, 30000, K.GZIP), (K.TINY, 150, K.ZLIB)):
+        cases.append((cont, bytes(K.compress(K.generate(kind, 99, n), 6, cont))))
+    state = {"unchecked": 0, "match": 1, "mismatch": 2}
+    compared = skipped = 0
+    for cont, s in cases:
+        for _ in range(20):
+            cuts = sorted(rnd.randrange(1, len(s)) for _ in range(rnd.choice((1, 1, 2, 3))))
+            parts = [s[a:b] for a, b in zip([0] + cuts, cuts + [len(s)])]
+            o = O.Inflater(raw=cont == K.RAW)
+            try:
+                oshape = [[len(x) for x in o.append(p)] for p in parts]
+            except O.OracleThrow:
+                skipped += 1
+                continue
+            g = sdzlib.Inflater(raw=cont == K.RAW)
+            gchunks = [g.append(p) for p in parts]
+            assert [[len(x) for x in c] for c in gchunks] == oshape, (cont, cuts)
+            orr, grr = o.finish(), g.finish()
+            assert (grr.success, grr.complete, state[grr.checksum], state[grr.fileSize]) == \
+                   (bool(orr.success), bool(orr.complete), orr.checksum_state, orr.size_state), (cont, cuts)
+            assert grr.fileName == orr.file_name
+            compared += 1
+    assert compared >= 80 and skipped < compared
