@@ -41,6 +41,9 @@ namespace sdz {
 #ifndef SDZ_CAPMARGIN
 #define SDZ_CAPMARGIN 2                // step_flat(): output room below which step_general() takes over (2: fold + literal)
 #endif
+#ifndef SDZ_TWOSLOT
+#define SDZ_TWOSLOT 1                  // far matches of 17..32 bytes take both staging slots (one half each) instead of a synchronous copy
+#endif
 #ifndef SDZ_CHUNKED
 #define SDZ_CHUNKED 0                  // 1: long far matches are issued as 16-byte deferred pieces, one per lockstep iteration
                                        // (measured slower, 104.3 vs 107.0 GB/s: the extra iterations cost more issue slots than the
@@ -470,7 +473,9 @@ __device__ __noinline__ TreeInfo build_tables(GroupSmem* S, uint16_t* gsorted, i
         if (st == 2) { T.msg = SDZ_MSG_INCOMPLETE_DIST_TREE; return T; }
         if (st == 3 && nl > 257) { T.msg = SDZ_MSG_EMPTY_DIST_TREE; return T; }
     }
-    make_lut<G, 0, RL>(aux, lens, nl, nz_l, S->cnt_l, S->start, gsorted, S->lut_l, glane, gmask);
+    // (the 288-symbol counting sort is a serial read-modify-write chain on aux[]: it runs on the not yet built
+    // distance LUT's shared memory instead of the global scratch - ~30 instead of ~500 cycles per symbol)
+    make_lut<G, 0, RL>(reinterpret_cast<uint32_t*>(S->lut_d), lens, nl, nz_l, S->cnt_l, S->start, gsorted, S->lut_l, glane, gmask);
 #if SDZ_LONG_SMEM > 0
     {
         const int i0 = (int)S->start[1], nc = nl - nz_l;
@@ -771,7 +776,28 @@ struct Decoder {
             // only ordered before the reads below by a group sync; a deferred match reads pos - 1 iff dist == len
             if (hazard || !simple || (lit_now && bdist == blen)) __syncwarp(gmask);
             uint8_t* dst = out + bpos;
-            if (simple) {
+#if SDZ_TWOSLOT
+            const bool two = G <= MAX_G_DEFERRED && !simple && bdist >= blen && blen <= 32u && bdist <= bpos;
+#else
+            const bool two = false;
+#endif
+            if (two) {
+                // 17..32 bytes, not overlapping: both staging slots are emptied and take one half of the match each,
+                // so this copy has no load-to-store round trip either (the warp's other groups are waiting here)
+                if ((o_meta | n_meta) != 0u) { flush_pending(); __syncwarp(gmask); }
+                const uint8_t* src = dst - bdist;
+                const uint32_t so = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
+                const uint32_t jb = (uint32_t)DB * (uint32_t)glane;
+                const uint8_t* w0 = src - so + jb;
+                #pragma unroll
+                for (int k = 0; k < DW; k++) cp_async4_if(&S->stage[8 * ptog + DW * glane + k], w0 + 4 * k, jb + 4u * k < 16u + so);
+                cp_async_commit();
+                #pragma unroll
+                for (int k = 0; k < DW; k++) cp_async4_if(&S->stage[8 * (ptog ^ 1u) + DW * glane + k], w0 + 16 + 4 * k, jb + 4u * k < blen - 16u + so);
+                cp_async_commit();
+                o_dst = bpos; o_meta = 16u | (so << 8);
+                n_dst = bpos + 16u; n_meta = (blen - 16u) | (so << 8);
+            } else if (simple) {
                 // the older pending match was issued two matches ago: wait for it (only), store it, and
                 // reuse its staging slot for this match
                 cp_async_wait_but_one();
@@ -1129,11 +1155,26 @@ struct Decoder {
             rem = (far && left > PIECE) ? ((left - PIECE) | (dist << 9)) : 0u;
         }
         const uint32_t bpos = pos * E, blen = len * E, bdist = dist * E;
-        const bool simple = G <= MAX_G_DEFERRED && ismatch && bdist >= blen && blen <= 16u && bdist <= bpos && !(fold && bdist == blen) &&
+        bool cm = ismatch;                                 // a copy that reads earlier output
+        if (MARK && G <= MAX_G_DEFERRED) {
+            // marker mode: a short match whose source lies entirely before the piece reads nothing - its symbols are
+            // markers (256 + index into the 32 KiB window before the piece; zeros before the start of the stream, Q6)
+            // computed and stored here; pending copies are not disturbed (early in a piece this is the common match)
+            const bool pre = ismatch && dist >= pos + len && len <= 8u;
+            #pragma unroll
+            for (uint32_t q = 0; q < 2u; q++) {
+                const uint32_t i = 2u * (uint32_t)glane + q;
+                const uint32_t before = dist - pos - i;                         // 1 .. 32768 source symbols before the piece
+                const uint32_t v = (uint64_t)before > abs_start ? 0u : 256u + 32768u - before;
+                st_u16_if(out16 + pos + i, v, pre && i < len);
+            }
+            cm = ismatch && !pre;
+        }
+        const bool simple = G <= MAX_G_DEFERRED && cm && bdist >= blen && blen <= 16u && bdist <= bpos && !(fold && bdist == blen) &&
                             len <= cap - pos;
         const uint32_t first_pending = o_meta ? o_dst : n_dst;
         const bool hazard = (o_meta | n_meta) != 0u && (bdist > bpos || bpos - bdist + blen > first_pending);
-        if (ismatch && (!simple || hazard)) return copy_match(len, dist, fold);     // long / overlapping / marker / early source, pending bytes
+        if (cm && (!simple || hazard)) return copy_match(len, dist, fold);     // long / overlapping / marker / early source, pending bytes
         // plain deferred copy, predicated on `simple` (nothing happens for a literal)
         if constexpr (G <= MAX_G_DEFERRED) {
         cp_async_wait_but_one();
