@@ -45,6 +45,10 @@ namespace sdz {
 #ifndef SDZ_REFILL_IF
 #define SDZ_REFILL_IF 0                // 1: the top-up as a short `if` block (ptxas makes it a real branch: 123.5 vs 124.7 GB/s)
 #endif
+#ifndef SDZ_SLOTS
+#define SDZ_SLOTS 2                    // staging slots = deferred matches in flight per stream (2 or 3).  3 (wait_group 2, one more
+                                       // iteration of slack for the window read) was measured slower: 122.3 vs 127.1 GB/s
+#endif
 #ifndef SDZ_TWOSLOT
 #define SDZ_TWOSLOT 1                  // far matches of 17..32 bytes take both staging slots (one half each) instead of a synchronous copy
 #endif
@@ -57,6 +61,8 @@ namespace sdz {
 #define SDZ_LONG_SMEM 32               // literal/length symbols with codes longer than the root kept in shared memory (0 or 32):
                                        // 8 blocks x (16 x 1,760 B + 1 KiB) = exactly the 228 KiB of one SM (+1.5 %)
 #endif
+// the third staging slot takes 32 of the 64 spare bytes per stream: 16 long-code symbols stay in shared memory
+constexpr int SDZ_LONG_N = SDZ_LONG_SMEM > 0 ? (SDZ_SLOTS == 3 ? SDZ_LONG_SMEM / 2 : SDZ_LONG_SMEM) : 0;
 constexpr int RL = 9;                  // literal/length LUT root bits
 constexpr int RD = 7;                  // distance LUT root bits
 constexpr int CH = 128;                // bytes per TMA bulk copy
@@ -77,9 +83,9 @@ struct alignas(16) GroupSmem {
     uint16_t cnt_d[16];
     uint16_t start[4];                 // canonical-walk state after the root bits: first_l, index_l, first_d, index_d
     uint16_t pad_[4];
-    uint32_t stage[16];                // 2 slots x 8 words: source words of the two pending (deferred) matches
+    uint32_t stage[8 * SDZ_SLOTS];     // slots x 8 words: source words of the pending (deferred) matches
 #if SDZ_LONG_SMEM > 0
-    uint16_t long_l[SDZ_LONG_SMEM];    // first symbols (canonical order) whose literal/length code is longer than RL bits
+    uint16_t long_l[SDZ_LONG_N];       // first symbols (canonical order) whose literal/length code is longer than RL bits
 #endif
 };
 constexpr int MAX_G_DEFERRED = 4;      // groups wider than this use the synchronous copy only (stage[] holds 8 words)
@@ -483,7 +489,7 @@ __device__ __noinline__ TreeInfo build_tables(GroupSmem* S, uint16_t* gsorted, i
 #if SDZ_LONG_SMEM > 0
     {
         const int i0 = (int)S->start[1], nc = nl - nz_l;
-        for (int j = glane; j < SDZ_LONG_SMEM; j += G) S->long_l[j] = i0 + j < nc ? gsorted[i0 + j] : (uint16_t)0;
+        for (int j = glane; j < SDZ_LONG_N; j += G) S->long_l[j] = i0 + j < nc ? gsorted[i0 + j] : (uint16_t)0;
         __syncwarp(gmask);
     }
 #endif
@@ -583,6 +589,21 @@ struct Decoder {
     // `n_` the newer one.  len | soff << 8 is packed in *_meta (0 = empty); the older one's words
     // live in staging slot `ptog`, the newer one's in slot `ptog ^ 1`.
     uint32_t o_dst, o_meta, n_dst, n_meta, ptog;
+#if SDZ_SLOTS == 3
+    // three slots: o (oldest, slot ptog), m (slot ptog + 1), n (newest, slot ptog + 2), indices mod 3; every iteration
+    // of the flat loop commits one cp.async group, so wait_group 2 guarantees copies issued three iterations ago
+    uint32_t m_dst, m_meta;
+#endif
+    __device__ __forceinline__ bool pending_any() const
+    {
+#if SDZ_SLOTS == 3
+        return (o_meta | m_meta | n_meta) != 0u;
+#else
+        return (o_meta | n_meta) != 0u;
+#endif
+    }
+    static constexpr uint32_t NSLOT = SDZ_SLOTS;
+    static __device__ __forceinline__ uint32_t slot_after(uint32_t p) { return NSLOT == 2 ? p ^ 1u : (p == 2u ? 0u : p + 1u); }
     // rest of a long match that is being issued piecewise: (symbols left) | distance << 9, 0 = none
     uint32_t rem;
 
@@ -746,8 +767,16 @@ struct Decoder {
         if (STORE && G <= MAX_G_DEFERRED) {
             cp_async_wait_all();
             commit_slot(o_dst, o_meta, ptog);
+#if SDZ_SLOTS == 3
+            commit_slot(m_dst, m_meta, slot_after(ptog));
+            commit_slot(n_dst, n_meta, slot_after(slot_after(ptog)));
+#else
             commit_slot(n_dst, n_meta, ptog ^ 1u);
+#endif
         }
+#if SDZ_SLOTS == 3
+        m_meta = 0;
+#endif
         o_meta = 0; n_meta = 0;
     }
 
@@ -760,7 +789,7 @@ struct Decoder {
         if (len > cap - pos) return R_OUTFULL;
         if (MARK && dist > pos) {
             // reaches before the piece: those symbols become markers (synchronous; group sync inside)
-            if ((o_meta | n_meta) != 0u) flush_pending();
+            if (pending_any()) flush_pending();
             copy_match_marked(len, dist);
         } else if (STORE) {
             // Marker mode: a symbol is two bytes, and a copy that stays inside the piece is an ordinary copy of
@@ -770,8 +799,13 @@ struct Decoder {
             const bool simple = G <= MAX_G_DEFERRED && bdist >= blen && blen <= 16u && bdist <= bpos;
             // the new source must not overlap bytes that are still pending (the older pending match has
             // the lower destination); copies on the synchronous path read arbitrary earlier bytes
+#if SDZ_SLOTS == 3
+            const uint32_t first_pending = o_meta ? o_dst : (m_meta ? m_dst : n_dst);
+            const bool any_pending = (o_meta | m_meta | n_meta) != 0;
+#else
             const uint32_t first_pending = o_meta ? o_dst : n_dst;
             const bool any_pending = (o_meta | n_meta) != 0;
+#endif
             // (a copy on the synchronous path whose source lies entirely below the pending destinations can
             // overtake them: its own destination is disjoint from theirs)
             const bool hazard = any_pending && (bdist > bpos || bpos - bdist + blen > first_pending);
@@ -788,7 +822,7 @@ struct Decoder {
             if (two) {
                 // 17..32 bytes, not overlapping: both staging slots are emptied and take one half of the match each,
                 // so this copy has no load-to-store round trip either (the warp's other groups are waiting here)
-                if ((o_meta | n_meta) != 0u) { flush_pending(); __syncwarp(gmask); }
+                if (any_pending) { flush_pending(); __syncwarp(gmask); }
                 const uint8_t* src = dst - bdist;
                 const uint32_t so = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
                 const uint32_t jb = (uint32_t)DB * (uint32_t)glane;
@@ -797,14 +831,19 @@ struct Decoder {
                 for (int k = 0; k < DW; k++) cp_async4_if(&S->stage[8 * ptog + DW * glane + k], w0 + 4 * k, jb + 4u * k < 16u + so);
                 cp_async_commit();
                 #pragma unroll
-                for (int k = 0; k < DW; k++) cp_async4_if(&S->stage[8 * (ptog ^ 1u) + DW * glane + k], w0 + 16 + 4 * k, jb + 4u * k < blen - 16u + so);
+                for (int k = 0; k < DW; k++) cp_async4_if(&S->stage[8 * slot_after(ptog) + DW * glane + k], w0 + 16 + 4 * k, jb + 4u * k < blen - 16u + so);
                 cp_async_commit();
                 o_dst = bpos; o_meta = 16u | (so << 8);
+#if SDZ_SLOTS == 3
+                cp_async_commit();                        // (empty) the first half must not be among the two newest groups at the next push
+                m_dst = bpos + 16u; m_meta = (blen - 16u) | (so << 8);
+#else
                 n_dst = bpos + 16u; n_meta = (blen - 16u) | (so << 8);
+#endif
             } else if (simple) {
                 // the older pending match was issued two matches ago: wait for it (only), store it, and
                 // reuse its staging slot for this match
-                cp_async_wait_but_one();
+                if (NSLOT == 3) cp_async_wait_but_two(); else cp_async_wait_but_one();
                 commit_slot(o_dst, o_meta, ptog);
                 const uint8_t* src = dst - bdist;
                 const uint32_t so = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
@@ -813,9 +852,14 @@ struct Decoder {
                 #pragma unroll
                 for (int k = 0; k < DW; k++) cp_async4_if(&S->stage[8 * ptog + DW * glane + k], w0 + 4 * k, jb + 4u * k < blen + so);
                 cp_async_commit();
+#if SDZ_SLOTS == 3
+                o_dst = m_dst; o_meta = m_meta;
+                m_dst = n_dst; m_meta = n_meta;
+#else
                 o_dst = n_dst; o_meta = n_meta;
+#endif
                 n_dst = bpos; n_meta = blen | (so << 8);
-                ptog ^= 1u;
+                ptog = slot_after(ptog);
             } else if (bdist <= bpos) {
                 const uint8_t* src = dst - bdist;
                 if (bdist >= blen) {
@@ -1033,7 +1077,7 @@ struct Decoder {
             slow = true;
             if (e == E_LONG) {
 #if SDZ_LONG_SMEM > 0
-                const uint32_t r = canon_long(S->cnt_l, gsorted, RL, g_l, S->start, (uint32_t)bb, S->long_l, SDZ_LONG_SMEM);
+                const uint32_t r = canon_long(S->cnt_l, gsorted, RL, g_l, S->start, (uint32_t)bb, S->long_l, SDZ_LONG_N);
 #else
                 const uint32_t r = canon_long(S->cnt_l, gsorted, RL, g_l, S->start, (uint32_t)bb);
 #endif
@@ -1110,7 +1154,7 @@ struct Decoder {
             bool ok = false;
             if (e == E_LONG) {
 #if SDZ_LONG_SMEM > 0
-                const uint32_t r = canon_long(S->cnt_l, gsorted, RL, g_l, S->start, (uint32_t)bb, S->long_l, SDZ_LONG_SMEM);
+                const uint32_t r = canon_long(S->cnt_l, gsorted, RL, g_l, S->start, (uint32_t)bb, S->long_l, SDZ_LONG_N);
 #else
                 const uint32_t r = canon_long(S->cnt_l, gsorted, RL, g_l, S->start, (uint32_t)bb);
 #endif
@@ -1181,12 +1225,17 @@ struct Decoder {
         // (room for a deferred match, <= 16 bytes, is guaranteed by the margin test at the top when SDZ_CAPMARGIN >= 18)
         const bool simple = G <= MAX_G_DEFERRED && cm && bdist >= blen && blen <= 16u && bdist <= bpos && !(fold && bdist == blen) &&
                             (SDZ_CAPMARGIN >= 18 || len <= cap - pos);
+#if SDZ_SLOTS == 3
+        const uint32_t first_pending = o_meta ? o_dst : (m_meta ? m_dst : n_dst);
+        const bool hazard = (o_meta | m_meta | n_meta) != 0u && (bdist > bpos || bpos - bdist + blen > first_pending);
+#else
         const uint32_t first_pending = o_meta ? o_dst : n_dst;
         const bool hazard = (o_meta | n_meta) != 0u && (bdist > bpos || bpos - bdist + blen > first_pending);
+#endif
         if (cm && (!simple || hazard)) return copy_match(len, dist, fold);     // long / overlapping / marker / early source, pending bytes
         // plain deferred copy, predicated on `simple` (nothing happens for a literal)
         if constexpr (G <= MAX_G_DEFERRED) {
-        cp_async_wait_but_one();
+        if (NSLOT == 3) cp_async_wait_but_two(); else cp_async_wait_but_one();
         commit_slot(o_dst, simple ? o_meta : 0u, ptog);
         {
             const uint8_t* src = out + bpos - bdist;
@@ -1196,9 +1245,14 @@ struct Decoder {
             #pragma unroll
             for (int k = 0; k < DW; k++) cp_async4_if(&S->stage[8 * ptog + DW * glane + k], w0 + 4 * k, simple && jb + 4u * k < blen + so);
             cp_async_commit();
+#if SDZ_SLOTS == 3
+            o_dst = simple ? m_dst : o_dst; o_meta = simple ? m_meta : o_meta;
+            m_dst = simple ? n_dst : m_dst; m_meta = simple ? n_meta : m_meta;
+#else
             o_dst = simple ? n_dst : o_dst; o_meta = simple ? n_meta : o_meta;
+#endif
             n_dst = simple ? bpos : n_dst; n_meta = simple ? (blen | (so << 8)) : n_meta;
-            ptog ^= simple ? 1u : 0u;
+            ptog = simple ? slot_after(ptog) : ptog;
         }
         }
         pos += len;
@@ -1256,6 +1310,9 @@ struct Decoder {
         lbits = dbits = g_l = g_d = 0; eob_len = 0;
         ring.init(0);
         o_dst = o_meta = n_dst = n_meta = 0; rem = 0;
+#if SDZ_SLOTS == 3
+        m_dst = m_meta = 0;
+#endif
         is_gzip = false; method = 0; n_blocks = 0; mtime = 0; name_off = 0; name_len = 0; last = 0; raw = true;
         const uint64_t sb = P.task_bit[i];
         if ((sb >> 3) >= (uint64_t)in_len) { finish_task(P, R_STALL); return; }
@@ -1314,6 +1371,9 @@ struct Decoder {
         lbits = dbits = g_l = g_d = 0; eob_len = 0;
         ring.init(0);
         o_dst = o_meta = n_dst = n_meta = 0; rem = 0;
+#if SDZ_SLOTS == 3
+        m_dst = m_meta = 0;
+#endif
         is_gzip = false; method = 0; n_blocks = 0; mtime = 0; name_off = 0; name_len = 0; last = 0;
 
         int thrown = SDZ_THROW_NONE, thrown_inflate = 0, zstatus = SDZ_Z_OK;
@@ -1587,6 +1647,9 @@ __global__ void __launch_bounds__(128, SDZ_MINBLOCKS) inflate_kernel(InflatePara
     d.gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - d.glane));
     d.issued_abs = 0; d.waited_abs = 0; d.chunk0 = 0; d.phasebits = 0;
     d.ptog = 0; d.o_dst = d.o_meta = d.n_dst = d.n_meta = 0; d.rem = 0;
+#if SDZ_SLOTS == 3
+    d.m_dst = d.m_meta = 0;
+#endif
     d.phase = PH_FETCH;
     if (d.glane == 0) {
         for (int i = 0; i < NBUF; i++) mbar_init(&S->mbar[i], 1);
