@@ -49,6 +49,9 @@ namespace sdz {
 #define SDZ_SLOTS 2                    // staging slots = deferred matches in flight per stream (2 or 3).  3 (wait_group 2, one more
                                        // iteration of slack for the window read) was measured slower: 122.3 vs 127.1 GB/s
 #endif
+#ifndef SDZ_MARK_WIDE
+#define SDZ_MARK_WIDE 1                // marker mode: 8 bytes (4 symbols) per lane in the deferred copy path
+#endif
 #ifndef SDZ_TWOSLOT
 #define SDZ_TWOSLOT 1                  // far matches of 17..32 bytes take both staging slots (one half each) instead of a synchronous copy
 #endif
@@ -62,7 +65,7 @@ namespace sdz {
                                        // 8 blocks x (16 x 1,760 B + 1 KiB) = exactly the 228 KiB of one SM (+1.5 %)
 #endif
 // the third staging slot takes 32 of the 64 spare bytes per stream: 16 long-code symbols stay in shared memory
-constexpr int SDZ_LONG_N = SDZ_LONG_SMEM > 0 ? (SDZ_SLOTS == 3 ? SDZ_LONG_SMEM / 2 : SDZ_LONG_SMEM) : 0;
+constexpr int STAGE_LONG_WORDS = 32;
 constexpr int RL = 9;                  // literal/length LUT root bits
 constexpr int RD = 7;                  // distance LUT root bits
 constexpr int CH = 128;                // bytes per TMA bulk copy
@@ -83,10 +86,10 @@ struct alignas(16) GroupSmem {
     uint16_t cnt_d[16];
     uint16_t start[4];                 // canonical-walk state after the root bits: first_l, index_l, first_d, index_d
     uint16_t pad_[4];
-    uint32_t stage[8 * SDZ_SLOTS];     // slots x 8 words: source words of the pending (deferred) matches
-#if SDZ_LONG_SMEM > 0
-    uint16_t long_l[SDZ_LONG_N];       // first symbols (canonical order) whose literal/length code is longer than RL bits
-#endif
+    // staging slots of the pending (deferred) matches, then - in what is left of the 128 bytes - the first symbols (canonical
+    // order) whose literal/length code is longer than RL bits.  Byte mode: 2 slots x 8 words + 32 symbols; marker mode
+    // (two-byte symbols, 8 bytes per lane): 2 slots x 12 words + 16 symbols; see Decoder::SLOTW / LONG_OFF / LONG_N.
+    uint32_t stage_long[STAGE_LONG_WORDS];
 };
 constexpr int MAX_G_DEFERRED = 4;      // groups wider than this use the synchronous copy only (stage[] holds 8 words)
 
@@ -458,7 +461,8 @@ __device__ __forceinline__ void make_lut(uint32_t* aux, const uint8_t* lens, int
 // lit/len + distance tables for lens[0..nl) and lens[nl..nl+nd) with the reference's checks
 // and messages (inflate_trees_dynamic, src/inftree.ts:333-379).  fixed: no checks.
 template <int G>
-__device__ __noinline__ TreeInfo build_tables(GroupSmem* S, uint16_t* gsorted, int nl, int nd, bool fixed, int glane, unsigned gmask)
+__device__ __noinline__ TreeInfo build_tables(GroupSmem* S, uint16_t* gsorted, int nl, int nd, bool fixed, int glane, unsigned gmask,
+                                              uint16_t* long_l, int long_n)
 {
     TreeInfo T;
     T.msg = SDZ_MSG_NONE; T.lbits = T.dbits = T.g_l = T.g_d = 0;
@@ -489,7 +493,7 @@ __device__ __noinline__ TreeInfo build_tables(GroupSmem* S, uint16_t* gsorted, i
 #if SDZ_LONG_SMEM > 0
     {
         const int i0 = (int)S->start[1], nc = nl - nz_l;
-        for (int j = glane; j < SDZ_LONG_N; j += G) S->long_l[j] = i0 + j < nc ? gsorted[i0 + j] : (uint16_t)0;
+        for (int j = glane; j < long_n; j += G) long_l[j] = i0 + j < nc ? gsorted[i0 + j] : (uint16_t)0;
         __syncwarp(gmask);
     }
 #endif
@@ -736,8 +740,16 @@ struct Decoder {
     }
 
     // bytes of a deferred match each lane moves, and the aligned words it stages for them
-    static constexpr int DB = G <= MAX_G_DEFERRED ? 16 / G : 4;
+    // marker mode moves two-byte symbols: a lane takes 8 bytes (4 symbols), so that copies of up to 16 symbols are deferred
+    static constexpr int WIDE = (MARK && SDZ_SLOTS == 2 && G == 4 && SDZ_MARK_WIDE) ? 2 : 1;
+    static constexpr int DB = (G <= MAX_G_DEFERRED ? 16 / G : 4) * WIDE;
     static constexpr int DW = DB / 4 + 1;
+    static constexpr int SLOTW = (G <= MAX_G_DEFERRED ? G : 4) * DW;            // words per staging slot
+    static constexpr uint32_t DEFER_MAX = 16u * WIDE;                            // bytes a deferred copy can move
+    static constexpr int LONG_OFF = SDZ_SLOTS * SLOTW;
+    static constexpr int LONG_N = SDZ_LONG_SMEM > 0 ? (STAGE_LONG_WORDS - LONG_OFF) * 2 : 0;
+    static_assert(LONG_OFF <= STAGE_LONG_WORDS, "staging slots do not fit");
+    __device__ __forceinline__ uint16_t* long_l() const { return reinterpret_cast<uint16_t*>(S->stage_long + LONG_OFF); }
 
     // move one pending match from its staging slot to its destination (straight-line, predicated:
     // nothing happens when meta == 0)
@@ -745,7 +757,7 @@ struct Decoder {
     {
         const uint32_t plen = meta & 0xffu, soff = meta >> 8;
         const uint32_t jb = (uint32_t)DB * (uint32_t)glane;
-        const uint32_t* st = &S->stage[8 * slot + DW * glane];
+        const uint32_t* st = &S->stage_long[SLOTW * slot + DW * glane];
         uint8_t* dst = out + dst_off + jb;
         const uint32_t nb = plen > jb ? plen - jb : 0u;
         uint32_t w[DW];
@@ -754,10 +766,15 @@ struct Decoder {
         #pragma unroll
         for (int q = 0; q < DB / 4; q++) {
             const uint32_t v = __funnelshift_r(w[q], w[q + 1], soff * 8u);
-            st_u8_if(dst + 4 * q, v, nb > 4u * q);
-            st_u8_if(dst + 4 * q + 1, v >> 8, nb > 4u * q + 1);
-            st_u8_if(dst + 4 * q + 2, v >> 16, nb > 4u * q + 2);
-            st_u8_if(dst + 4 * q + 3, v >> 24, nb > 4u * q + 3);
+            if (MARK) {                                  // two-byte symbols: everything is 2-byte aligned
+                st_u16_if(reinterpret_cast<uint16_t*>(dst + 4 * q), v & 0xffffu, nb > 4u * q);
+                st_u16_if(reinterpret_cast<uint16_t*>(dst + 4 * q + 2), v >> 16, nb > 4u * q + 2);
+            } else {
+                st_u8_if(dst + 4 * q, v, nb > 4u * q);
+                st_u8_if(dst + 4 * q + 1, v >> 8, nb > 4u * q + 1);
+                st_u8_if(dst + 4 * q + 2, v >> 16, nb > 4u * q + 2);
+                st_u8_if(dst + 4 * q + 3, v >> 24, nb > 4u * q + 3);
+            }
         }
     }
 
@@ -796,7 +813,7 @@ struct Decoder {
             // 2 len bytes at distance 2 dist in the symbol buffer - everything below runs in BYTE units.
             constexpr uint32_t E = MARK ? 2u : 1u;
             const uint32_t bpos = pos * E, blen = len * E, bdist = dist * E;
-            const bool simple = G <= MAX_G_DEFERRED && bdist >= blen && blen <= 16u && bdist <= bpos;
+            const bool simple = G <= MAX_G_DEFERRED && bdist >= blen && blen <= DEFER_MAX && bdist <= bpos;
             // the new source must not overlap bytes that are still pending (the older pending match has
             // the lower destination); copies on the synchronous path read arbitrary earlier bytes
 #if SDZ_SLOTS == 3
@@ -815,7 +832,7 @@ struct Decoder {
             if (hazard || !simple || (lit_now && bdist == blen)) __syncwarp(gmask);
             uint8_t* dst = out + bpos;
 #if SDZ_TWOSLOT
-            const bool two = G <= MAX_G_DEFERRED && !simple && bdist >= blen && blen <= 32u && bdist <= bpos;
+            const bool two = G <= MAX_G_DEFERRED && !simple && bdist >= blen && blen <= 2u * DEFER_MAX && bdist <= bpos;
 #else
             const bool two = false;
 #endif
@@ -828,17 +845,17 @@ struct Decoder {
                 const uint32_t jb = (uint32_t)DB * (uint32_t)glane;
                 const uint8_t* w0 = src - so + jb;
                 #pragma unroll
-                for (int k = 0; k < DW; k++) cp_async4_if(&S->stage[8 * ptog + DW * glane + k], w0 + 4 * k, jb + 4u * k < 16u + so);
+                for (int k = 0; k < DW; k++) cp_async4_if(&S->stage_long[SLOTW * ptog + DW * glane + k], w0 + 4 * k, jb + 4u * k < DEFER_MAX + so);
                 cp_async_commit();
                 #pragma unroll
-                for (int k = 0; k < DW; k++) cp_async4_if(&S->stage[8 * slot_after(ptog) + DW * glane + k], w0 + 16 + 4 * k, jb + 4u * k < blen - 16u + so);
+                for (int k = 0; k < DW; k++) cp_async4_if(&S->stage_long[SLOTW * slot_after(ptog) + DW * glane + k], w0 + DEFER_MAX + 4 * k, jb + 4u * k < blen - DEFER_MAX + so);
                 cp_async_commit();
-                o_dst = bpos; o_meta = 16u | (so << 8);
+                o_dst = bpos; o_meta = DEFER_MAX | (so << 8);
 #if SDZ_SLOTS == 3
                 cp_async_commit();                        // (empty) the first half must not be among the two newest groups at the next push
-                m_dst = bpos + 16u; m_meta = (blen - 16u) | (so << 8);
+                m_dst = bpos + DEFER_MAX; m_meta = (blen - DEFER_MAX) | (so << 8);
 #else
-                n_dst = bpos + 16u; n_meta = (blen - 16u) | (so << 8);
+                n_dst = bpos + DEFER_MAX; n_meta = (blen - DEFER_MAX) | (so << 8);
 #endif
             } else if (simple) {
                 // the older pending match was issued two matches ago: wait for it (only), store it, and
@@ -850,7 +867,7 @@ struct Decoder {
                 const uint32_t jb = (uint32_t)DB * (uint32_t)glane;
                 const uint8_t* w0 = src - so + jb;
                 #pragma unroll
-                for (int k = 0; k < DW; k++) cp_async4_if(&S->stage[8 * ptog + DW * glane + k], w0 + 4 * k, jb + 4u * k < blen + so);
+                for (int k = 0; k < DW; k++) cp_async4_if(&S->stage_long[SLOTW * ptog + DW * glane + k], w0 + 4 * k, jb + 4u * k < blen + so);
                 cp_async_commit();
 #if SDZ_SLOTS == 3
                 o_dst = m_dst; o_meta = m_meta;
@@ -1077,7 +1094,7 @@ struct Decoder {
             slow = true;
             if (e == E_LONG) {
 #if SDZ_LONG_SMEM > 0
-                const uint32_t r = canon_long(S->cnt_l, gsorted, RL, g_l, S->start, (uint32_t)bb, S->long_l, SDZ_LONG_N);
+                const uint32_t r = canon_long(S->cnt_l, gsorted, RL, g_l, S->start, (uint32_t)bb, long_l(), LONG_N);
 #else
                 const uint32_t r = canon_long(S->cnt_l, gsorted, RL, g_l, S->start, (uint32_t)bb);
 #endif
@@ -1154,7 +1171,7 @@ struct Decoder {
             bool ok = false;
             if (e == E_LONG) {
 #if SDZ_LONG_SMEM > 0
-                const uint32_t r = canon_long(S->cnt_l, gsorted, RL, g_l, S->start, (uint32_t)bb, S->long_l, SDZ_LONG_N);
+                const uint32_t r = canon_long(S->cnt_l, gsorted, RL, g_l, S->start, (uint32_t)bb, long_l(), LONG_N);
 #else
                 const uint32_t r = canon_long(S->cnt_l, gsorted, RL, g_l, S->start, (uint32_t)bb);
 #endif
@@ -1212,10 +1229,11 @@ struct Decoder {
             // marker mode: a short match whose source lies entirely before the piece reads nothing - its symbols are
             // markers (256 + index into the 32 KiB window before the piece; zeros before the start of the stream, Q6)
             // computed and stored here; pending copies are not disturbed (early in a piece this is the common match)
-            const bool pre = ismatch && dist >= pos + len && len <= 8u;
+            constexpr uint32_t SPL = (uint32_t)DB / 2u;                         // symbols per lane
+            const bool pre = ismatch && dist >= pos + len && len <= (uint32_t)G * SPL;
             #pragma unroll
-            for (uint32_t q = 0; q < 2u; q++) {
-                const uint32_t i = 2u * (uint32_t)glane + q;
+            for (uint32_t q = 0; q < SPL; q++) {
+                const uint32_t i = SPL * (uint32_t)glane + q;
                 const uint32_t before = dist - pos - i;                         // 1 .. 32768 source symbols before the piece
                 const uint32_t v = (uint64_t)before > abs_start ? 0u : 256u + 32768u - before;
                 st_u16_if(out16 + pos + i, v, pre && i < len);
@@ -1223,7 +1241,7 @@ struct Decoder {
             cm = ismatch && !pre;
         }
         // (room for a deferred match, <= 16 bytes, is guaranteed by the margin test at the top when SDZ_CAPMARGIN >= 18)
-        const bool simple = G <= MAX_G_DEFERRED && cm && bdist >= blen && blen <= 16u && bdist <= bpos && !(fold && bdist == blen) &&
+        const bool simple = G <= MAX_G_DEFERRED && cm && bdist >= blen && blen <= DEFER_MAX && bdist <= bpos && !(fold && bdist == blen) &&
                             (SDZ_CAPMARGIN >= 18 || len <= cap - pos);
 #if SDZ_SLOTS == 3
         const uint32_t first_pending = o_meta ? o_dst : (m_meta ? m_dst : n_dst);
@@ -1243,7 +1261,7 @@ struct Decoder {
             const uint32_t jb = (uint32_t)DB * (uint32_t)glane;
             const uint8_t* w0 = src - so + jb;
             #pragma unroll
-            for (int k = 0; k < DW; k++) cp_async4_if(&S->stage[8 * ptog + DW * glane + k], w0 + 4 * k, simple && jb + 4u * k < blen + so);
+            for (int k = 0; k < DW; k++) cp_async4_if(&S->stage_long[SLOTW * ptog + DW * glane + k], w0 + 4 * k, simple && jb + 4u * k < blen + so);
             cp_async_commit();
 #if SDZ_SLOTS == 3
             o_dst = simple ? m_dst : o_dst; o_meta = simple ? m_meta : o_meta;
@@ -1577,7 +1595,7 @@ struct Decoder {
             r = dynamic_header(&nl, &nd);
             if (r != R_OK) { finish_stream(P, r); return; }
         }
-        TreeInfo T = build_tables<G>(S, gsorted, nl, nd, type == 1, glane, gmask);
+        TreeInfo T = build_tables<G>(S, gsorted, nl, nd, type == 1, glane, gmask, long_l(), LONG_N);
         if (T.msg) { msg = T.msg; finish_stream(P, R_ERROR); return; }
         lbits = T.lbits; dbits = T.dbits; g_l = T.g_l; g_d = T.g_d;
         if (MARK && resume_bit) {                                       // continue in the middle of the block
