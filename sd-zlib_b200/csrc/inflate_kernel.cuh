@@ -12,14 +12,19 @@
 // tail, so that records stay bit-exact wherever the reference terminates.
 //
 // Data layout / staging:
-//   * compressed input is staged per group into a 4 x 128 B shared-memory ring by TMA bulk
+//   * compressed input is staged per group into a 2 x 128 B shared-memory ring by TMA bulk
 //     copies (cp.async.bulk + mbarrier); the decoder keeps a 64-bit bit buffer and one
 //     prefetched word in registers, so the ring read is off the decode critical path;
 //   * per-group decode tables live in shared memory: a 2^RL-entry u16 literal/length LUT and
 //     a 2^RD-entry u16 distance LUT with base/extra pre-baked; codes longer than the root
 //     fall back to a canonical (count/sorted-symbol) decode;
 //   * every lane of a group holds the same decoder state (no shuffles on the critical path);
-//     lanes only differ in which bytes of a match / stored block they move.
+//     lanes only differ in which bytes of a match / stored block they move;
+//   * the groups of a warp run the symbol loop in lockstep and one iteration is straight-line
+//     predicated code (Decoder::step_flat): literal groups execute the match path with its side
+//     effects switched off, so the warp never diverges between literals and matches.
+// Knobs that were measured and rejected (piecewise long matches, a third staging slot, G = 2 / 8,
+// an if-form top-up, FMA-pipe address arithmetic) are recorded in DESIGN.md section 6, not kept here.
 #pragma once
 #include "sdz_device.cuh"
 #include "../../include/sdz_codes.h"
@@ -30,25 +35,9 @@ namespace sdz {
 #define SDZ_LIT_RUN 2                  // plain literals folded in front of every lockstep symbol (branchy loop: 0 -> 90, 1 -> 99, 2 -> 97 GB/s;
                                        // straight-line loop, where a fold is ~13 predicated instructions: 1 -> 127.0, 2 -> 128.8 GB/s)
 #endif
-#ifndef SDZ_FLAT
-#define SDZ_FLAT 1                     // straight-line (predicated) lockstep iteration, see step_flat()
-#endif
-#ifndef SDZ_CONT
-#define SDZ_CONT 0                     // 1: step_flat() issues a long far match as 16-byte deferred pieces, one per iteration, as
-                                       // predicated straight-line code (the group decodes nothing while pieces are left).
-                                       // Measured slower (112.8 vs 122.8 GB/s): the synchronous copy of the 3 % long matches is
-                                       // cheaper than the iterations their groups lose
-#endif
 #ifndef SDZ_CAPMARGIN
 #define SDZ_CAPMARGIN 18               // step_flat(): output room below which step_general() takes over (fold + literal or a deferred
                                        // match of <= 16 bytes always fit, so the fast path needs no room test: 124.7 -> 127.0 GB/s)
-#endif
-#ifndef SDZ_REFILL_IF
-#define SDZ_REFILL_IF 0                // 1: the top-up as a short `if` block (ptxas makes it a real branch: 123.5 vs 124.7 GB/s)
-#endif
-#ifndef SDZ_SLOTS
-#define SDZ_SLOTS 2                    // staging slots = deferred matches in flight per stream (2 or 3).  3 (wait_group 2, one more
-                                       // iteration of slack for the window read) was measured slower: 122.3 vs 127.1 GB/s
 #endif
 #ifndef SDZ_MARK_WIDE
 #define SDZ_MARK_WIDE 1                // marker mode: 8 bytes (4 symbols) per lane in the deferred copy path
@@ -56,17 +45,11 @@ namespace sdz {
 #ifndef SDZ_TWOSLOT
 #define SDZ_TWOSLOT 1                  // far matches of 17..32 bytes take both staging slots (one half each) instead of a synchronous copy
 #endif
-#ifndef SDZ_CHUNKED
-#define SDZ_CHUNKED 0                  // 1: long far matches are issued as 16-byte deferred pieces, one per lockstep iteration
-                                       // (measured slower, 104.3 vs 107.0 GB/s: the extra iterations cost more issue slots than the
-                                       // load-to-store round trip of the synchronous copy, which only idles one warp)
-#endif
 #ifndef SDZ_LONG_SMEM
 #define SDZ_LONG_SMEM 32               // literal/length symbols with codes longer than the root kept in shared memory (0 or 32):
                                        // 8 blocks x (16 x 1,760 B + 1 KiB) = exactly the 228 KiB of one SM (+1.5 %)
 #endif
-// the third staging slot takes 32 of the 64 spare bytes per stream: 16 long-code symbols stay in shared memory
-constexpr int STAGE_LONG_WORDS = 32;
+constexpr int STAGE_LONG_WORDS = 32;   // staging slots + long-code symbols share 128 bytes per stream (GroupSmem::stage_long)
 constexpr int RL = 9;                  // literal/length LUT root bits
 constexpr int RD = 7;                  // distance LUT root bits
 constexpr int CH = 128;                // bytes per TMA bulk copy
@@ -594,23 +577,12 @@ struct Decoder {
     // `n_` the newer one.  len | soff << 8 is packed in *_meta (0 = empty); the older one's words
     // live in staging slot `ptog`, the newer one's in slot `ptog ^ 1`.
     uint32_t o_dst, o_meta, n_dst, n_meta, ptog;
-#if SDZ_SLOTS == 3
-    // three slots: o (oldest, slot ptog), m (slot ptog + 1), n (newest, slot ptog + 2), indices mod 3; every iteration
-    // of the flat loop commits one cp.async group, so wait_group 2 guarantees copies issued three iterations ago
-    uint32_t m_dst, m_meta;
-#endif
     __device__ __forceinline__ bool pending_any() const
     {
-#if SDZ_SLOTS == 3
-        return (o_meta | m_meta | n_meta) != 0u;
-#else
         return (o_meta | n_meta) != 0u;
-#endif
     }
-    static constexpr uint32_t NSLOT = SDZ_SLOTS;
-    static __device__ __forceinline__ uint32_t slot_after(uint32_t p) { return NSLOT == 2 ? p ^ 1u : (p == 2u ? 0u : p + 1u); }
-    // rest of a long match that is being issued piecewise: (symbols left) | distance << 9, 0 = none
-    uint32_t rem;
+    static constexpr uint32_t NSLOT = 2;               // staging slots = deferred matches in flight per stream
+    static __device__ __forceinline__ uint32_t slot_after(uint32_t p) { return p ^ 1u; }
 
     RingModel ring;
     int msg;
@@ -742,12 +714,12 @@ struct Decoder {
 
     // bytes of a deferred match each lane moves, and the aligned words it stages for them
     // marker mode moves two-byte symbols: a lane takes 8 bytes (4 symbols), so that copies of up to 16 symbols are deferred
-    static constexpr int WIDE = (MARK && SDZ_SLOTS == 2 && G == 4 && SDZ_MARK_WIDE) ? 2 : 1;
+    static constexpr int WIDE = (MARK && G == 4 && SDZ_MARK_WIDE) ? 2 : 1;
     static constexpr int DB = (G <= MAX_G_DEFERRED ? 16 / G : 4) * WIDE;
     static constexpr int DW = DB / 4 + 1;
     static constexpr int SLOTW = (G <= MAX_G_DEFERRED ? G : 4) * DW;            // words per staging slot
     static constexpr uint32_t DEFER_MAX = 16u * WIDE;                            // bytes a deferred copy can move
-    static constexpr int LONG_OFF = SDZ_SLOTS * SLOTW;
+    static constexpr int LONG_OFF = (int)NSLOT * SLOTW;
     static constexpr int LONG_N = SDZ_LONG_SMEM > 0 ? (STAGE_LONG_WORDS - LONG_OFF) * 2 : 0;
     static_assert(LONG_OFF <= STAGE_LONG_WORDS, "staging slots do not fit");
     __device__ __forceinline__ uint16_t* long_l() const { return reinterpret_cast<uint16_t*>(S->stage_long + LONG_OFF); }
@@ -785,16 +757,8 @@ struct Decoder {
         if (STORE && G <= MAX_G_DEFERRED) {
             cp_async_wait_all();
             commit_slot(o_dst, o_meta, ptog);
-#if SDZ_SLOTS == 3
-            commit_slot(m_dst, m_meta, slot_after(ptog));
-            commit_slot(n_dst, n_meta, slot_after(slot_after(ptog)));
-#else
             commit_slot(n_dst, n_meta, ptog ^ 1u);
-#endif
         }
-#if SDZ_SLOTS == 3
-        m_meta = 0;
-#endif
         o_meta = 0; n_meta = 0;
     }
 
@@ -817,13 +781,8 @@ struct Decoder {
             const bool simple = G <= MAX_G_DEFERRED && bdist >= blen && blen <= DEFER_MAX && bdist <= bpos;
             // the new source must not overlap bytes that are still pending (the older pending match has
             // the lower destination); copies on the synchronous path read arbitrary earlier bytes
-#if SDZ_SLOTS == 3
-            const uint32_t first_pending = o_meta ? o_dst : (m_meta ? m_dst : n_dst);
-            const bool any_pending = (o_meta | m_meta | n_meta) != 0;
-#else
             const uint32_t first_pending = o_meta ? o_dst : n_dst;
             const bool any_pending = (o_meta | n_meta) != 0;
-#endif
             // (a copy on the synchronous path whose source lies entirely below the pending destinations can
             // overtake them: its own destination is disjoint from theirs)
             const bool hazard = any_pending && (bdist > bpos || bpos - bdist + blen > first_pending);
@@ -852,16 +811,11 @@ struct Decoder {
                 for (int k = 0; k < DW; k++) cp_async4_if(&S->stage_long[SLOTW * slot_after(ptog) + DW * glane + k], w0 + DEFER_MAX + 4 * k, jb + 4u * k < blen - DEFER_MAX + so);
                 cp_async_commit();
                 o_dst = bpos; o_meta = DEFER_MAX | (so << 8);
-#if SDZ_SLOTS == 3
-                cp_async_commit();                        // (empty) the first half must not be among the two newest groups at the next push
-                m_dst = bpos + DEFER_MAX; m_meta = (blen - DEFER_MAX) | (so << 8);
-#else
                 n_dst = bpos + DEFER_MAX; n_meta = (blen - DEFER_MAX) | (so << 8);
-#endif
             } else if (simple) {
                 // the older pending match was issued two matches ago: wait for it (only), store it, and
                 // reuse its staging slot for this match
-                if (NSLOT == 3) cp_async_wait_but_two(); else cp_async_wait_but_one();
+                cp_async_wait_but_one();
                 commit_slot(o_dst, o_meta, ptog);
                 const uint8_t* src = dst - bdist;
                 const uint32_t so = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
@@ -870,12 +824,7 @@ struct Decoder {
                 #pragma unroll
                 for (int k = 0; k < DW; k++) cp_async4_if(&S->stage_long[SLOTW * ptog + DW * glane + k], w0 + 4 * k, jb + 4u * k < blen + so);
                 cp_async_commit();
-#if SDZ_SLOTS == 3
-                o_dst = m_dst; o_meta = m_meta;
-                m_dst = n_dst; m_meta = n_meta;
-#else
                 o_dst = n_dst; o_meta = n_meta;
-#endif
                 n_dst = bpos; n_meta = blen | (so << 8);
                 ptog = slot_after(ptog);
             } else if (bdist <= bpos) {
@@ -1017,16 +966,12 @@ struct Decoder {
 
     // branch-free top-up used by the fast path (at least five whole input words remain):
     // predicated instructions only, except for the rare hop into the next 128-byte chunk
-    __device__ __forceinline__ void refill_fast(bool enable = true)
+    __device__ __forceinline__ void refill_fast()
     {
-        const bool take = enable && bc <= 32;
-#if SDZ_REFILL_IF
-        if (take) { bb |= (uint64_t)nw << bc; bc += 32; wp++; }          // short block: ptxas predicates it
-#else
+        const bool take = bc <= 32;
         bb |= take ? ((uint64_t)nw << bc) : 0ull;
         bc += take ? 32 : 0;
         wp += take ? 1u : 0u;
-#endif
         // chunk(wp) had been waited for, so wp < waited_abs * CHW held before the increment
         if (take && wp == waited_abs * CHW) {                             // rare: first word of the next 128-byte chunk
             uint64_t r = chunk_cross(S, gsrc, wp / CHW, chunk0, issued_abs, total_chunks, phasebits, gmask, glane);
@@ -1038,110 +983,6 @@ struct Decoder {
         nw = take ? w : nw;
     }
 
-    // One symbol on the fast path.  The stream tail and every irregular case (long / invalid
-    // root entry) go through step_general().  (Folding a run of literals into the same lockstep
-    // iteration was measured slower: the warp pays the longest run of its eight groups.)
-    // A long match whose source lies well before the pending copies (distance >= 64 bytes) is not copied
-    // synchronously: it is cut into pieces of 16 bytes that go through the deferred path, one piece per
-    // lockstep iteration (the group decodes nothing while pieces are left).  The copy instructions are
-    // executed by the warp in every iteration anyway, so the pieces cost no extra issue slots and no
-    // load-to-store round trip.  Returns the length of the piece to copy now.
-    static constexpr uint32_t PIECE = (MARK ? 8u : 16u);               // symbols per piece (16 bytes)
-    __device__ __forceinline__ uint32_t first_piece(uint32_t len, uint32_t dist)
-    {
-#if SDZ_CHUNKED
-        if (STORE && G <= MAX_G_DEFERRED && TM != TM_INDEX && len > PIECE && dist >= 4u * PIECE && dist <= pos && len <= cap - pos) {
-            rem = (len - PIECE) | (dist << 9);
-            return PIECE;
-        }
-#endif
-        return len;
-    }
-
-    __device__ __forceinline__ int step()
-    {
-#if SDZ_CHUNKED
-        if (STORE && rem != 0u) {                       // next piece of a long match
-            const uint32_t left = rem & 0x1ffu, dist = rem >> 9;
-            const uint32_t now = left > PIECE ? PIECE : left;
-            rem = left > PIECE ? rem - PIECE : 0u;
-            return copy_match(now, dist, false);
-        }
-#endif
-        // stream tail: the two refills below need whole words, and only step_general() knows the stall rules
-        // (one call site for step_general(): it is inlined once)
-        bool slow = wp + 5 > end_wp;
-        bool lit_now = false;
-        uint32_t e = 0;
-        if (!slow) {
-        // ONE top-up serves a folded literal (<= RL bits) and the literal/length code with its extra bits
-        // (<= 15 + 5): at least 33 bits are valid afterwards
-        refill_fast();
-        e = S->lut_l[(uint32_t)bb & ((1u << RL) - 1u)];
-#if SDZ_LIT_RUN > 0
-        // leading literal: every lockstep iteration pays for the match path anyway, so a plain literal in
-        // front of a match is folded into the same iteration
-        // (marker mode: never the last symbol of the piece, so that the piece still ends on a symbol boundary)
-        if (e >= 0x1000u && (e & 0xf00u) == 0u && pos < cap && (!MARK || pos + 1u < limit)) {
-            const uint32_t n0 = e >> 12;
-            bb >>= n0; bc -= (int)n0;
-            store_lit(e & 0xffu);
-            pos++;
-            lit_now = true;
-            e = S->lut_l[(uint32_t)bb & ((1u << RL) - 1u)];
-        }
-#endif
-        if ((e >> 12) == 0) {                           // code longer than the root (or invalid)
-            slow = true;
-            if (e == E_LONG) {
-#if SDZ_LONG_SMEM > 0
-                const uint32_t r = canon_long(S->cnt_l, gsorted, RL, g_l, S->start, (uint32_t)bb, long_l(), LONG_N);
-#else
-                const uint32_t r = canon_long(S->cnt_l, gsorted, RL, g_l, S->start, (uint32_t)bb);
-#endif
-                const uint32_t sym = r & 0xffffu;
-                if (r != 0 && sym <= 256) { e = ((r >> 16) << 12) | sym; slow = false; }
-                else if (r != 0 && sym - 257 <= 28) {
-                    const uint32_t i = sym - 257;
-                    const uint32_t xb = i < 8 ? 0 : (i == 28 ? 0 : (i >> 2) - 1);
-                    const uint32_t base = i < 8 ? 3 + i : (i == 28 ? 258 : 3 + ((4 + (i & 3)) << xb));
-                    e = ((r >> 16) << 12) | 0x800 | (xb << 8) | (base - 3);
-                    slow = false;
-                }
-            }
-        }
-        }
-        if (slow) return step_general(lit_now);
-        const uint32_t n = e >> 12, p = e & 0xfff;
-        if (p < 256) {
-            if (pos >= cap) return R_OUTFULL;
-            bb >>= n; bc -= (int)n;
-            store_lit(p);
-            pos++;
-            return R_OK;
-        }
-        if (p == 256) { bb >>= n; bc -= (int)n; eob_len = (int)n; return R_EOB; }
-        // code and extra bits leave the bit buffer in one shift (n + xb <= 20)
-        const uint32_t xb = (p >> 8) & 7;
-        const uint32_t len = 3 + (p & 0xff) + (((uint32_t)bb >> n) & ((1u << xb) - 1u));
-        bb >>= (n + xb); bc -= (int)(n + xb);
-        refill_fast();
-        uint32_t de = S->lut_d[(uint32_t)bb & ((1u << RD) - 1u)];
-        uint32_t dn = de >> 12;
-        if (dn == 0) {
-            uint32_t r = de == E_LONG ? canon_long(S->cnt_d, gsorted + SORTED_L, RD, g_d, S->start + 2, (uint32_t)bb) : 0u;
-            const uint32_t ds = r & 0xffffu;
-            if (r == 0 || ds > 29) { msg = SDZ_MSG_BAD_DIST_CODE; return R_ERROR; }     // far from the tail: no stall possible
-            dn = r >> 16;
-            de = ((ds < 4 ? 0u : (ds >> 1) - 1u) << 8) | (ds < 4 ? ds : 2u + (ds & 1u));
-        }
-        const uint32_t dx = (de >> 8) & 15;
-        const uint32_t dist = 1 + ((de & 3) << dx) + (((uint32_t)bb >> dn) & ((1u << dx) - 1u));     // dn + dx <= 28
-        bb >>= (dn + dx); bc -= (int)(dn + dx);
-        return copy_match(first_piece(len, dist), dist, lit_now);
-    }
-
-
     // One lockstep iteration as straight-line code.  The warp executes the match path in practically every
     // iteration (one of its eight groups almost always has a match), so literal groups run it too, with
     // every side effect predicated off: no divergence between literal and match groups, no reconvergence
@@ -1151,16 +992,14 @@ struct Decoder {
     __device__ __forceinline__ int step_flat()
     {
         constexpr uint32_t LMASK = (1u << RL) - 1u, DMASK = (1u << RD) - 1u;
-        // `cont`: pieces of a long match are left; the group neither reads nor consumes input in this iteration
-        const bool cont = SDZ_CONT && STORE && G <= MAX_G_DEFERRED && rem != 0u;
-        bool general = !cont && (wp + 5 > end_wp || cap - pos < (uint32_t)SDZ_CAPMARGIN);     // (one call site for step_general(): it is inlined once)
+        bool general = wp + 5 > end_wp || cap - pos < (uint32_t)SDZ_CAPMARGIN;     // (one call site for step_general(): it is inlined once)
         bool fold = false;
         uint32_t e = 0;
         if (!general) {
-        refill_fast(!cont);
+        refill_fast();
         e = S->lut_l[(uint32_t)bb & LMASK];
         // leading plain literal (marker mode: never the last symbol of the piece)
-        fold = SDZ_LIT_RUN > 0 && !cont && e >= 0x1000u && (e & 0xf00u) == 0u && (!MARK || pos + 1u < limit);
+        fold = SDZ_LIT_RUN > 0 && e >= 0x1000u && (e & 0xf00u) == 0u && (!MARK || pos + 1u < limit);
         {
             const uint32_t n0 = fold ? e >> 12 : 0u;
             if (STORE) { if (MARK) st_u16_if(out16 + pos, e & 0xffu, fold && glane == 0); else st_u8_if(out + pos, e & 0xffu, fold && glane == 0); }
@@ -1179,7 +1018,7 @@ struct Decoder {
             e = S->lut_l[(uint32_t)bb & LMASK];
         }
 #endif
-        if (!cont && ((e >> 12) == 0u || (e & 0xfffu) == 0x100u)) {    // rare: code longer than the root, invalid code, end of block
+        if ((e >> 12) == 0u || (e & 0xfffu) == 0x100u) {    // rare: code longer than the root, invalid code, end of block
             bool ok = false;
             if (e == E_LONG) {
 #if SDZ_LONG_SMEM > 0
@@ -1202,17 +1041,17 @@ struct Decoder {
         }
         }
         if (general) return step_general(fold);
-        const uint32_t n = cont ? 0u : e >> 12, p = e & 0xfffu;
-        const bool ismatch = cont || p >= 256u;
+        const uint32_t n = e >> 12, p = e & 0xfffu;
+        const bool ismatch = p >= 256u;
         if (STORE) { if (MARK) st_u16_if(out16 + pos, p, !ismatch && glane == 0); else st_u8_if(out + pos, p, !ismatch && glane == 0); }
         // a literal is a "match" of length 1 without extra bits: one consume and one `pos +=` serve both
-        const uint32_t xb = (ismatch && !cont) ? (p >> 8) & 7u : 0u;
-        uint32_t len = ismatch ? 3u + (p & 0xffu) + (((uint32_t)bb >> n) & ((1u << xb) - 1u)) : 1u;
+        const uint32_t xb = ismatch ? (p >> 8) & 7u : 0u;
+        const uint32_t len = ismatch ? 3u + (p & 0xffu) + (((uint32_t)bb >> n) & ((1u << xb) - 1u)) : 1u;
         bb >>= (n + xb); bc -= (int)(n + xb);
-        refill_fast(!cont);                                // harmless for literal groups: at least five whole words remain
+        refill_fast();                                     // harmless for literal groups: at least five whole words remain
         uint32_t de = S->lut_d[(uint32_t)bb & DMASK];
         uint32_t dn = de >> 12;
-        if (ismatch && !cont && dn == 0u) {                // rare: distance code longer than the root, or invalid
+        if (ismatch && dn == 0u) {                         // rare: distance code longer than the root, or invalid
             const uint32_t r = de == E_LONG ? canon_long(S->cnt_d, gsorted + SORTED_L, RD, g_d, S->start + 2, (uint32_t)bb) : 0u;
             const uint32_t ds = r & 0xffffu;
             if (r == 0u || ds > 29u) { msg = SDZ_MSG_BAD_DIST_CODE; return R_ERROR; }     // far from the tail: no stall possible
@@ -1220,21 +1059,12 @@ struct Decoder {
             de = ((ds < 4 ? 0u : (ds >> 1) - 1u) << 8) | (ds < 4 ? ds : 2u + (ds & 1u));
         }
         const uint32_t dx = (de >> 8) & 15u;
-        uint32_t dist = 1u + ((de & 3u) << dx) + (((uint32_t)bb >> dn) & ((1u << dx) - 1u));
-        const uint32_t dcons = (ismatch && !cont) ? dn + dx : 0u;
+        const uint32_t dist = 1u + ((de & 3u) << dx) + (((uint32_t)bb >> dn) & ((1u << dx) - 1u));
+        const uint32_t dcons = ismatch ? dn + dx : 0u;
         bb >>= dcons; bc -= (int)dcons;
         if (!STORE) { pos += len; return R_OK; }
         // ---- copy (byte units; a marker symbol is two bytes)
         constexpr uint32_t E = MARK ? 2u : 1u;
-        if (SDZ_CONT && G <= MAX_G_DEFERRED) {
-            // next piece of the match in progress, or the first piece of a long match whose source is far enough
-            // behind that the pieces never read pending bytes (64 bytes; the whole match must fit the output slot)
-            const uint32_t left = cont ? rem & 0x1ffu : len;
-            dist = cont ? rem >> 9 : dist;
-            const bool far = cont || (ismatch && left > PIECE && dist >= 4u * PIECE && dist <= pos && left <= cap - pos);
-            len = (far && left > PIECE) ? PIECE : left;
-            rem = (far && left > PIECE) ? ((left - PIECE) | (dist << 9)) : 0u;
-        }
         const uint32_t bpos = pos * E, blen = len * E, bdist = dist * E;
         bool cm = ismatch;                                 // a copy that reads earlier output
         if (MARK && G <= MAX_G_DEFERRED) {
@@ -1255,17 +1085,12 @@ struct Decoder {
         // (room for a deferred match, <= 16 bytes, is guaranteed by the margin test at the top when SDZ_CAPMARGIN >= 18)
         const bool simple = G <= MAX_G_DEFERRED && cm && bdist >= blen && blen <= DEFER_MAX && bdist <= bpos && !(fold && bdist == blen) &&
                             (SDZ_CAPMARGIN >= 18 || len <= cap - pos);
-#if SDZ_SLOTS == 3
-        const uint32_t first_pending = o_meta ? o_dst : (m_meta ? m_dst : n_dst);
-        const bool hazard = (o_meta | m_meta | n_meta) != 0u && (bdist > bpos || bpos - bdist + blen > first_pending);
-#else
         const uint32_t first_pending = o_meta ? o_dst : n_dst;
         const bool hazard = (o_meta | n_meta) != 0u && (bdist > bpos || bpos - bdist + blen > first_pending);
-#endif
         if (cm && (!simple || hazard)) return copy_match(len, dist, fold);     // long / overlapping / marker / early source, pending bytes
         // plain deferred copy, predicated on `simple` (nothing happens for a literal)
         if constexpr (G <= MAX_G_DEFERRED) {
-        if (NSLOT == 3) cp_async_wait_but_two(); else cp_async_wait_but_one();
+        cp_async_wait_but_one();
         commit_slot(o_dst, simple ? o_meta : 0u, ptog);
         {
             const uint8_t* src = out + bpos - bdist;
@@ -1275,12 +1100,7 @@ struct Decoder {
             #pragma unroll
             for (int k = 0; k < DW; k++) cp_async4_if(&S->stage_long[SLOTW * ptog + DW * glane + k], w0 + 4 * k, simple && jb + 4u * k < blen + so);
             cp_async_commit();
-#if SDZ_SLOTS == 3
-            o_dst = simple ? m_dst : o_dst; o_meta = simple ? m_meta : o_meta;
-            m_dst = simple ? n_dst : m_dst; m_meta = simple ? n_meta : m_meta;
-#else
             o_dst = simple ? n_dst : o_dst; o_meta = simple ? n_meta : o_meta;
-#endif
             n_dst = simple ? bpos : n_dst; n_meta = simple ? (blen | (so << 8)) : n_meta;
             ptog = simple ? slot_after(ptog) : ptog;
         }
@@ -1339,10 +1159,7 @@ struct Decoder {
         D = 0; dict_tail = nullptr;
         lbits = dbits = g_l = g_d = 0; eob_len = 0;
         ring.init(0);
-        o_dst = o_meta = n_dst = n_meta = 0; rem = 0;
-#if SDZ_SLOTS == 3
-        m_dst = m_meta = 0;
-#endif
+        o_dst = o_meta = n_dst = n_meta = 0;
         is_gzip = false; method = 0; n_blocks = 0; mtime = 0; name_off = 0; name_len = 0; last = 0; raw = true;
         const uint64_t sb = P.task_bit[i];
         if ((sb >> 3) >= (uint64_t)in_len) { finish_task(P, R_STALL); return; }
@@ -1400,10 +1217,7 @@ struct Decoder {
         D = 0; dict_tail = nullptr;
         lbits = dbits = g_l = g_d = 0; eob_len = 0;
         ring.init(0);
-        o_dst = o_meta = n_dst = n_meta = 0; rem = 0;
-#if SDZ_SLOTS == 3
-        m_dst = m_meta = 0;
-#endif
+        o_dst = o_meta = n_dst = n_meta = 0;
         is_gzip = false; method = 0; n_blocks = 0; mtime = 0; name_off = 0; name_len = 0; last = 0;
 
         int thrown = SDZ_THROW_NONE, thrown_inflate = 0, zstatus = SDZ_Z_OK;
@@ -1676,10 +1490,7 @@ __global__ void __launch_bounds__(128, SDZ_MINBLOCKS) inflate_kernel(InflatePara
     const int lane = threadIdx.x & 31;
     d.gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - d.glane));
     d.issued_abs = 0; d.waited_abs = 0; d.chunk0 = 0; d.phasebits = 0;
-    d.ptog = 0; d.o_dst = d.o_meta = d.n_dst = d.n_meta = 0; d.rem = 0;
-#if SDZ_SLOTS == 3
-    d.m_dst = d.m_meta = 0;
-#endif
+    d.ptog = 0; d.o_dst = d.o_meta = d.n_dst = d.n_meta = 0;
     d.phase = PH_FETCH;
     if (d.glane == 0) {
         for (int i = 0; i < NBUF; i++) mbar_init(&S->mbar[i], 1);
@@ -1697,11 +1508,7 @@ __global__ void __launch_bounds__(128, SDZ_MINBLOCKS) inflate_kernel(InflatePara
             __syncwarp();                            // re-converge + order the stores of earlier iterations
             if (d.phase == PH_CODES) {
                 if (TM == TM_INDEX) d.checkpoint(P);
-#if SDZ_FLAT
                 int r = d.step_flat();
-#else
-                int r = d.step();
-#endif
                 if (TM == TM_MARK && r == R_OK && d.pos >= d.limit) r = R_EOB;     // the piece is complete
                 if (r != R_OK) d.block_end(P, r);
             }

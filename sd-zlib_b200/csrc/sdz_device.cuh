@@ -89,9 +89,6 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // all groups except the most recently committed one are complete
 __device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
-// all groups except the two most recently committed ones are complete
-__device__ __forceinline__ void cp_async_wait_but_two() { asm volatile("cp.async.wait_group 2;" ::: "memory"); }
-
 __device__ __forceinline__ uint32_t lane_id()
 {
     uint32_t l;
