@@ -59,6 +59,13 @@ uint64_t sdz_launch_count(sdz_ctx* ctx);
 /* device time of the most recent call's kernels in milliseconds (CUDA events on the ctx
  * stream), split by phase: [0] inflate kernel, [1] checksum kernel, [2] whole device phase */
 int sdz_last_timing(sdz_ctx* ctx, float ms[3]);
+/* the same for the most recent batched inflate, by kernel: [0] phase A (Huffman decode -> tokens), [1] phase B
+ * (tokens -> bytes), [2] the general decoder (streams handed over by phase A; the whole batch when the fast
+ * path is off), [3] finalize (checksums + records), [4] all of it */
+int sdz_last_phase_timing(sdz_ctx* ctx, float ms[5]);
+/* most recent fast-path launch (the last sub-batch of a pipelined call): out[0] = streams finished by the two-phase
+ * path, out[1] = streams it handed to the general decoder */
+int sdz_last_fast_stats(sdz_ctx* ctx, uint64_t out[2]);
 
 /* Pinned host memory helpers (so that callers can hand over DMA-able buffers). */
 void* sdz_host_alloc(size_t bytes);

@@ -1,0 +1,614 @@
+// fast_kernels.cuh - two-phase batched inflate for sm_100a (the common case of inflate_kernel.cuh).
+//
+// inflate_kernel.cuh decodes a stream with a sub-warp group whose lanes all replicate the Huffman decoder
+// state and whose copies are done a few bytes per lane: ~25 warp instructions per symbol, issue-bound
+// (profiles/r01e_full_summary.md).  Here the two halves of the reference's hot loop
+// (inflate_fast, src/infcodes.ts:62-301) are split:
+//
+//   phase A  huff_tokens_kernel   ONE LANE per stream: 32 streams per warp run the symbol loop in lockstep,
+//            straight-line and predicated, and do nothing but Huffman decoding (src/infcodes.ts:96-158,
+//            tables of src/inftree.ts:95-299 as shared-memory LUTs per lane).  Every symbol becomes one
+//            32-bit token (literal byte, or length + distance) in HBM; four tokens leave a lane as one
+//            16-byte store.  No window, no copies.
+//   phase B  lz_resolve_kernel    ONE WARP per stream: 32 tokens at a time, a warp scan of their lengths
+//            gives the output offsets, then the bytes are produced 32 per step with lane = output byte:
+//            the token that covers a byte is found with one REDUX + POPC, its source byte is read from
+//            the stream's own earlier output (or taken from the token), bytes whose source lies in the
+//            same 32-byte row are resolved by pointer jumping over shuffles, and the row leaves the warp
+//            as ONE coalesced 32-byte store (src/infcodes.ts:160-207 is what this replaces).
+//
+// Phase A decodes optimistically and validates at the end of the stream; it only finishes streams whose
+// record is the plain "decoded completely" one: container header without preset dictionary / FEXTRA,
+// fixed and dynamic blocks whose trees the reference accepts (complete codes, table arena within MANY,
+// SURVEY Q9 / Q10), no distance reaching before the start of the output (Q6), the whole trailer present
+// and nothing after it (Q4), and - raw streams - enough lookahead for the reference's final lookups (Q15).
+// EVERYTHING else (stored blocks with their Q2 rule, errors, truncation, dictionaries, slots that are too
+// small ...) is handed, whole stream, to the general decoder inflate_kernel<4> through a device-side list,
+// so records stay bit-exact with the reference in every case.  There is no CPU path.
+#pragma once
+#include "inflate_kernel.cuh"
+
+namespace sdz {
+
+constexpr uint32_t TOK_LIT = 0x80000000u;      // literal: TOK_LIT | byte.  match: (dist - 1) << 9 | len.  0: no-op
+constexpr uint32_t NTOK_HANDED_OVER = 0xffffffffu;
+constexpr int FA_RL = 9, FA_RD = 7;            // LUT root widths (entry formats of make_lut())
+
+// per-lane (= per resident stream) decode tables
+struct alignas(4) LaneSmem {
+    uint16_t lut_l[1 << FA_RL];        // while a dynamic header is parsed: the block's code lengths (320 bytes)
+    uint16_t lut_d[1 << FA_RD];        // while a dynamic header is parsed: code-length-code lengths + its 7-bit LUT
+    uint16_t cnt_l[16];                // [1..15] codes per length; [0] = longest code after the build
+    uint16_t cnt_d[16];
+    uint16_t start[4];                 // canonical-walk state after the root bits (canon_long)
+    uint16_t long_l[32];               // first literal/length symbols whose code is longer than the root
+    uint16_t sorted_d[32];             // distance symbols in canonical order
+    uint16_t pad_[2];                  // 371 words: an odd stride spreads the 32 lanes' tables over the banks
+};
+static_assert(sizeof(LaneSmem) == 1484, "LaneSmem layout");
+constexpr int FA_WARP_SMEM = 32 * (int)sizeof(LaneSmem) + SCRATCH_U16 * 2;      // + build scratch of the warp
+
+struct FastParams {
+    InflateParams I;                   // the batch
+    uint32_t* tokens;
+    const uint64_t* tok_off;           // first token of every stream (multiple of 4); tok_off[n] = arena size
+    uint32_t* ntok;                    // tokens written per stream (multiple of 4), or NTOK_HANDED_OVER
+    uint32_t* fb_list;                 // streams handed to the general decoder
+    unsigned long long* fb_count;
+    unsigned long long* counter_a;
+    unsigned long long* counter_b;
+    uint16_t* sorted_l;                // 288 u16 per lane of the phase-A grid
+};
+
+// token capacity of a stream: a token needs at least one output byte, and streams with fewer than four
+// input bits per symbol are left to the general decoder (extremely repetitive data)
+__device__ __host__ __forceinline__ uint64_t token_cap(uint32_t in_len, uint32_t out_cap)
+{
+    uint64_t c = 2ull * in_len;
+    if (c > out_cap) c = out_cap;
+    return (c + 32 + 3) & ~3ull;
+}
+
+// exclusive scan of the token capacities (one block; n is a few 10^4)
+__global__ void __launch_bounds__(1024) token_offsets_kernel(const uint32_t* in_len, const uint32_t* out_cap, unsigned long long n,
+                                                             uint64_t* tok_off)
+{
+    __shared__ uint64_t wsum[32];
+    __shared__ uint64_t carry_s;
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (unsigned long long base = 0; base < n; base += 1024) {
+        const unsigned long long i = base + threadIdx.x;
+        const uint64_t v = i < n ? token_cap(in_len[i], out_cap ? out_cap[i] : 0xffffffffu) : 0;
+        uint64_t incl = v;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint64_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += t; }
+        if (lane == 31) wsum[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            uint64_t s = wsum[lane];
+            #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint64_t t = __shfl_up_sync(0xffffffffu, s, d); if (lane >= (uint32_t)d) s += t; }
+            wsum[lane] = s;
+        }
+        __syncthreads();
+        const uint64_t carry = carry_s;
+        const uint64_t before = carry + (w ? wsum[w - 1] : 0) + incl - v;
+        if (i < n) tok_off[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + wsum[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tok_off[n] = carry_s;
+}
+
+// ---------------------------------------------------------------------- phase A
+
+// container header of a stream the fast path may finish (src/inflate.ts:142-401).  false: anything else
+// (errors, truncation, FDICT, FEXTRA ...) - the general decoder writes that record.
+struct Container {
+    uint32_t hp;                       // first byte of the deflate data
+    int32_t mtime;
+    uint32_t name_off, name_len;
+    int method;
+    bool raw, is_gzip;
+};
+__device__ __forceinline__ bool parse_container_clean(const uint8_t* src, uint32_t in_len, uint8_t mode_raw, Container& C)
+{
+    const int mode = mode_raw & 0x7f;
+    const bool has_dict = (mode_raw & 0x80) != 0;
+    C.hp = 0; C.mtime = 0; C.name_off = 0; C.name_len = 0; C.method = 0; C.is_gzip = false;
+    C.raw = mode == SDZ_MODE_RAW;
+    if (in_len == 0) return false;
+    if (mode == SDZ_MODE_SNIFF) {                                       // inflate(): src/sd-inflate.ts:194-207
+        if (in_len < 2) return false;
+        const uint32_t b0 = src[0], b1 = src[1];
+        const bool ident = (b0 == 0x78 && (((b0 << 8) + b1) % 31) == 0) || (b0 == 0x1f && b1 == 0x8b);
+        C.raw = !ident;
+    }
+    if (C.raw) return !has_dict;                                        // RangeError otherwise (src/sd-inflate.ts:69-71)
+    uint32_t hp = 0, b;
+    if (src[hp] == 0x1f) {
+        hp++;
+        if (hp >= in_len) return false;
+        if (src[hp++] != 0x8b) return false;
+        C.is_gzip = true;
+    }
+    if (hp >= in_len) return false;
+    C.method = src[hp++];
+    if ((C.method & 0xf) != 8 || (C.method >> 4) + 8 > 15) return false;
+    if (hp >= in_len) return false;
+    b = src[hp++];
+    if (C.is_gzip) {
+        const uint32_t gflags = b;
+        if (hp + 6 > in_len) return false;                              // MTIME, XFL, OS
+        C.mtime = (int32_t)((uint32_t)src[hp] | ((uint32_t)src[hp + 1] << 8) | ((uint32_t)src[hp + 2] << 16) | ((uint32_t)src[hp + 3] << 24));
+        hp += 6;
+        if (gflags & 4) return false;                                   // FEXTRA
+        if (gflags & 8) {
+            C.name_off = hp;
+            for (;;) { if (hp >= in_len) return false; b = src[hp++]; if (b == 0) break; C.name_len++; }
+        }
+        if (gflags & 16)
+            for (;;) { if (hp >= in_len) return false; b = src[hp++]; if (b == 0) break; }
+        if (gflags & 2) { if (hp + 2 > in_len) return false; hp += 2; }
+    } else {
+        if ((((uint32_t)C.method << 8) + b) % 31 != 0) return false;
+        if (b & 0x20) return false;                                     // FDICT: preset dictionary
+    }
+    C.hp = hp;
+    return true;
+}
+
+enum : int { LS_CODES = 0, LS_DONE = 1, LS_FETCH = 2, LS_BLOCK = 3, LS_BUILD = 4, LS_FINISH = 5, LS_HANDOVER = 6 };
+
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t s)
+{
+    uint32_t r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(s));              // shift amounts >= 32 give 0
+    return r;
+}
+__device__ __forceinline__ uint32_t bfe_u32(uint32_t v, uint32_t pos, uint32_t len)
+{
+    uint32_t r;
+    asm("bfe.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(v), "r"(pos), "r"(len));
+    return r;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
+{
+    uint16_t r;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r) : "r"(addr));
+    return r;
+}
+
+// One lane per stream.  Persistent warps: a lane that finishes its stream takes the next one from the
+// atomic counter; block headers, table builds and stream changes are serviced between lockstep runs
+// (headers by the lanes that need one, each for itself; table builds by the whole warp, one lane's
+// tables at a time).
+__global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t lane = threadIdx.x;
+    constexpr unsigned FULL = 0xffffffffu;
+    LaneSmem* const lanes = reinterpret_cast<LaneSmem*>(smem_raw);
+    LaneSmem* const L = lanes + lane;
+    uint16_t* const wscr = reinterpret_cast<uint16_t*>(smem_raw + 32 * sizeof(LaneSmem));     // sorted_l | sorted_d | lens | aux
+    uint16_t* const my_sorted = P.sorted_l + ((size_t)blockIdx.x * 32 + lane) * SORTED_L;
+
+    // ---- lane state
+    int state = LS_FETCH;
+    uint32_t idx = 0;
+    const uint32_t* wbase = nullptr;
+    uint64_t bb = 0;
+    int bc = 0;
+    uint32_t nw = 0, wp = 0, lim_wp = 0, in_len = 0;
+    uint32_t pos = 0, cap = 0, ntok = 0, cap_tok = 0, n_blocks = 0;
+    uint32_t* tokp = nullptr;
+    int last = 0, eob_len = 0, lbits = 0, g_l = 0, g_d = 0;
+    int nl = 0, nd = 0;
+    bool fixed = false;
+
+    auto refill = [&]() {
+        if (bc <= 32) {
+            bb |= (uint64_t)nw << bc;
+            bc += 32;
+            wp++;
+            nw = wp < lim_wp ? __ldg(wbase + wp) : 0u;
+        }
+    };
+    auto drop = [&](int n) { bb >>= n; bc -= n; };
+
+    for (;;) {
+        // ================================================================ service (divergent code is fine here)
+        // ---- new streams
+        while (state == LS_FETCH || state == LS_HANDOVER || state == LS_FINISH) {
+            if (state == LS_FINISH) {
+                // final block complete: trailer (src/inflate.ts:409-463) and the record - when this really is the
+                // plain complete stream
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(wbase);
+                const uint64_t consumed = (uint64_t)wp * 32 - (uint64_t)bc, total_bits = (uint64_t)in_len * 8;
+                bool ok = consumed <= total_bits;
+                Container C;
+                ok = ok && parse_container_clean(src, in_len, P.I.mode[idx], C);
+                uint32_t tp = (uint32_t)((consumed + 7) >> 3);
+                int32_t stored = 0, isize = 0;
+                if (ok) {
+                    if (C.raw) {
+                        // the reference looks up a symbol only when its table's root width is available;
+                        // nothing follows the final end-of-block code of a raw stream
+                        ok = lbits == 9 && eob_len <= 9 && total_bits - (consumed - (uint64_t)eob_len) >= 9;
+                    } else {
+                        const uint32_t nbytes = C.is_gzip ? 8u : 4u;
+                        ok = tp + nbytes <= in_len;
+                        if (ok) {
+                            if (C.is_gzip) {
+                                stored = (int32_t)((uint32_t)src[tp] | ((uint32_t)src[tp + 1] << 8) | ((uint32_t)src[tp + 2] << 16) | ((uint32_t)src[tp + 3] << 24));
+                                isize = (int32_t)((uint32_t)src[tp + 4] | ((uint32_t)src[tp + 5] << 8) | ((uint32_t)src[tp + 6] << 16) | ((uint32_t)src[tp + 7] << 24));
+                            } else {
+                                stored = (int32_t)(((uint32_t)src[tp] << 24) | ((uint32_t)src[tp + 1] << 16) | ((uint32_t)src[tp + 2] << 8) | (uint32_t)src[tp + 3]);
+                            }
+                            tp += nbytes;
+                        }
+                    }
+                    ok = ok && tp == in_len;                            // bytes after the end: append() spins
+                }
+                if (ok) {
+                    sdz_result R;
+                    R.out_off = P.I.out_off ? P.I.out_off[idx] : 0;
+                    R.out_len = pos;
+                    R.total_in = tp;
+                    R.zstatus = SDZ_Z_STREAM_END;
+                    R.stored_checksum = stored;
+                    R.running_checksum = 0;
+                    R.stored_isize = isize;
+                    R.mtime = C.mtime;
+                    R.name_off = C.name_len ? C.name_off : 0;
+                    R.name_len = C.name_len;
+                    R.n_blocks = n_blocks;
+                    R.msg_id = SDZ_MSG_NONE;
+                    R.thrown_append = SDZ_THROW_NONE;
+                    R.thrown_inflate = 0;
+                    R.container = (uint8_t)(C.is_gzip ? SDZ_GZIP : (C.method == 0 ? SDZ_RAW : SDZ_ZLIB));
+                    R.complete = 1;
+                    R.checksum_state = R.size_state = R.success = R.have_running = 0;
+                    for (int k = 0; k < 7; k++) R.reserved[k] = 0;
+                    P.I.res[idx] = R;
+                    P.ntok[idx] = ntok;
+                    state = LS_FETCH;
+                } else state = LS_HANDOVER;
+            }
+            if (state == LS_HANDOVER) {
+                const unsigned long long slot = atomicAdd(P.fb_count, 1ull);
+                P.fb_list[slot] = idx;
+                P.ntok[idx] = NTOK_HANDED_OVER;
+                state = LS_FETCH;
+            }
+            // LS_FETCH
+            const unsigned long long i = atomicAdd(P.counter_a, 1ull);
+            if (i >= P.I.n) {
+                // out of streams: the lane idles through the lockstep loop on zeroed tables (every lookup is a "literal"
+                // of zero bits) with a full bit buffer, so it never loads and never consumes
+                state = LS_DONE; lim_wp = 0xfffffff0u; wp = 0; nw = 0; bb = 0; bc = 64;
+                uint32_t* z = reinterpret_cast<uint32_t*>(L->lut_l);
+                for (int k = 0; k < ((1 << FA_RL) + (1 << FA_RD)) / 2; k++) z[k] = 0u;
+                break;
+            }
+            idx = (uint32_t)i;
+            in_len = P.I.in_len[i];
+            const uint8_t* src = P.I.in + P.I.in_off[i];
+            wbase = reinterpret_cast<const uint32_t*>(src);
+            Container C;
+            if (!parse_container_clean(src, in_len, P.I.mode[i], C)) { state = LS_HANDOVER; continue; }
+            lim_wp = (in_len + 3) / 4;
+            pos = 0;
+            cap = P.I.out_cap ? P.I.out_cap[i] : 0xffffffffu;
+            ntok = 0;
+            cap_tok = (uint32_t)(P.tok_off[i + 1] - P.tok_off[i]);
+            tokp = P.tokens + P.tok_off[i];
+            n_blocks = 0; last = 0; eob_len = 0;
+            // seek(hp)
+            wp = C.hp >> 2; bb = 0; bc = 0;
+            nw = wp < lim_wp ? __ldg(wbase + wp) : 0u;
+            refill();
+            drop((int)(C.hp & 3) * 8);
+            state = LS_BLOCK;
+        }
+        if (__all_sync(FULL, state == LS_DONE)) break;
+
+        // ---- block headers (src/infblocks.ts:159-523), every lane for its own stream
+        if (state == LS_BLOCK) {
+            refill();
+            const uint32_t t3 = (uint32_t)bb & 7u;
+            drop(3);
+            last = (int)(t3 & 1u);
+            n_blocks++;
+            const uint32_t type = t3 >> 1;
+            uint8_t* lens = reinterpret_cast<uint8_t*>(L->lut_l);
+            state = LS_BUILD;
+            if (type == 0 || type == 3) state = LS_HANDOVER;            // stored / invalid: the general decoder's
+            else if (type == 1) {
+                for (int k = 0; k < 320; k++) lens[k] = (uint8_t)(k < 144 ? 8 : (k < 256 ? 9 : (k < 280 ? 7 : (k < 288 ? 8 : 5))));
+                nl = 288; nd = 30; fixed = true;
+            } else {
+                fixed = false;
+                refill();
+                const uint32_t t = (uint32_t)bb & 0x3fffu;
+                if ((t & 0x1f) > 29 || ((t >> 5) & 0x1f) > 29) state = LS_HANDOVER;
+                else {
+                    drop(14);
+                    nl = 257 + (int)(t & 0x1f); nd = 1 + (int)((t >> 5) & 0x1f);
+                    const int ncl = 4 + (int)(t >> 10), total = nl + nd;
+                    uint8_t* cl = reinterpret_cast<uint8_t*>(L->lut_d);
+                    uint8_t* blut = cl + 32;
+                    uint16_t* cnt = L->cnt_l;
+                    for (int i = 0; i < 19; i++) cl[i] = 0;
+                    for (int i = 0; i < 16; i++) cnt[i] = 0;
+                    for (int i = 0; i < ncl; i++) { refill(); cl[c_border[i]] = (uint8_t)((uint32_t)bb & 7u); drop(3); }
+                    for (int i = 0; i < 19; i++) cnt[cl[i]]++;
+                    // code-length code: only complete sets here (src/inftree.ts:313-331; the reference also accepts a
+                    // lone 1-bit code, SURVEY Q11: the general decoder's business)
+                    int y = 1, g = 0;
+                    bool over = false;
+                    for (int k = 1; k <= 7; k++) { y = 2 * y - (int)cnt[k]; if (cnt[k]) g = k; if (y < 0) over = true; }
+                    if (cnt[0] == 19 || over || y != 0) state = LS_HANDOVER;
+                    else {
+                        const int l = g;                                // = min(7, longest)
+                        uint32_t code = 0;
+                        for (int k = 1; k <= g; k++) {
+                            for (int s = 0; s < 19; s++) {
+                                if (cl[s] != k) continue;
+                                const uint32_t rev = __brev(code) >> (32 - k);
+                                for (uint32_t q = rev; q < (1u << l); q += (1u << k)) blut[q] = (uint8_t)(s | (k << 5));
+                                code++;
+                            }
+                            code <<= 1;
+                        }
+                        int index = 0;
+                        uint32_t prev = 0;
+                        while (index < total) {
+                            refill();
+                            const uint32_t e = blut[(uint32_t)bb & ((1u << l) - 1u)];
+                            const int tb = (int)(e >> 5), c = (int)(e & 31);
+                            if (c < 16) {
+                                drop(tb);
+                                lens[index++] = (uint8_t)c;
+                                prev = (uint32_t)c;
+                            } else {
+                                const int xi = c == 18 ? 7 : c - 14;
+                                int j = c == 18 ? 11 : 3;
+                                drop(tb);
+                                j += (int)((uint32_t)bb & ((1u << xi) - 1u));
+                                drop(xi);
+                                if (index + j > total || (c == 16 && index < 1)) { state = LS_HANDOVER; break; }
+                                const uint8_t v = c == 16 ? (uint8_t)prev : (uint8_t)0;
+                                prev = v;
+                                for (int q = 0; q < j; q++) lens[index + q] = v;
+                                index += j;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- table builds: the warp builds one lane's tables at a time (src/inftree.ts:95-379)
+        {
+            unsigned todo = __ballot_sync(FULL, state == LS_BUILD);
+            while (todo) {
+                const int who = __ffs(todo) - 1;
+                todo &= todo - 1;
+                LaneSmem* const T = lanes + who;
+                const int t_nl = __shfl_sync(FULL, nl, who), t_nd = __shfl_sync(FULL, nd, who);
+                const bool t_fixed = __shfl_sync(FULL, (int)fixed, who) != 0;
+                {
+                    const uint32_t* s32 = reinterpret_cast<const uint32_t*>(T->lut_l);
+                    uint32_t* d32 = reinterpret_cast<uint32_t*>(wscr + SORTED_L + SORTED_D);
+                    for (uint32_t i = lane; i < 80; i += 32) d32[i] = s32[i];
+                }
+                __syncwarp();
+                const TreeInfo TI = build_tables<32>(T, wscr, t_nl, t_nd, t_fixed, (int)lane, FULL, T->long_l, 32);
+                __syncwarp();
+                if (TI.msg == SDZ_MSG_NONE) {
+                    uint16_t* gs = P.sorted_l + ((size_t)blockIdx.x * 32 + who) * SORTED_L;
+                    for (uint32_t i = lane; i < (uint32_t)SORTED_L; i += 32) gs[i] = wscr[i];
+                    T->sorted_d[lane] = wscr[SORTED_L + lane];
+                    // end-of-block entries join the "rare" class of the symbol loop (one compare): 0x100 | code length
+                    for (uint32_t i = lane; i < (1u << FA_RL); i += 32) {
+                        const uint32_t e = T->lut_l[i];
+                        if (e >= 0x1000u && (e & 0xfffu) == 0x100u) T->lut_l[i] = (uint16_t)(0x100u | (e >> 12));
+                    }
+                }
+                __syncwarp();
+                if ((int)lane == who) {
+                    if (TI.msg != SDZ_MSG_NONE) state = LS_HANDOVER;    // the general decoder reproduces the message
+                    else { lbits = TI.lbits; g_l = TI.g_l; g_d = TI.g_d; state = LS_CODES; }
+                }
+            }
+        }
+        __syncwarp();
+        if (__any_sync(FULL, state >= LS_FETCH)) continue;             // hand-overs found by the header / build steps
+
+        // ================================================================ lockstep symbol loop
+        // During one run every lane is either decoding (`live`) or out of streams; the run ends for the whole warp as
+        // soon as one lane meets an end-of-block code or anything the general decoder has to look at.  The iteration is
+        // straight-line predicated code with three warp-voted side exits (code longer than the root / end of block /
+        // invalid code, the same for distances, and a second top-up of the bit buffer).  Checks that can wait (slot
+        // full, distance before the start of the output, input overrun, token arena full) are accumulated and looked
+        // at once per group of four symbols; phase A writes no output bytes, so a late hand-over costs nothing.
+        {
+            const bool live = state == LS_CODES;
+            const uint32_t a_l = smem_addr(L->lut_l), a_d = smem_addr(L->lut_d);
+            int ev = 0;                                                 // 1: end of block, 2: hand the stream over
+            for (;;) {
+                uint32_t tk[4] = { 0u, 0u, 0u, 0u };
+                bool early = false;                                     // a distance reached before the start of the output
+                #pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    {   // top-up: at least 32 valid bits (lanes without a stream sit at bc = 64)
+                        const bool take = bc < 32;
+                        const uint32_t pw = take ? shl_clamp(1u, (uint32_t)bc) : 0u;
+                        asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(bb) : "r"(nw), "r"(pw));     // bits above bc are zero: add == or
+                        bc += take ? 32 : 0;
+                        wp += take ? 1u : 0u;
+                        if (take) nw = __ldg(wbase + wp);
+                    }
+                    const uint32_t lo = (uint32_t)bb;
+                    uint32_t e = lds_u16(a_l + (lo & ((1u << FA_RL) - 1u)) * 2u);
+                    if (__any_sync(FULL, live && e < 0x1000u)) {
+                        // rare: code longer than the root, end of block, invalid code
+                        if (live && e < 0x1000u) {
+                            if (e == E_LONG) {
+                                const uint32_t r = canon_long(L->cnt_l, my_sorted, FA_RL, g_l, L->start, lo, L->long_l, 32);
+                                const uint32_t sym = r & 0xffffu;
+                                if (r != 0u && sym < 256u) e = ((r >> 16) << 12) | sym;
+                                else if (r != 0u && sym == 256u) e = 0x100u | (r >> 16);
+                                else if (r != 0u && sym - 257u <= 28u) {
+                                    const uint32_t i = sym - 257u;
+                                    const uint32_t xb = i < 8 ? 0 : (i == 28 ? 0 : (i >> 2) - 1);
+                                    const uint32_t base = i < 8 ? 3 + i : (i == 28 ? 258 : 3 + ((4 + (i & 3)) << xb));
+                                    e = ((r >> 16) << 12) | 0x800u | (xb << 8) | (base - 3u);
+                                } else e = E_INVALID;
+                            }
+                            if (e < 0x1000u) {
+                                if ((e & 0xf00u) == 0x100u) {           // end of block (LUT fix-up after the build: 0x100 | code length)
+                                    const int n = (int)(e & 0xffu);
+                                    bb >>= n; bc -= n; eob_len = n;
+                                    ev = 1;
+                                } else ev = 2;                          // invalid literal/length code
+                            }
+                        }
+                        if (__any_sync(FULL, ev != 0)) break;           // (lanes without an event have consumed nothing of symbol u)
+                    }
+                    // (lanes without a stream read zeroed tables: a "literal" of zero bits)
+                    const uint32_t n = e >> 12;
+                    const bool ismatch = (e & 0x800u) != 0u;
+                    const uint32_t xb = (e >> 8) & 7u;                  // 0 for a literal
+                    const uint32_t c1 = n + xb;
+                    const uint32_t lenf = (e & 0xffu) + ((lo >> n) & ((1u << xb) - 1u));     // length - 3 (literal: the byte)
+                    const uint32_t len = ismatch ? lenf + 3u : 1u;
+                    // ---- distance: the root lookup needs 7 of the >= 12 bits that are left
+                    uint32_t lo2 = (uint32_t)(bb >> c1);
+                    uint32_t de = lds_u16(a_d + (lo2 & ((1u << FA_RD) - 1u)) * 2u);
+                    if (__any_sync(FULL, live && ismatch && (de < 0x1000u || bc < (int)c1 + 20))) {
+                        // rare: the buffer may not cover code + extra bits, code longer than the root, invalid code
+                        if (live && ismatch) {
+                            if (bc < 32) {
+                                bb |= (uint64_t)nw << bc;
+                                bc += 32; wp++;
+                                nw = __ldg(wbase + wp);
+                                lo2 = (uint32_t)(bb >> c1);
+                            }
+                            if (de < 0x1000u) {
+                                const uint32_t r = (de == E_LONG && g_d > FA_RD) ? canon_long(L->cnt_d, L->sorted_d, FA_RD, g_d, L->start + 2, lo2) : 0u;
+                                const uint32_t ds = r & 0xffffu;
+                                if (r == 0u || ds > 29u) { early = true; de = 0x1000u; }     // invalid distance code: hand over
+                                else de = ((r >> 16) << 12) | ((ds < 4 ? 0u : (ds >> 1) - 1u) << 8) | (ds < 4 ? ds : 2u + (ds & 1u));
+                            }
+                        }
+                    }
+                    const uint32_t dn = de >> 12, dx = (de >> 8) & 15u;
+                    const uint32_t dm1 = ((de & 3u) << dx) + ((lo2 >> dn) & ((1u << dx) - 1u));   // distance - 1
+                    {
+                        const uint32_t c = c1 + (ismatch ? dn + dx : 0u);       // <= 48
+                        bb >>= c; bc -= (int)c;
+                    }
+                    early = early || (ismatch && dm1 >= pos);           // the general decoder's
+                    pos += len;
+                    tk[u] = ismatch ? dm1 * 512u + len : (TOK_LIT | lenf);
+                }
+                if (live) {
+                    // (after an early exit the unprocessed slots of the group are still no-ops)
+                    if (early || pos > cap || wp > lim_wp + 1u || ntok + 4u > cap_tok) ev = 2;
+                    else {
+                        *reinterpret_cast<uint4*>(tokp + ntok) = make_uint4(tk[0], tk[1], tk[2], tk[3]);
+                        ntok += 4u;
+                    }
+                }
+                if (__any_sync(FULL, ev != 0)) break;
+            }
+            if (ev == 2) state = LS_HANDOVER;
+            else if (ev == 1) state = last ? LS_FINISH : LS_BLOCK;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------- phase B
+
+__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.global.cs.u32 %0, [%1];" : "=r"(v) : "l"(p));      // read once: evict first
+    return v;
+}
+
+// One warp per stream.  32 tokens per batch; their bytes are produced in rows of 32 (lane = output byte).
+__global__ void __launch_bounds__(256) lz_resolve_kernel(FastParams P)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t le_mask = 0xffffffffu >> (31u - lane);
+    for (;;) {
+        unsigned long long idx = 0;
+        if (lane == 0) idx = atomicAdd(P.counter_b, 1ull);
+        idx = __shfl_sync(FULL, idx, 0);
+        if (idx >= P.I.n) break;
+        const uint32_t nt = P.ntok[idx];
+        if (nt == NTOK_HANDED_OVER) continue;
+        const uint32_t* tk = P.tokens + P.tok_off[idx];
+        uint8_t* out = P.I.out + P.I.out_off[idx];
+        uint32_t P0 = 0;                                               // output bytes of the batches before this one
+        for (uint32_t base = 0; base < nt; base += 32) {
+            uint32_t t = base + lane < nt ? ld_stream_u32(tk + base + lane) : 0u;
+            {
+                // no-op tokens (end of a block inside a group of four) are squeezed out: the row loop indexes tokens
+                const uint32_t nz = __ballot_sync(FULL, t != 0u);
+                if (nz & (nz + 1u)) {
+                    const uint32_t srcl = __fns(nz, 0, (int)lane + 1);
+                    const uint32_t t2 = __shfl_sync(FULL, t, srcl & 31u);
+                    t = srcl < 32u ? t2 : 0u;
+                }
+            }
+            const bool lit = (int32_t)t < 0;
+            const uint32_t len = lit ? 1u : (t & 511u);
+            uint32_t incl = len;
+            #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, d); if (lane >= (uint32_t)d) incl += v; }
+            const uint32_t S = incl - len;                             // first byte of my token, relative to P0
+            const uint32_t N = __shfl_sync(FULL, incl, 31);
+            uint32_t nxt = 0;                                          // tokens that started in earlier rows
+            for (uint32_t R = 0; R < N; R += 32) {
+                const uint32_t rel = S - R;
+                const uint32_t bit = (len != 0u && rel < 32u) ? (1u << rel) : 0u;
+                const uint32_t m = __reduce_or_sync(FULL, bit);       // bit b: a token starts at byte R + b
+                const uint32_t k = __popc(m & le_mask);
+                const uint32_t tt = __shfl_sync(FULL, t, (nxt + k - 1u) & 31u);   // k == 0: the token that began in an earlier row
+                nxt += __popc(m);
+                const uint32_t b = R + lane;
+                const bool valid = b < N;
+                const bool tlit = (int32_t)tt < 0;
+                const uint32_t td = ((tt >> 9) & 0x7fffu) + 1u;
+                const int32_t srel = (int32_t)b - (int32_t)td;          // source, relative to P0 (phase A guarantees P0 + srel >= 0)
+                const bool inrow = valid && !tlit && srel >= (int32_t)R;
+                uint32_t v = tt & 0xffu;
+                if (valid && !tlit && !inrow) v = out[(int64_t)P0 + (int64_t)srel];
+                if (__any_sync(FULL, inrow)) {
+                    // sources inside this row: pointer jumping over the lanes (depth <= 31: five doublings)
+                    uint32_t q = inrow ? (uint32_t)(srel - (int32_t)R) : lane;
+                    for (int r = 0; r < 6; r++) {
+                        const uint32_t vv = __shfl_sync(FULL, v, q), qq = __shfl_sync(FULL, q, q);
+                        const bool moved = __any_sync(FULL, qq != q);
+                        if (q != lane) { v = vv; q = qq; }
+                        if (!moved) break;
+                    }
+                }
+                if (valid) out[P0 + b] = (uint8_t)v;
+                __syncwarp();
+            }
+            P0 += N;
+        }
+    }
+}
+
+}  // namespace sdz

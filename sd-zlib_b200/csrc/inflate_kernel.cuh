@@ -113,6 +113,10 @@ struct InflateParams {
     uint32_t ckpt_step;                // power of two
     unsigned long long n;
     unsigned long long* counter;       // dynamic stream scheduler
+    // hand-over from the two-phase fast path (fast_kernels.cuh): work item i is stream list[i], and the number of
+    // work items is only known on the device
+    const uint32_t* list;
+    const unsigned long long* n_dev;
 };
 
 // resume point inside a block (TM_INDEX): the symbol at bit `bit` produces output byte `pos` of task `task`
@@ -444,8 +448,8 @@ __device__ __forceinline__ void make_lut(uint32_t* aux, const uint8_t* lens, int
 
 // lit/len + distance tables for lens[0..nl) and lens[nl..nl+nd) with the reference's checks
 // and messages (inflate_trees_dynamic, src/inftree.ts:333-379).  fixed: no checks.
-template <int G>
-__device__ __noinline__ TreeInfo build_tables(GroupSmem* S, uint16_t* gsorted, int nl, int nd, bool fixed, int glane, unsigned gmask,
+template <int G, class SM>
+__device__ __noinline__ TreeInfo build_tables(SM* S, uint16_t* gsorted, int nl, int nd, bool fixed, int glane, unsigned gmask,
                                               uint16_t* long_l, int long_n)
 {
     TreeInfo T;
@@ -765,8 +769,8 @@ struct Decoder {
     // Memory ordering: the lockstep loop executes a full-mask __syncwarp() at the top of every
     // iteration, so stores of earlier iterations (literals, committed matches) are ordered before
     // the reads issued here.  Only bytes committed in THIS iteration need an extra group sync.
-    // `lit_now`: a literal was stored by lane 0 earlier in THIS lockstep iteration (at pos - 1).
-    __device__ __forceinline__ int copy_match(uint32_t len, uint32_t dist, bool lit_now)
+    // `lit_now`: number of literals lane 0 stored earlier in THIS lockstep iteration (at pos - lit_now .. pos - 1).
+    __device__ __forceinline__ int copy_match(uint32_t len, uint32_t dist, uint32_t lit_now)
     {
         if (len > cap - pos) return R_OUTFULL;
         if (MARK && dist > pos) {
@@ -787,9 +791,10 @@ struct Decoder {
             // overtake them: its own destination is disjoint from theirs)
             const bool hazard = any_pending && (bdist > bpos || bpos - bdist + blen > first_pending);
             if (hazard) flush_pending();
-            // bytes written in this iteration (just-committed matches, the folded literal at pos - 1) are
-            // only ordered before the reads below by a group sync; a deferred match reads pos - 1 iff dist == len
-            if (hazard || !simple || (lit_now && bdist == blen)) __syncwarp(gmask);
+            // bytes written in this iteration (just-committed matches, the folded literals at pos - lit_now .. pos - 1)
+            // are only ordered before the reads below by a group sync; a deferred match (dist >= len) reads one of
+            // the folded literals iff dist < len + lit_now
+            if (hazard || !simple || bdist < blen + lit_now * E) __syncwarp(gmask);
             uint8_t* dst = out + bpos;
 #if SDZ_TWOSLOT
             const bool two = G <= MAX_G_DEFERRED && !simple && bdist >= blen && blen <= 2u * DEFER_MAX && bdist <= bpos;
@@ -910,7 +915,7 @@ struct Decoder {
     // `tail` (fewer than five input words left) and root entries marked long/invalid go through
     // slow_lookup(), which also enforces the reference's lookahead rule; everything else is
     // one shared-memory LUT read per code.
-    __device__ __forceinline__ int step_general(bool lit_now)
+    __device__ __forceinline__ int step_general(uint32_t lit_now)
     {
         refill();
         const bool tail = wp + 5 > end_wp;
@@ -994,6 +999,7 @@ struct Decoder {
         constexpr uint32_t LMASK = (1u << RL) - 1u, DMASK = (1u << RD) - 1u;
         bool general = wp + 5 > end_wp || cap - pos < (uint32_t)SDZ_CAPMARGIN;     // (one call site for step_general(): it is inlined once)
         bool fold = false;
+        uint32_t nfold = 0;                                // literals stored by this iteration's folds
         uint32_t e = 0;
         if (!general) {
         refill_fast();
@@ -1004,6 +1010,7 @@ struct Decoder {
             const uint32_t n0 = fold ? e >> 12 : 0u;
             if (STORE) { if (MARK) st_u16_if(out16 + pos, e & 0xffu, fold && glane == 0); else st_u8_if(out + pos, e & 0xffu, fold && glane == 0); }
             pos += fold ? 1u : 0u;
+            nfold = fold ? 1u : 0u;
             bb >>= n0; bc -= (int)n0;
             e = S->lut_l[(uint32_t)bb & LMASK];          // the same entry again when nothing was folded
         }
@@ -1016,6 +1023,7 @@ struct Decoder {
             const uint32_t n0 = fold2 ? e >> 12 : 0u;
             if (STORE) { if (MARK) st_u16_if(out16 + pos, e & 0xffu, fold2 && glane == 0); else st_u8_if(out + pos, e & 0xffu, fold2 && glane == 0); }
             pos += fold2 ? 1u : 0u;
+            nfold += fold2 ? 1u : 0u;
             bb >>= n0; bc -= (int)n0;
             e = S->lut_l[(uint32_t)bb & LMASK];
         }
@@ -1042,7 +1050,7 @@ struct Decoder {
             else if ((e & 0xfffu) == 0x100u) { const uint32_t n = e >> 12; bb >>= n; bc -= (int)n; eob_len = (int)n; return R_EOB; }
         }
         }
-        if (general) return step_general(fold);
+        if (general) return step_general(nfold);
         const uint32_t n = e >> 12, p = e & 0xfffu;
         const bool ismatch = p >= 256u;
         if (STORE) { if (MARK) st_u16_if(out16 + pos, p, !ismatch && glane == 0); else st_u8_if(out + pos, p, !ismatch && glane == 0); }
@@ -1085,11 +1093,13 @@ struct Decoder {
             cm = ismatch && !pre;
         }
         // (room for a deferred match, <= 16 bytes, is guaranteed by the margin test at the top when SDZ_CAPMARGIN >= 18)
-        const bool simple = G <= MAX_G_DEFERRED && cm && bdist >= blen && blen <= DEFER_MAX && bdist <= bpos && !(fold && bdist == blen) &&
+        // (a deferred copy issues its cp.async without a group sync, so its source must not contain a literal folded in
+        //  this iteration: those sit at pos - nfold .. pos - 1, i.e. inside the source iff dist < len + nfold)
+        const bool simple = G <= MAX_G_DEFERRED && cm && bdist >= blen + nfold * E && blen <= DEFER_MAX && bdist <= bpos &&
                             (SDZ_CAPMARGIN >= 18 || len <= cap - pos);
         const uint32_t first_pending = o_meta ? o_dst : n_dst;
         const bool hazard = (o_meta | n_meta) != 0u && (bdist > bpos || bpos - bdist + blen > first_pending);
-        if (cm && (!simple || hazard)) return copy_match(len, dist, fold);     // long / overlapping / marker / early source, pending bytes
+        if (cm && (!simple || hazard)) return copy_match(len, dist, nfold);     // long / overlapping / marker / early source, pending bytes
         // plain deferred copy, predicated on `simple` (nothing happens for a literal)
         if constexpr (G <= MAX_G_DEFERRED) {
         cp_async_wait_but_one();
@@ -1199,7 +1209,8 @@ struct Decoder {
         unsigned long long i = 0;
         if (glane == 0) i = atomicAdd(P.counter, 1ull);
         i = __shfl_sync(gmask, i, 0, G);
-        if (i >= P.n) { phase = PH_EXIT; return; }
+        if (i >= (P.n_dev ? *P.n_dev : P.n)) { phase = PH_EXIT; return; }
+        if (P.list) i = P.list[i];
         idx = i;
         if (TM != TM_NONE) { fetch_task(P, i); return; }
         in_len = P.in_len[i];

@@ -15,6 +15,7 @@
 
 #include "checksum_kernels.cuh"
 #include "inflate_kernel.cuh"
+#include "fast_kernels.cuh"
 #include "large_kernels.cuh"
 
 namespace {
@@ -55,6 +56,15 @@ struct sdz_ctx {
     int cur_lane = 0;
     int group = 4;                     // lanes per stream
     int block_threads = 64;
+    // two-phase fast path (fast_kernels.cuh): per compute lane the token arena, the per-stream arrays
+    // (counters | tok_off | ntok | hand-over list) and the sorted-symbol scratch of phase A
+    bool fast = true;                  // SDZ_FAST=0: every stream goes through the general decoder
+    int b_blocks_per_sm = 4;           // phase B: 256-thread blocks per SM (SDZ_B_BLOCKS)
+    DevBuf fast_tok[N_LANES], fast_meta[N_LANES], fast_sorted[N_LANES];
+    cudaEvent_t ev_fast[4] = { nullptr, nullptr, nullptr, nullptr };   // before A, after A, after B, after the hand-over run
+    bool fast_timed = false;
+    const unsigned long long* last_fb_count = nullptr;   // device counter of the most recent fast-path launch
+    uint64_t last_fast_n = 0;
     bool poison = false;               // SDZ_POISON=1 (tests): fill the device output arena with 0xA5 before every decode
 };
 
@@ -200,7 +210,70 @@ int launch_finalize(sdz_ctx* ctx, const uint8_t* d_out, sdz_result* d_res, uint6
     return SDZ_OK;
 }
 
-int run_batch_device(sdz_ctx* ctx, const sdz_batch_dev* b, bool sizes_only, bool first = true, bool last = true)
+// Two-phase fast path: token offsets -> phase A (Huffman -> tokens) -> phase B (tokens -> bytes) -> the general
+// decoder for the streams phase A handed over.  `tok_total`: size of the token arena when the caller knows it
+// (host path: computed from the host copies of in_len / out_cap), 0 = read it back from the device.
+int launch_fast(sdz_ctx* ctx, const sdz::InflateParams& P, uint64_t tok_total, bool timed)
+{
+    const uint64_t n = P.n;
+    if (n == 0) return SDZ_OK;
+    if (n >= 0xffffffffull) return SDZ_E_ARG;
+    const int lane = ctx->cur_lane;
+    cudaStream_t st = ctx->lane_stream[lane];
+    int rc;
+    const size_t off_tokoff = 64, off_ntok = off_tokoff + (n + 1) * 8, off_list = off_ntok + align_up(n * 4, 8);
+    if ((rc = grow(ctx, ctx->fast_meta[lane], off_list + n * 4))) return rc;
+    uint8_t* fm = (uint8_t*)ctx->fast_meta[lane].p;
+    unsigned long long* counters = (unsigned long long*)fm;
+    uint64_t* tok_off = (uint64_t*)(fm + off_tokoff);
+    CK(cudaMemsetAsync(counters, 0, 64, st));
+    sdz::token_offsets_kernel<<<1, 1024, 0, st>>>(P.in_len, P.out_cap, n, tok_off);
+    ctx->launches++;
+    if (!tok_total) {
+        CK(cudaMemcpyAsync(&tok_total, tok_off + n, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    if ((rc = grow(ctx, ctx->fast_tok[lane], tok_total * 4 + 64))) return rc;
+
+    auto kern = sdz::huff_tokens_kernel;
+    const size_t smem = sdz::FA_WARP_SMEM;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    const unsigned grid_a = (unsigned)std::min<uint64_t>((n + 31) / 32, (uint64_t)ctx->sm_count * per_sm);
+    if ((rc = grow(ctx, ctx->fast_sorted[lane], (size_t)grid_a * 32 * sdz::SORTED_L * sizeof(uint16_t)))) return rc;
+
+    sdz::FastParams F;
+    F.I = P;
+    F.tokens = (uint32_t*)ctx->fast_tok[lane].p;
+    F.tok_off = tok_off;
+    F.ntok = (uint32_t*)(fm + off_ntok);
+    F.fb_list = (uint32_t*)(fm + off_list);
+    F.counter_a = counters; F.counter_b = counters + 1; F.fb_count = counters + 2;
+    F.sorted_l = (uint16_t*)ctx->fast_sorted[lane].p;
+    if (timed) CK(cudaEventRecord(ctx->ev_fast[0], st));
+    kern<<<grid_a, 32, smem, st>>>(F);
+    if (timed) CK(cudaEventRecord(ctx->ev_fast[1], st));
+    const unsigned grid_b = (unsigned)std::min<uint64_t>((n + 7) / 8, (uint64_t)ctx->sm_count * ctx->b_blocks_per_sm);
+    sdz::lz_resolve_kernel<<<grid_b, 256, 0, st>>>(F);
+    if (timed) CK(cudaEventRecord(ctx->ev_fast[2], st));
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    // hand-over run: the general decoder over the list (its length is only known on the device)
+    sdz::InflateParams Q = P;
+    Q.list = F.fb_list;
+    Q.n_dev = F.fb_count;
+    rc = launch_inflate<true>(ctx, Q);
+    if (rc) return rc;
+    if (timed) CK(cudaEventRecord(ctx->ev_fast[3], st));
+    ctx->fast_timed = timed;
+    ctx->last_fb_count = F.fb_count;
+    ctx->last_fast_n = n;
+    return SDZ_OK;
+}
+
+int run_batch_device(sdz_ctx* ctx, const sdz_batch_dev* b, bool sizes_only, bool first = true, bool last = true, uint64_t tok_total = 0)
 {
     sdz::InflateParams P;
     memset(&P, 0, sizeof P);
@@ -210,7 +283,8 @@ int run_batch_device(sdz_ctx* ctx, const sdz_batch_dev* b, bool sizes_only, bool
     P.res = b->d_results; P.n = b->n; P.counter = ctx->d_counter; P.scratch = nullptr;
     cudaStream_t st = ctx->lane_stream[ctx->cur_lane];
     if (first) CK(cudaEventRecord(ctx->ev[0], st));
-    int rc = sizes_only ? launch_inflate<false>(ctx, P) : launch_inflate<true>(ctx, P);
+    ctx->fast_timed = false;
+    int rc = sizes_only ? launch_inflate<false>(ctx, P) : (ctx->fast ? launch_fast(ctx, P, tok_total, first && last) : launch_inflate<true>(ctx, P));
     if (rc) return rc;
     if (last) CK(cudaEventRecord(ctx->ev[1], st));
     if (!sizes_only) {
@@ -273,6 +347,10 @@ int sdz_ctx_create(int device, uint32_t flags, sdz_ctx** out)
     if (cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) != cudaSuccess) return fail(SDZ_E_CUDA);
     for (auto& e : ctx->ev)
         if (cudaEventCreate(&e) != cudaSuccess) return fail(SDZ_E_CUDA);
+    for (auto& e : ctx->ev_fast)
+        if (cudaEventCreate(&e) != cudaSuccess) return fail(SDZ_E_CUDA);
+    if (const char* f = getenv("SDZ_FAST")) ctx->fast = atoi(f) != 0;
+    if (const char* f = getenv("SDZ_B_BLOCKS")) { int v = atoi(f); if (v >= 1 && v <= 8) ctx->b_blocks_per_sm = v; }
     if (cudaMalloc(&ctx->d_counter, (4 + 2 * sdz_ctx::N_LANES) * sizeof(unsigned long long)) != cudaSuccess) return fail(SDZ_E_NOMEM);
     ctx->lane_stream[0] = ctx->stream;
     for (int l = 1; l < sdz_ctx::N_LANES; l++)
@@ -299,6 +377,11 @@ void sdz_ctx_destroy(sdz_ctx* ctx)
         if (ctx->lane_stream[l]) { cudaStreamSynchronize(ctx->lane_stream[l]); cudaStreamDestroy(ctx->lane_stream[l]); }
         if (ctx->lane_scratch[l].p) cudaFree(ctx->lane_scratch[l].p);
     }
+    for (int l = 0; l < sdz_ctx::N_LANES; l++)
+        for (DevBuf* b : { &ctx->fast_tok[l], &ctx->fast_meta[l], &ctx->fast_sorted[l] })
+            if (b->p) cudaFree(b->p);
+    for (auto& e : ctx->ev_fast)
+        if (e) cudaEventDestroy(e);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->h_res) cudaFreeHost(ctx->h_res);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
@@ -323,6 +406,38 @@ int sdz_last_timing(sdz_ctx* ctx, float ms[3])
     CK(cudaEventElapsedTime(&ms[0], ctx->ev[0], ctx->ev[1]));
     CK(cudaEventElapsedTime(&ms[1], ctx->ev[1], ctx->ev[2]));
     CK(cudaEventElapsedTime(&ms[2], ctx->ev[0], ctx->ev[2]));
+    return SDZ_OK;
+}
+
+int sdz_last_phase_timing(sdz_ctx* ctx, float ms[5])
+{
+    if (!ctx || !ms) return SDZ_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventSynchronize(ctx->ev[2]));
+    for (int i = 0; i < 5; i++) ms[i] = 0.f;
+    if (ctx->fast_timed) {
+        CK(cudaEventElapsedTime(&ms[0], ctx->ev_fast[0], ctx->ev_fast[1]));
+        CK(cudaEventElapsedTime(&ms[1], ctx->ev_fast[1], ctx->ev_fast[2]));
+        CK(cudaEventElapsedTime(&ms[2], ctx->ev_fast[2], ctx->ev_fast[3]));
+    } else {
+        CK(cudaEventElapsedTime(&ms[2], ctx->ev[0], ctx->ev[1]));
+    }
+    CK(cudaEventElapsedTime(&ms[3], ctx->ev[1], ctx->ev[2]));
+    CK(cudaEventElapsedTime(&ms[4], ctx->ev[0], ctx->ev[2]));
+    return SDZ_OK;
+}
+
+int sdz_last_fast_stats(sdz_ctx* ctx, uint64_t out[2])
+{
+    if (!ctx || !out) return SDZ_E_ARG;
+    out[0] = out[1] = 0;
+    if (!ctx->last_fb_count) return SDZ_OK;
+    CK(cudaSetDevice(ctx->device));
+    for (int l = 0; l < sdz_ctx::N_LANES; l++) CK(cudaStreamSynchronize(ctx->lane_stream[l]));
+    unsigned long long fb = 0;
+    CK(cudaMemcpy(&fb, ctx->last_fb_count, sizeof fb, cudaMemcpyDeviceToHost));
+    out[0] = ctx->last_fast_n - fb;
+    out[1] = fb;
     return SDZ_OK;
 }
 
@@ -725,7 +840,10 @@ static int inflate_host(sdz_ctx* ctx, const sdz_in* in, uint64_t n, uint8_t* out
         bc.d_in_off += lo; bc.d_dict_off += lo; bc.d_out_off += lo; bc.d_in_len += lo; bc.d_dict_len += lo;
         bc.d_out_cap += lo; bc.d_dict_adler += lo; bc.d_mode += lo; bc.d_results += lo;
         bc.n = hi - lo;
-        rc = run_batch_device(ctx, &bc, sizes_only, c == 0, c == K - 1);
+        uint64_t tok_total = 0;                          // token arena of this sub-batch (the device computes the same sum)
+        if (!sizes_only && ctx->fast)
+            for (uint64_t i = lo; i < hi; i++) tok_total += sdz::token_cap(in_len[i], d_out_cap[i]);
+        rc = run_batch_device(ctx, &bc, sizes_only, c == 0, c == K - 1, tok_total);
         ctx->cur_lane = 0;
         if (rc) return rc;
         CK(cudaEventRecord(ctx->pipe_ev[2 * c + 1], lane_st));
