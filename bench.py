@@ -256,7 +256,7 @@ def main():
 
     def step():
         ctx.check(ctx.lib.sdz_inflate_batch_device(ctx.h, C.byref(b), 0, 1))
-        t = ctx.last_timing()
+        t = ctx.last_timing() + ctx.last_phase_timing()
         if world > 1:   # K8: gather the fixed-size records (never payload) to every rank
             parts = [torch.empty_like(d_res) for _ in range(world)]
             dist.all_gather(parts, d_res)
@@ -287,9 +287,12 @@ def main():
     torch.cuda.synchronize()
     t_wall0 = time.perf_counter()
     k_inf = k_fin = k_tot = 0.0
+    k_phase = [0.0] * 5
     for _ in range(args.steps):
         t = step()
         k_inf += t[0]; k_fin += t[1]; k_tot += t[2]
+        k_phase = [a + x for a, x in zip(k_phase, t[3:8])]
+    k_phase = [x / args.steps for x in k_phase]
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -390,6 +393,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "device_ms_per_step": round(dev_ms, 3),
+            "phase_ms": {"huff_tokens": round(k_phase[0], 3), "lz_resolve": round(k_phase[1], 3), "general_decoder": round(k_phase[2], 3),
+                         "finalize": round(k_phase[3], 3), "fast_path_streams": list(ctx.last_fast_stats())},
             "checksums": checks,
         }))
     if world > 1:

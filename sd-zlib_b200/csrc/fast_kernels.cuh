@@ -46,7 +46,16 @@ struct alignas(4) LaneSmem {
     uint16_t pad_[2];                  // 371 words: an odd stride spreads the 32 lanes' tables over the banks
 };
 static_assert(sizeof(LaneSmem) == 1484, "LaneSmem layout");
-constexpr int FA_WARP_SMEM = 32 * (int)sizeof(LaneSmem) + SCRATCH_U16 * 2;      // + build scratch of the warp
+// compressed input of the symbol loop: per lane a ring of FA_RING_CHUNKS x 16 bytes in shared memory, filled by 16-byte
+// cp.async (LDGSTS) several groups of symbols ahead of the reader.  A plain `nw = input[wp]` costs the whole warp one
+// global-memory round trip per ITERATION: the lanes take their next word in different iterations, but the register
+// scoreboard is per warp, so the consumer of iteration i waits for the load some other lane issued in iteration i - 1
+// (first version: 26 ms for the 65,536-stream batch, 12 cycles per issued instruction).  LDGSTS is tracked by
+// commit/wait groups instead, so the copies stay in flight across iterations.
+// Layout: chunk slot u of lane l at ((u * 32 + l) * 16) - one LDGSTS writes 16 contiguous bytes.
+constexpr int FA_RING_CHUNKS = 8;
+constexpr int FA_RING_BYTES = FA_RING_CHUNKS * 32 * 16;
+constexpr int FA_WARP_SMEM = 32 * (int)sizeof(LaneSmem) + SCRATCH_U16 * 2 + FA_RING_BYTES;      // tables | build scratch | input ring
 
 struct FastParams {
     InflateParams I;                   // the batch
@@ -175,6 +184,19 @@ __device__ __forceinline__ uint32_t bfe_u32(uint32_t v, uint32_t pos, uint32_t l
     asm("bfe.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(v), "r"(pos), "r"(len));
     return r;
 }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
+    return r;
+}
+// 16-byte asynchronous copy global -> shared (LDGSTS.128), predicated; L1 is bypassed (.cg): every byte is read once
+__device__ __forceinline__ void cp_async16_if(uint32_t dst_smem, const void* src_gmem, bool pred)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q cp.async.cg.shared.global [%0], [%1], 16;\n\t}" ::"r"(dst_smem),
+                 "l"(src_gmem), "r"((uint32_t)pred)
+                 : "memory");
+}
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
 {
     uint16_t r;
@@ -195,6 +217,7 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
     LaneSmem* const L = lanes + lane;
     uint16_t* const wscr = reinterpret_cast<uint16_t*>(smem_raw + 32 * sizeof(LaneSmem));     // sorted_l | sorted_d | lens | aux
     uint16_t* const my_sorted = P.sorted_l + ((size_t)blockIdx.x * 32 + lane) * SORTED_L;
+    const uint32_t ring_l = smem_addr(smem_raw + 32 * sizeof(LaneSmem) + SCRATCH_U16 * 2) + lane * 16u;    // my slot 0
 
     // ---- lane state
     int state = LS_FETCH;
@@ -208,6 +231,8 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
     int last = 0, eob_len = 0, lbits = 0, g_l = 0, g_d = 0;
     int nl = 0, nd = 0;
     bool fixed = false;
+    uint32_t ci = 0;                                                    // input ring: next 16-byte chunk to request
+    bool fresh = false;                                                 // the ring has to be (re)filled at the reader's position
 
     auto refill = [&]() {
         if (bc <= 32) {
@@ -423,7 +448,7 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                 __syncwarp();
                 if ((int)lane == who) {
                     if (TI.msg != SDZ_MSG_NONE) state = LS_HANDOVER;    // the general decoder reproduces the message
-                    else { lbits = TI.lbits; g_l = TI.g_l; g_d = TI.g_d; state = LS_CODES; }
+                    else { lbits = TI.lbits; g_l = TI.g_l; g_d = TI.g_d; state = LS_CODES; fresh = true; }
                 }
             }
         }
@@ -441,6 +466,19 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
             const bool live = state == LS_CODES;
             const uint32_t a_l = smem_addr(L->lut_l), a_d = smem_addr(L->lut_d);
             int ev = 0;                                                 // 1: end of block, 2: hand the stream over
+            // lanes that come from a block header: the ring takes over at word wp + 1 (nw already holds word wp)
+            {
+                const bool fill = live && fresh;
+                if (fill) ci = (wp + 1u) >> 2;
+                #pragma unroll
+                for (int k = 0; k < FA_RING_CHUNKS; k++) {
+                    cp_async16_if(ring_l + ((ci & (FA_RING_CHUNKS - 1u)) << 9), reinterpret_cast<const uint8_t*>(wbase) + (size_t)ci * 16u, fill);
+                    ci += fill ? 1u : 0u;
+                }
+                cp_async_commit();
+                cp_async_wait_all();
+                fresh = false;
+            }
             for (;;) {
                 uint32_t tk[4] = { 0u, 0u, 0u, 0u };
                 bool early = false;                                     // a distance reached before the start of the output
@@ -452,7 +490,8 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                         asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(bb) : "r"(nw), "r"(pw));     // bits above bc are zero: add == or
                         bc += take ? 32 : 0;
                         wp += take ? 1u : 0u;
-                        if (take) nw = __ldg(wbase + wp);
+                        const uint32_t w = lds_u32(ring_l + ((wp & (4u * FA_RING_CHUNKS - 4u)) << 7) + ((wp & 3u) << 2));
+                        nw = take ? w : nw;
                     }
                     const uint32_t lo = (uint32_t)bb;
                     uint32_t e = lds_u16(a_l + (lo & ((1u << FA_RL) - 1u)) * 2u);
@@ -485,7 +524,7 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                     const uint32_t n = e >> 12;
                     const bool ismatch = (e & 0x800u) != 0u;
                     const uint32_t xb = (e >> 8) & 7u;                  // 0 for a literal
-                    const uint32_t c1 = n + xb;
+                    uint32_t c1 = n + xb;
                     const uint32_t lenf = (e & 0xffu) + ((lo >> n) & ((1u << xb) - 1u));     // length - 3 (literal: the byte)
                     const uint32_t len = ismatch ? lenf + 3u : 1u;
                     // ---- distance: the root lookup needs 7 of the >= 12 bits that are left
@@ -494,12 +533,13 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                     if (__any_sync(FULL, live && ismatch && (de < 0x1000u || bc < (int)c1 + 20))) {
                         // rare: the buffer may not cover code + extra bits, code longer than the root, invalid code
                         if (live && ismatch) {
+                            bb >>= c1; bc -= (int)c1; c1 = 0u;          // (the literal/length bits leave the buffer now)
                             if (bc < 32) {
                                 bb |= (uint64_t)nw << bc;
                                 bc += 32; wp++;
-                                nw = __ldg(wbase + wp);
-                                lo2 = (uint32_t)(bb >> c1);
+                                nw = lds_u32(ring_l + ((wp & (4u * FA_RING_CHUNKS - 4u)) << 7) + ((wp & 3u) << 2));
                             }
+                            lo2 = (uint32_t)bb;
                             if (de < 0x1000u) {
                                 const uint32_t r = (de == E_LONG && g_d > FA_RD) ? canon_long(L->cnt_d, L->sorted_d, FA_RD, g_d, L->start + 2, lo2) : 0u;
                                 const uint32_t ds = r & 0xffffu;
@@ -518,6 +558,18 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                     pos += len;
                     tk[u] = ismatch ? dm1 * 512u + len : (TOK_LIT | lenf);
                 }
+                // input ring: request the chunks whose slots have been read completely (the reader holds word wp in a
+                // register: chunk ci - FA_RING_CHUNKS is free once wp has reached its last word).  A group of four symbols
+                // takes at most six words, so two requests keep up; a chunk is requested >= 4.5 groups before its first
+                // word is read, and wait_group 3 has completed it by then.
+                #pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    const bool need = live && 4u * ci <= wp + (4u * FA_RING_CHUNKS - 3u);
+                    cp_async16_if(ring_l + ((ci & (FA_RING_CHUNKS - 1u)) << 9), reinterpret_cast<const uint8_t*>(wbase) + (size_t)ci * 16u, need);
+                    ci += need ? 1u : 0u;
+                }
+                cp_async_commit();
+                asm volatile("cp.async.wait_group 3;" ::: "memory");
                 if (live) {
                     // (after an early exit the unprocessed slots of the group are still no-ops)
                     if (early || pos > cap || wp > lim_wp + 1u || ntok + 4u > cap_tok) ev = 2;
