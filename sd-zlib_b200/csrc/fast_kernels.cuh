@@ -607,12 +607,14 @@ __global__ void __launch_bounds__(256) lz_resolve_kernel(FastParams P)
         idx = __shfl_sync(FULL, idx, 0);
         if (idx >= P.I.n) break;
         const uint32_t nt = P.ntok[idx];
-        if (nt == NTOK_HANDED_OVER) continue;
+        if (nt == NTOK_HANDED_OVER || nt == 0u) continue;
         const uint32_t* tk = P.tokens + P.tok_off[idx];
-        uint8_t* out = P.I.out + P.I.out_off[idx];
-        uint32_t P0 = 0;                                               // output bytes of the batches before this one
+        uint8_t* const out = P.I.out + P.I.out_off[idx];
+        uint32_t ab = lane;                                            // my byte of the current row, as an offset into the stream's output
+        uint32_t tnext = lane < nt ? ld_stream_u32(tk + lane) : 0u;    // (the next batch's tokens are requested one batch ahead)
         for (uint32_t base = 0; base < nt; base += 32) {
-            uint32_t t = base + lane < nt ? ld_stream_u32(tk + base + lane) : 0u;
+            uint32_t t = tnext;
+            tnext = base + 32u + lane < nt ? ld_stream_u32(tk + base + 32u + lane) : 0u;
             {
                 // no-op tokens (end of a block inside a group of four) are squeezed out: the row loop indexes tokens
                 const uint32_t nz = __ballot_sync(FULL, t != 0u);
@@ -626,28 +628,28 @@ __global__ void __launch_bounds__(256) lz_resolve_kernel(FastParams P)
             const uint32_t len = lit ? 1u : (t & 511u);
             uint32_t incl = len;
             #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, d); if (lane >= (uint32_t)d) incl += v; }
-            const uint32_t S = incl - len;                             // first byte of my token, relative to P0
-            const uint32_t N = __shfl_sync(FULL, incl, 31);
-            uint32_t nxt = 0;                                          // tokens that started in earlier rows
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, d); incl += lane >= (uint32_t)d ? v : 0u; }
+            const uint32_t N = __shfl_sync(FULL, incl, 31);            // bytes of this batch
+            // what a byte needs to know about its token: a literal keeps its (negative) word, a match becomes its distance
+            const uint32_t tinfo = lit ? t : (t >> 9) + 1u;
+            uint32_t first = len ? incl - len : 0xffffffffu;           // row-relative position of my token's first byte
+            const uint32_t ab_end = ab - lane + N;                     // end of the batch
+            uint32_t row0 = ab - lane;                                 // first byte of the row (uniform)
+            uint32_t nxt = 0xffffffffu;                                // (tokens that started in earlier rows) - 1
             for (uint32_t R = 0; R < N; R += 32) {
-                const uint32_t rel = S - R;
-                const uint32_t bit = (len != 0u && rel < 32u) ? (1u << rel) : 0u;
-                const uint32_t m = __reduce_or_sync(FULL, bit);       // bit b: a token starts at byte R + b
-                const uint32_t k = __popc(m & le_mask);
-                const uint32_t tt = __shfl_sync(FULL, t, (nxt + k - 1u) & 31u);   // k == 0: the token that began in an earlier row
+                const uint32_t m = __reduce_or_sync(FULL, shl_clamp(1u, first));       // bit b: a token starts at byte b of this row
+                const uint32_t ti = nxt + __popc(m & le_mask);          // no start at or before my byte: the token that began in an earlier row
+                const uint32_t tt = __shfl_sync(FULL, tinfo, ti);
                 nxt += __popc(m);
-                const uint32_t b = R + lane;
-                const bool valid = b < N;
-                const bool tlit = (int32_t)tt < 0;
-                const uint32_t td = ((tt >> 9) & 0x7fffu) + 1u;
-                const int32_t srel = (int32_t)b - (int32_t)td;          // source, relative to P0 (phase A guarantees P0 + srel >= 0)
-                const bool inrow = valid && !tlit && srel >= (int32_t)R;
+                const bool valid = ab < ab_end;
+                const bool tmatch = (int32_t)tt >= 0;
+                const uint32_t so = ab - tt;                            // source byte (phase A guarantees dist <= position)
+                const bool inrow = valid && tmatch && so >= row0;
                 uint32_t v = tt & 0xffu;
-                if (valid && !tlit && !inrow) v = out[(int64_t)P0 + (int64_t)srel];
+                if (valid && tmatch && so < row0) v = out[so];
                 if (__any_sync(FULL, inrow)) {
                     // sources inside this row: pointer jumping over the lanes (depth <= 31: five doublings)
-                    uint32_t q = inrow ? (uint32_t)(srel - (int32_t)R) : lane;
+                    uint32_t q = inrow ? so - row0 : lane;
                     for (int r = 0; r < 6; r++) {
                         const uint32_t vv = __shfl_sync(FULL, v, q), qq = __shfl_sync(FULL, q, q);
                         const bool moved = __any_sync(FULL, qq != q);
@@ -655,10 +657,11 @@ __global__ void __launch_bounds__(256) lz_resolve_kernel(FastParams P)
                         if (!moved) break;
                     }
                 }
-                if (valid) out[P0 + b] = (uint8_t)v;
+                if (valid) out[ab] = (uint8_t)v;
                 __syncwarp();
+                first -= 32u; ab += 32u; row0 += 32u;
             }
-            P0 += N;
+            ab = ab_end + lane;
         }
     }
 }

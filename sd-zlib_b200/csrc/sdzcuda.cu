@@ -59,7 +59,7 @@ struct sdz_ctx {
     // two-phase fast path (fast_kernels.cuh): per compute lane the token arena, the per-stream arrays
     // (counters | tok_off | ntok | hand-over list) and the sorted-symbol scratch of phase A
     bool fast = true;                  // SDZ_FAST=0: every stream goes through the general decoder
-    int b_blocks_per_sm = 4;           // phase B: 256-thread blocks per SM (SDZ_B_BLOCKS)
+    int b_blocks_per_sm = 8;           // phase B: 256-thread blocks per SM (SDZ_B_BLOCKS)
     DevBuf fast_tok[N_LANES], fast_meta[N_LANES], fast_sorted[N_LANES];
     cudaEvent_t ev_fast[4] = { nullptr, nullptr, nullptr, nullptr };   // before A, after A, after B, after the hand-over run
     bool fast_timed = false;
