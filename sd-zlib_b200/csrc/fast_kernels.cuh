@@ -64,8 +64,9 @@ struct FastParams {
     uint32_t* ntok;                    // tokens written per stream (multiple of 4), or NTOK_HANDED_OVER
     uint32_t* fb_list;                 // streams handed to the general decoder
     unsigned long long* fb_count;
-    unsigned long long* counter_a;
+    unsigned long long* counter_a;     // work counters of THIS launch: the launch covers streams [first, first + count)
     unsigned long long* counter_b;
+    uint32_t first, count;
     uint16_t* sorted_l;                // 288 u16 per lane of the phase-A grid
 };
 
@@ -310,8 +311,9 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                 state = LS_FETCH;
             }
             // LS_FETCH
-            const unsigned long long i = atomicAdd(P.counter_a, 1ull);
-            if (i >= P.I.n) {
+            unsigned long long i = atomicAdd(P.counter_a, 1ull);
+            if (i < P.count) i += P.first;
+            else {
                 // out of streams: the lane idles through the lockstep loop on zeroed tables (every lookup is a "literal"
                 // of zero bits) with a full bit buffer, so it never loads and never consumes
                 state = LS_DONE; lim_wp = 0xfffffff0u; wp = 0; nw = 0; bb = 0; bc = 64;
@@ -605,7 +607,8 @@ __global__ void __launch_bounds__(256) lz_resolve_kernel(FastParams P)
         unsigned long long idx = 0;
         if (lane == 0) idx = atomicAdd(P.counter_b, 1ull);
         idx = __shfl_sync(FULL, idx, 0);
-        if (idx >= P.I.n) break;
+        if (idx >= P.count) break;
+        idx += P.first;
         const uint32_t nt = P.ntok[idx];
         if (nt == NTOK_HANDED_OVER || nt == 0u) continue;
         const uint32_t* tk = P.tokens + P.tok_off[idx];

@@ -60,6 +60,10 @@ struct sdz_ctx {
     // (counters | tok_off | ntok | hand-over list) and the sorted-symbol scratch of phase A
     bool fast = true;                  // SDZ_FAST=0: every stream goes through the general decoder
     int b_blocks_per_sm = 8;           // phase B: 256-thread blocks per SM (SDZ_B_BLOCKS)
+    static constexpr int MAX_FAST_CHUNKS = 15;
+    int fast_chunks = 8;               // chunks of the phase A / phase B pipeline (SDZ_FAST_CHUNKS)
+    cudaStream_t fast_sb[N_LANES] = { nullptr, nullptr, nullptr };     // phase B streams
+    cudaEvent_t fast_ev[N_LANES][MAX_FAST_CHUNKS + 1] = {};
     DevBuf fast_tok[N_LANES], fast_meta[N_LANES], fast_sorted[N_LANES];
     cudaEvent_t ev_fast[4] = { nullptr, nullptr, nullptr, nullptr };   // before A, after A, after B, after the hand-over run
     bool fast_timed = false;
@@ -221,12 +225,12 @@ int launch_fast(sdz_ctx* ctx, const sdz::InflateParams& P, uint64_t tok_total, b
     const int lane = ctx->cur_lane;
     cudaStream_t st = ctx->lane_stream[lane];
     int rc;
-    const size_t off_tokoff = 64, off_ntok = off_tokoff + (n + 1) * 8, off_list = off_ntok + align_up(n * 4, 8);
+    const size_t off_tokoff = 256, off_ntok = off_tokoff + (n + 1) * 8, off_list = off_ntok + align_up(n * 4, 8);
     if ((rc = grow(ctx, ctx->fast_meta[lane], off_list + n * 4))) return rc;
     uint8_t* fm = (uint8_t*)ctx->fast_meta[lane].p;
     unsigned long long* counters = (unsigned long long*)fm;
     uint64_t* tok_off = (uint64_t*)(fm + off_tokoff);
-    CK(cudaMemsetAsync(counters, 0, 64, st));
+    CK(cudaMemsetAsync(counters, 0, 256, st));
     sdz::token_offsets_kernel<<<1, 1024, 0, st>>>(P.in_len, P.out_cap, n, tok_off);
     ctx->launches++;
     if (!tok_total) {
@@ -250,15 +254,31 @@ int launch_fast(sdz_ctx* ctx, const sdz::InflateParams& P, uint64_t tok_total, b
     F.tok_off = tok_off;
     F.ntok = (uint32_t*)(fm + off_ntok);
     F.fb_list = (uint32_t*)(fm + off_list);
-    F.counter_a = counters; F.counter_b = counters + 1; F.fb_count = counters + 2;
+    F.fb_count = counters;
     F.sorted_l = (uint16_t*)ctx->fast_sorted[lane].p;
+    // The batch is cut into chunks: phase A of chunk c + 1 (latency-bound, one warp per scheduler, all of the shared
+    // memory) runs next to phase B of chunk c (issue-bound, no shared memory) on a second stream, so the two kernels
+    // fill each other's idle issue slots on the same SMs.
+    const unsigned n_chunks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->fast_chunks, n / 2048));
+    cudaStream_t sb = ctx->fast_sb[lane];
     if (timed) CK(cudaEventRecord(ctx->ev_fast[0], st));
-    kern<<<grid_a, 32, smem, st>>>(F);
+    for (unsigned c = 0; c < n_chunks; c++) {
+        const uint64_t lo = n * c / n_chunks, hi = n * (c + 1) / n_chunks;
+        if (lo == hi) continue;
+        F.first = (uint32_t)lo; F.count = (uint32_t)(hi - lo);
+        F.counter_a = counters + 1 + 2 * c; F.counter_b = counters + 2 + 2 * c;
+        const unsigned ga = (unsigned)std::min<uint64_t>((hi - lo + 31) / 32, grid_a);
+        kern<<<ga, 32, smem, st>>>(F);
+        CK(cudaEventRecord(ctx->fast_ev[lane][c], st));
+        CK(cudaStreamWaitEvent(sb, ctx->fast_ev[lane][c], 0));
+        const unsigned gb = (unsigned)std::min<uint64_t>((hi - lo + 7) / 8, (uint64_t)ctx->sm_count * ctx->b_blocks_per_sm);
+        sdz::lz_resolve_kernel<<<gb, 256, 0, sb>>>(F);
+        ctx->launches += 2;
+    }
     if (timed) CK(cudaEventRecord(ctx->ev_fast[1], st));
-    const unsigned grid_b = (unsigned)std::min<uint64_t>((n + 7) / 8, (uint64_t)ctx->sm_count * ctx->b_blocks_per_sm);
-    sdz::lz_resolve_kernel<<<grid_b, 256, 0, st>>>(F);
+    CK(cudaEventRecord(ctx->fast_ev[lane][sdz_ctx::MAX_FAST_CHUNKS], sb));
+    CK(cudaStreamWaitEvent(st, ctx->fast_ev[lane][sdz_ctx::MAX_FAST_CHUNKS], 0));
     if (timed) CK(cudaEventRecord(ctx->ev_fast[2], st));
-    ctx->launches += 2;
     CK(cudaGetLastError());
     // hand-over run: the general decoder over the list (its length is only known on the device)
     sdz::InflateParams Q = P;
@@ -351,6 +371,12 @@ int sdz_ctx_create(int device, uint32_t flags, sdz_ctx** out)
         if (cudaEventCreate(&e) != cudaSuccess) return fail(SDZ_E_CUDA);
     if (const char* f = getenv("SDZ_FAST")) ctx->fast = atoi(f) != 0;
     if (const char* f = getenv("SDZ_B_BLOCKS")) { int v = atoi(f); if (v >= 1 && v <= 8) ctx->b_blocks_per_sm = v; }
+    if (const char* f = getenv("SDZ_FAST_CHUNKS")) { int v = atoi(f); if (v >= 1 && v <= sdz_ctx::MAX_FAST_CHUNKS) ctx->fast_chunks = v; }
+    for (int l = 0; l < sdz_ctx::N_LANES; l++) {
+        if (cudaStreamCreateWithFlags(&ctx->fast_sb[l], cudaStreamNonBlocking) != cudaSuccess) return fail(SDZ_E_CUDA);
+        for (auto& e : ctx->fast_ev[l])
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail(SDZ_E_CUDA);
+    }
     if (cudaMalloc(&ctx->d_counter, (4 + 2 * sdz_ctx::N_LANES) * sizeof(unsigned long long)) != cudaSuccess) return fail(SDZ_E_NOMEM);
     ctx->lane_stream[0] = ctx->stream;
     for (int l = 1; l < sdz_ctx::N_LANES; l++)
@@ -382,6 +408,11 @@ void sdz_ctx_destroy(sdz_ctx* ctx)
             if (b->p) cudaFree(b->p);
     for (auto& e : ctx->ev_fast)
         if (e) cudaEventDestroy(e);
+    for (int l = 0; l < sdz_ctx::N_LANES; l++) {
+        if (ctx->fast_sb[l]) { cudaStreamSynchronize(ctx->fast_sb[l]); cudaStreamDestroy(ctx->fast_sb[l]); }
+        for (auto& e : ctx->fast_ev[l])
+            if (e) cudaEventDestroy(e);
+    }
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->h_res) cudaFreeHost(ctx->h_res);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
