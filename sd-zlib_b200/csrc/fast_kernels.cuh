@@ -52,9 +52,12 @@ static_assert(sizeof(LaneSmem) == 1484, "LaneSmem layout");
 // scoreboard is per warp, so the consumer of iteration i waits for the load some other lane issued in iteration i - 1
 // (first version: 26 ms for the 65,536-stream batch, 12 cycles per issued instruction).  LDGSTS is tracked by
 // commit/wait groups instead, so the copies stay in flight across iterations.
-// Layout: chunk slot u of lane l at ((u * 32 + l) * 16) - one LDGSTS writes 16 contiguous bytes.
+// Layout: lane l owns FA_RING_CHUNKS * 16 contiguous bytes at l * FA_RING_STRIDE (word w of the stream sits at
+// (w mod 32) * 4: one AND + one multiply-add per read); the 16 bytes of padding per lane keep the stride a multiple
+// of 16 (LDGSTS.128 alignment) and spread lanes over the banks (4-way conflict when all lanes read the same slot).
 constexpr int FA_RING_CHUNKS = 8;
-constexpr int FA_RING_BYTES = FA_RING_CHUNKS * 32 * 16;
+constexpr int FA_RING_STRIDE = FA_RING_CHUNKS * 16 + 16;
+constexpr int FA_RING_BYTES = 32 * FA_RING_STRIDE;
 constexpr int FA_WARP_SMEM = 32 * (int)sizeof(LaneSmem) + SCRATCH_U16 * 2 + FA_RING_BYTES;      // tables | build scratch | input ring
 
 struct FastParams {
@@ -218,7 +221,7 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
     LaneSmem* const L = lanes + lane;
     uint16_t* const wscr = reinterpret_cast<uint16_t*>(smem_raw + 32 * sizeof(LaneSmem));     // sorted_l | sorted_d | lens | aux
     uint16_t* const my_sorted = P.sorted_l + ((size_t)blockIdx.x * 32 + lane) * SORTED_L;
-    const uint32_t ring_l = smem_addr(smem_raw + 32 * sizeof(LaneSmem) + SCRATCH_U16 * 2) + lane * 16u;    // my slot 0
+    const uint32_t ring_l = smem_addr(smem_raw + 32 * sizeof(LaneSmem) + SCRATCH_U16 * 2) + lane * (uint32_t)FA_RING_STRIDE;
 
     // ---- lane state
     int state = LS_FETCH;
@@ -474,7 +477,7 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                 if (fill) ci = (wp + 1u) >> 2;
                 #pragma unroll
                 for (int k = 0; k < FA_RING_CHUNKS; k++) {
-                    cp_async16_if(ring_l + ((ci & (FA_RING_CHUNKS - 1u)) << 9), reinterpret_cast<const uint8_t*>(wbase) + (size_t)ci * 16u, fill);
+                    cp_async16_if(ring_l + ((ci & (FA_RING_CHUNKS - 1u)) << 4), reinterpret_cast<const uint8_t*>(wbase) + (size_t)ci * 16u, fill);
                     ci += fill ? 1u : 0u;
                 }
                 cp_async_commit();
@@ -483,20 +486,33 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
             }
             for (;;) {
                 uint32_t tk[4] = { 0u, 0u, 0u, 0u };
-                bool early = false;                                     // a distance reached before the start of the output
+                uint32_t early = 0u;                                    // a distance reached before the start of the output
                 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    {   // top-up: at least 32 valid bits (lanes without a stream sit at bc = 64)
-                        const bool take = bc < 32;
-                        const uint32_t pw = take ? shl_clamp(1u, (uint32_t)bc) : 0u;
-                        asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(bb) : "r"(nw), "r"(pw));     // bits above bc are zero: add == or
-                        bc += take ? 32 : 0;
-                        wp += take ? 1u : 0u;
-                        const uint32_t w = lds_u32(ring_l + ((wp & (4u * FA_RING_CHUNKS - 4u)) << 7) + ((wp & 3u) << 2));
-                        nw = take ? w : nw;
-                    }
-                    const uint32_t lo = (uint32_t)bb;
-                    uint32_t e = lds_u16(a_l + (lo & ((1u << FA_RL) - 1u)) * 2u);
+                    // The straight-line part of the iteration is written as three PTX blocks (predicated instructions
+                    // instead of the select / move chains the compiler makes of the C++ form: 105 -> ~65 instructions per
+                    // symbol); the rare paths between them stay C++.
+                    uint32_t lo, e;
+                    // ---- (1) top-up to at least 32 valid bits (lanes without a stream sit at bc = 64), literal/length lookup
+                    asm volatile("{\n\t"
+                        ".reg .pred pt;\n\t"
+                        ".reg .b32 pw, ra, t;\n\t"
+                        "setp.lt.s32 pt, %1, 32;\n\t"
+                        "mov.b32 pw, 0;\n\t"
+                        "@pt shl.b32 pw, 1, %1;\n\t"
+                        "mad.wide.u32 %0, %3, pw, %0;\n\t"              // bits above bc are zero: add == or
+                        "@pt add.s32 %1, %1, 32;\n\t"
+                        "@pt add.u32 %2, %2, 1;\n\t"
+                        "and.b32 t, %2, 31;\n\t"
+                        "mad.lo.u32 ra, t, 4, %6;\n\t"
+                        "@pt ld.shared.u32 %3, [ra];\n\t"
+                        "cvt.u32.u64 %4, %0;\n\t"
+                        "and.b32 t, %4, 511;\n\t"
+                        "mad.lo.u32 ra, t, 2, %7;\n\t"
+                        "ld.shared.u16 %5, [ra];\n\t"
+                        "}"
+                        : "+l"(bb), "+r"(bc), "+r"(wp), "+r"(nw), "=r"(lo), "=r"(e)
+                        : "r"(ring_l), "r"(a_l));
                     if (__any_sync(FULL, live && e < 0x1000u)) {
                         // rare: code longer than the root, end of block, invalid code
                         if (live && e < 0x1000u) {
@@ -522,43 +538,87 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                         }
                         if (__any_sync(FULL, ev != 0)) break;           // (lanes without an event have consumed nothing of symbol u)
                     }
+                    // ---- (2) literal/length fields, root lookup of the distance (it needs 7 of the >= 12 bits that are left)
                     // (lanes without a stream read zeroed tables: a "literal" of zero bits)
-                    const uint32_t n = e >> 12;
-                    const bool ismatch = (e & 0x800u) != 0u;
-                    const uint32_t xb = (e >> 8) & 7u;                  // 0 for a literal
-                    uint32_t c1 = n + xb;
-                    const uint32_t lenf = (e & 0xffu) + ((lo >> n) & ((1u << xb) - 1u));     // length - 3 (literal: the byte)
-                    const uint32_t len = ismatch ? lenf + 3u : 1u;
-                    // ---- distance: the root lookup needs 7 of the >= 12 bits that are left
-                    uint32_t lo2 = (uint32_t)(bb >> c1);
-                    uint32_t de = lds_u16(a_d + (lo2 & ((1u << FA_RD) - 1u)) * 2u);
-                    if (__any_sync(FULL, live && ismatch && (de < 0x1000u || bc < (int)c1 + 20))) {
-                        // rare: the buffer may not cover code + extra bits, code longer than the root, invalid code
-                        if (live && ismatch) {
+                    uint32_t c1, lenf, len, ism, lo2, de, need, dn, dx;
+                    asm volatile("{\n\t"
+                        ".reg .pred pm, p1, p2;\n\t"
+                        ".reg .b32 n, xb, t, b, ra, c2, rem;\n\t"
+                        ".reg .b64 w;\n\t"
+                        "shr.u32 n, %9, 12;\n\t"
+                        "bfe.u32 xb, %9, 8, 3;\n\t"                     // 0 for a literal
+                        "add.u32 %0, n, xb;\n\t"
+                        "shr.u32 t, %10, n;\n\t"
+                        "shl.b32 b, 0xffffffff, xb;\n\t"
+                        "lop3.b32 t, t, b, 0, 0x30;\n\t"             // t & ~b: the extra bits
+                        "and.b32 b, %9, 255;\n\t"
+                        "add.u32 %1, b, t;\n\t"                         // length - 3 (literal: the byte)
+                        "and.b32 t, %9, 2048;\n\t"
+                        "setp.ne.u32 pm, t, 0;\n\t"
+                        "add.u32 t, %1, 3;\n\t"
+                        "selp.u32 %2, t, 1, pm;\n\t"
+                        "selp.u32 %3, 1, 0, pm;\n\t"
+                        "shr.u64 w, %11, %0;\n\t"
+                        "cvt.u32.u64 %4, w;\n\t"
+                        "and.b32 t, %4, 127;\n\t"
+                        "mad.lo.u32 ra, t, 2, %13;\n\t"
+                        "ld.shared.u16 %5, [ra];\n\t"
+                        "shr.u32 %7, %5, 12;\n\t"
+                        "bfe.u32 %8, %5, 8, 4;\n\t"
+                        "add.u32 c2, %7, %8;\n\t"
+                        "sub.s32 rem, %12, %0;\n\t"
+                        "setp.lt.s32 p1, rem, c2;\n\t"                  // the buffer does not cover code + extra bits
+                        "setp.lt.u32 p2, %5, 4096;\n\t"                 // code longer than the root, invalid code
+                        "or.pred p1, p1, p2;\n\t"
+                        "and.pred p1, p1, pm;\n\t"
+                        "setp.ne.and.u32 p1, %14, 0, p1;\n\t"
+                        "selp.u32 %6, 1, 0, p1;\n\t"
+                        "}"
+                        : "=r"(c1), "=r"(lenf), "=r"(len), "=r"(ism), "=r"(lo2), "=r"(de), "=r"(need), "=r"(dn), "=r"(dx)
+                        : "r"(e), "r"(lo), "l"(bb), "r"(bc), "r"(a_d), "r"((uint32_t)live));
+                    if (__any_sync(FULL, need != 0u)) {
+                        if (need) {
                             bb >>= c1; bc -= (int)c1; c1 = 0u;          // (the literal/length bits leave the buffer now)
                             if (bc < 32) {
                                 bb |= (uint64_t)nw << bc;
                                 bc += 32; wp++;
-                                nw = lds_u32(ring_l + ((wp & (4u * FA_RING_CHUNKS - 4u)) << 7) + ((wp & 3u) << 2));
+                                nw = lds_u32(ring_l + ((wp & 31u) << 2));
                             }
                             lo2 = (uint32_t)bb;
                             if (de < 0x1000u) {
                                 const uint32_t r = (de == E_LONG && g_d > FA_RD) ? canon_long(L->cnt_d, L->sorted_d, FA_RD, g_d, L->start + 2, lo2) : 0u;
                                 const uint32_t ds = r & 0xffffu;
-                                if (r == 0u || ds > 29u) { early = true; de = 0x1000u; }     // invalid distance code: hand over
+                                if (r == 0u || ds > 29u) { early = 1u; de = 0x1000u; }     // invalid distance code: hand over
                                 else de = ((r >> 16) << 12) | ((ds < 4 ? 0u : (ds >> 1) - 1u) << 8) | (ds < 4 ? ds : 2u + (ds & 1u));
+                                dn = de >> 12; dx = (de >> 8) & 15u;
                             }
                         }
                     }
-                    const uint32_t dn = de >> 12, dx = (de >> 8) & 15u;
-                    const uint32_t dm1 = ((de & 3u) << dx) + ((lo2 >> dn) & ((1u << dx) - 1u));   // distance - 1
-                    {
-                        const uint32_t c = c1 + (ismatch ? dn + dx : 0u);       // <= 48
-                        bb >>= c; bc -= (int)c;
-                    }
-                    early = early || (ismatch && dm1 >= pos);           // the general decoder's
-                    pos += len;
-                    tk[u] = ismatch ? dm1 * 512u + len : (TOK_LIT | lenf);
+                    // ---- (3) distance, consumption, token
+                    asm volatile("{\n\t"
+                        ".reg .pred pm, pe;\n\t"
+                        ".reg .b32 c2, t, m, dm1, c, tl;\n\t"
+                        "setp.ne.u32 pm, %6, 0;\n\t"
+                        "add.u32 c2, %11, %12;\n\t"
+                        "shr.u32 t, %7, %11;\n\t"
+                        "shl.b32 m, 0xffffffff, %12;\n\t"
+                        "lop3.b32 t, t, m, 0, 0x30;\n\t"
+                        "and.b32 m, %5, 3;\n\t"
+                        "shl.b32 m, m, %12;\n\t"
+                        "add.u32 dm1, m, t;\n\t"                        // distance - 1
+                        "selp.u32 c2, c2, 0, pm;\n\t"
+                        "add.u32 c, c2, %8;\n\t"                        // <= 48
+                        "shr.u64 %0, %0, c;\n\t"
+                        "sub.s32 %1, %1, c;\n\t"
+                        "setp.ge.and.u32 pe, dm1, %2, pm;\n\t"          // the general decoder's
+                        "@pe mov.b32 %3, 1;\n\t"
+                        "add.u32 %2, %2, %10;\n\t"
+                        "mad.lo.u32 t, dm1, 512, %10;\n\t"
+                        "or.b32 tl, %9, 0x80000000;\n\t"
+                        "selp.u32 %4, t, tl, pm;\n\t"
+                        "}"
+                        : "+l"(bb), "+r"(bc), "+r"(pos), "+r"(early), "=r"(tk[u])
+                        : "r"(de), "r"(ism), "r"(lo2), "r"(c1), "r"(lenf), "r"(len), "r"(dn), "r"(dx));
                 }
                 // input ring: request the chunks whose slots have been read completely (the reader holds word wp in a
                 // register: chunk ci - FA_RING_CHUNKS is free once wp has reached its last word).  A group of four symbols
@@ -567,14 +627,14 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                 #pragma unroll
                 for (int k = 0; k < 2; k++) {
                     const bool need = live && 4u * ci <= wp + (4u * FA_RING_CHUNKS - 3u);
-                    cp_async16_if(ring_l + ((ci & (FA_RING_CHUNKS - 1u)) << 9), reinterpret_cast<const uint8_t*>(wbase) + (size_t)ci * 16u, need);
+                    cp_async16_if(ring_l + ((ci & (FA_RING_CHUNKS - 1u)) << 4), reinterpret_cast<const uint8_t*>(wbase) + (size_t)ci * 16u, need);
                     ci += need ? 1u : 0u;
                 }
                 cp_async_commit();
                 asm volatile("cp.async.wait_group 3;" ::: "memory");
                 if (live) {
                     // (after an early exit the unprocessed slots of the group are still no-ops)
-                    if (early || pos > cap || wp > lim_wp + 1u || ntok + 4u > cap_tok) ev = 2;
+                    if (early != 0u || pos > cap || wp > lim_wp + 1u || ntok + 4u > cap_tok) ev = 2;
                     else {
                         *reinterpret_cast<uint4*>(tokp + ntok) = make_uint4(tk[0], tk[1], tk[2], tk[3]);
                         ntok += 4u;

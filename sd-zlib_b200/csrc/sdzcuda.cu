@@ -61,7 +61,7 @@ struct sdz_ctx {
     bool fast = true;                  // SDZ_FAST=0: every stream goes through the general decoder
     int b_blocks_per_sm = 8;           // phase B: 256-thread blocks per SM (SDZ_B_BLOCKS)
     static constexpr int MAX_FAST_CHUNKS = 15;
-    int fast_chunks = 8;               // chunks of the phase A / phase B pipeline (SDZ_FAST_CHUNKS)
+    int fast_chunks = 0;               // chunks of the phase A / phase B pipeline (SDZ_FAST_CHUNKS; 0 = one per wave of phase A)
     cudaStream_t fast_sb[N_LANES] = { nullptr, nullptr, nullptr };     // phase B streams
     cudaEvent_t fast_ev[N_LANES][MAX_FAST_CHUNKS + 1] = {};
     DevBuf fast_tok[N_LANES], fast_meta[N_LANES], fast_sorted[N_LANES];
@@ -259,7 +259,13 @@ int launch_fast(sdz_ctx* ctx, const sdz::InflateParams& P, uint64_t tok_total, b
     // The batch is cut into chunks: phase A of chunk c + 1 (latency-bound, one warp per scheduler, all of the shared
     // memory) runs next to phase B of chunk c (issue-bound, no shared memory) on a second stream, so the two kernels
     // fill each other's idle issue slots on the same SMs.
-    const unsigned n_chunks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->fast_chunks, n / 2048));
+    // A chunk is at most ONE wave of phase A (every lane of the grid gets one stream): phase A's time per launch is
+    // the time of its slowest lane, so a chunk that gives some lanes a second stream takes twice as long, and a chunk
+    // much smaller than a wave leaves lanes idle for the whole launch (measured: 4 chunks 25.4 ms, 8 chunks 43.7 ms).
+    const uint64_t wave = (uint64_t)grid_a * 32;
+    unsigned n_chunks = (unsigned)std::min<uint64_t>((n + wave - 1) / wave, sdz_ctx::MAX_FAST_CHUNKS);
+    if (ctx->fast_chunks > 0) n_chunks = (unsigned)std::min<uint64_t>((uint64_t)ctx->fast_chunks, std::max<uint64_t>(1, n / 2048));
+    if (n_chunks < 1) n_chunks = 1;
     cudaStream_t sb = ctx->fast_sb[lane];
     if (timed) CK(cudaEventRecord(ctx->ev_fast[0], st));
     for (unsigned c = 0; c < n_chunks; c++) {
@@ -371,7 +377,7 @@ int sdz_ctx_create(int device, uint32_t flags, sdz_ctx** out)
         if (cudaEventCreate(&e) != cudaSuccess) return fail(SDZ_E_CUDA);
     if (const char* f = getenv("SDZ_FAST")) ctx->fast = atoi(f) != 0;
     if (const char* f = getenv("SDZ_B_BLOCKS")) { int v = atoi(f); if (v >= 1 && v <= 8) ctx->b_blocks_per_sm = v; }
-    if (const char* f = getenv("SDZ_FAST_CHUNKS")) { int v = atoi(f); if (v >= 1 && v <= sdz_ctx::MAX_FAST_CHUNKS) ctx->fast_chunks = v; }
+    if (const char* f = getenv("SDZ_FAST_CHUNKS")) { int v = atoi(f); if (v >= 0 && v <= sdz_ctx::MAX_FAST_CHUNKS) ctx->fast_chunks = v; }
     for (int l = 0; l < sdz_ctx::N_LANES; l++) {
         if (cudaStreamCreateWithFlags(&ctx->fast_sb[l], cudaStreamNonBlocking) != cudaSuccess) return fail(SDZ_E_CUDA);
         for (auto& e : ctx->fast_ev[l])
