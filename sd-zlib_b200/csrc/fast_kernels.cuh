@@ -462,11 +462,18 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
 
         // ================================================================ lockstep symbol loop
         // During one run every lane is either decoding (`live`) or out of streams; the run ends for the whole warp as
-        // soon as one lane meets an end-of-block code or anything the general decoder has to look at.  The iteration is
-        // straight-line predicated code with three warp-voted side exits (code longer than the root / end of block /
-        // invalid code, the same for distances, and a second top-up of the bit buffer).  Checks that can wait (slot
-        // full, distance before the start of the output, input overrun, token arena full) are accumulated and looked
-        // at once per group of four symbols; phase A writes no output bytes, so a late hand-over costs nothing.
+        // soon as one lane meets an end-of-block code or anything the general decoder has to look at.
+        //
+        // Symbols are decoded in groups of four.  The four symbols are ONE straight-line PTX block without a single
+        // branch or vote: the per-symbol warp votes of the first version sat on the dependent chain (table read ->
+        // compare -> VOTE -> BRA -> next table read: about half of all issue slots were spent waiting on them with one
+        // warp per scheduler).  A lane that meets anything rare - a code longer than the table root, end of block, an
+        // invalid code, a bit buffer that does not cover a distance code with its extra bits - switches itself off for
+        // the rest of the group (predicate `pa`: nothing is consumed, its token slots stay no-ops) and remembers the
+        // slot; after the group ONE vote sends those lanes through the general single-symbol decoder below, whose token
+        // goes into the remembered slot.  Checks that can wait (slot full, distance before the start of the output,
+        // input overrun, token arena full) are accumulated and looked at once per group; phase A writes no output
+        // bytes, so a late hand-over costs nothing.
         {
             const bool live = state == LS_CODES;
             const uint32_t a_l = smem_addr(L->lut_l), a_d = smem_addr(L->lut_d);
@@ -485,140 +492,151 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                 fresh = false;
             }
             for (;;) {
-                uint32_t tk[4] = { 0u, 0u, 0u, 0u };
+                uint32_t tk0, tk1, tk2, tk3;
                 uint32_t early = 0u;                                    // a distance reached before the start of the output
-                #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    // The straight-line part of the iteration is written as three PTX blocks (predicated instructions
-                    // instead of the select / move chains the compiler makes of the C++ form: 105 -> ~65 instructions per
-                    // symbol); the rare paths between them stay C++.
-                    uint32_t lo, e;
-                    // ---- (1) top-up to at least 32 valid bits (lanes without a stream sit at bc = 64), literal/length lookup
-                    asm volatile("{\n\t"
-                        ".reg .pred pt;\n\t"
-                        ".reg .b32 pw, ra, t;\n\t"
-                        "setp.lt.s32 pt, %1, 32;\n\t"
-                        "mov.b32 pw, 0;\n\t"
-                        "@pt shl.b32 pw, 1, %1;\n\t"
-                        "mad.wide.u32 %0, %3, pw, %0;\n\t"              // bits above bc are zero: add == or
-                        "@pt add.s32 %1, %1, 32;\n\t"
-                        "@pt add.u32 %2, %2, 1;\n\t"
-                        "and.b32 t, %2, 31;\n\t"
-                        "mad.lo.u32 ra, t, 4, %6;\n\t"
-                        "@pt ld.shared.u32 %3, [ra];\n\t"
-                        "cvt.u32.u64 %4, %0;\n\t"
-                        "and.b32 t, %4, 511;\n\t"
-                        "mad.lo.u32 ra, t, 2, %7;\n\t"
-                        "ld.shared.u16 %5, [ra];\n\t"
-                        "}"
-                        : "+l"(bb), "+r"(bc), "+r"(wp), "+r"(nw), "=r"(lo), "=r"(e)
-                        : "r"(ring_l), "r"(a_l));
-                    if (__any_sync(FULL, live && e < 0x1000u)) {
-                        // rare: code longer than the root, end of block, invalid code
-                        if (live && e < 0x1000u) {
-                            if (e == E_LONG) {
-                                const uint32_t r = canon_long(L->cnt_l, my_sorted, FA_RL, g_l, L->start, lo, L->long_l, 32);
-                                const uint32_t sym = r & 0xffffu;
-                                if (r != 0u && sym < 256u) e = ((r >> 16) << 12) | sym;
-                                else if (r != 0u && sym == 256u) e = 0x100u | (r >> 16);
-                                else if (r != 0u && sym - 257u <= 28u) {
-                                    const uint32_t i = sym - 257u;
-                                    const uint32_t xb = i < 8 ? 0 : (i == 28 ? 0 : (i >> 2) - 1);
-                                    const uint32_t base = i < 8 ? 3 + i : (i == 28 ? 258 : 3 + ((4 + (i & 3)) << xb));
-                                    e = ((r >> 16) << 12) | 0x800u | (xb << 8) | (base - 3u);
-                                } else e = E_INVALID;
-                            }
-                            if (e < 0x1000u) {
-                                if ((e & 0xf00u) == 0x100u) {           // end of block (LUT fix-up after the build: 0x100 | code length)
-                                    const int n = (int)(e & 0xffu);
-                                    bb >>= n; bc -= n; eob_len = n;
-                                    ev = 1;
-                                } else ev = 2;                          // invalid literal/length code
+                uint32_t act = live ? 1u : 0u, su = 4u;                 // su: the slot in which the lane switched itself off
+#define SDZ_FA_SYMBOL(U, TK)                                                                                              \
+                    /* top-up to at least 32 valid bits */                                                                \
+                    "setp.lt.s32 pt, %1, 32;\n\t"                                                                         \
+                    "mov.b32 pw, 0;\n\t"                                                                                  \
+                    "@pt shl.b32 pw, 1, %1;\n\t"                                                                          \
+                    "mad.wide.u32 %0, %3, pw, %0;\n\t"            /* bits above bc are zero: add == or */                 \
+                    "@pt add.s32 %1, %1, 32;\n\t"                                                                         \
+                    "@pt add.u32 %2, %2, 1;\n\t"                                                                          \
+                    "and.b32 t, %2, 31;\n\t"                                                                              \
+                    "mad.lo.u32 ra, t, 4, %12;\n\t"                                                                       \
+                    "@pt ld.shared.u32 %3, [ra];\n\t"                                                                     \
+                    /* literal/length lookup and fields */                                                                \
+                    "cvt.u32.u64 lo, %0;\n\t"                                                                             \
+                    "and.b32 t, lo, 511;\n\t"                                                                             \
+                    "mad.lo.u32 ra, t, 2, %13;\n\t"                                                                       \
+                    "ld.shared.u16 e, [ra];\n\t"                                                                          \
+                    "shr.u32 n, e, 12;\n\t"                                                                               \
+                    "bfe.u32 xb, e, 8, 3;\n\t"                    /* 0 for a literal */                                   \
+                    "add.u32 c1, n, xb;\n\t"                                                                              \
+                    "shr.u32 t, lo, n;\n\t"                                                                               \
+                    "shl.b32 b, 0xffffffff, xb;\n\t"                                                                      \
+                    "lop3.b32 t, t, b, 0, 0x30;\n\t"              /* t & ~b: the extra bits */                            \
+                    "and.b32 b, e, 255;\n\t"                                                                              \
+                    "add.u32 lenf, b, t;\n\t"                     /* length - 3 (literal: the byte) */                    \
+                    "and.b32 t, e, 2048;\n\t"                                                                             \
+                    "setp.ne.u32 pm, t, 0;\n\t"                                                                           \
+                    /* distance: the root lookup needs 7 of the >= 12 bits that are left */                               \
+                    "shr.u64 w, %0, c1;\n\t"                                                                              \
+                    "cvt.u32.u64 lo2, w;\n\t"                                                                             \
+                    "and.b32 t, lo2, 127;\n\t"                                                                            \
+                    "mad.lo.u32 ra, t, 2, %14;\n\t"                                                                       \
+                    "ld.shared.u16 de, [ra];\n\t"                                                                         \
+                    "shr.u32 dn, de, 12;\n\t"                                                                             \
+                    "bfe.u32 dx, de, 8, 4;\n\t"                                                                           \
+                    "add.u32 c2, dn, dx;\n\t"                                                                             \
+                    "sub.s32 rem, %1, c1;\n\t"                                                                            \
+                    /* rare: no root entry for either code, or the buffer does not cover the distance */                 \
+                    "setp.lt.s32 p1, rem, c2;\n\t"                                                                        \
+                    "setp.lt.u32 p2, de, 4096;\n\t"                                                                       \
+                    "or.pred p1, p1, p2;\n\t"                                                                             \
+                    "and.pred p1, p1, pm;\n\t"                                                                            \
+                    "setp.lt.u32 p2, e, 4096;\n\t"                                                                        \
+                    "or.pred p1, p1, p2;\n\t"                                                                             \
+                    "and.pred p2, pa, p1;\n\t"                                                                            \
+                    "@p2 mov.b32 %7, " U ";\n\t"                                                                          \
+                    "and.pred pa, pa, !p1;\n\t"                                                                           \
+                    "shr.u32 t, lo2, dn;\n\t"                                                                             \
+                    "shl.b32 m, 0xffffffff, dx;\n\t"                                                                      \
+                    "lop3.b32 t, t, m, 0, 0x30;\n\t"                                                                      \
+                    "and.b32 m, de, 3;\n\t"                                                                               \
+                    "shl.b32 m, m, dx;\n\t"                                                                               \
+                    "add.u32 dm1, m, t;\n\t"                      /* distance - 1 */                                      \
+                    /* consumption (nothing when the lane is off), token */                                               \
+                    "selp.u32 c2, c2, 0, pm;\n\t"                                                                         \
+                    "add.u32 c, c1, c2;\n\t"                      /* <= 48 */                                             \
+                    "selp.u32 c, c, 0, pa;\n\t"                                                                           \
+                    "shr.u64 %0, %0, c;\n\t"                                                                              \
+                    "sub.s32 %1, %1, c;\n\t"                                                                              \
+                    "add.u32 len, lenf, 3;\n\t"                                                                           \
+                    "selp.u32 len, len, 1, pm;\n\t"                                                                       \
+                    "and.pred p2, pa, pm;\n\t"                                                                            \
+                    "setp.ge.and.u32 p2, dm1, %4, p2;\n\t"        /* the general decoder's */                  \
+                    "@p2 mov.b32 %5, 1;\n\t"                                                                              \
+                    "@pa add.u32 %4, %4, len;\n\t"                                                                        \
+                    "mad.lo.u32 t, dm1, 512, len;\n\t"                                                                    \
+                    "or.b32 tl, lenf, 0x80000000;\n\t"                                                                    \
+                    "selp.u32 t, t, tl, pm;\n\t"                                                                          \
+                    "selp.u32 " TK ", t, 0, pa;\n\t"
+                asm volatile("{\n\t"
+                    ".reg .pred pt, pm, p1, p2, pa;\n\t"
+                    ".reg .b32 pw, ra, t, lo, e, n, xb, c1, b, lenf, lo2, de, dn, dx, c2, rem, m, dm1, c, len, tl;\n\t"
+                    ".reg .b64 w;\n\t"
+                    "setp.ne.u32 pa, %6, 0;\n\t"
+                    SDZ_FA_SYMBOL("0", "%8")
+                    SDZ_FA_SYMBOL("1", "%9")
+                    SDZ_FA_SYMBOL("2", "%10")
+                    SDZ_FA_SYMBOL("3", "%11")
+                    "}"
+                    : "+l"(bb), "+r"(bc), "+r"(wp), "+r"(nw), "+r"(pos), "+r"(early), "+r"(act), "+r"(su),
+                      "=r"(tk0), "=r"(tk1), "=r"(tk2), "=r"(tk3)
+                    : "r"(ring_l), "r"(a_l), "r"(a_d));
+#undef SDZ_FA_SYMBOL
+                // ---- lanes that switched themselves off: one symbol through the general decoder
+                if (__any_sync(FULL, su < 4u)) {
+                    if (su < 4u) {
+                        uint32_t tslow = 0u;
+                        if (bc < 32) {
+                            bb |= (uint64_t)nw << bc;
+                            bc += 32; wp++;
+                            nw = lds_u32(ring_l + ((wp & 31u) << 2));
+                        }
+                        const uint32_t lo = (uint32_t)bb;
+                        uint32_t e = L->lut_l[lo & ((1u << FA_RL) - 1u)];
+                        if (e == E_LONG) {
+                            const uint32_t r = canon_long(L->cnt_l, my_sorted, FA_RL, g_l, L->start, lo, L->long_l, 32);
+                            const uint32_t sym = r & 0xffffu;
+                            if (r != 0u && sym < 256u) e = ((r >> 16) << 12) | sym;
+                            else if (r != 0u && sym == 256u) e = 0x100u | (r >> 16);
+                            else if (r != 0u && sym - 257u <= 28u) {
+                                const uint32_t i = sym - 257u;
+                                const uint32_t xb = i < 8 ? 0 : (i == 28 ? 0 : (i >> 2) - 1);
+                                const uint32_t base = i < 8 ? 3 + i : (i == 28 ? 258 : 3 + ((4 + (i & 3)) << xb));
+                                e = ((r >> 16) << 12) | 0x800u | (xb << 8) | (base - 3u);
+                            } else e = E_INVALID;
+                        }
+                        if (e < 0x1000u) {
+                            if ((e & 0xf00u) == 0x100u) {               // end of block (LUT fix-up after the build: 0x100 | code length)
+                                const int n = (int)(e & 0xffu);
+                                bb >>= n; bc -= n; eob_len = n;
+                                ev = 1;
+                            } else ev = 2;                              // invalid literal/length code
+                        } else {
+                            const uint32_t n = e >> 12, xb = (e >> 8) & 7u;
+                            const bool ismatch = (e & 0x800u) != 0u;
+                            const uint32_t lenf = (e & 0xffu) + ((lo >> n) & ((1u << xb) - 1u));
+                            bb >>= (n + xb); bc -= (int)(n + xb);
+                            if (!ismatch) { tslow = TOK_LIT | lenf; pos += 1u; }
+                            else {
+                                if (bc < 32) {
+                                    bb |= (uint64_t)nw << bc;
+                                    bc += 32; wp++;
+                                    nw = lds_u32(ring_l + ((wp & 31u) << 2));
+                                }
+                                const uint32_t lo2 = (uint32_t)bb;
+                                uint32_t de = L->lut_d[lo2 & ((1u << FA_RD) - 1u)];
+                                if (de < 0x1000u) {
+                                    const uint32_t r = (de == E_LONG && g_d > FA_RD) ? canon_long(L->cnt_d, L->sorted_d, FA_RD, g_d, L->start + 2, lo2) : 0u;
+                                    const uint32_t ds = r & 0xffffu;
+                                    if (r == 0u || ds > 29u) { ev = 2; de = 0x1000u; }         // invalid distance code
+                                    else de = ((r >> 16) << 12) | ((ds < 4 ? 0u : (ds >> 1) - 1u) << 8) | (ds < 4 ? ds : 2u + (ds & 1u));
+                                }
+                                const uint32_t dn = de >> 12, dx = (de >> 8) & 15u;
+                                const uint32_t dm1 = ((de & 3u) << dx) + ((lo2 >> dn) & ((1u << dx) - 1u));
+                                bb >>= (dn + dx); bc -= (int)(dn + dx);
+                                if (dm1 >= pos) early = 1u;
+                                pos += lenf + 3u;
+                                tslow = dm1 * 512u + lenf + 3u;
                             }
                         }
-                        if (__any_sync(FULL, ev != 0)) break;           // (lanes without an event have consumed nothing of symbol u)
+                        tk0 = su == 0u ? tslow : tk0; tk1 = su == 1u ? tslow : tk1;
+                        tk2 = su == 2u ? tslow : tk2; tk3 = su == 3u ? tslow : tk3;
                     }
-                    // ---- (2) literal/length fields, root lookup of the distance (it needs 7 of the >= 12 bits that are left)
-                    // (lanes without a stream read zeroed tables: a "literal" of zero bits)
-                    uint32_t c1, lenf, len, ism, lo2, de, need, dn, dx;
-                    asm volatile("{\n\t"
-                        ".reg .pred pm, p1, p2;\n\t"
-                        ".reg .b32 n, xb, t, b, ra, c2, rem;\n\t"
-                        ".reg .b64 w;\n\t"
-                        "shr.u32 n, %9, 12;\n\t"
-                        "bfe.u32 xb, %9, 8, 3;\n\t"                     // 0 for a literal
-                        "add.u32 %0, n, xb;\n\t"
-                        "shr.u32 t, %10, n;\n\t"
-                        "shl.b32 b, 0xffffffff, xb;\n\t"
-                        "lop3.b32 t, t, b, 0, 0x30;\n\t"             // t & ~b: the extra bits
-                        "and.b32 b, %9, 255;\n\t"
-                        "add.u32 %1, b, t;\n\t"                         // length - 3 (literal: the byte)
-                        "and.b32 t, %9, 2048;\n\t"
-                        "setp.ne.u32 pm, t, 0;\n\t"
-                        "add.u32 t, %1, 3;\n\t"
-                        "selp.u32 %2, t, 1, pm;\n\t"
-                        "selp.u32 %3, 1, 0, pm;\n\t"
-                        "shr.u64 w, %11, %0;\n\t"
-                        "cvt.u32.u64 %4, w;\n\t"
-                        "and.b32 t, %4, 127;\n\t"
-                        "mad.lo.u32 ra, t, 2, %13;\n\t"
-                        "ld.shared.u16 %5, [ra];\n\t"
-                        "shr.u32 %7, %5, 12;\n\t"
-                        "bfe.u32 %8, %5, 8, 4;\n\t"
-                        "add.u32 c2, %7, %8;\n\t"
-                        "sub.s32 rem, %12, %0;\n\t"
-                        "setp.lt.s32 p1, rem, c2;\n\t"                  // the buffer does not cover code + extra bits
-                        "setp.lt.u32 p2, %5, 4096;\n\t"                 // code longer than the root, invalid code
-                        "or.pred p1, p1, p2;\n\t"
-                        "and.pred p1, p1, pm;\n\t"
-                        "setp.ne.and.u32 p1, %14, 0, p1;\n\t"
-                        "selp.u32 %6, 1, 0, p1;\n\t"
-                        "}"
-                        : "=r"(c1), "=r"(lenf), "=r"(len), "=r"(ism), "=r"(lo2), "=r"(de), "=r"(need), "=r"(dn), "=r"(dx)
-                        : "r"(e), "r"(lo), "l"(bb), "r"(bc), "r"(a_d), "r"((uint32_t)live));
-                    if (__any_sync(FULL, need != 0u)) {
-                        if (need) {
-                            bb >>= c1; bc -= (int)c1; c1 = 0u;          // (the literal/length bits leave the buffer now)
-                            if (bc < 32) {
-                                bb |= (uint64_t)nw << bc;
-                                bc += 32; wp++;
-                                nw = lds_u32(ring_l + ((wp & 31u) << 2));
-                            }
-                            lo2 = (uint32_t)bb;
-                            if (de < 0x1000u) {
-                                const uint32_t r = (de == E_LONG && g_d > FA_RD) ? canon_long(L->cnt_d, L->sorted_d, FA_RD, g_d, L->start + 2, lo2) : 0u;
-                                const uint32_t ds = r & 0xffffu;
-                                if (r == 0u || ds > 29u) { early = 1u; de = 0x1000u; }     // invalid distance code: hand over
-                                else de = ((r >> 16) << 12) | ((ds < 4 ? 0u : (ds >> 1) - 1u) << 8) | (ds < 4 ? ds : 2u + (ds & 1u));
-                                dn = de >> 12; dx = (de >> 8) & 15u;
-                            }
-                        }
-                    }
-                    // ---- (3) distance, consumption, token
-                    asm volatile("{\n\t"
-                        ".reg .pred pm, pe;\n\t"
-                        ".reg .b32 c2, t, m, dm1, c, tl;\n\t"
-                        "setp.ne.u32 pm, %6, 0;\n\t"
-                        "add.u32 c2, %11, %12;\n\t"
-                        "shr.u32 t, %7, %11;\n\t"
-                        "shl.b32 m, 0xffffffff, %12;\n\t"
-                        "lop3.b32 t, t, m, 0, 0x30;\n\t"
-                        "and.b32 m, %5, 3;\n\t"
-                        "shl.b32 m, m, %12;\n\t"
-                        "add.u32 dm1, m, t;\n\t"                        // distance - 1
-                        "selp.u32 c2, c2, 0, pm;\n\t"
-                        "add.u32 c, c2, %8;\n\t"                        // <= 48
-                        "shr.u64 %0, %0, c;\n\t"
-                        "sub.s32 %1, %1, c;\n\t"
-                        "setp.ge.and.u32 pe, dm1, %2, pm;\n\t"          // the general decoder's
-                        "@pe mov.b32 %3, 1;\n\t"
-                        "add.u32 %2, %2, %10;\n\t"
-                        "mad.lo.u32 t, dm1, 512, %10;\n\t"
-                        "or.b32 tl, %9, 0x80000000;\n\t"
-                        "selp.u32 %4, t, tl, pm;\n\t"
-                        "}"
-                        : "+l"(bb), "+r"(bc), "+r"(pos), "+r"(early), "=r"(tk[u])
-                        : "r"(de), "r"(ism), "r"(lo2), "r"(c1), "r"(lenf), "r"(len), "r"(dn), "r"(dx));
                 }
                 // input ring: request the chunks whose slots have been read completely (the reader holds word wp in a
                 // register: chunk ci - FA_RING_CHUNKS is free once wp has reached its last word).  A group of four symbols
@@ -633,10 +651,9 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                 cp_async_commit();
                 asm volatile("cp.async.wait_group 3;" ::: "memory");
                 if (live) {
-                    // (after an early exit the unprocessed slots of the group are still no-ops)
                     if (early != 0u || pos > cap || wp > lim_wp + 1u || ntok + 4u > cap_tok) ev = 2;
-                    else {
-                        *reinterpret_cast<uint4*>(tokp + ntok) = make_uint4(tk[0], tk[1], tk[2], tk[3]);
+                    else if ((tk0 | tk1 | tk2 | tk3) != 0u) {
+                        *reinterpret_cast<uint4*>(tokp + ntok) = make_uint4(tk0, tk1, tk2, tk3);
                         ntok += 4u;
                     }
                 }
@@ -661,6 +678,7 @@ __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p)
 __global__ void __launch_bounds__(256) lz_resolve_kernel(FastParams P)
 {
     constexpr unsigned FULL = 0xffffffffu;
+    __shared__ uint32_t squeeze[8][32];
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t le_mask = 0xffffffffu >> (31u - lane);
     for (;;) {
@@ -679,12 +697,14 @@ __global__ void __launch_bounds__(256) lz_resolve_kernel(FastParams P)
             uint32_t t = tnext;
             tnext = base + 32u + lane < nt ? ld_stream_u32(tk + base + 32u + lane) : 0u;
             {
-                // no-op tokens (end of a block inside a group of four) are squeezed out: the row loop indexes tokens
+                // no-op tokens (slots of a lane that had switched itself off in phase A) are squeezed out - the row loop
+                // indexes tokens by counting starts: scatter through shared memory to the rank among the real tokens
                 const uint32_t nz = __ballot_sync(FULL, t != 0u);
-                if (nz & (nz + 1u)) {
-                    const uint32_t srcl = __fns(nz, 0, (int)lane + 1);
-                    const uint32_t t2 = __shfl_sync(FULL, t, srcl & 31u);
-                    t = srcl < 32u ? t2 : 0u;
+                if (nz != 0xffffffffu) {
+                    __syncwarp();
+                    if (t != 0u) squeeze[threadIdx.x >> 5][__popc(nz & (le_mask >> 1))] = t;
+                    __syncwarp();
+                    t = lane < (uint32_t)__popc(nz) ? squeeze[threadIdx.x >> 5][lane] : 0u;
                 }
             }
             const bool lit = (int32_t)t < 0;
