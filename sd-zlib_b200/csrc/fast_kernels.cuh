@@ -174,6 +174,113 @@ __device__ __forceinline__ bool parse_container_clean(const uint8_t* src, uint32
     return true;
 }
 
+// ---- table construction for phase A: the warp builds one lane's tables.  Same results as build_tables<32>() of
+// inflate_kernel.cuh (same acceptance rules, same LUT / sorted-symbol / start formats); two things are done
+// differently because 32 builds per warp run back to back whenever the lanes of a warp reach a block boundary
+// together (20 % of phase A's time in the first profile):
+//   * the counting sort of the symbols by code length is done 32 symbols at a time (match_any ranks the lanes with
+//     equal lengths) instead of serially by lane 0;
+//   * the reference's table-arena limit (MANY = 1400 entries) needs the exact sub-table walk
+//     (ref_table_total; huft_build's multi-level splitting has no simple closed-form bound) only when a code is longer
+//     than its root: 2^lbits + 2^dbits <= 576 entries otherwise.
+
+template <int KIND, int R>
+__device__ __forceinline__ void make_lut_warp(uint32_t* aux, const uint8_t* lens, int n, int nzero, const uint16_t* cnt, uint16_t* start,
+                                              uint16_t* sorted, uint16_t* lut, uint32_t lane)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    if (lane == 0) {
+        uint32_t off = 0, code = 0;
+        for (int k = 1; k <= 15; k++) {
+            aux[k] = off;
+            aux[16 + k] = code;
+            off += cnt[k];
+            code = (code + cnt[k]) << 1;
+        }
+        // canonical-walk state after R bits (canon_long)
+        uint32_t first = 0, index = 0;
+        for (int k = 1; k <= R && k <= 15; k++) { index += cnt[k]; first = (first + cnt[k]) << 1; }
+        start[0] = (uint16_t)first; start[1] = (uint16_t)index;
+    }
+    uint32_t* lut32 = reinterpret_cast<uint32_t*>(lut);
+    for (uint32_t i = lane; i < (1u << R) / 2; i += 32) lut32[i] = E_INVALID | (E_INVALID << 16);
+    __syncwarp();
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (int base = 0; base < n; base += 32) {
+        const int sidx = base + (int)lane;
+        const uint32_t k = sidx < n ? lens[sidx] : 0u;
+        const uint32_t same = __match_any_sync(FULL, k);
+        if (k) sorted[aux[k] + __popc(same & lt_mask)] = (uint16_t)(sidx | (k << 12));
+        __syncwarp();
+        if (k && (same & lt_mask) == 0u) aux[k] += __popc(same);        // (after the loop: one past the last symbol of this length)
+        __syncwarp();
+    }
+    const int ncodes = n - nzero;
+    for (int k = (int)lane; k < ncodes; k += 32) {
+        const uint32_t e = sorted[k];
+        const uint32_t sym = e & 0xfff, len = e >> 12;
+        const uint32_t idx = (uint32_t)k - (aux[len] - cnt[len]);
+        const uint32_t code = aux[16 + len] + idx;
+        const uint32_t rev = __brev(code) >> (32 - len);
+        if (len > (uint32_t)R) { lut[rev & ((1u << R) - 1u)] = (uint16_t)E_LONG; continue; }
+        uint32_t entry;
+        if (KIND == 0) {
+            if (sym < 256) entry = sym;
+            else if (sym == 256) entry = 0x100;
+            else {
+                const uint32_t i = sym - 257;
+                if (i > 28) continue;                                   // 286/287: invalid (fixed block only)
+                const uint32_t xb = i < 8 ? 0 : (i == 28 ? 0 : (i >> 2) - 1);
+                const uint32_t base = i < 8 ? 3 + i : (i == 28 ? 258 : 3 + ((4 + (i & 3)) << xb));
+                entry = 0x800 | (xb << 8) | (base - 3);
+            }
+        } else {
+            if (sym > 29) continue;                                     // 30/31: invalid (fixed block only)
+            const uint32_t xb = sym < 4 ? 0 : (sym >> 1) - 1;
+            const uint32_t m = sym < 4 ? sym : 2 + (sym & 1);
+            entry = (xb << 8) | m;
+        }
+        entry |= len << 12;
+        for (uint32_t j = rev; j < (1u << R); j += (1u << len)) lut[j] = (uint16_t)entry;
+    }
+    __syncwarp();
+}
+
+__device__ __noinline__ TreeInfo build_tables_warp(LaneSmem* S, uint16_t* wscr, int nl, int nd, bool fixed, uint32_t lane)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    TreeInfo T;
+    T.msg = SDZ_MSG_NONE; T.lbits = T.dbits = T.g_l = T.g_d = 0;
+    int pad_l = 0, pad_d = 0, nz_l = 0, nz_d = 0;
+    const uint8_t* lens = reinterpret_cast<const uint8_t*>(wscr + SORTED_L + SORTED_D);
+    uint32_t* aux = reinterpret_cast<uint32_t*>(wscr + SORTED_L + SORTED_D + 160);
+    const int st_l = classify<32>(lens, nl, 9, S->cnt_l, aux, &T.lbits, &T.g_l, &pad_l, &nz_l, (int)lane, FULL);
+    if (!fixed && st_l != 0) { T.msg = st_l == 1 ? SDZ_MSG_OVERSUB_LITLEN_TREE : SDZ_MSG_INCOMPLETE_LITLEN_TREE; return T; }
+    const int st_d = classify<32>(lens + nl, nd, fixed ? 5 : 6, S->cnt_d, aux, &T.dbits, &T.g_d, &pad_d, &nz_d, (int)lane, FULL);
+    if (!fixed) {
+        if (st_d == 1) { T.msg = SDZ_MSG_OVERSUB_DIST_TREE; return T; }
+        if (st_d == 2) { T.msg = SDZ_MSG_INCOMPLETE_DIST_TREE; return T; }
+        if (st_d == 3 && nl > 257) { T.msg = SDZ_MSG_EMPTY_DIST_TREE; return T; }
+        // MANY = 1400 entries for both tables
+        if (T.g_l > T.lbits || T.g_d > T.dbits) {
+            const int used = ref_table_total<32>(S->cnt_l, T.g_l, pad_l, T.lbits, (int)lane, FULL);
+            if (used > 1400) { T.msg = SDZ_MSG_OVERSUB_LITLEN_TREE; return T; }
+            if (st_d != 3 && used + ref_table_total<32>(S->cnt_d, T.g_d, pad_d, T.dbits, (int)lane, FULL) > 1400) {
+                T.msg = SDZ_MSG_OVERSUB_DIST_TREE; return T;
+            }
+        }
+    }
+    make_lut_warp<0, FA_RL>(reinterpret_cast<uint32_t*>(S->lut_d), lens, nl, nz_l, S->cnt_l, S->start, wscr, S->lut_l, lane);
+    {
+        const int i0 = (int)S->start[1], nc = nl - nz_l;
+        S->long_l[lane] = i0 + (int)lane < nc ? wscr[i0 + lane] : (uint16_t)0;
+        __syncwarp();
+    }
+    make_lut_warp<1, FA_RD>(aux, lens + nl, nd, nz_d, S->cnt_d, S->start + 2, wscr + SORTED_L, S->lut_d, lane);
+    if (fixed) { T.lbits = 9; T.dbits = 5; }
+    return T;
+}
+
 enum : int { LS_CODES = 0, LS_DONE = 1, LS_FETCH = 2, LS_BLOCK = 3, LS_BUILD = 4, LS_FINISH = 5, LS_HANDOVER = 6 };
 
 __device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t s)
@@ -438,7 +545,7 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                     for (uint32_t i = lane; i < 80; i += 32) d32[i] = s32[i];
                 }
                 __syncwarp();
-                const TreeInfo TI = build_tables<32>(T, wscr, t_nl, t_nd, t_fixed, (int)lane, FULL, T->long_l, 32);
+                const TreeInfo TI = build_tables_warp(T, wscr, t_nl, t_nd, t_fixed, lane);
                 __syncwarp();
                 if (TI.msg == SDZ_MSG_NONE) {
                     uint16_t* gs = P.sorted_l + ((size_t)blockIdx.x * 32 + who) * SORTED_L;
