@@ -66,6 +66,11 @@ int sdz_last_phase_timing(sdz_ctx* ctx, float ms[5]);
 /* most recent fast-path launch (the last sub-batch of a pipelined call): out[0] = streams finished by the two-phase
  * path, out[1] = streams it handed to the general decoder */
 int sdz_last_fast_stats(sdz_ctx* ctx, uint64_t out[2]);
+/* White-box TEST entry (not bound by the N-API shim): for n code-length sets (320 bytes each: nl[i] literal/length lengths
+ * followed by nd[i] distance lengths) the acceptance class (0 ok, 1 oversubscribed, 2 incomplete, 3 empty) and the number of
+ * table entries the reference's huft_build allocates (src/inftree.ts:217-246) as the kernels re-derive it in closed form -
+ * out[4 i .. 4 i + 3] = { class_lit, entries_lit, class_dist, entries_dist }.  group = 4 (general decoder) or 32 (fast path). */
+int sdz_debug_table_totals(sdz_ctx* ctx, const uint8_t* lens, const int32_t* nl, const int32_t* nd, uint64_t n, int group, int32_t* out);
 
 /* Pinned host memory helpers (so that callers can hand over DMA-able buffers). */
 void* sdz_host_alloc(size_t bytes);

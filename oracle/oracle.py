@@ -218,6 +218,16 @@ def inflate_batch_mt(in_arena, in_off, in_len, out_off, out_cap, n_threads, mode
     return out_arena, res
 
 
+def table_usage(lit_lens, dist_lens):
+    """(lit entries, dist entries, status_lit, status_dist) of huft_build with the MANY limit lifted"""
+    lens = bytes(lit_lens) + bytes(dist_lens)
+    buf, _ = _buf(lens)
+    a, b = C.c_int(), C.c_int()
+    st = (C.c_int * 2)()
+    lib().sdzo_table_usage(buf, len(lit_lens), len(dist_lens), C.byref(a), C.byref(b), st)
+    return a.value, b.value, st[0], st[1]
+
+
 def fixed_tables():
     tl, td = C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)()
     ntl, ntd = C.c_int(), C.c_int()

@@ -143,6 +143,7 @@ typedef struct {
     int x[BMAX + 1];
     int v[288];
     int hn;
+    int many;       /* arena limit: MANY in the decoder; raised only by the white-box sdzo_table_usage() */
 } tree_work;
 
 static void init_work_area(tree_work* W)
@@ -219,7 +220,7 @@ static int huft_build(const uint8_t* b, int bindex, int n, int s, const int* d, 
                     }
                 }
                 z = 1 << j;
-                if (W->hn + z > MANY) return SDZ_Z_DATA_ERROR;     /* :242-244 */
+                if (W->hn + z > W->many) return SDZ_Z_DATA_ERROR;  /* :242-244 */
                 u[h] = q = W->hn;
                 W->hn += z;
                 if (h != 0) {
@@ -267,6 +268,7 @@ static int trees_bits(const uint8_t* c, int* bb, int* tb, int32_t* hp, tree_work
     /* src/inftree.ts:313-331 */
     init_work_area(W);
     W->hn = 0;
+    W->many = MANY;
     int result = huft_build(c, 0, 19, 19, NULL, NULL, tb, bb, hp, W);
     if (result == SDZ_Z_DATA_ERROR) {
         z->msg = SDZ_MSG_OVERSUB_BITS_TREE;
@@ -283,6 +285,7 @@ static int trees_dynamic(int nl, int nd, const uint8_t* c, int* bl, int* bd, int
     /* src/inftree.ts:333-379 */
     init_work_area(W);
     W->hn = 0;
+    W->many = MANY;
     int result = huft_build(c, 0, nl, 257, cplens, cplext, tl, bl, hp, W);
     if (result != SDZ_Z_OK || *bl == 0) {
         if (result == SDZ_Z_DATA_ERROR) {
@@ -329,7 +332,7 @@ static void build_fixed(void)
     for (; k < 256; k++) c[k] = 9;
     for (; k < 280; k++) c[k] = 7;
     for (; k < 288; k++) c[k] = 8;
-    init_work_area(&W); W.hn = 0; m = 9;
+    init_work_area(&W); W.hn = 0; W.many = MANY; m = 9;
     huft_build(c, 0, 288, 257, cplens, cplext, &t, &m, arena, &W);
     memcpy(fixed_tl, arena + t * 3, sizeof fixed_tl);
     for (k = 0; k < 30; k++) c[k] = 5;
@@ -337,6 +340,26 @@ static void build_fixed(void)
     memset(arena, 0, sizeof arena);
     huft_build(c, 0, 30, 0, cpdist, cpdext, &t, &m, arena, &W);   /* incomplete (30 of 32): BUF_ERROR ignored */
     memcpy(fixed_td, arena + t * 3, sizeof fixed_td);
+}
+
+/* White-box: entries huft_build allocates for a literal/length set (lens[0..nl)) and a distance set
+ * (lens[nl..nl+nd)) with the arena limit lifted - what src/inftree.ts:242-244 compares with MANY.
+ * status[0], status[1]: huft_build's return value for each (Z_OK / Z_DATA_ERROR / Z_BUF_ERROR). */
+int sdzo_table_usage(const uint8_t* lens, int nl, int nd, int* lit_entries, int* dist_entries, int* status)
+{
+    enum { BIG = 1 << 17 };
+    int32_t* arena = (int32_t*)calloc((size_t)BIG * 3, sizeof(int32_t));
+    if (!arena) return -1;
+    tree_work W;
+    int t = 0, m = 9;
+    init_work_area(&W); W.hn = 0; W.many = BIG;
+    status[0] = huft_build(lens, 0, nl, 257, cplens, cplext, &t, &m, arena, &W);
+    *lit_entries = W.hn;
+    init_work_area(&W); m = 6;
+    status[1] = huft_build(lens, nl, nd, 0, cpdist, cpdext, &t, &m, arena, &W);
+    *dist_entries = W.hn - *lit_entries;
+    free(arena);
+    return 0;
 }
 
 int sdzo_fixed_tables(const int32_t** tl, int* n_tl, const int32_t** td, int* n_td)

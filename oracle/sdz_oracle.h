@@ -68,6 +68,10 @@ int sdzo_inflate_batch_mt(const uint8_t* in, const uint64_t* in_off, const uint6
                           const uint8_t* modes, uint64_t n, uint8_t* out, const uint64_t* out_off,
                           const uint64_t* out_cap, sdz_result* res, int n_threads);
 
+/* White-box for the table-arena limit (MANY = 1400, src/inftree.ts:242-244, src/common.ts:41): entries huft_build
+ * allocates for lens[0..nl) as a literal/length set and lens[nl..nl+nd) as a distance set, with the limit lifted. */
+int sdzo_table_usage(const uint8_t* lens, int nl, int nd, int* lit_entries, int* dist_entries, int* status);
+
 /* huft_build table exposure for white-box tests: builds the reference's fixed tables
  * (src/inftree.ts:19-63) the way zlib 1.1.3 generated them; returns entry counts. */
 int sdzo_fixed_tables(const int32_t** tl, int* n_tl, const int32_t** td, int* n_td);

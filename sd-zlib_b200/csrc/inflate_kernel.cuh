@@ -256,7 +256,7 @@ __device__ __noinline__ int ref_table_total(const uint16_t* cnt, int g, int pad,
 // Decode one code the slow way (canonical counts), applying the reference's lookahead rule
 // (SURVEY Q15): a lookup happens only when the table's index width is available.
 // bits = next 32 bits of the stream (LSB first), A = bits left in the input (capped).
-// Returns status << 28 | code_length << 16 | symbol; status = R_OK / R_STALL / R_ERROR.
+// Returns status << 28 | index width needed << 24 | code_length << 16 | symbol; status = R_OK / R_STALL / R_ERROR.
 __device__ __noinline__ uint32_t slow_lookup(const uint16_t* cnt, const uint16_t* sorted, int l, int g, uint32_t bits, int A)
 {
     if (A < l) return (uint32_t)R_STALL << 28;
@@ -265,7 +265,7 @@ __device__ __noinline__ uint32_t slow_lookup(const uint16_t* cnt, const uint16_t
     const int pad = y;                                  // unused codes of length g
     if (g == 1 && ncodes == 1) {                        // the one incomplete set the reference accepts
         if (bits & 1) return (uint32_t)R_ERROR << 28;   // exop 192: invalid code
-        return (1u << 16) | (sorted[0] & 0xfffu);
+        return (1u << 24) | (1u << 16) | (sorted[0] & 0xfffu);
     }
     int code = 0, first = 0, index = 0, klen = 0;
     bool found = false;
@@ -282,7 +282,7 @@ __device__ __noinline__ uint32_t slow_lookup(const uint16_t* cnt, const uint16_t
         index += count; first += count; first <<= 1; code <<= 1;
     }
     const uint32_t ok = ((uint32_t)klen << 16) | sym;
-    if (found && klen <= l) return ok;
+    if (found && klen <= l) return ok | ((uint32_t)l << 24);
     if (!found && A >= g) return (uint32_t)R_ERROR << 28;   // every bit of the longest code is there: no such code
     // walk the reference's table levels
     int w = l;
@@ -291,7 +291,7 @@ __device__ __noinline__ uint32_t slow_lookup(const uint16_t* cnt, const uint16_t
         uint32_t prefix = __brev(bits) >> (32 - w);
         int j = ref_subtable_width(cnt, g, pad, l, w, prefix);
         if (A - w < j) return (uint32_t)R_STALL << 28;
-        if (found && klen <= w + j) return ok;
+        if (found && klen <= w + j) return ok | ((uint32_t)(w + j) << 24);      // bits 24..27: index width of the last table level
         if (j == 0 || (!found && w + j >= 15)) return (uint32_t)R_ERROR << 28;
         w += l;
     }
@@ -589,6 +589,13 @@ struct Decoder {
     static __device__ __forceinline__ uint32_t slot_after(uint32_t p) { return p ^ 1u; }
 
     RingModel ring;
+    // Model of the reference's input frontier near the end of the input (src/infcodes.ts:339, :96-100, :287-291): whether
+    // a symbol - in particular an end-of-block code - is decoded by inflate_fast() or by the one-symbol slow path depends
+    // on how many input BYTES the reference has already loaded into its bit buffer (n >= 10 at the START check / at the
+    // end of every fast symbol), and the two paths end a block differently (block_end()).  ref_F = bytes loaded so far.
+    uint32_t ref_F, ref_Fentry, ring_done;
+    uint64_t blk_sym0_bit;             // bit position of the first symbol of the current block
+    bool ref_on, ref_burst, ref_forced_slow, eob_emu, eob_fast;
     int msg;
     int stall_kind;
     int lbits, dbits, g_l, g_d;
@@ -862,6 +869,7 @@ struct Decoder {
     __device__ __forceinline__ int dynamic_header(int* nl_out, int* nd_out)
     {
         if (!ensure(14)) { stall_kind = ST_OTHER; return R_STALL; }
+        if (TM == TM_NONE) ref_need(bit_pos(), 14u);
         uint32_t t = peek(14);
         if ((t & 0x1f) > 29 || ((t >> 5) & 0x1f) > 29) { msg = SDZ_MSG_TOO_MANY_SYMS; return R_ERROR; }
         drop(14);
@@ -874,6 +882,7 @@ struct Decoder {
         __syncwarp(gmask);
         for (int i = 0; i < ncl; i++) {
             if (!ensure(3)) { stall_kind = ST_DYNHDR; return R_STALL; }
+            if (TM == TM_NONE) ref_need(bit_pos(), 3u);
             if (glane == 0) cl[c_border[i]] = (uint8_t)peek(3);
             drop(3);
         }
@@ -885,6 +894,7 @@ struct Decoder {
         uint32_t prev = 0;
         while (index < total) {
             if (!ensure(bb_bits)) { stall_kind = ST_DYNHDR; return R_STALL; }
+            if (TM == TM_NONE) ref_need(bit_pos(), (uint32_t)bb_bits);
             uint32_t e = blut[peek(bb_bits)];
             int tbits = (int)(e >> 5), c = (int)(e & 31);
             if (c < 16) {
@@ -896,6 +906,7 @@ struct Decoder {
                 int i = c == 18 ? 7 : c - 14;
                 int j = c == 18 ? 11 : 3;
                 if (bc < tbits + i) { stall_kind = ST_DYNHDR; return R_STALL; }     // ensure() above left >= 33 bits unless the input ends
+                if (TM == TM_NONE) ref_need(bit_pos(), (uint32_t)(tbits + i));
                 drop(tbits);
                 j += (int)peek(i);
                 drop(i);
@@ -915,10 +926,45 @@ struct Decoder {
     // `tail` (fewer than five input words left) and root entries marked long/invalid go through
     // slow_lookup(), which also enforces the reference's lookahead rule; everything else is
     // one shared-memory LUT read per code.
+    static __device__ __forceinline__ uint32_t ceil8(uint64_t bits) { return (uint32_t)((bits + 7) >> 3); }
+    // the reference loads input until `need` bits from bit position p are in its buffer
+    __device__ __forceinline__ void ref_need(uint64_t p, uint32_t need) { ref_F = max(ref_F, ceil8(p + need)); }
+    // a symbol starts at bit p0 within the last 16 bytes of the input: does inflate_fast() decode it?
+    __device__ __noinline__ bool ref_symbol_begin(uint64_t p0)
+    {
+        if (!ref_on) {
+            ring.write(pos - ring_done); ring_done = pos;
+            const bool fresh = p0 == blk_sym0_bit;                       // first symbol of its block: the START check is pending
+            ref_burst = !fresh && ring.room() >= 258;                   // (n >= 10 held up to here)
+            if (!fresh) ref_F = ceil8(p0);
+            ref_Fentry = 0; ref_forced_slow = false; ref_on = true;
+        }
+        bool fast = ref_burst;
+        if (!fast && !ref_forced_slow && ring.room() >= 258 && in_len >= ref_F + 10u) { fast = true; ref_burst = true; ref_Fentry = ref_F; }
+        ref_forced_slow = false;
+        return fast;
+    }
+    // whole unused bytes go back to the input when inflate_fast() returns (src/infcodes.ts:287-291)
+    __device__ __forceinline__ void ref_give_back(uint64_t p_after)
+    {
+        const uint32_t k = (uint32_t)((uint64_t)ref_F * 8 - p_after);
+        ref_F -= min(k >> 3, ref_F - ref_Fentry);
+        ref_burst = false;
+    }
+    __device__ __noinline__ void ref_symbol_end(bool fast, uint32_t n_out)
+    {
+        ring.write(n_out); ring_done = pos;
+        if (fast && !(ring.room() >= 258 && in_len >= ref_F + 10u)) { ref_give_back(bit_pos()); ref_forced_slow = true; }
+    }
+
     __device__ __forceinline__ int step_general(uint32_t lit_now)
     {
         refill();
         const bool tail = wp + 5 > end_wp;
+        const uint64_t p0 = bit_pos();
+        const bool emu = TM == TM_NONE && (uint64_t)in_len - (p0 >> 3) <= 16u;
+        const bool fastsym = emu ? ref_symbol_begin(p0) : false;
+        uint32_t need1 = 20u;
         uint32_t e = S->lut_l[(uint32_t)bb & ((1u << RL) - 1u)];
         uint32_t n = e >> 12, p = e & 0xfff;
         if (tail || n == 0) {
@@ -926,6 +972,7 @@ struct Decoder {
             uint32_t st = r >> 28;
             if (st) { if (st == (uint32_t)R_ERROR) msg = SDZ_MSG_BAD_LITLEN_CODE; return (int)st; }
             n = (r >> 16) & 0xff;
+            need1 = (r >> 24) & 15u;
             uint32_t sym = r & 0xffff;
             if (sym <= 256) p = sym;
             else {
@@ -936,19 +983,33 @@ struct Decoder {
                 p = 0x800 | (xb << 8) | (base - 3);
             }
         }
+        if (emu) ref_need(p0, fastsym ? 20u : need1);
         bb >>= n; bc -= (int)n;
         if (p < 256) {
             if (pos >= cap) return R_OUTFULL;
             store_lit(p);
             pos++;
+            if (emu) ref_symbol_end(fastsym, 1u);
             return R_OK;
         }
-        if (p == 256) { eob_len = (int)n; return R_EOB; }
+        if (p == 256) {
+            eob_len = (int)n; eob_emu = emu; eob_fast = fastsym;
+            if (emu) {
+                // the block's codes object hands whole unused bytes back: all of them after inflate_fast(), at most one in
+                // WASH (src/infcodes.ts:620-624)
+                if (fastsym) ref_give_back(bit_pos());
+                else if ((uint64_t)ref_F * 8 - bit_pos() > 7) ref_F--;
+                ref_burst = false; ref_forced_slow = false;
+            }
+            return R_EOB;
+        }
         uint32_t xb = (p >> 8) & 7;
         if (tail && avail_bits() < (int)xb) return R_STALL;
+        if (emu && !fastsym) ref_need(p0 + n, xb);
         uint32_t len = 3 + (p & 0xff) + ((uint32_t)bb & ((1u << xb) - 1u));
         bb >>= xb; bc -= (int)xb;
         refill();
+        uint32_t need2 = 15u;
         uint32_t de = S->lut_d[(uint32_t)bb & ((1u << RD) - 1u)];
         uint32_t dn = de >> 12;
         if (tail || dn == 0) {
@@ -957,16 +1018,21 @@ struct Decoder {
             uint32_t st = r >> 28;
             if (st) { if (st == (uint32_t)R_ERROR) msg = SDZ_MSG_BAD_DIST_CODE; return (int)st; }
             dn = (r >> 16) & 0xff;
+            need2 = (r >> 24) & 15u;
             uint32_t ds = r & 0xffff;
             if (ds > 29) { msg = SDZ_MSG_BAD_DIST_CODE; return R_ERROR; }
             de = ((ds < 4 ? 0u : (ds >> 1) - 1u) << 8) | (ds < 4 ? ds : 2u + (ds & 1u));
         }
+        if (emu) ref_need(p0 + n + xb, fastsym ? 15u : need2);
         bb >>= dn; bc -= (int)dn;
         uint32_t dx = (de >> 8) & 15;
         if (tail && avail_bits() < (int)dx) return R_STALL;
+        if (emu) ref_need(p0 + n + xb + dn, dx);
         uint32_t dist = 1 + ((de & 3) << dx) + ((uint32_t)bb & ((1u << dx) - 1u));
         bb >>= dx; bc -= (int)dx;
-        return copy_match(len, dist, lit_now);
+        const int rc = copy_match(len, dist, lit_now);
+        if (emu && rc == R_OK) ref_symbol_end(fastsym, len);
+        return rc;
     }
 
     // branch-free top-up used by the fast path (at least five whole input words remain):
@@ -997,7 +1063,9 @@ struct Decoder {
     __device__ __forceinline__ int step_flat()
     {
         constexpr uint32_t LMASK = (1u << RL) - 1u, DMASK = (1u << RD) - 1u;
-        bool general = wp + 5 > end_wp || cap - pos < (uint32_t)SDZ_CAPMARGIN;     // (one call site for step_general(): it is inlined once)
+        // (seven words: every symbol that starts within the last 16 bytes of the input goes through step_general(), which
+        //  models the reference's input frontier there; one call site for step_general(): it is inlined once)
+        bool general = wp + 7 > end_wp || cap - pos < (uint32_t)SDZ_CAPMARGIN;
         bool fold = false;
         uint32_t nfold = 0;                                // literals stored by this iteration's folds
         uint32_t e = 0;
@@ -1047,7 +1115,7 @@ struct Decoder {
                 }
             } else if ((e >> 12) != 0u) ok = true;          // end of block with a root-table code
             if (!ok) general = true;
-            else if ((e & 0xfffu) == 0x100u) { const uint32_t n = e >> 12; bb >>= n; bc -= (int)n; eob_len = (int)n; return R_EOB; }
+            else if ((e & 0xfffu) == 0x100u) { const uint32_t n = e >> 12; bb >>= n; bc -= (int)n; eob_len = (int)n; eob_emu = false; return R_EOB; }
         }
         }
         if (general) return step_general(nfold);
@@ -1171,6 +1239,7 @@ struct Decoder {
         D = 0; dict_tail = nullptr;
         lbits = dbits = g_l = g_d = 0; eob_len = 0;
         ring.init(0);
+        ref_F = ref_Fentry = ring_done = 0; blk_sym0_bit = 0; ref_on = ref_burst = ref_forced_slow = eob_emu = eob_fast = false;
         o_dst = o_meta = n_dst = n_meta = 0;
         is_gzip = false; method = 0; n_blocks = 0; mtime = 0; name_off = 0; name_len = 0; last = 0; raw = true;
         const uint64_t sb = P.task_bit[i];
@@ -1230,6 +1299,7 @@ struct Decoder {
         D = 0; dict_tail = nullptr;
         lbits = dbits = g_l = g_d = 0; eob_len = 0;
         ring.init(0);
+        ref_F = ref_Fentry = ring_done = 0; blk_sym0_bit = 0; ref_on = ref_burst = ref_forced_slow = eob_emu = eob_fast = false;
         o_dst = o_meta = n_dst = n_meta = 0;
         is_gzip = false; method = 0; n_blocks = 0; mtime = 0; name_off = 0; name_len = 0; last = 0;
 
@@ -1400,11 +1470,13 @@ struct Decoder {
     __device__ __forceinline__ void block_begin(const InflateParams& P)
     {
         if (!ensure(3)) { stall_kind = ST_OTHER; finish_stream(P, R_STALL); return; }
+        if (TM == TM_NONE) ref_need(bit_pos(), 3u);
         uint32_t t = peek(3);
         drop(3);
         last = (int)(t & 1);
         n_blocks++;
         start_pos = pos;
+        ring_done = pos;
         const uint32_t type = t >> 1;
         if (TM != TM_NONE) method = (int)type;                           // block-task records carry BTYPE
         int r;
@@ -1443,6 +1515,8 @@ struct Decoder {
             if (bc < skip) { finish_task(P, R_STALL); return; }
             drop(skip);
         }
+        blk_sym0_bit = bit_pos();
+        ref_burst = false; ref_forced_slow = false;                    // a new codes object: the START check comes first
         phase = PH_CODES;
     }
 
@@ -1462,18 +1536,17 @@ struct Decoder {
     __device__ __forceinline__ void block_end(const InflateParams& P, int r)
     {
         if (TM != TM_NONE) { finish_task(P, r); return; }
-        ring.write(pos - start_pos);
+        ring.write(pos - ring_done); ring_done = pos;
         if (r != R_EOB) { if (r == R_STALL) stall_kind = ST_OTHER; finish_stream(P, r); return; }
         // End of block.  When inflate_fast() decodes the EOB its STREAM_END status leaks through
         // WASH's early return (src/infcodes.ts:264,:357,:627-638 -> src/infblocks.ts:560-564), so
         // the block completes after ONE flush attempt; only a slow-path EOB (fewer than 258 bytes
         // of window room or fewer than 10 unread input bytes, src/infcodes.ts:339) washes the
-        // window completely, returning to append() as often as needed.
+        // window completely, returning to append() as often as needed.  Far from the end of the input only the
+        // window room decides; within the last 16 bytes step_general() has followed the reference's input frontier
+        // symbol by symbol (ref_symbol_begin).
         {
-            uint64_t b_before = bit_pos() - (uint64_t)eob_len;
-            uint32_t kcur = 4u + ((0u - (uint32_t)b_before - 4u) & 7u);     // reference bit-buffer fill (approx.)
-            uint64_t loaded = (b_before + kcur) >> 3;
-            bool fast_eob = ring.room() >= 258 && (uint64_t)in_len >= loaded + 10;
+            const bool fast_eob = eob_emu ? eob_fast : ring.room() >= 258;
             if (fast_eob) ring.flush(); else ring.wash();
         }
         if (last) { ring.wash(); finish_stream(P, R_EOB); return; }         // DRY (src/infblocks.ts:579-594)

@@ -346,6 +346,37 @@ void parallel_copy(const std::vector<std::pair<uint8_t*, std::pair<const uint8_t
 
 }  // namespace
 
+// ---- white-box test entry: the reference-table geometry the kernels re-derive in closed form
+namespace sdz {
+template <int G>
+__global__ void __launch_bounds__(128) debug_table_totals_kernel(const uint8_t* lens, const int32_t* nl, const int32_t* nd, unsigned long long n,
+                                                                  int32_t* out)
+{
+    __shared__ uint8_t s_lens[128 / G][320];
+    __shared__ uint16_t s_cnt[128 / G][16];
+    __shared__ uint32_t s_aux[128 / G][16];
+    const int gid = threadIdx.x / G, glane = threadIdx.x % G;
+    const int lane = threadIdx.x & 31;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - glane));
+    const unsigned long long groups = (unsigned long long)gridDim.x * (128 / G);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * (128 / G) + gid; i < (n + groups - 1) / groups * groups; i += groups) {
+        const bool on = i < n;                           // (all groups of a warp run the same number of rounds)
+        const int a = on ? nl[i] : 257, b = on ? nd[i] : 1;
+        for (int k = glane; k < 320; k += G) s_lens[gid][k] = on ? lens[i * 320 + k] : (uint8_t)(k < 2 || k == 257 ? 1 : 0);
+        __syncwarp(gmask);
+        int res[4];
+        for (int t = 0; t < 2; t++) {
+            int l = 0, g = 0, pad = 0, nz = 0;
+            const int st = classify<G>(s_lens[gid] + (t ? a : 0), t ? b : a, t ? 6 : 9, s_cnt[gid], s_aux[gid], &l, &g, &pad, &nz, glane, gmask);
+            res[2 * t] = st;
+            res[2 * t + 1] = (st == 0 || st == 2) ? ref_table_total<G>(s_cnt[gid], g, pad, l, glane, gmask) : 0;
+            __syncwarp(gmask);
+        }
+        if (on && glane == 0) for (int k = 0; k < 4; k++) out[i * 4 + k] = res[k];
+    }
+}
+}  // namespace sdz
+
 // ============================================================================ C ABI
 
 extern "C" {
@@ -461,6 +492,30 @@ int sdz_last_phase_timing(sdz_ctx* ctx, float ms[5])
     }
     CK(cudaEventElapsedTime(&ms[3], ctx->ev[1], ctx->ev[2]));
     CK(cudaEventElapsedTime(&ms[4], ctx->ev[0], ctx->ev[2]));
+    return SDZ_OK;
+}
+
+int sdz_debug_table_totals(sdz_ctx* ctx, const uint8_t* lens, const int32_t* nl, const int32_t* nd, uint64_t n, int group, int32_t* out)
+{
+    if (!ctx || !lens || !nl || !nd || !out || (group != 4 && group != 32)) return SDZ_E_ARG;
+    if (n == 0) return SDZ_OK;
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = grow(ctx, ctx->d_in, n * 320 + 16))) return rc;
+    if ((rc = grow(ctx, ctx->d_meta, n * 8 + n * 16 + 16))) return rc;
+    int32_t* d_nl = (int32_t*)ctx->d_meta.p;
+    int32_t* d_nd = d_nl + n;
+    int32_t* d_out = d_nd + n;
+    CK(cudaMemcpyAsync(ctx->d_in.p, lens, n * 320, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_nl, nl, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_nd, nd, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    const unsigned grid = (unsigned)std::min<uint64_t>((n * group + 127) / 128, (uint64_t)ctx->sm_count * 4);
+    if (group == 4) sdz::debug_table_totals_kernel<4><<<grid, 128, 0, ctx->stream>>>((const uint8_t*)ctx->d_in.p, d_nl, d_nd, n, d_out);
+    else sdz::debug_table_totals_kernel<32><<<grid, 128, 0, ctx->stream>>>((const uint8_t*)ctx->d_in.p, d_nl, d_nd, n, d_out);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, d_out, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return SDZ_OK;
 }
 

@@ -14,7 +14,7 @@ _ERR_NAME = {-1: "no sm_100a CUDA device", -2: "CUDA error", -3: "bad argument",
              -5: "output slot too small", -6: "unsupported"}
 
 EXPORTS = [
-    "sdz_ctx_create", "sdz_ctx_destroy", "sdz_last_error", "sdz_version", "sdz_launch_count", "sdz_last_timing", "sdz_last_phase_timing", "sdz_last_fast_stats",
+    "sdz_ctx_create", "sdz_ctx_destroy", "sdz_last_error", "sdz_version", "sdz_launch_count", "sdz_last_timing", "sdz_last_phase_timing", "sdz_last_fast_stats", "sdz_debug_table_totals",
     "sdz_host_alloc", "sdz_host_free", "sdz_device_alloc", "sdz_device_free", "sdz_memcpy_h2d", "sdz_memcpy_d2h",
     "sdz_adler32", "sdz_crc32", "sdz_adler32_chain", "sdz_crc32_chain", "sdz_checksum_batch",
     "sdz_inflate_batch", "sdz_inflate_sizes", "sdz_inflate_batch_device", "sdz_inflate_large", "sdz_sync",
@@ -89,6 +89,7 @@ def load():
         L.sdz_last_timing.argtypes = [vp, C.POINTER(C.c_float * 3)]
         L.sdz_last_phase_timing.argtypes = [vp, C.POINTER(C.c_float * 5)]
         L.sdz_last_fast_stats.argtypes = [vp, C.POINTER(C.c_uint64 * 2)]
+        L.sdz_debug_table_totals.argtypes = [vp, vp, vp, vp, u64, C.c_int, vp]
         L.sdz_host_alloc.argtypes = [C.c_size_t]
         L.sdz_host_alloc.restype = vp
         L.sdz_host_free.argtypes = [vp]

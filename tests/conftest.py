@@ -10,6 +10,7 @@ os.environ.setdefault("SDZ_POISON", "1")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "sd-zlib_b200", "host"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 FIXTURES = os.path.join(ROOT, "tests", "golden", "ref_fixtures")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
