@@ -32,20 +32,57 @@ namespace sdz {
 
 constexpr uint32_t TOK_LIT = 0x80000000u;      // literal: TOK_LIT | byte.  match: (dist - 1) << 9 | len.  0: no-op
 constexpr uint32_t NTOK_HANDED_OVER = 0xffffffffu;
-constexpr int FA_RL = 9, FA_RD = 7;            // LUT root widths (entry formats of make_lut())
+// LUT root widths (entry formats of make_lut()).  Phase A is latency-bound with ONE warp per scheduler when the
+// literal/length root is 9 bits wide (1,484 bytes of tables per lane -> 4 warps per SM: profiles/r02a_summary.md, every
+// issued instruction waits 3 more cycles).  An 8-bit root lets 6 warps share an SM, a 7-bit root 7 (8 with a 4-chunk
+// input ring).  Codes longer than the root go through the per-group general decoder (canon_long), so a narrower root
+// trades residency for more of those (synthetic text: 0.5 % of the symbols at 8 or 9 bits, 0.9 % at 7; English text
+// 1.6 % at 9).  Measured on the 65,536-stream batch (gpurun_out/variants_r02b.log): phase A 17.6 ms at 9 bits,
+// 14.9 ms at 8, 11.2 ms at 7.
+#ifndef SDZ_FA_RL
+#define SDZ_FA_RL 7
+#endif
+#ifndef SDZ_FA_RING
+#define SDZ_FA_RING 8
+#endif
+#if SDZ_FA_RL == 9
+#define SDZ_FA_RL_MASK 511
+#elif SDZ_FA_RL == 8
+#define SDZ_FA_RL_MASK 255
+#else
+#define SDZ_FA_RL_MASK 127
+#endif
+// commit groups that may still be in flight when a group of symbols ends: a chunk is requested when its slot is free,
+// i.e. RING - 1 chunks (4 RING - 3 words) ahead of the reader, and a group of four symbols reads at most six words
+#if SDZ_FA_RING == 8
+#define SDZ_FA_RING_WAIT 3
+#define SDZ_FA_RING_WMASK 31
+#elif SDZ_FA_RING == 4
+#define SDZ_FA_RING_WAIT 1
+#define SDZ_FA_RING_WMASK 15
+#else
+#error "SDZ_FA_RING: 4 or 8 chunks of 16 bytes"
+#endif
+#define SDZ_STR2(x) #x
+#define SDZ_STR(x) SDZ_STR2(x)
+constexpr int FA_RL = SDZ_FA_RL, FA_RD = 7;
+static_assert(FA_RL >= 7 && FA_RL <= 9, "literal/length root width");
+// while a dynamic header is parsed the lane's table area holds the block's code lengths (320 bytes from the start of
+// lut_l, running into lut_d when the root is 7 bits wide), the code-length-code lengths and their 7-bit LUT (tail of lut_d)
+constexpr int FA_HDR_CL = (1 << FA_RL) * 2 + 96, FA_HDR_BLUT = (1 << FA_RL) * 2 + 128;
 
 // per-lane (= per resident stream) decode tables
 struct alignas(4) LaneSmem {
-    uint16_t lut_l[1 << FA_RL];        // while a dynamic header is parsed: the block's code lengths (320 bytes)
-    uint16_t lut_d[1 << FA_RD];        // while a dynamic header is parsed: code-length-code lengths + its 7-bit LUT
+    uint16_t lut_l[1 << FA_RL];
+    uint16_t lut_d[1 << FA_RD];
     uint16_t cnt_l[16];                // [1..15] codes per length; [0] = longest code after the build
     uint16_t cnt_d[16];
     uint16_t start[4];                 // canonical-walk state after the root bits (canon_long)
     uint16_t long_l[32];               // first literal/length symbols whose code is longer than the root
     uint16_t sorted_d[32];             // distance symbols in canonical order
-    uint16_t pad_[2];                  // 371 words: an odd stride spreads the 32 lanes' tables over the banks
+    uint16_t pad_[2];                  // an odd number of words: the stride spreads the 32 lanes' tables over the banks
 };
-static_assert(sizeof(LaneSmem) == 1484, "LaneSmem layout");
+static_assert(sizeof(LaneSmem) == 460 + (2 << FA_RL) && (sizeof(LaneSmem) / 4) % 2 == 1, "LaneSmem layout");
 // compressed input of the symbol loop: per lane a ring of FA_RING_CHUNKS x 16 bytes in shared memory, filled by 16-byte
 // cp.async (LDGSTS) several groups of symbols ahead of the reader.  A plain `nw = input[wp]` costs the whole warp one
 // global-memory round trip per ITERATION: the lanes take their next word in different iterations, but the register
@@ -55,7 +92,7 @@ static_assert(sizeof(LaneSmem) == 1484, "LaneSmem layout");
 // Layout: lane l owns FA_RING_CHUNKS * 16 contiguous bytes at l * FA_RING_STRIDE (word w of the stream sits at
 // (w mod 32) * 4: one AND + one multiply-add per read); the 16 bytes of padding per lane keep the stride a multiple
 // of 16 (LDGSTS.128 alignment) and spread lanes over the banks (4-way conflict when all lanes read the same slot).
-constexpr int FA_RING_CHUNKS = 8;
+constexpr int FA_RING_CHUNKS = SDZ_FA_RING;
 constexpr int FA_RING_STRIDE = FA_RING_CHUNKS * 16 + 16;
 constexpr int FA_RING_BYTES = 32 * FA_RING_STRIDE;
 constexpr int FA_WARP_SMEM = 32 * (int)sizeof(LaneSmem) + SCRATCH_U16 * 2 + FA_RING_BYTES;      // tables | build scratch | input ring
@@ -476,8 +513,8 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                     drop(14);
                     nl = 257 + (int)(t & 0x1f); nd = 1 + (int)((t >> 5) & 0x1f);
                     const int ncl = 4 + (int)(t >> 10), total = nl + nd;
-                    uint8_t* cl = reinterpret_cast<uint8_t*>(L->lut_d);
-                    uint8_t* blut = cl + 32;
+                    uint8_t* cl = lens + FA_HDR_CL;
+                    uint8_t* blut = lens + FA_HDR_BLUT;
                     uint16_t* cnt = L->cnt_l;
                     for (int i = 0; i < 19; i++) cl[i] = 0;
                     for (int i = 0; i < 16; i++) cnt[i] = 0;
@@ -610,12 +647,12 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                     "mad.wide.u32 %0, %3, pw, %0;\n\t"            /* bits above bc are zero: add == or */                 \
                     "@pt add.s32 %1, %1, 32;\n\t"                                                                         \
                     "@pt add.u32 %2, %2, 1;\n\t"                                                                          \
-                    "and.b32 t, %2, 31;\n\t"                                                                              \
+                    "and.b32 t, %2, " SDZ_STR(SDZ_FA_RING_WMASK) ";\n\t"                                                                      \
                     "mad.lo.u32 ra, t, 4, %12;\n\t"                                                                       \
                     "@pt ld.shared.u32 %3, [ra];\n\t"                                                                     \
                     /* literal/length lookup and fields */                                                                \
                     "cvt.u32.u64 lo, %0;\n\t"                                                                             \
-                    "and.b32 t, lo, 511;\n\t"                                                                             \
+                    "and.b32 t, lo, " SDZ_STR(SDZ_FA_RL_MASK) ";\n\t"                                                                       \
                     "mad.lo.u32 ra, t, 2, %13;\n\t"                                                                       \
                     "ld.shared.u16 e, [ra];\n\t"                                                                          \
                     "shr.u32 n, e, 12;\n\t"                                                                               \
@@ -691,7 +728,7 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                         if (bc < 32) {
                             bb |= (uint64_t)nw << bc;
                             bc += 32; wp++;
-                            nw = lds_u32(ring_l + ((wp & 31u) << 2));
+                            nw = lds_u32(ring_l + ((wp & (4u * FA_RING_CHUNKS - 1u)) << 2));
                         }
                         const uint32_t lo = (uint32_t)bb;
                         uint32_t e = L->lut_l[lo & ((1u << FA_RL) - 1u)];
@@ -723,7 +760,7 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                                 if (bc < 32) {
                                     bb |= (uint64_t)nw << bc;
                                     bc += 32; wp++;
-                                    nw = lds_u32(ring_l + ((wp & 31u) << 2));
+                                    nw = lds_u32(ring_l + ((wp & (4u * FA_RING_CHUNKS - 1u)) << 2));
                                 }
                                 const uint32_t lo2 = (uint32_t)bb;
                                 uint32_t de = L->lut_d[lo2 & ((1u << FA_RD) - 1u)];
@@ -756,7 +793,7 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                     ci += need ? 1u : 0u;
                 }
                 cp_async_commit();
-                asm volatile("cp.async.wait_group 3;" ::: "memory");
+                asm volatile("cp.async.wait_group " SDZ_STR(SDZ_FA_RING_WAIT) ";" ::: "memory");
                 if (live) {
                     if (early != 0u || pos > cap || wp > lim_wp + 1u || ntok + 4u > cap_tok) ev = 2;
                     else if ((tk0 | tk1 | tk2 | tk3) != 0u) {

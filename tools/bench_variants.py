@@ -15,14 +15,22 @@ if args and args[0] == "--streams":
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 out = open(os.path.join(ROOT, "gpurun_out", "variants.jsonl"), "a")
 for name in args:
+    # name[,ENV=value...]: environment knobs of the library for this run
+    name, *knobs = name.split(",")
     lib = os.path.join(ROOT, "sd-zlib_b200", "csrc", "variants", name + ".so")
     env = dict(os.environ, SDZ_LIB=lib, SDZ_CORPUS_CACHE="/dev/shm/sdz_corpus")
+    for k in knobs:
+        env[k.split("=")[0]] = k.split("=")[1]
+    name = ",".join([name] + knobs)
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--no-checksums", "--no-e2e", "--cpu-sample", "0",
                         "--streams", streams, "--steps", "5", "--warmup", "3"], env=env, capture_output=True, text=True)
     line = p.stdout.strip().splitlines()[-1] if p.stdout.strip() else ""
     try:
         j = json.loads(line)
-        print("%-16s %7.2f GB/s  kernel %.3f ms  clocks %s" % (name, j["value"], j["roofline"]["kernel_ms"], j["clocks"]["sm_mhz"]), flush=True)
+        ph = j.get("phase_ms", {})
+        print("%-16s %7.2f GB/s  kernel %.3f ms  A %.2f  B-tail %.2f  general %.2f  clocks %s" % (
+            name, j["value"], j["roofline"]["kernel_ms"], ph.get("huff_tokens", 0), ph.get("lz_resolve", 0), ph.get("general_decoder", 0),
+            j["clocks"]["sm_mhz"]), flush=True)
         j["variant"] = name
         out.write(json.dumps(j) + "\n")
     except Exception:
