@@ -14,6 +14,6 @@ SHORT="python bench.py --steps 1 --warmup 3 --no-e2e --no-checksums --cpu-sample
 $SHORT > gpurun_out/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv $SHORT > gpurun_out/${TAG}_ncu1.log 2>&1
 $SHORT > gpurun_out/${TAG}_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'huff_tokens|lz_resolve' -s 24 -c 4 -o gpurun_out/${TAG}_full $SHORT > gpurun_out/${TAG}_ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'huff_tokens|lz_resolve' -s 12 -c 4 -o gpurun_out/${TAG}_full $SHORT > gpurun_out/${TAG}_ncu2.log 2>&1
 tail -5 gpurun_out/${TAG}_ncu2.log
 ls -la gpurun_out
