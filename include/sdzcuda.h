@@ -51,6 +51,19 @@ typedef struct sdz_ctx sdz_ctx;
 
 /* Context = one CUDA device + its streams, staging buffers and constant tables. */
 int  sdz_ctx_create(int device, uint32_t flags, sdz_ctx** out);
+/* Multi-device context (SURVEY 8b `sdz_ctx_create(devices[], ndev)`, 8e): one child context per entry of `devices`
+ * (an index may repeat: several independent pipelines on one GPU, which is also how the partition logic is tested on a
+ * one-GPU box).  sdz_inflate_batch / sdz_inflate_sizes on such a context partition the batch PER STREAM: device d
+ * decodes the contiguous range of streams whose compressed bytes come closest to an equal share (greedy sweep over the
+ * prefix sum), one host thread and one copy/compute pipeline per device, records and bytes written in caller order;
+ * nothing crosses between devices.  This is what `inflateBatch(buffers[])` (the one entry point added to
+ * dist/sd-zlib.d.ts:43-67's API) sits on when a box has several B200s.  Every other entry point of a multi-device
+ * context runs on its first device. */
+int  sdz_ctx_create_multi(const int* devices, int ndev, uint32_t flags, sdz_ctx** out);
+int  sdz_ctx_device_count(sdz_ctx* ctx);
+/* partition of the most recent batch of a multi-device context: device d took streams [cut[d], cut[d + 1]);
+ * n_cut >= device count + 1 */
+int  sdz_last_partition(sdz_ctx* ctx, uint64_t* cut, int n_cut);
 void sdz_ctx_destroy(sdz_ctx* ctx);
 const char* sdz_last_error(sdz_ctx* ctx);          /* text of the last failure on this ctx   */
 const char* sdz_version(void);
@@ -75,6 +88,10 @@ int sdz_debug_table_totals(sdz_ctx* ctx, const uint8_t* lens, const int32_t* nl,
 /* Pinned host memory helpers (so that callers can hand over DMA-able buffers). */
 void* sdz_host_alloc(size_t bytes);
 void  sdz_host_free(void* p);
+/* Pinned host memory on the NUMA node next to ctx's device (mmap + mbind + cudaHostRegister, portable across devices);
+ * the library's own staging buffers are allocated this way.  sdz_ctx_numa_node: that node, or -1 when unknown. */
+void* sdz_host_alloc_near(sdz_ctx* ctx, size_t bytes);
+int   sdz_ctx_numa_node(sdz_ctx* ctx);
 /* Device memory helpers for callers that keep data resident in HBM. */
 void* sdz_device_alloc(sdz_ctx* ctx, size_t bytes);
 void  sdz_device_free(sdz_ctx* ctx, void* p);

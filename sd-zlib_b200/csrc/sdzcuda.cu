@@ -9,6 +9,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -17,6 +19,12 @@
 #include "inflate_kernel.cuh"
 #include "fast_kernels.cuh"
 #include "large_kernels.cuh"
+
+// (after the kernels: unistd.h defines R_OK as a macro)
+#include <sched.h>
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 namespace {
 
@@ -70,9 +78,22 @@ struct sdz_ctx {
     const unsigned long long* last_fb_count = nullptr;   // device counter of the most recent fast-path launch
     uint64_t last_fast_n = 0;
     bool poison = false;               // SDZ_POISON=1 (tests): fill the device output arena with 0xA5 before every decode
+    // multi-device context (sdz_ctx_create_multi): one child context per entry of the device list; this object then only
+    // partitions batches (inflate_multi) and owns no streams of its own.  numa_node: host memory node next to the device
+    // (-1 unknown), used for the pinned staging buffers and sdz_host_alloc_near.
+    std::vector<sdz_ctx*> peers;
+    std::vector<uint64_t> last_cut;    // partition of the most recent batch: peer d decoded streams [last_cut[d], last_cut[d + 1])
+    int numa_node = -1;
 };
 
 namespace {
+
+// entry points other than the batched host path run on the first device of a multi-device context
+#define ENTER(ctx)                                                                                 \
+    do {                                                                                           \
+        if (!(ctx)->peers.empty()) (ctx) = (ctx)->peers[0];                                        \
+        CK(cudaSetDevice((ctx)->device));                                                          \
+    } while (0)
 
 #define CK(call)                                                                                   \
     do {                                                                                           \
@@ -94,13 +115,94 @@ int grow(sdz_ctx* ctx, DevBuf& b, size_t bytes)
     return SDZ_OK;
 }
 
+// ---- pinned host memory next to a device.  cudaMallocHost places pages wherever the calling thread happens to run; on a
+// two-socket box that puts half of the ranks' staging buffers across the socket interconnect from their GPU.  These
+// allocations are mmap'ed, bound to the device's NUMA node with mbind(MPOL_PREFERRED) (raw syscall: no libnuma in the
+// image) and then registered with CUDA (portable: every device may DMA from them).
+std::mutex g_pin_mu;
+std::map<void*, size_t> g_pin_regions;
+
+int device_numa_node(int device)
+{
+    char id[32] = { 0 };
+    if (cudaDeviceGetPCIBusId(id, sizeof id, device) != cudaSuccess) { cudaGetLastError(); return -1; }
+    for (char* c = id; *c; c++) if (*c >= 'A' && *c <= 'Z') *c = (char)(*c - 'A' + 'a');
+    std::string path = std::string("/sys/bus/pci/devices/") + id + "/numa_node";
+    FILE* f = fopen(path.c_str(), "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+}
+
+void* pinned_alloc(size_t bytes, int node)
+{
+    if (bytes == 0) bytes = 1;
+    const size_t page = 4096, len = (bytes + page - 1) / page * page;
+    void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (p == MAP_FAILED) return nullptr;
+#ifdef SYS_mbind
+    if (node >= 0 && node < 64) {
+        unsigned long mask = 1ul << node;
+        syscall(SYS_mbind, p, len, 1 /* MPOL_PREFERRED */, &mask, 65ul, 0u);       // best effort
+    }
+#endif
+    if (cudaHostRegister(p, len, cudaHostRegisterPortable) != cudaSuccess) {
+        cudaGetLastError();
+        munmap(p, len);
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> g(g_pin_mu);
+    g_pin_regions[p] = len;
+    return p;
+}
+
+void pinned_free(void* p)
+{
+    if (!p) return;
+    size_t len = 0;
+    {
+        std::lock_guard<std::mutex> g(g_pin_mu);
+        auto it = g_pin_regions.find(p);
+        if (it != g_pin_regions.end()) { len = it->second; g_pin_regions.erase(it); }
+    }
+    if (len) { cudaHostUnregister(p); munmap(p, len); }
+    else cudaFreeHost(p);
+}
+
+// run the calling thread on the cores of a NUMA node (best effort; the copy threads of a device sit next to its memory)
+void bind_thread_to_node(int node)
+{
+    if (node < 0) return;
+    char path[96];
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    FILE* f = fopen(path, "r");
+    if (!f) return;
+    char buf[1024] = { 0 };
+    const bool ok = fgets(buf, sizeof buf, f) != nullptr;
+    fclose(f);
+    if (!ok) return;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int any = 0;
+    for (char* tok = strtok(buf, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int a = 0, b = 0;
+        const int k = sscanf(tok, "%d-%d", &a, &b);
+        if (k < 1) continue;
+        if (k == 1) b = a;
+        for (int c = a; c <= b && c < CPU_SETSIZE; c++) { CPU_SET(c, &set); any = 1; }
+    }
+    if (any) sched_setaffinity(0, sizeof set, &set);
+}
+
 int grow_stage(sdz_ctx* ctx, size_t bytes)
 {
     if (bytes <= ctx->h_stage_cap) return SDZ_OK;
-    if (ctx->h_stage) { cudaFreeHost(ctx->h_stage); ctx->h_stage = nullptr; ctx->h_stage_cap = 0; }
+    if (ctx->h_stage) { pinned_free(ctx->h_stage); ctx->h_stage = nullptr; ctx->h_stage_cap = 0; }
     size_t want = (bytes + (1u << 20)) & ~((size_t(1) << 20) - 1);
-    cudaError_t e = cudaMallocHost(&ctx->h_stage, want);
-    if (e != cudaSuccess) { ctx->err = std::string("cudaMallocHost: ") + cudaGetErrorString(e); return SDZ_E_NOMEM; }
+    ctx->h_stage = pinned_alloc(want, ctx->numa_node);
+    if (!ctx->h_stage) { ctx->err = "pinned host allocation failed (staging)"; return SDZ_E_NOMEM; }
     ctx->h_stage_cap = want;
     return SDZ_OK;
 }
@@ -108,10 +210,10 @@ int grow_stage(sdz_ctx* ctx, size_t bytes)
 int grow_res(sdz_ctx* ctx, size_t bytes)
 {
     if (bytes <= ctx->h_res_cap) return SDZ_OK;
-    if (ctx->h_res) { cudaFreeHost(ctx->h_res); ctx->h_res = nullptr; ctx->h_res_cap = 0; }
+    if (ctx->h_res) { pinned_free(ctx->h_res); ctx->h_res = nullptr; ctx->h_res_cap = 0; }
     size_t want = (bytes + (1u << 20)) & ~((size_t(1) << 20) - 1);
-    cudaError_t e = cudaMallocHost(&ctx->h_res, want);
-    if (e != cudaSuccess) { ctx->err = std::string("cudaMallocHost: ") + cudaGetErrorString(e); return SDZ_E_NOMEM; }
+    ctx->h_res = pinned_alloc(want, ctx->numa_node);
+    if (!ctx->h_res) { ctx->err = "pinned host allocation failed (records)"; return SDZ_E_NOMEM; }
     ctx->h_res_cap = want;
     return SDZ_OK;
 }
@@ -397,6 +499,7 @@ int sdz_ctx_create(int device, uint32_t flags, sdz_ctx** out)
     sdz_ctx* ctx = new sdz_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->numa_node = getenv("SDZ_NO_NUMA") ? -1 : device_numa_node(device);
     auto fail = [&](int rc) { sdz_ctx_destroy(ctx); return rc; };
     if (cudaSetDevice(device) != cudaSuccess) return fail(SDZ_E_CUDA);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(SDZ_E_CUDA);
@@ -428,9 +531,42 @@ int sdz_ctx_create(int device, uint32_t flags, sdz_ctx** out)
     return SDZ_OK;
 }
 
+int sdz_ctx_create_multi(const int* devices, int ndev, uint32_t flags, sdz_ctx** out)
+{
+    if (!out) return SDZ_E_ARG;
+    *out = nullptr;
+    if (!devices || ndev < 1 || ndev > 64) return SDZ_E_ARG;
+    sdz_ctx* m = new sdz_ctx();
+    m->device = devices[0];
+    for (int d = 0; d < ndev; d++) {
+        sdz_ctx* c = nullptr;
+        const int rc = sdz_ctx_create(devices[d], flags, &c);
+        if (rc) { sdz_ctx_destroy(m); return rc; }
+        m->peers.push_back(c);
+    }
+    m->sm_count = m->peers[0]->sm_count;
+    *out = m;
+    return SDZ_OK;
+}
+
+int sdz_ctx_device_count(sdz_ctx* ctx) { return !ctx ? 0 : (ctx->peers.empty() ? 1 : (int)ctx->peers.size()); }
+
+int sdz_last_partition(sdz_ctx* ctx, uint64_t* cut, int n_cut)
+{
+    if (!ctx || !cut) return SDZ_E_ARG;
+    if (ctx->peers.empty() || ctx->last_cut.empty() || n_cut < (int)ctx->last_cut.size()) return SDZ_E_ARG;
+    for (size_t i = 0; i < ctx->last_cut.size(); i++) cut[i] = ctx->last_cut[i];
+    return SDZ_OK;
+}
+
 void sdz_ctx_destroy(sdz_ctx* ctx)
 {
     if (!ctx) return;
+    if (!ctx->peers.empty()) {
+        for (sdz_ctx* c : ctx->peers) sdz_ctx_destroy(c);
+        delete ctx;
+        return;
+    }
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (DevBuf* b : { &ctx->d_in, &ctx->d_out, &ctx->d_meta, &ctx->d_res, &ctx->d_part, &ctx->d_misc, &ctx->d_sym, &ctx->d_task,
@@ -450,8 +586,8 @@ void sdz_ctx_destroy(sdz_ctx* ctx)
         for (auto& e : ctx->fast_ev[l])
             if (e) cudaEventDestroy(e);
     }
-    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
-    if (ctx->h_res) cudaFreeHost(ctx->h_res);
+    pinned_free(ctx->h_stage);
+    pinned_free(ctx->h_res);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
     for (auto& e : ctx->ev)
         if (e) cudaEventDestroy(e);
@@ -464,12 +600,18 @@ void sdz_ctx_destroy(sdz_ctx* ctx)
 }
 
 const char* sdz_last_error(sdz_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
-uint64_t sdz_launch_count(sdz_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t sdz_launch_count(sdz_ctx* ctx)
+{
+    if (!ctx) return 0;
+    uint64_t v = ctx->launches;
+    for (sdz_ctx* c : ctx->peers) v += c->launches;
+    return v;
+}
 
 int sdz_last_timing(sdz_ctx* ctx, float ms[3])
 {
     if (!ctx) return SDZ_E_ARG;
-    CK(cudaSetDevice(ctx->device));
+    ENTER(ctx);
     CK(cudaEventSynchronize(ctx->ev[2]));
     CK(cudaEventElapsedTime(&ms[0], ctx->ev[0], ctx->ev[1]));
     CK(cudaEventElapsedTime(&ms[1], ctx->ev[1], ctx->ev[2]));
@@ -480,7 +622,7 @@ int sdz_last_timing(sdz_ctx* ctx, float ms[3])
 int sdz_last_phase_timing(sdz_ctx* ctx, float ms[5])
 {
     if (!ctx || !ms) return SDZ_E_ARG;
-    CK(cudaSetDevice(ctx->device));
+    ENTER(ctx);
     CK(cudaEventSynchronize(ctx->ev[2]));
     for (int i = 0; i < 5; i++) ms[i] = 0.f;
     if (ctx->fast_timed) {
@@ -499,7 +641,7 @@ int sdz_debug_table_totals(sdz_ctx* ctx, const uint8_t* lens, const int32_t* nl,
 {
     if (!ctx || !lens || !nl || !nd || !out || (group != 4 && group != 32)) return SDZ_E_ARG;
     if (n == 0) return SDZ_OK;
-    CK(cudaSetDevice(ctx->device));
+    ENTER(ctx);
     int rc;
     if ((rc = grow(ctx, ctx->d_in, n * 320 + 16))) return rc;
     if ((rc = grow(ctx, ctx->d_meta, n * 8 + n * 16 + 16))) return rc;
@@ -524,7 +666,7 @@ int sdz_last_fast_stats(sdz_ctx* ctx, uint64_t out[2])
     if (!ctx || !out) return SDZ_E_ARG;
     out[0] = out[1] = 0;
     if (!ctx->last_fb_count) return SDZ_OK;
-    CK(cudaSetDevice(ctx->device));
+    ENTER(ctx);
     for (int l = 0; l < sdz_ctx::N_LANES; l++) CK(cudaStreamSynchronize(ctx->lane_stream[l]));
     unsigned long long fb = 0;
     CK(cudaMemcpy(&fb, ctx->last_fb_count, sizeof fb, cudaMemcpyDeviceToHost));
@@ -539,7 +681,20 @@ void* sdz_host_alloc(size_t bytes)
     if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
     return p;
 }
-void sdz_host_free(void* p) { if (p) cudaFreeHost(p); }
+void sdz_host_free(void* p) { pinned_free(p); }
+
+void* sdz_host_alloc_near(sdz_ctx* ctx, size_t bytes)
+{
+    if (!ctx) return nullptr;
+    if (!ctx->peers.empty()) ctx = ctx->peers[0];
+    cudaSetDevice(ctx->device);
+    return pinned_alloc(bytes, ctx->numa_node);
+}
+int sdz_ctx_numa_node(sdz_ctx* ctx)
+{
+    if (!ctx) return -1;
+    return ctx->peers.empty() ? ctx->numa_node : ctx->peers[0]->numa_node;
+}
 
 void* sdz_device_alloc(sdz_ctx* ctx, size_t bytes)
 {
@@ -554,7 +709,7 @@ void sdz_device_free(sdz_ctx* ctx, void* p) { if (ctx && p) { cudaSetDevice(ctx-
 int sdz_memcpy_h2d(sdz_ctx* ctx, void* dst, const void* src, size_t bytes)
 {
     if (!ctx) return SDZ_E_ARG;
-    CK(cudaSetDevice(ctx->device));
+    ENTER(ctx);
     CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return SDZ_OK;
@@ -562,7 +717,7 @@ int sdz_memcpy_h2d(sdz_ctx* ctx, void* dst, const void* src, size_t bytes)
 int sdz_memcpy_d2h(sdz_ctx* ctx, void* dst, const void* src, size_t bytes)
 {
     if (!ctx) return SDZ_E_ARG;
-    CK(cudaSetDevice(ctx->device));
+    ENTER(ctx);
     CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return SDZ_OK;
@@ -570,7 +725,7 @@ int sdz_memcpy_d2h(sdz_ctx* ctx, void* dst, const void* src, size_t bytes)
 int sdz_sync(sdz_ctx* ctx)
 {
     if (!ctx) return SDZ_E_ARG;
-    CK(cudaSetDevice(ctx->device));
+    ENTER(ctx);
     CK(cudaStreamSynchronize(ctx->stream));
     return SDZ_OK;
 }
@@ -581,7 +736,7 @@ static int checksum_chain(sdz_ctx* ctx, bool crc, const uint8_t* p, const uint64
                           int32_t seed, int on_device, int32_t* out_values, int32_t* out_last)
 {
     if (!ctx || !out_last || (n_seg && !seg_len)) return SDZ_E_ARG;
-    CK(cudaSetDevice(ctx->device));
+    ENTER(ctx);
     if (n_seg == 0) { *out_last = seed; return SDZ_OK; }
     if (n_seg > 0xffffffffull) return SDZ_E_ARG;
     uint64_t total = 0;
@@ -680,7 +835,7 @@ int sdz_checksum_batch(sdz_ctx* ctx, const uint8_t* const* bufs, const uint64_t*
 {
     if (!ctx || (n && (!bufs || !lens || !kind || !out))) return SDZ_E_ARG;
     if (n == 0) return SDZ_OK;
-    CK(cudaSetDevice(ctx->device));
+    ENTER(ctx);
     std::vector<uint64_t> off(n);
     size_t total = 0;
     for (uint64_t i = 0; i < n; i++) {
@@ -737,11 +892,66 @@ int sdz_inflate_batch_device(sdz_ctx* ctx, const sdz_batch_dev* batch, uint32_t 
 {
     if (!ctx || !batch) return SDZ_E_ARG;
     if (flags & SDZ_PARITY_SPEC) return SDZ_E_UNSUPPORTED;
-    CK(cudaSetDevice(ctx->device));
+    ENTER(ctx);
     int rc = run_batch_device(ctx, batch, batch->d_out == nullptr);
     if (rc) return rc;
     if (sync) CK(cudaStreamSynchronize(ctx->stream));
     return SDZ_OK;
+}
+
+static int inflate_host(sdz_ctx* ctx, const sdz_in* in, uint64_t n, uint8_t* out_arena, const uint64_t* out_off,
+                        const uint64_t* out_cap, sdz_result* results, uint64_t* out_len, uint32_t flags, bool sizes_only);
+
+// Partition of one batch over the devices of a multi-device context ("partition streams across GPUs by greedy
+// balance on compressed bytes").  Streams keep the caller's order: device d takes the contiguous range
+// [cut[d], cut[d + 1]) whose compressed bytes (+ a constant per stream for the per-stream work: header, table builds,
+// record) come closest to an equal share - a greedy sweep over the prefix sum.  Contiguous ranges keep the records in
+// caller order and each device's output slots dense, so every device still returns its bytes with few large copies.
+static void partition_streams(const sdz_in* in, uint64_t n, unsigned ndev, std::vector<uint64_t>& cut)
+{
+    constexpr uint64_t PER_STREAM = 512;
+    cut.assign(ndev + 1, n);
+    cut[0] = 0;
+    uint64_t total = 0;
+    for (uint64_t i = 0; i < n; i++) total += in[i].len + PER_STREAM;
+    uint64_t acc = 0, i = 0;
+    for (unsigned d = 1; d < ndev; d++) {
+        const uint64_t target = total / ndev * d + (total % ndev) * d / ndev;
+        while (i < n && acc + (in[i].len + PER_STREAM) / 2 <= target) { acc += in[i].len + PER_STREAM; i++; }
+        cut[d] = i;
+    }
+}
+
+// One host thread per device; each runs the ordinary pipelined host path (staging, H2D, kernels, D2H) on its share.
+// No collective and no device-to-device traffic: the streams are independent, records land in the caller's array.
+static int inflate_multi(sdz_ctx* ctx, const sdz_in* in, uint64_t n, uint8_t* out_arena, const uint64_t* out_off,
+                         const uint64_t* out_cap, sdz_result* results, uint64_t* out_len, uint32_t flags, bool sizes_only)
+{
+    const unsigned ndev = (unsigned)ctx->peers.size();
+    partition_streams(in, n, ndev, ctx->last_cut);
+    const std::vector<uint64_t>& cut = ctx->last_cut;
+    std::vector<int> rcs(ndev, SDZ_OK);
+    std::vector<std::thread> th;
+    for (unsigned d = 0; d < ndev; d++) {
+        const uint64_t lo = cut[d], hi = cut[d + 1];
+        if (lo == hi) continue;
+        th.emplace_back([&, d, lo, hi] {
+            sdz_ctx* c = ctx->peers[d];
+            bind_thread_to_node(c->numa_node);
+            rcs[d] = inflate_host(c, in + lo, hi - lo, out_arena, out_off ? out_off + lo : nullptr, out_cap ? out_cap + lo : nullptr,
+                                  results ? results + lo : nullptr, out_len ? out_len + lo : nullptr, flags, sizes_only);
+        });
+    }
+    for (auto& t : th) t.join();
+    int ret = SDZ_OK;
+    for (unsigned d = 0; d < ndev; d++) {
+        if (rcs[d] == SDZ_OK) continue;
+        if (rcs[d] != SDZ_E_OUT_CAP || ret == SDZ_OK) {       // a hard error wins over "some slot was too small"
+            if (rcs[d] != SDZ_E_OUT_CAP) ctx->err = "device " + std::to_string(ctx->peers[d]->device) + ": " + ctx->peers[d]->err;
+            if (ret == SDZ_OK || ret == SDZ_E_OUT_CAP) ret = rcs[d];
+        }
+    }
+    return ret;
 }
 
 // shared host path: stage inputs, run, fetch records (and bytes unless sizes_only)
@@ -752,7 +962,8 @@ static int inflate_host(sdz_ctx* ctx, const sdz_in* in, uint64_t n, uint8_t* out
     if (flags & SDZ_PARITY_SPEC) return SDZ_E_UNSUPPORTED;
     if (!sizes_only && (!results || (n && (!out_arena || !out_off || !out_cap)))) return SDZ_E_ARG;
     if (n == 0) return SDZ_OK;
-    CK(cudaSetDevice(ctx->device));
+    if (!ctx->peers.empty()) return inflate_multi(ctx, in, n, out_arena, out_off, out_cap, results, out_len, flags, sizes_only);
+    ENTER(ctx);
 
     // ---- layout of the compressed arena, the dictionary arena and the per-stream arrays
     std::vector<uint64_t> in_off(n), dict_off(n), d_out_off(n);
@@ -1166,7 +1377,7 @@ extern "C" int sdz_large_open(sdz_ctx* ctx, const uint8_t* data, uint64_t len, u
     if (!ctx || !out || (len && !data) || mode > SDZ_MODE_RAW) return SDZ_E_ARG;
     if (len >= (1ull << 32) - 64) return SDZ_E_ARG;
     *out = nullptr;
-    CK(cudaSetDevice(ctx->device));
+    ENTER(ctx);
     // ---- container header on the host (a few bytes; src/inflate.ts:142-401).  Anything but a plain, complete
     // header goes to the sequential decoder, which knows every corner of the reference's state machine.
     uint8_t head[1024];
@@ -1266,7 +1477,7 @@ extern "C" int sdz_large_index(sdz_large* L, uint32_t part, uint32_t n_parts, co
 {
     if (!L || !n_parts || part >= n_parts || !blocks || !n_blocks || !ckpts || !n_ckpts) return SDZ_E_ARG;
     sdz_ctx* ctx = L->ctx;
-    CK(cudaSetDevice(ctx->device));
+    ENTER(ctx);
     L->blocks.clear(); L->ckpts.clear();
     const uint64_t span_all = L->total_bits - L->first_bit;
     uint64_t lo = L->first_bit + span_all / n_parts * part, hi = part + 1 == n_parts ? L->total_bits : L->first_bit + span_all / n_parts * (part + 1);
@@ -1318,7 +1529,7 @@ extern "C" int sdz_large_plan(sdz_large* L, const sdz_large_block* blocks, uint6
 {
     if (!L || (n_blocks && !blocks) || (n_ckpts && !ckpts)) return SDZ_E_ARG;
     sdz_ctx* ctx = L->ctx;
-    CK(cudaSetDevice(ctx->device));
+    ENTER(ctx);
     auto seq = [&]() { ctx->err = "stream needs the sequential decoder"; return SDZ_E_UNSUPPORTED; };
     std::vector<sdz_large_block> B(blocks, blocks + n_blocks);
     std::vector<sdz_large_ckpt> C(ckpts, ckpts + n_ckpts);
@@ -1424,7 +1635,7 @@ extern "C" int sdz_large_decode(sdz_large* L, uint32_t part, uint32_t n_parts, u
 {
     if (!L || !L->planned || !n_parts || part >= n_parts) return SDZ_E_ARG;
     sdz_ctx* ctx = L->ctx;
-    CK(cudaSetDevice(ctx->device));
+    ENTER(ctx);
     uint64_t lo, hi;
     sdz_large_range(L, part, n_parts, &lo, &hi);
     L->p_lo = (uint64_t)(std::lower_bound(L->t_off.begin(), L->t_off.end() - 1, lo) - L->t_off.begin());
@@ -1493,7 +1704,7 @@ extern "C" int sdz_large_windows(sdz_large* L)
 {
     if (!L || !L->planned) return SDZ_E_ARG;
     sdz_ctx* ctx = L->ctx;
-    CK(cudaSetDevice(ctx->device));
+    ENTER(ctx);
     const uint64_t nt = L->p_hi - L->p_lo;
     if (!nt) return SDZ_OK;
     const uint64_t lo = L->off_lo();
@@ -1510,7 +1721,7 @@ extern "C" int sdz_large_resolve(sdz_large* L)
 {
     if (!L || !L->planned) return SDZ_E_ARG;
     sdz_ctx* ctx = L->ctx;
-    CK(cudaSetDevice(ctx->device));
+    ENTER(ctx);
     const uint64_t nt = L->p_hi - L->p_lo;
     if (nt) {
         const uint64_t lo = L->off_lo();
@@ -1577,7 +1788,7 @@ extern "C" int sdz_inflate_large(sdz_ctx* ctx, const uint8_t* data, uint64_t len
 {
     if (!ctx || !res || (len && !data) || mode > SDZ_MODE_RAW) return SDZ_E_ARG;
     if (len >= (1ull << 32) - 64) return SDZ_E_ARG;
-    CK(cudaSetDevice(ctx->device));
+    ENTER(ctx);
     memset(res, 0, sizeof *res);
     sdz_large* L = nullptr;
     auto fallback = [&]() -> int {

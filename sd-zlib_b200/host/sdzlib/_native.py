@@ -14,7 +14,7 @@ _ERR_NAME = {-1: "no sm_100a CUDA device", -2: "CUDA error", -3: "bad argument",
              -5: "output slot too small", -6: "unsupported"}
 
 EXPORTS = [
-    "sdz_ctx_create", "sdz_ctx_destroy", "sdz_last_error", "sdz_version", "sdz_launch_count", "sdz_last_timing", "sdz_last_phase_timing", "sdz_last_fast_stats", "sdz_debug_table_totals",
+    "sdz_ctx_create", "sdz_ctx_create_multi", "sdz_ctx_device_count", "sdz_last_partition", "sdz_host_alloc_near", "sdz_ctx_numa_node", "sdz_ctx_destroy", "sdz_last_error", "sdz_version", "sdz_launch_count", "sdz_last_timing", "sdz_last_phase_timing", "sdz_last_fast_stats", "sdz_debug_table_totals",
     "sdz_host_alloc", "sdz_host_free", "sdz_device_alloc", "sdz_device_free", "sdz_memcpy_h2d", "sdz_memcpy_d2h",
     "sdz_adler32", "sdz_crc32", "sdz_adler32_chain", "sdz_crc32_chain", "sdz_checksum_batch",
     "sdz_inflate_batch", "sdz_inflate_sizes", "sdz_inflate_batch_device", "sdz_inflate_large", "sdz_sync",
@@ -79,6 +79,12 @@ def load():
         L = C.CDLL(LIB_PATH)
         vp, u64, i32, u32 = C.c_void_p, C.c_uint64, C.c_int32, C.c_uint32
         L.sdz_ctx_create.argtypes = [C.c_int, u32, C.POINTER(vp)]
+        L.sdz_ctx_create_multi.argtypes = [C.POINTER(C.c_int), C.c_int, u32, C.POINTER(vp)]
+        L.sdz_ctx_device_count.argtypes = [vp]
+        L.sdz_last_partition.argtypes = [vp, vp, C.c_int]
+        L.sdz_host_alloc_near.argtypes = [vp, C.c_size_t]
+        L.sdz_host_alloc_near.restype = vp
+        L.sdz_ctx_numa_node.argtypes = [vp]
         L.sdz_ctx_destroy.argtypes = [vp]
         L.sdz_ctx_destroy.restype = None
         L.sdz_last_error.argtypes = [vp]
@@ -131,13 +137,27 @@ class Context:
     """sdz_ctx wrapper: one per (process, device)."""
 
     def __init__(self, device=0):
+        """device: one index, or a list of indices (multi-device context: batches are partitioned per stream)."""
         self.lib = load()
         h = C.c_void_p()
-        rc = self.lib.sdz_ctx_create(device, 0, C.byref(h))
+        if isinstance(device, (list, tuple)):
+            devs = (C.c_int * len(device))(*device)
+            rc = self.lib.sdz_ctx_create_multi(devs, len(device), 0, C.byref(h))
+        else:
+            rc = self.lib.sdz_ctx_create(device, 0, C.byref(h))
         if rc != SDZ_OK:
-            raise NativeError("sdz_ctx_create(device=%d) failed: %s" % (device, _ERR_NAME.get(rc, rc)))
+            raise NativeError("sdz_ctx_create(device=%s) failed: %s" % (device, _ERR_NAME.get(rc, rc)))
         self.h = h
         self.device = device
+
+    def device_count(self):
+        return int(self.lib.sdz_ctx_device_count(self.h))
+
+    def last_partition(self):
+        n = self.device_count() + 1
+        cut = (C.c_uint64 * n)()
+        self.check(self.lib.sdz_last_partition(self.h, cut, n))
+        return [int(x) for x in cut]
 
     def check(self, rc, allow=()):
         if rc != SDZ_OK and rc not in allow:

@@ -322,18 +322,25 @@ def test_cfg4_mixed_container_batch():
     """BASELINE configs[3] on one GPU: gzip + raw + zlib (+ preset dictionary), levels 1/6/9, text / binary /
     tiny (fixed blocks) / incompressible <= 49,151 B (stored blocks) / runs - one batch, every finish() record
     and every byte compared with the oracle."""
+    streams, dicts, modes = _cfg4_batch(1500)
+    got = check_against_oracle(streams, dicts, modes)
+    assert sum(1 for _, r in got if r.success) > 1300          # raw streams may be incomplete by Q15
+    assert {r.container for _, r in got} == {0, 1, 2}
+
+
+def _cfg4_batch(n_streams, seed0=7000):
     dic = bytes(K.generate(K.TEXT, 4242, 470))
     dictid = O.adler32(dic)
     rnd = random.Random(44)
     streams, dicts, modes = [], [], []
     kinds = [(K.TEXT, 65536), (K.BINARY, 65536), (K.TINY, 0), (K.RANDOM, 0), (K.RUNS, 65536), (K.TEXT, 20000)]
-    for i in range(1500):
+    for i in range(n_streams):
         kind, n = kinds[i % len(kinds)]
         if kind == K.TINY:
             n = 1 + rnd.randrange(200)
         elif kind == K.RANDOM:
             n = 1 + rnd.randrange(49151)
-        plain = K.generate(kind, 7000 + i, n)
+        plain = K.generate(kind, seed0 + i, n)
         level = (1, 6, 9)[i % 3]
         cont = (K.GZIP, K.RAW, K.ZLIB, K.GZIP_NAME, K.ZLIB_DICT)[i % 5]
         if cont == K.ZLIB_DICT:
@@ -341,9 +348,58 @@ def test_cfg4_mixed_container_batch():
         else:
             streams.append(K.compress(plain, level, cont)); dicts.append(None)
             modes.append(O.MODE_RAW if cont == K.RAW and i % 2 else O.MODE_SNIFF)
-    got = check_against_oracle(streams, dicts, modes)
-    assert sum(1 for _, r in got if r.success) > 1300          # raw streams may be incomplete by Q15
-    assert {r.container for _, r in got} == {0, 1, 2}
+    return streams, dicts, modes
+
+
+def test_multi_device_context_partitions_one_batch():
+    """X2 / SURVEY 8e: ONE batch handed to a multi-device context is partitioned per stream (contiguous ranges balanced
+    on compressed bytes), decoded by one pipeline per device, and comes back - bytes and records, in caller order -
+    bit-identical to the single-device result and to the oracle.  On a one-GPU box the device list repeats device 0
+    (three independent pipelines): the same partition / thread / gather code runs."""
+    import torch
+    from sdzlib import _native as N
+    ndev = torch.cuda.device_count()
+    devices = list(range(ndev)) if ndev > 1 else [0, 0, 0]
+    streams, dicts, modes = _cfg4_batch(1200, seed0=9100)
+    streams += [b"", b"\x78", b"\x78\x01\x07"]                     # degenerate inputs ride along
+    dicts += [None] * 3
+    modes += [O.MODE_SNIFF] * 3
+    views = [np.frombuffer(bytes(s), dtype=np.uint8) for s in streams]
+    single = A.inflate_batch_raw(views, dicts, modes, None)
+    mctx = N.Context(devices)
+    assert mctx.device_count() == len(devices)
+    arena, off, res = A.inflate_batch_raw(views, dicts, modes, None, ctx=mctx)
+    cut = mctx.last_partition()
+    assert cut[0] == 0 and cut[-1] == len(streams) and all(a <= b for a, b in zip(cut, cut[1:]))
+    share = [sum(len(streams[i]) for i in range(cut[d], cut[d + 1])) for d in range(len(devices))]
+    assert max(share) - min(share) <= 2 * max(len(s) for s in streams) + 2048, share      # balanced on compressed bytes
+    assert list(off) == list(single[1])
+    for i, s in enumerate(streams):
+        r, r1 = res[i], single[2][i]
+        assert r.observable() == r1.observable(), i
+        n = int(r.out_len)
+        if not r.thrown_append:
+            assert bytes(arena[int(off[i]):int(off[i]) + n]) == bytes(single[0][int(off[i]):int(off[i]) + n]), i
+        if i % 7 == 0:
+            eb, er = O.inflate_oneshot(bytes(s), dictionary=dicts[i], mode=modes[i])
+            assert r.observable() == er.observable(), i
+            if not er.thrown_append:
+                assert bytes(arena[int(off[i]):int(off[i]) + n]) == eb, i
+    # a second, larger call reuses the grown buffers of every child; sizes pass goes through the partition too
+    sizes = np.zeros(len(views), dtype=np.uint64)
+    ins = (N.In * len(views))()
+    keep = []
+    for i, v in enumerate(views):
+        ins[i].data = v.ctypes.data if v.size else None
+        ins[i].len = int(v.size)
+        ins[i].mode = modes[i]
+        if dicts[i] is not None:
+            dv = np.frombuffer(dicts[i], dtype=np.uint8)
+            keep.append(dv)
+            ins[i].dict = dv.ctypes.data; ins[i].dict_len = int(dv.size)
+    mctx.check(mctx.lib.sdz_inflate_sizes(mctx.h, ins, len(views), sizes.ctypes.data, 0))
+    assert [int(x) for x in sizes] == [int(r.out_len) for r in res]
+    mctx.close()
 
 
 def test_checksum_batch():
