@@ -143,6 +143,35 @@ typedef struct sdz_result {
     uint8_t  reserved[7];
 } sdz_result;
 
+/* Where an Inflater stopped at the end of the input it had been given - the state the reference keeps between
+ * append() calls (src/inflate.ts:79-95, src/infblocks.ts:40-50, src/infcodes.ts:44-60), reduced to what the device
+ * decoder needs to continue: it re-parses the header of the current block (tables are rebuilt, not stored) and goes on at
+ * the symbol the reference was waiting on.  Lives in device memory; written and read by inflate_kernel. */
+enum sdz_resume_kind {
+    SDZ_RESUME_START = 0,      /* nothing consumed yet (the container header is incomplete)                            */
+    SDZ_RESUME_AT_BLOCK = 1,   /* a block header starts at block_bit (TYPE / LENS / TABLE are re-entrant)              */
+    SDZ_RESUME_IN_CODES = 2,   /* inside the block whose header is at block_bit; the next symbol starts at sym_bit     */
+    SDZ_RESUME_AT_TRAILER = 3, /* the final block ended at block_bit; the container trailer is incomplete              */
+    SDZ_RESUME_BROKEN_Q3 = 4,  /* input ended inside BTREE / DTREE: the next append() throws               */
+    SDZ_RESUME_DONE = 5,       /* stream complete: more input makes append() spin                          */
+    SDZ_RESUME_FAILED = 6      /* append() threw                                                                       */
+};
+typedef struct sdz_resume {
+    uint64_t block_bit;
+    uint64_t sym_bit;
+    uint32_t pos;              /* bytes produced so far (z.total_out)                                                  */
+    int32_t  ring_q;           /* InfBlocks.write == read: append() returns with the window flushed                    */
+    uint32_t n_blocks;
+    int32_t  mtime;
+    uint32_t name_off, name_len;
+    uint32_t prev_len;         /* input bytes seen so far: the reference had loaded all of them into its bit buffer    */
+    uint16_t dict_used;        /* bytes of the preset dictionary in the window                            */
+    uint8_t  kind;             /* enum sdz_resume_kind                                                                 */
+    uint8_t  flags;            /* 1: gzip, 2: raw, 4: BFINAL of the current block                                      */
+    uint8_t  method;           /* zlib CMF / gzip CM byte                                                              */
+    uint8_t  reserved[11];
+} sdz_resume;
+
 #ifdef __cplusplus
 }
 #endif

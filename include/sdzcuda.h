@@ -177,6 +177,29 @@ typedef struct sdz_batch_dev {
 } sdz_batch_dev;
 int sdz_inflate_batch_device(sdz_ctx* ctx, const sdz_batch_dev* batch, uint32_t flags, int sync);
 
+/* ---------------------------------------------------------------- streaming: class Inflater over several append() calls
+ * One sdz_inflater == one `new Inflater({raw, dictionary})` (src/sd-inflate.ts:54-80).  The state the reference carries
+ * between calls (src/inflate.ts:79-95, src/infblocks.ts:40-50, src/infcodes.ts:44-60: mode, bit buffer, window, tables) is
+ * kept as an sdz_resume record + the decoded bytes in HBM, so an append() decodes only what is new.  Behaviour at the
+ * boundaries is the reference's, defects included: input that ends inside a dynamic block header makes the NEXT append()
+ * throw "inflate error: " (BTREE / DTREE are not re-entrant), a stored block ends where its append() ended
+ * (`left` is a local of proc(), Q2), bytes after the end of the stream make append() spin when they arrive in the same
+ * call as the end (Q4: SDZ_THROW_HANG) and throw "inflate error: bad input data" when they arrive in a later one.
+ *   sdz_inflater_append   = Inflater.append(data) (src/sd-inflate.ts:87-153): *new_bytes = bytes this call produced (the
+ *                           caller cuts them into <= 16 KiB chunks, exactly the shapes the reference returns, because
+ *                           every append() starts with an empty 16 KiB buffer); res->thrown_append != 0: the call throws
+ *                           and its output is lost
+ *   sdz_inflater_read     copies the bytes of the most recent append() to host memory
+ *   sdz_inflater_finish   = Inflater.finish() (src/sd-inflate.ts:159-179): the record as of now */
+typedef struct sdz_inflater sdz_inflater;
+int  sdz_inflater_create(sdz_ctx* ctx, int raw, const uint8_t* dict, uint32_t dict_len, sdz_inflater** out);
+int  sdz_inflater_append(sdz_inflater* s, const uint8_t* data, uint64_t len, uint64_t* new_bytes, sdz_result* res);
+int  sdz_inflater_read(sdz_inflater* s, uint8_t* dst, uint64_t cap);
+int  sdz_inflater_finish(sdz_inflater* s, sdz_result* res);
+/* bytes [off, off + len) of the input received so far (e.g. the gzip FNAME at res->name_off) */
+int  sdz_inflater_input(sdz_inflater* s, uint64_t off, uint64_t len, uint8_t* dst);
+void sdz_inflater_destroy(sdz_inflater* s);
+
 /* ONE large stream (BASELINE config 5), decoded by all SMs: pass 1 indexes the deflate block boundaries
  * (speculative header search + per-block extents, chained from the first block), pass 2 decodes every
  * block in parallel with 16-bit marker symbols for back-references into the unknown 32 KiB window,

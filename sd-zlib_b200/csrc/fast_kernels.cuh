@@ -45,6 +45,9 @@ constexpr uint32_t NTOK_HANDED_OVER = 0xffffffffu;
 #ifndef SDZ_FA_RING
 #define SDZ_FA_RING 8
 #endif
+#ifndef SDZ_FA_DEFER
+#define SDZ_FA_DEFER 4u               // the general single-symbol decoder runs every n-th group of four symbols (power of two)
+#endif
 #if SDZ_FA_RL == 9
 #define SDZ_FA_RL_MASK 511
 #elif SDZ_FA_RL == 8
@@ -381,6 +384,8 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
     bool fixed = false;
     uint32_t ci = 0;                                                    // input ring: next 16-byte chunk to request
     bool fresh = false;                                                 // the ring has to be (re)filled at the reader's position
+    bool pending = false;                                               // the next symbol has to go through the general decoder
+    uint32_t it = 0;
 
     auto refill = [&]() {
         if (bc <= 32) {
@@ -396,6 +401,7 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
         // ================================================================ service (divergent code is fine here)
         // ---- new streams
         while (state == LS_FETCH || state == LS_HANDOVER || state == LS_FINISH) {
+            pending = false;                                            // (a lane can leave its stream while it waits for the general decoder)
             if (state == LS_FINISH) {
                 // final block complete: trailer (src/inflate.ts:409-463) and the record - when this really is the
                 // plain complete stream
@@ -480,7 +486,7 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
             ntok = 0;
             cap_tok = (uint32_t)(P.tok_off[i + 1] - P.tok_off[i]);
             tokp = P.tokens + P.tok_off[i];
-            n_blocks = 0; last = 0; eob_len = 0;
+            n_blocks = 0; last = 0; eob_len = 0; pending = false;
             // seek(hp)
             wp = C.hp >> 2; bb = 0; bc = 0;
             nw = wp < lim_wp ? __ldg(wbase + wp) : 0u;
@@ -597,7 +603,7 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                 __syncwarp();
                 if ((int)lane == who) {
                     if (TI.msg != SDZ_MSG_NONE) state = LS_HANDOVER;    // the general decoder reproduces the message
-                    else { lbits = TI.lbits; g_l = TI.g_l; g_d = TI.g_d; state = LS_CODES; fresh = true; }
+                    else { lbits = TI.lbits; g_l = TI.g_l; g_d = TI.g_d; state = LS_CODES; fresh = true; pending = false; }
                 }
             }
         }
@@ -638,7 +644,10 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
             for (;;) {
                 uint32_t tk0, tk1, tk2, tk3;
                 uint32_t early = 0u;                                    // a distance reached before the start of the output
-                uint32_t act = live ? 1u : 0u, su = 4u;                 // su: the slot in which the lane switched itself off
+                // su: the slot in which the lane switched itself off.  A lane that is waiting for the general decoder
+                // (`pending`) sits out whole groups: its slots stay no-ops until its symbol lands in slot 0 of the group
+                // after which the decoder ran.
+                uint32_t act = live && !pending ? 1u : 0u, su = pending ? 0u : 4u;
 #define SDZ_FA_SYMBOL(U, TK)                                                                                              \
                     /* top-up to at least 32 valid bits */                                                                \
                     "setp.lt.s32 pt, %1, 32;\n\t"                                                                         \
@@ -721,9 +730,17 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                       "=r"(tk0), "=r"(tk1), "=r"(tk2), "=r"(tk3)
                     : "r"(ring_l), "r"(a_l), "r"(a_d));
 #undef SDZ_FA_SYMBOL
-                // ---- lanes that switched themselves off: one symbol through the general decoder
-                if (__any_sync(FULL, su < 4u)) {
-                    if (su < 4u) {
+                // ---- lanes that switched themselves off: one symbol through the general decoder.  The decoder's ~130
+                // instructions are paid by the whole warp, and with 128 symbols per group some lane needs it in two groups
+                // out of three (profiles/r02c_summary.md: a third of all issued instructions, 1.5 lanes active).  So it
+                // runs every SDZ_FA_DEFER-th group only, or as soon as a quarter of the warp is waiting; waiting lanes sit
+                // out (a lane meets a rare symbol every ~28 groups, so the wait costs it a few per cent).
+                pending = su < 4u;
+                const unsigned pend = __ballot_sync(FULL, pending);
+                it++;
+                if (pend != 0u && ((it & (SDZ_FA_DEFER - 1u)) == 0u || __popc(pend) >= 8)) {
+                    if (pending) {
+                        pending = false;
                         uint32_t tslow = 0u;
                         if (bc < 32) {
                             bb |= (uint64_t)nw << bc;
@@ -890,6 +907,202 @@ __global__ void __launch_bounds__(256) lz_resolve_kernel(FastParams P)
             }
             ab = ab_end + lane;
         }
+    }
+}
+
+// ---------------------------------------------------------------------- phase B, token-centric (default)
+//
+// lz_resolve_kernel above is byte-centric: lane = output byte, one byte gather per lane and row, 39 warp instructions
+// and one exposed global-memory round trip per 32 output bytes (profiles/r02c_summary.md: 7.15 G warp instructions per
+// 65,536-stream batch, long_scoreboard 16.6 of 25 stall cycles per issued instruction, window reads missing L2 because
+// 9,472 resident streams x 32 KiB of live window do not fit).  Here lane = TOKEN:
+//
+//   * the stream's write frontier lives in a 1 KiB shared-memory ring per warp; tokens write their bytes into the ring
+//     (literals one byte, matches up to 16 bytes read as three aligned 8-byte words from HBM/L2 - or from the ring when
+//     the source is less than 480 bytes back - shifted into place and stored byte-wise), all 32 tokens of a batch at once:
+//     one global round trip per ~140 output bytes, and the loads of 32 matches in flight together;
+//   * complete 16-byte vectors leave the ring as coalesced 16-byte vector stores (STG.128), the only global stores of
+//     the kernel apart from the unaligned head / tail of a stream;
+//   * tokens that depend on bytes of their own batch, are longer than 16 bytes or overlap themselves (dist < len) are
+//     "hard": after the parallel step they are replayed one at a time, in order, by the whole warp (lane = byte of the
+//     match, lane-strided replicate src[i mod dist] for overlapping copies).
+// Positions are kept in g-coordinates: g = stream position + (address of the stream's first byte & 15), so that
+// multiples of 16 are 16-byte aligned global addresses whatever the caller's out_off is.
+constexpr uint32_t B2_RING = 1024;     // bytes per warp (ring index = g & 1023), + 16 bytes of spill behind it
+constexpr uint32_t B2_HIST = 480;      // sources at most this far behind the frontier are read from the ring
+constexpr uint32_t B2_SUB = 512;       // bytes produced per parallel step (ring size - history - alignment slack)
+constexpr int B2_WARPS = 4;
+#ifndef SDZ_B2_MINBLOCKS
+#define SDZ_B2_MINBLOCKS 12            // blocks per SM the register allocation aims for (12: 40 registers: eight blocks fit next to phase A)
+#endif
+
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+// bytes K .. K + 3 of a piece: word >> 0 / 8 / 16 / 24 to [addr + K ..], byte b only when n > K + b (predicated, no branches)
+#define SDZ_STS4(K)                                                                                                           \
+    __device__ __forceinline__ void sts4_##K(uint32_t addr, uint32_t w, uint32_t n)                                           \
+    {                                                                                                                         \
+        asm volatile("{\n\t.reg .pred p0, p1, p2, p3;\n\t.reg .b32 a, b, c;\n\t"                                               \
+                     "setp.gt.u32 p0, %2, " #K " + 0;\n\tsetp.gt.u32 p1, %2, " #K " + 1;\n\t"                                   \
+                     "setp.gt.u32 p2, %2, " #K " + 2;\n\tsetp.gt.u32 p3, %2, " #K " + 3;\n\t"                                   \
+                     "shr.u32 a, %1, 8;\n\tshr.u32 b, %1, 16;\n\tshr.u32 c, %1, 24;\n\t"                                        \
+                     "@p0 st.shared.u8 [%0 + " #K " + 0], %1;\n\t@p1 st.shared.u8 [%0 + " #K " + 1], a;\n\t"                     \
+                     "@p2 st.shared.u8 [%0 + " #K " + 2], b;\n\t@p3 st.shared.u8 [%0 + " #K " + 3], c;\n\t}" ::"r"(addr),       \
+                     "r"(w), "r"(n)                                                                                           \
+                     : "memory");                                                                                             \
+    }
+SDZ_STS4(0)
+SDZ_STS4(4)
+SDZ_STS4(8)
+SDZ_STS4(12)
+#undef SDZ_STS4
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
+{
+    uint32_t r;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(addr) : "memory");
+    return r;
+}
+__device__ __forceinline__ uint2 lds_v2(uint32_t addr)
+{
+    uint2 r;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr) : "memory");
+    return r;
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr)
+{
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+    return r;
+}
+__device__ __forceinline__ uint2 ldg_v2(const uint8_t* p)
+{
+    uint2 r;
+    asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
+    return r;
+}
+
+__global__ void __launch_bounds__(32 * B2_WARPS, SDZ_B2_MINBLOCKS) lz_resolve2_kernel(FastParams P)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    __shared__ __align__(16) uint8_t ring_all[B2_WARPS][B2_RING + 16];
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t ring = smem_addr(ring_all[threadIdx.x >> 5]);
+    for (;;) {
+        unsigned long long idx = 0;
+        if (lane == 0) idx = atomicAdd(P.counter_b, 1ull);
+        idx = __shfl_sync(FULL, idx, 0);
+        if (idx >= P.count) break;
+        idx += P.first;
+        const uint32_t nt = P.ntok[idx];
+        if (nt == NTOK_HANDED_OVER || nt == 0u) continue;
+        const uint32_t* tk = P.tokens + P.tok_off[idx];
+        uint8_t* const out = P.I.out + P.I.out_off[idx];
+        const uint32_t gb = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u);   // g-coordinate of the stream's first byte
+        uint8_t* const outg = out - gb;                                 // g-coordinate 0: a 16-byte aligned address
+        uint32_t pos = gb;                                              // write frontier (uniform)
+        uint32_t flushed = 0;                                           // bytes below are in global memory; multiple of 16
+        __syncwarp();                                                   // the previous stream's ring reads are over
+        uint32_t tnext = lane < nt ? ld_stream_u32(tk + lane) : 0u;
+        for (uint32_t base = 0; base < nt; base += 32) {
+            const uint32_t t = tnext;
+            tnext = base + 32u + lane < nt ? ld_stream_u32(tk + base + 32u + lane) : 0u;
+            const bool lit = (int32_t)t < 0;
+            const uint32_t len = lit ? 1u : (t & 511u);                 // 0: no-op slot
+            uint32_t incl = len;
+            #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, d); incl += lane >= (uint32_t)d ? v : 0u; }
+            const uint32_t N = __shfl_sync(FULL, incl, 31);
+            const uint32_t excl = incl - len;
+            const uint32_t dist = (t >> 9) + 1u;                        // (matches only)
+            uint32_t done = 0;
+            while (done < N) {                                          // one pass unless the batch is longer than B2_SUB bytes
+                // ---- the tokens of this step: the longest prefix of the remaining ones that fits B2_SUB bytes
+                const bool mine = len != 0u && excl >= done && incl - done <= B2_SUB;
+                const uint32_t step_end = N - done <= B2_SUB ? N : __reduce_max_sync(FULL, mine ? incl : done);
+                const uint32_t dst = pos + (excl - done);               // g-coordinate of my token's first byte
+                const uint32_t src = dst - dist;
+                const uint32_t rd = ring + (dst & (B2_RING - 1u));
+                const bool match = mine && !lit;
+                // simple: the whole source lies before this step's bytes and the copy is one 16-byte piece
+                const uint32_t o = src & 7u, a = src - o;
+                const bool simple = match && len <= 16u && src + len <= pos && a >= gb;
+                const bool hard = match && !simple;
+                if (mine && lit) sts_u8(rd, t);
+                // ---- parallel step: every simple match
+                {
+                    const bool from_ring = src + B2_HIST >= pos;
+                    const bool third = o + len > 16u;
+                    uint2 w0 = make_uint2(0u, 0u), w1 = w0, w2 = w0;
+                    if (simple) {
+                        if (from_ring) {
+                            w0 = lds_v2(ring + (a & (B2_RING - 1u)));
+                            w1 = lds_v2(ring + ((a + 8u) & (B2_RING - 1u)));
+                            if (third) w2 = lds_v2(ring + ((a + 16u) & (B2_RING - 1u)));
+                        } else {
+                            w0 = ldg_v2(outg + a);
+                            w1 = ldg_v2(outg + a + 8u);
+                            if (third) w2 = ldg_v2(outg + a + 16u);
+                        }
+                    }
+                    const uint32_t sh = (o & 3u) * 8u;
+                    const uint32_t y0 = __funnelshift_r(w0.x, w0.y, sh), y1 = __funnelshift_r(w0.y, w1.x, sh),
+                                   y2 = __funnelshift_r(w1.x, w1.y, sh), y3 = __funnelshift_r(w1.y, w2.x, sh),
+                                   y4 = __funnelshift_r(w2.x, w2.y, sh);
+                    const bool hi = (o & 4u) != 0u;
+                    const uint32_t x0 = hi ? y1 : y0, x1 = hi ? y2 : y1, x2 = hi ? y3 : y2, x3 = hi ? y4 : y3;
+                    const uint32_t sl = simple ? len : 0u;
+                    const uint32_t lmax = __reduce_max_sync(FULL, sl);
+                    if (lmax > 0u) sts4_0(rd, x0, sl);
+                    if (lmax > 4u) sts4_4(rd, x1, sl);
+                    if (lmax > 8u) sts4_8(rd, x2, sl);
+                    if (lmax > 12u) sts4_12(rd, x3, sl);
+                    // a simple match that ran over the end of the ring wrote into the 16 spill bytes: bring them round
+                    const unsigned sp = __ballot_sync(FULL, simple && (dst & (B2_RING - 1u)) + len > B2_RING);
+                    if (sp) {
+                        const uint32_t cnt = __shfl_sync(FULL, (dst & (B2_RING - 1u)) + len - B2_RING, __ffs(sp) - 1);
+                        __syncwarp();
+                        if (lane < cnt) sts_u8(ring + lane, lds_u8(ring + B2_RING + lane));
+                    }
+                }
+                __syncwarp();
+                // ---- hard matches, in order, the warp on one at a time (lane = byte of the match)
+                unsigned hm = __ballot_sync(FULL, hard);
+                while (hm) {
+                    const int k = __ffs(hm) - 1;
+                    hm &= hm - 1;
+                    const uint32_t h_dst = __shfl_sync(FULL, dst, k), h_len = __shfl_sync(FULL, len, k), h_dist = __shfl_sync(FULL, dist, k);
+                    const uint32_t h_src = h_dst - h_dist;
+                    for (uint32_t c = 0; c < h_len; c += 32u) {
+                        const uint32_t i = c + lane;
+                        if (i < h_len) {
+                            // dist >= 32: bytes at or after h_dst were written by earlier rounds of this loop;
+                            // dist < 32: replicate the dist bytes before the match
+                            const uint32_t q = h_src + (h_dist < 32u ? i % h_dist : i);
+                            const uint32_t v = q >= flushed ? lds_u8(ring + (q & (B2_RING - 1u))) : (uint32_t)outg[q];
+                            sts_u8(ring + ((h_dst + i) & (B2_RING - 1u)), v);
+                        }
+                        __syncwarp();
+                    }
+                }
+                // ---- complete 16-byte vectors leave the ring
+                pos += step_end - done;
+                done = step_end;
+                const uint32_t upto = pos & ~15u;
+                for (uint32_t g = flushed + lane * 16u; g < upto; g += 512u) {
+                    const uint4 v = lds_v4(ring + (g & (B2_RING - 1u)));
+                    if (g >= gb) *reinterpret_cast<uint4*>(outg + g) = v;
+                    else {                                              // the vector that holds the stream's first byte
+                        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+                        #pragma unroll
+                        for (uint32_t b = 0; b < 16u; b++)
+                            if (g + b >= gb) outg[g + b] = (uint8_t)(w[b >> 2] >> ((b & 3u) * 8u));
+                    }
+                }
+                flushed = upto;
+                __syncwarp();
+            }
+        }
+        // tail of the stream: the bytes of the last, incomplete vector
+        if (flushed + lane < pos && flushed + lane >= gb) outg[flushed + lane] = (uint8_t)lds_u8(ring + ((flushed + lane) & (B2_RING - 1u)));
     }
 }
 

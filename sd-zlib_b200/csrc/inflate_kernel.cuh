@@ -117,6 +117,10 @@ struct InflateParams {
     // work items is only known on the device
     const uint32_t* list;
     const unsigned long long* n_dev;
+    // streaming sessions (sdz_inflater_*, src/sd-inflate.ts:87-153): where every stream stopped at the end of the input it
+    // had (resume_out), and where to pick it up now that the input has grown (resume_in).  nullptr: plain one-shot decode.
+    const sdz_resume* resume_in;
+    sdz_resume* resume_out;
 };
 
 // resume point inside a block (TM_INDEX): the symbol at bit `bit` produces output byte `pos` of task `task`
@@ -132,7 +136,9 @@ enum { TM_NONE = 0, TM_MARK = 1, TM_INDEX = 2 };
 enum : int { R_OK = 0, R_EOB = 1, R_STALL = 2, R_ERROR = 3, R_OUTFULL = 4 };
 
 // where input ran out (only the classes the record depends on)
-enum : int { ST_NONE = 0, ST_OTHER = 1, ST_DYNHDR = 2 /* BTREE/DTREE: not resumable, SURVEY Q3 */ };
+enum : int { ST_NONE = 0, ST_OTHER = 1 /* a block header state the reference can re-enter */, ST_DYNHDR = 2 /* BTREE/DTREE: not
+              resumable, SURVEY Q3 */, ST_STORED = 3 /* inside stored data: `left` is lost on re-entry (src/infblocks.ts:134) */,
+              ST_CODES = 4 /* inside a symbol: InfCodes.proc is resumable at any bit */ };
 
 __device__ __constant__ uint8_t c_border[19] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 };
 
@@ -609,6 +615,12 @@ struct Decoder {
     int32_t mtime;
     int last, method;
     bool raw, is_gzip;
+    // streaming sessions: bit position of the current block's header and of the symbol being decoded; the first symbol
+    // after a resume point continues in the reference's one-symbol path whatever the input (it re-enters InfCodes.proc
+    // past its START check, src/infcodes.ts:339-357); ref_floor = input bytes the reference had loaded when it stopped
+    uint64_t blk_hdr_bit, last_sym_bit;
+    uint32_t ref_floor;
+    bool resume_first, hdr_counted;
 
     // ------------------------------------------------------------------ input staging
     __device__ __forceinline__ uint32_t load_word(uint32_t w)
@@ -936,7 +948,7 @@ struct Decoder {
             ring.write(pos - ring_done); ring_done = pos;
             const bool fresh = p0 == blk_sym0_bit;                       // first symbol of its block: the START check is pending
             ref_burst = !fresh && ring.room() >= 258;                   // (n >= 10 held up to here)
-            if (!fresh) ref_F = ceil8(p0);
+            if (!fresh) ref_F = max(ceil8(p0), ref_floor);
             ref_Fentry = 0; ref_forced_slow = false; ref_on = true;
         }
         bool fast = ref_burst;
@@ -963,7 +975,14 @@ struct Decoder {
         const bool tail = wp + 5 > end_wp;
         const uint64_t p0 = bit_pos();
         const bool emu = TM == TM_NONE && (uint64_t)in_len - (p0 >> 3) <= 16u;
-        const bool fastsym = emu ? ref_symbol_begin(p0) : false;
+        bool fastsym = emu ? ref_symbol_begin(p0) : false;
+        bool rf = false;
+        if constexpr (TM == TM_NONE) {
+            last_sym_bit = p0;
+            rf = resume_first;
+            resume_first = false;
+            if (rf) { fastsym = false; ref_burst = false; }
+        }
         uint32_t need1 = 20u;
         uint32_t e = S->lut_l[(uint32_t)bb & ((1u << RL) - 1u)];
         uint32_t n = e >> 12, p = e & 0xfff;
@@ -993,7 +1012,7 @@ struct Decoder {
             return R_OK;
         }
         if (p == 256) {
-            eob_len = (int)n; eob_emu = emu; eob_fast = fastsym;
+            eob_len = (int)n; eob_emu = emu || rf; eob_fast = fastsym;
             if (emu) {
                 // the block's codes object hands whole unused bytes back: all of them after inflate_fast(), at most one in
                 // WASH (src/infcodes.ts:620-624)
@@ -1066,6 +1085,7 @@ struct Decoder {
         // (seven words: every symbol that starts within the last 16 bytes of the input goes through step_general(), which
         //  models the reference's input frontier there; one call site for step_general(): it is inlined once)
         bool general = wp + 7 > end_wp || cap - pos < (uint32_t)SDZ_CAPMARGIN;
+        if constexpr (TM == TM_NONE) general = general || resume_first;
         bool fold = false;
         uint32_t nfold = 0;                                // literals stored by this iteration's folds
         uint32_t e = 0;
@@ -1197,7 +1217,7 @@ struct Decoder {
         uint32_t copied = 0;
         int r = R_OK;
         while (left) {
-            if (n_in == 0) { stall_kind = ST_OTHER; r = R_STALL; break; }
+            if (n_in == 0) { stall_kind = ST_STORED; r = R_STALL; break; }
             if (ring.room() == 0) {
                 int returns = ring.make_room();
                 if (returns) { left = 0; break; }      // `left` is a local of proc(): lost on return
@@ -1302,10 +1322,29 @@ struct Decoder {
         ref_F = ref_Fentry = ring_done = 0; blk_sym0_bit = 0; ref_on = ref_burst = ref_forced_slow = eob_emu = eob_fast = false;
         o_dst = o_meta = n_dst = n_meta = 0;
         is_gzip = false; method = 0; n_blocks = 0; mtime = 0; name_off = 0; name_len = 0; last = 0;
+        blk_hdr_bit = last_sym_bit = 0; ref_floor = 0; resume_first = false; hdr_counted = false; resume_bit = 0;
 
         int thrown = SDZ_THROW_NONE, thrown_inflate = 0, zstatus = SDZ_Z_OK;
         bool decode = true;
         raw = mode == SDZ_MODE_RAW;
+        if (P.resume_in && P.resume_in[i].kind >= SDZ_RESUME_AT_BLOCK && P.resume_in[i].kind <= SDZ_RESUME_AT_TRAILER) {
+            // a streaming session past its container header: put the decoder where the reference stopped
+            const sdz_resume z = P.resume_in[i];
+            is_gzip = (z.flags & 1) != 0; raw = (z.flags & 2) != 0; last = (z.flags & 4) ? 1 : 0;
+            method = z.method; mtime = z.mtime; name_off = z.name_off; name_len = z.name_len;
+            n_blocks = z.n_blocks; pos = z.pos;
+            D = (int)z.dict_used;
+            if (D) dict_tail = P.dict + P.dict_off[i] + (P.dict_len[i] - (uint32_t)D);
+            ring.q = ring.r = z.ring_q; ring.ao = OUTBUF;               // append() returned with the window flushed
+            ring_done = pos;
+            ref_F = ref_floor = z.prev_len;
+            seek((uint32_t)(z.block_bit >> 3));
+            drop((int)(z.block_bit & 7));
+            if (z.kind == SDZ_RESUME_AT_TRAILER) { finish_stream(P, R_EOB); return; }
+            if (z.kind == SDZ_RESUME_IN_CODES) { resume_bit = z.sym_bit; resume_first = true; }
+            phase = PH_BLOCK;
+            return;
+        }
         if (mode == SDZ_MODE_SNIFF) {                                   // inflate(): src/sd-inflate.ts:194-207
             if (in_len < 2) { thrown_inflate = SDZ_THROW_TOO_SMALL; decode = false; }
             else {
@@ -1382,6 +1421,13 @@ struct Decoder {
         }
         if (!decode) {
             write_record(P, thrown, thrown_inflate, zstatus, false, 0, 0, end_byte);
+            if (P.resume_out && glane == 0) {                           // the container header is parsed again from byte 0
+                sdz_resume z;
+                memset(&z, 0, sizeof z);
+                z.kind = (uint8_t)(thrown || thrown_inflate ? SDZ_RESUME_FAILED : SDZ_RESUME_START);
+                z.prev_len = in_len;
+                P.resume_out[idx] = z;
+            }
             return;                                                     // stays in PH_FETCH
         }
         seek(hp);
@@ -1423,14 +1469,27 @@ struct Decoder {
         bool done = false;
         int32_t stored = 0, isize = 0;
         uint32_t end_byte = byte_pos();
+        int rk = SDZ_RESUME_FAILED;                                     // streaming sessions: where the next append() continues
+        uint64_t rk_bit = 0;
         if (r == R_ERROR) { thrown = SDZ_THROW_INFLATE_ERROR; zstatus = SDZ_Z_DATA_ERROR; }
-        else if (r == R_OUTFULL) { zstatus = SDZ_Z_BUF_ERROR; }
+        else if (r == R_OUTFULL) { zstatus = SDZ_Z_BUF_ERROR; rk = -1; }
         else if (r == R_STALL) {
             // input exhausted.  proc() flushes; if that fills the 16 KiB buffer append() calls
             // again, and BTREE/DTREE cannot be re-entered -> STREAM_ERROR is thrown.
             if (stall_kind == ST_DYNHDR) {
                 ring.flush();
                 if (ring.ao == 0) { thrown = SDZ_THROW_INFLATE_ERROR; zstatus = SDZ_Z_STREAM_ERROR; msg = SDZ_MSG_NONE; }
+                else rk = SDZ_RESUME_BROKEN_Q3;
+            } else if (stall_kind == ST_STORED) {
+                // `left` is gone when proc() is entered again: the stored block ends where the input ended
+                rk = last ? SDZ_RESUME_AT_TRAILER : SDZ_RESUME_AT_BLOCK;
+                rk_bit = bit_pos();
+            } else if (stall_kind == ST_CODES) {
+                rk = SDZ_RESUME_IN_CODES;
+            } else {
+                rk = SDZ_RESUME_AT_BLOCK;
+                rk_bit = blk_hdr_bit;
+                if (hdr_counted) n_blocks--;                            // the header is parsed (and counted) again
             }
         } else {
             // final block done: unused whole bytes go back, partial bits are dropped (src/inflate.ts:409-421);
@@ -1456,12 +1515,35 @@ struct Decoder {
                 zstatus = SDZ_Z_STREAM_END;
                 if (tp < in_len) thrown = SDZ_THROW_HANG;   // bytes after the end: append() spins
             }
+            rk = done ? SDZ_RESUME_DONE : SDZ_RESUME_AT_TRAILER;
+            rk_bit = bit_pos();
             end_byte = tp;
         }
         flush_pending();
         drain();
         __syncwarp(gmask);
         write_record(P, thrown, 0, zstatus, done, stored, isize, end_byte);
+        if constexpr (TM == TM_NONE) {
+            if (P.resume_out && rk >= 0 && glane == 0) {
+                // append() returns: everything that fits leaves the window, and append() calls again for as long as the
+                // 16 KiB buffer comes back full (src/sd-inflate.ts:101-150), so the window is empty afterwards
+                for (;;) { ring.flush(); if (ring.ao != 0) break; ring.ao = OUTBUF; }
+                sdz_resume z;
+                memset(&z, 0, sizeof z);
+                z.kind = (uint8_t)(thrown ? SDZ_RESUME_FAILED : rk);
+                z.block_bit = rk == SDZ_RESUME_IN_CODES ? blk_hdr_bit : rk_bit;
+                z.sym_bit = rk == SDZ_RESUME_IN_CODES ? last_sym_bit : 0;
+                z.pos = pos;
+                z.ring_q = ring.q;
+                z.n_blocks = rk == SDZ_RESUME_IN_CODES ? n_blocks - 1u : n_blocks;
+                z.mtime = mtime; z.name_off = name_off; z.name_len = name_len;
+                z.prev_len = in_len;
+                z.dict_used = (uint16_t)D;
+                z.flags = (uint8_t)((is_gzip ? 1 : 0) | (raw ? 2 : 0) | (last ? 4 : 0));
+                z.method = (uint8_t)method;
+                P.resume_out[idx] = z;
+            }
+        }
         phase = PH_FETCH;
     }
 
@@ -1469,12 +1551,14 @@ struct Decoder {
     // the tables are built and the group joins the lockstep symbol loop (PH_CODES).
     __device__ __forceinline__ void block_begin(const InflateParams& P)
     {
+        if constexpr (TM == TM_NONE) { blk_hdr_bit = bit_pos(); hdr_counted = false; }
         if (!ensure(3)) { stall_kind = ST_OTHER; finish_stream(P, R_STALL); return; }
         if (TM == TM_NONE) ref_need(bit_pos(), 3u);
         uint32_t t = peek(3);
         drop(3);
         last = (int)(t & 1);
         n_blocks++;
+        hdr_counted = true;
         start_pos = pos;
         ring_done = pos;
         const uint32_t type = t >> 1;
@@ -1516,6 +1600,11 @@ struct Decoder {
             drop(skip);
         }
         blk_sym0_bit = bit_pos();
+        if (TM == TM_NONE && resume_bit) {                              // streaming session: the symbol the last append() stopped at
+            seek((uint32_t)(resume_bit >> 3));
+            drop((int)(resume_bit & 7));
+            resume_bit = 0;
+        }
         ref_burst = false; ref_forced_slow = false;                    // a new codes object: the START check comes first
         phase = PH_CODES;
     }
@@ -1537,7 +1626,7 @@ struct Decoder {
     {
         if (TM != TM_NONE) { finish_task(P, r); return; }
         ring.write(pos - ring_done); ring_done = pos;
-        if (r != R_EOB) { if (r == R_STALL) stall_kind = ST_OTHER; finish_stream(P, r); return; }
+        if (r != R_EOB) { if (r == R_STALL) stall_kind = ST_CODES; finish_stream(P, r); return; }
         // End of block.  When inflate_fast() decodes the EOB its STREAM_END status leaks through
         // WASH's early return (src/infcodes.ts:264,:357,:627-638 -> src/infblocks.ts:560-564), so
         // the block completes after ONE flush attempt; only a slow-path EOB (fewer than 258 bytes

@@ -67,7 +67,9 @@ struct sdz_ctx {
     // two-phase fast path (fast_kernels.cuh): per compute lane the token arena, the per-stream arrays
     // (counters | tok_off | ntok | hand-over list) and the sorted-symbol scratch of phase A
     bool fast = true;                  // SDZ_FAST=0: every stream goes through the general decoder
-    int b_blocks_per_sm = 8;           // phase B: 256-thread blocks per SM (SDZ_B_BLOCKS)
+    int b_blocks_per_sm = 8;           // byte-centric phase B (SDZ_B2=0): 256-thread blocks per SM (SDZ_B_BLOCKS)
+    bool b_tokenwise = true;           // token-centric phase B (lz_resolve2_kernel)
+    int b2_blocks_per_sm = 12;         // its 128-thread blocks per SM (SDZ_B2_BLOCKS)
     static constexpr int MAX_FAST_CHUNKS = 15;
     int fast_chunks = 0;               // chunks of the phase A / phase B pipeline (SDZ_FAST_CHUNKS; 0 = one per wave of phase A)
     cudaStream_t fast_sb[N_LANES] = { nullptr, nullptr, nullptr };     // phase B streams
@@ -379,8 +381,13 @@ int launch_fast(sdz_ctx* ctx, const sdz::InflateParams& P, uint64_t tok_total, b
         kern<<<ga, 32, smem, st>>>(F);
         CK(cudaEventRecord(ctx->fast_ev[lane][c], st));
         CK(cudaStreamWaitEvent(sb, ctx->fast_ev[lane][c], 0));
-        const unsigned gb = (unsigned)std::min<uint64_t>((hi - lo + 7) / 8, (uint64_t)ctx->sm_count * ctx->b_blocks_per_sm);
-        sdz::lz_resolve_kernel<<<gb, 256, 0, sb>>>(F);
+        if (ctx->b_tokenwise) {
+            const unsigned gb = (unsigned)std::min<uint64_t>((hi - lo + sdz::B2_WARPS - 1) / sdz::B2_WARPS, (uint64_t)ctx->sm_count * ctx->b2_blocks_per_sm);
+            sdz::lz_resolve2_kernel<<<gb, 32 * sdz::B2_WARPS, 0, sb>>>(F);
+        } else {
+            const unsigned gb = (unsigned)std::min<uint64_t>((hi - lo + 7) / 8, (uint64_t)ctx->sm_count * ctx->b_blocks_per_sm);
+            sdz::lz_resolve_kernel<<<gb, 256, 0, sb>>>(F);
+        }
         ctx->launches += 2;
     }
     if (timed) CK(cudaEventRecord(ctx->ev_fast[1], st));
@@ -511,6 +518,8 @@ int sdz_ctx_create(int device, uint32_t flags, sdz_ctx** out)
         if (cudaEventCreate(&e) != cudaSuccess) return fail(SDZ_E_CUDA);
     if (const char* f = getenv("SDZ_FAST")) ctx->fast = atoi(f) != 0;
     if (const char* f = getenv("SDZ_B_BLOCKS")) { int v = atoi(f); if (v >= 1 && v <= 8) ctx->b_blocks_per_sm = v; }
+    if (const char* f = getenv("SDZ_B2")) ctx->b_tokenwise = atoi(f) != 0;
+    if (const char* f = getenv("SDZ_B2_BLOCKS")) { int v = atoi(f); if (v >= 1 && v <= 16) ctx->b2_blocks_per_sm = v; }
     if (const char* f = getenv("SDZ_FAST_CHUNKS")) { int v = atoi(f); if (v >= 0 && v <= sdz_ctx::MAX_FAST_CHUNKS) ctx->fast_chunks = v; }
     for (int l = 0; l < sdz_ctx::N_LANES; l++) {
         if (cudaStreamCreateWithFlags(&ctx->fast_sb[l], cudaStreamNonBlocking) != cudaSuccess) return fail(SDZ_E_CUDA);
@@ -1202,6 +1211,227 @@ int sdz_inflate_sizes(sdz_ctx* ctx, const sdz_in* in, uint64_t n, uint64_t* out_
 {
     if (!out_len && n) return SDZ_E_ARG;
     return inflate_host(ctx, in, n, nullptr, nullptr, nullptr, nullptr, out_len, flags, true);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------- streaming sessions (class Inflater)
+//
+// One sdz_inflater = one `new Inflater(options)` fed with several append() calls (src/sd-inflate.ts:54-180).  The
+// compressed bytes received so far and the bytes decoded so far both stay in HBM; between calls the session keeps an
+// sdz_resume record - where the reference stopped - so that an append() costs the decode of the NEW input only (plus
+// rebuilding the tables of the block it stopped in), not a re-decode of everything (round 1).
+
+struct sdz_inflater {
+    sdz_ctx* ctx = nullptr;
+    bool raw = false, has_dict = false;
+    DevBuf d_in, d_out, d_meta, d_dict;
+    uint64_t in_len = 0;               // compressed bytes received
+    uint64_t emitted = 0;              // decoded bytes handed to the caller so far
+    uint64_t last_new = 0;             // bytes produced by the most recent append()
+    uint32_t dict_len = 0;
+    int32_t dict_adler = 1;
+    int cur = 0;                       // which of the two resume slots is current
+    int kind = SDZ_RESUME_START;
+    int32_t running = 0;               // Inflater.checksum: chained over the chunks append() emitted
+    bool have_running = false;
+    sdz_result rec;                    // record of the most recent append()
+    uint8_t* h_meta = nullptr;         // pinned mirror of the meta block
+};
+
+namespace {
+// meta block layout (device and pinned host copy)
+constexpr size_t SM_IN_OFF = 0, SM_DICT_OFF = 8, SM_OUT_OFF = 16, SM_IN_LEN = 24, SM_DICT_LEN = 28, SM_OUT_CAP = 32,
+                 SM_DICT_ADLER = 36, SM_MODE = 40, SM_RES = 64, SM_RESUME = SM_RES + ((sizeof(sdz_result) + 15) / 16) * 16,
+                 SM_BYTES = SM_RESUME + 2 * sizeof(sdz_resume);
+
+int grow_keep(sdz_ctx* ctx, DevBuf& b, size_t bytes, size_t keep)
+{
+    if (bytes <= b.cap) return SDZ_OK;
+    size_t want = std::max(bytes, b.cap * 2);
+    want = (want + (1u << 20)) & ~((size_t(1) << 20) - 1);
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { ctx->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return SDZ_E_NOMEM; }
+    if (b.p && keep) {
+        e = cudaMemcpyAsync(p, b.p, keep, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { ctx->err = std::string("cudaMemcpy: ") + cudaGetErrorString(e); cudaFree(p); return SDZ_E_CUDA; }
+    }
+    if (b.p) cudaFree(b.p);
+    b.p = p; b.cap = want;
+    return SDZ_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int sdz_inflater_create(sdz_ctx* ctx, int raw, const uint8_t* dict, uint32_t dict_len, sdz_inflater** out)
+{
+    if (!ctx || !out || (dict_len && !dict)) return SDZ_E_ARG;
+    *out = nullptr;
+    if (raw && dict) return SDZ_E_ARG;                       // RangeError in the reference (src/sd-inflate.ts:69-71)
+    ENTER(ctx);
+    sdz_inflater* s = new sdz_inflater();
+    s->ctx = ctx; s->raw = raw != 0; s->has_dict = dict != nullptr; s->dict_len = dict_len;
+    memset(&s->rec, 0, sizeof s->rec);
+    auto fail = [&](int rc) { sdz_inflater_destroy(s); return rc; };
+    int rc;
+    if ((rc = grow(ctx, s->d_meta, SM_BYTES))) return fail(rc);
+    s->h_meta = (uint8_t*)pinned_alloc(SM_BYTES, ctx->numa_node);
+    if (!s->h_meta) return fail(SDZ_E_NOMEM);
+    memset(s->h_meta, 0, SM_BYTES);
+    if (dict_len) {
+        if ((rc = grow(ctx, s->d_dict, dict_len + 16))) return fail(rc);
+        if (cudaMemcpyAsync(s->d_dict.p, dict, dict_len, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return fail(SDZ_E_CUDA);
+        uint64_t dl = dict_len;
+        if ((rc = checksum_chain(ctx, false, (const uint8_t*)s->d_dict.p, &dl, 1, 1, 1, nullptr, &s->dict_adler))) return fail(rc);
+    } else if ((rc = grow(ctx, s->d_dict, 16))) return fail(rc);
+    if (cudaMemsetAsync(s->d_meta.p, 0, SM_BYTES, ctx->stream) != cudaSuccess) return fail(SDZ_E_CUDA);
+    *out = s;
+    return SDZ_OK;
+}
+
+void sdz_inflater_destroy(sdz_inflater* s)
+{
+    if (!s) return;
+    if (s->ctx) {
+        cudaSetDevice(s->ctx->device);
+        cudaStreamSynchronize(s->ctx->stream);
+    }
+    for (DevBuf* b : { &s->d_in, &s->d_out, &s->d_meta, &s->d_dict })
+        if (b->p) cudaFree(b->p);
+    pinned_free(s->h_meta);
+    delete s;
+}
+
+int sdz_inflater_append(sdz_inflater* s, const uint8_t* data, uint64_t len, uint64_t* new_bytes, sdz_result* res)
+{
+    if (!s || !new_bytes || !res || (len && !data)) return SDZ_E_ARG;
+    sdz_ctx* ctx = s->ctx;
+    CK(cudaSetDevice(ctx->device));
+    *new_bytes = 0;
+    s->last_new = 0;
+    if (len == 0) { *res = s->rec; res->thrown_append = 0; return SDZ_OK; }          // append() of an empty chunk returns []
+    if (s->kind == SDZ_RESUME_FAILED) { *res = s->rec; return SDZ_OK; }              // the engine stays in its error state
+    if (s->kind == SDZ_RESUME_DONE || s->kind == SDZ_RESUME_BROKEN_Q3) {
+        if (s->kind == SDZ_RESUME_DONE) {
+            // DONE returns STREAM_END without consuming a byte of the new chunk: "inflate error: bad input data"
+            // (src/sd-inflate.ts:130-132).  (Bytes after the end inside the SAME chunk make append() spin instead)
+            s->rec.thrown_append = SDZ_THROW_BAD_INPUT_DATA;
+        } else {
+            // proc() is entered in BTREE / DTREE with its locals gone: `default:` -> STREAM_ERROR (src/infblocks.ts:616-625)
+            s->rec.thrown_append = SDZ_THROW_INFLATE_ERROR; s->rec.zstatus = SDZ_Z_STREAM_ERROR; s->rec.msg_id = SDZ_MSG_NONE;
+        }
+        s->rec.out_len = 0;
+        s->kind = SDZ_RESUME_FAILED;
+        *res = s->rec;
+        return SDZ_OK;
+    }
+    if (s->in_len + len >= (1ull << 32) - 64 - SDZ_IN_PAD) return SDZ_E_ARG;
+    int rc;
+    if ((rc = grow_keep(ctx, s->d_in, s->in_len + len + SDZ_IN_PAD + 16, s->in_len))) return rc;
+    CK(cudaMemcpyAsync((uint8_t*)s->d_in.p + s->in_len, data, len, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync((uint8_t*)s->d_in.p + s->in_len + len, 0, SDZ_IN_PAD, ctx->stream));
+    s->in_len += len;
+
+    uint8_t* hm = s->h_meta;
+    uint8_t* dm = (uint8_t*)s->d_meta.p;
+    const uint64_t have = s->emitted;                       // == resume.pos
+    uint64_t cap = have + std::max<uint64_t>(1u << 20, 16 * len);
+    for (;;) {
+        if (cap >= (1ull << 32) - 64) cap = (1ull << 32) - 65;
+        if ((rc = grow_keep(ctx, s->d_out, cap + 64, have))) return rc;
+        *(uint64_t*)(hm + SM_IN_OFF) = 0; *(uint64_t*)(hm + SM_DICT_OFF) = 0; *(uint64_t*)(hm + SM_OUT_OFF) = 0;
+        *(uint32_t*)(hm + SM_IN_LEN) = (uint32_t)s->in_len; *(uint32_t*)(hm + SM_DICT_LEN) = s->dict_len;
+        *(uint32_t*)(hm + SM_OUT_CAP) = (uint32_t)cap; *(int32_t*)(hm + SM_DICT_ADLER) = s->dict_adler;
+        hm[SM_MODE] = (uint8_t)((s->raw ? SDZ_MODE_RAW : SDZ_MODE_INFLATER) | (s->has_dict ? 0x80 : 0));
+        CK(cudaMemcpyAsync(dm, hm, SM_RES, cudaMemcpyHostToDevice, ctx->stream));     // (records and resume slots stay as they are)
+        sdz::InflateParams P;
+        memset(&P, 0, sizeof P);
+        P.in = (const uint8_t*)s->d_in.p; P.in_off = (const uint64_t*)(dm + SM_IN_OFF); P.in_len = (const uint32_t*)(dm + SM_IN_LEN);
+        P.mode = dm + SM_MODE;
+        P.dict = (const uint8_t*)s->d_dict.p; P.dict_off = (const uint64_t*)(dm + SM_DICT_OFF);
+        P.dict_len = (const uint32_t*)(dm + SM_DICT_LEN); P.dict_adler = (const int32_t*)(dm + SM_DICT_ADLER);
+        P.out = (uint8_t*)s->d_out.p; P.out_off = (const uint64_t*)(dm + SM_OUT_OFF); P.out_cap = (const uint32_t*)(dm + SM_OUT_CAP);
+        P.res = (sdz_result*)(dm + SM_RES); P.n = 1; P.counter = ctx->d_counter;
+        P.resume_in = (const sdz_resume*)(dm + SM_RESUME) + s->cur;
+        P.resume_out = (sdz_resume*)(dm + SM_RESUME) + (s->cur ^ 1);
+        ctx->cur_lane = 0;
+        if ((rc = launch_inflate_t<4, true>(ctx, P))) return rc;
+        CK(cudaMemcpyAsync(hm + SM_RES, dm + SM_RES, SM_BYTES - SM_RES, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        const sdz_result* r = (const sdz_result*)(hm + SM_RES);
+        if (r->zstatus != SDZ_Z_BUF_ERROR) break;
+        if (cap >= (1ull << 32) - 65) return SDZ_E_OUT_CAP;
+        cap = have + (cap - have) * 4;                      // the slot was too small: same input again, larger slot
+    }
+    sdz_result r = *(const sdz_result*)(hm + SM_RES);
+    const sdz_resume z = ((const sdz_resume*)(hm + SM_RESUME))[s->cur ^ 1];
+    s->cur ^= 1;
+    s->kind = z.kind;
+    // the record as finish() would see it now: checksum of the chunks emitted so far, chained over the <= 16 KiB chunks
+    // THIS call emits (src/sd-inflate.ts:133-149; Q1 fires on a final chunk of 5552 or 11104 bytes)
+    if (!r.thrown_append) {
+        const uint64_t total = z.pos;
+        const uint64_t fresh = total - have;
+        if (fresh) {
+            std::vector<uint64_t> segs;
+            if (r.container == SDZ_GZIP) segs.push_back(fresh);                       // CRC-32 chains exactly over any chunking
+            else for (uint64_t o = 0; o < fresh; o += 16384) segs.push_back(std::min<uint64_t>(16384, fresh - o));
+            int32_t v = 0;
+            rc = checksum_chain(ctx, r.container == SDZ_GZIP, (const uint8_t*)s->d_out.p + have, segs.data(), segs.size(),
+                                s->have_running ? s->running : (r.container == SDZ_GZIP ? 0 : 1), 1, nullptr, &v);
+            if (rc) return rc;
+            s->running = v; s->have_running = true;
+        }
+        s->emitted = total;
+        s->last_new = fresh;
+        *new_bytes = fresh;
+        r.out_len = total;
+    } else r.out_len = 0;
+    {
+        const int32_t stored = r.stored_checksum, isize = r.stored_isize;
+        const int cks = stored == 0 ? SDZ_UNCHECKED : ((s->have_running && stored == s->running) ? SDZ_MATCH : SDZ_MISMATCH);
+        const int fsz = isize == 0 ? SDZ_UNCHECKED : (((int64_t)isize == (int64_t)s->emitted) ? SDZ_MATCH : SDZ_MISMATCH);
+        r.running_checksum = s->have_running ? s->running : 0;
+        r.have_running = s->have_running ? 1 : 0;
+        r.checksum_state = (uint8_t)cks; r.size_state = (uint8_t)fsz;
+        r.success = (uint8_t)(r.complete && cks != SDZ_MISMATCH && fsz != SDZ_MISMATCH);
+    }
+    s->rec = r;
+    *res = r;
+    return SDZ_OK;
+}
+
+int sdz_inflater_read(sdz_inflater* s, uint8_t* dst, uint64_t cap)
+{
+    if (!s || (s->last_new && !dst) || cap < s->last_new) return SDZ_E_ARG;
+    sdz_ctx* ctx = s->ctx;
+    CK(cudaSetDevice(ctx->device));
+    if (!s->last_new) return SDZ_OK;
+    CK(cudaMemcpyAsync(dst, (const uint8_t*)s->d_out.p + (s->emitted - s->last_new), s->last_new, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SDZ_OK;
+}
+
+int sdz_inflater_input(sdz_inflater* s, uint64_t off, uint64_t len, uint8_t* dst)
+{
+    if (!s || (len && !dst) || off + len > s->in_len) return SDZ_E_ARG;
+    sdz_ctx* ctx = s->ctx;
+    CK(cudaSetDevice(ctx->device));
+    if (!len) return SDZ_OK;
+    CK(cudaMemcpyAsync(dst, (const uint8_t*)s->d_in.p + off, len, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SDZ_OK;
+}
+
+int sdz_inflater_finish(sdz_inflater* s, sdz_result* res)
+{
+    if (!s || !res) return SDZ_E_ARG;
+    *res = s->rec;
+    res->out_len = s->emitted;
+    return SDZ_OK;
 }
 
 }  // extern "C"

@@ -132,9 +132,25 @@ def _record_to_result(r, data_view) -> InflateResult:
     return InflateResult(bool(r.success), bool(r.complete), _CHECK[r.checksum_state], _CHECK[r.size_state], name, mod)
 
 
+class InflateError(ValueError):
+    """Error thrown by Inflater.append() / inflate(); .thrown / .msg_id are the record's codes."""
+
+    def __init__(self, text, thrown, msg_id):
+        super().__init__(text)
+        self.thrown, self.msg_id = thrown, msg_id
+
+
+class InflateHang(RuntimeError):
+    """The reference's append() never returns on this input; the drop-in raises instead of spinning."""
+
+    def __init__(self, text, thrown, msg_id):
+        super().__init__(text)
+        self.thrown, self.msg_id = thrown, msg_id
+
+
 def _raise_thrown(thrown, msg_id):
     text = _THROWN[thrown] + (_MSG[msg_id] if thrown == 4 else "")
-    raise ValueError(text) if thrown != 6 else RuntimeError(text)
+    raise (InflateError if thrown != 6 else InflateHang)(text, thrown, msg_id if thrown == 4 else 0)
 
 
 def inflate_batch_raw(views, dictionaries=None, modes=None, caps=None, ctx=None):
@@ -245,46 +261,79 @@ def inflate(data, dictionary=None, ctx=None) -> bytes:
 
 
 class Inflater:
-    """class Inflater - src/sd-inflate.ts:54-180.
+    """class Inflater - src/sd-inflate.ts:54-180, over a device session (sdz_inflater_*).
 
-    Round-1 streaming model: every append() re-decodes the bytes received so far on the
-    device and returns the output that is new since the previous call, cut into
-    <= 16 KiB chunks.  finish() reports the record of the whole input.  (The reference's
-    chunk boundaries and its Q2/Q3 mid-block defects across append() calls are not modelled.)
+    The compressed bytes received so far and the decoded bytes stay in HBM; between append() calls the session keeps
+    where the reference stopped (an sdz_resume record), so every call decodes only its own input.  The reference's
+    behaviour at chunk boundaries is reproduced, defects included: see include/sdzcuda.h.
     """
 
     def __init__(self, raw=None, dictionary=None, ctx=None):
         if raw is not None and raw is not True and raw is not False:
             raise TypeError("options.raw must be undefined or true or false")
         self._raw = bool(raw)
+        self._dict = None
         if dictionary is not None:
             if self._raw:
                 raise ValueError("options.dictionary cannot be set when options.raw is true")   # RangeError
-            _as_u8(dictionary, "options.dictionary must be undefined or a buffer or a buffer view")
-        self._dict = dictionary
+            self._dict = _as_u8(dictionary, "options.dictionary must be undefined or a buffer or a buffer view")
         self._ctx = ctx
-        self._buf = bytearray()
-        self._emitted = 0
+        self._h = None
         self._rec = None
-        self._view = np.zeros(0, dtype=np.uint8)
+
+    def _session(self):
+        if self._h is None:
+            self._ctx = self._ctx or N.default_context()
+            h = C.c_void_p()
+            d = self._dict
+            dptr = None
+            if d is not None:                      # a zero-length dictionary is still "a dictionary was supplied"
+                dptr = d.ctypes.data if d.size else C.cast(C.create_string_buffer(1), C.c_void_p).value
+            self._ctx.check(self._ctx.lib.sdz_inflater_create(self._ctx.h, int(self._raw), dptr, 0 if d is None else int(d.size), C.byref(h)))
+            self._h = h
+        return self._h
 
     def append(self, data) -> List[bytes]:
         chunk = _as_u8(data, "data must be an ArrayBuffer or buffer view")
         if chunk.size == 0:
             return []
-        self._buf += chunk.tobytes()
-        view = np.frombuffer(bytes(self._buf), dtype=np.uint8)
-        mode = MODE_RAW if self._raw else MODE_INFLATER
-        arena, off, res = inflate_batch_raw([view], [self._dict], [mode], None, self._ctx)
-        r = res[0]
-        self._rec, self._view = r, view
-        if r.thrown_append:
-            _raise_thrown(r.thrown_append, r.msg_id)
-        new = bytes(arena[self._emitted:int(r.out_len)])
-        self._emitted = int(r.out_len)
-        return [new[i:i + OUTPUT_BUFSIZE] for i in range(0, len(new), OUTPUT_BUFSIZE)]
+        h = self._session()
+        lib = self._ctx.lib
+        nb = C.c_uint64()
+        rec = N.Result()
+        self._ctx.check(lib.sdz_inflater_append(h, chunk.ctypes.data, int(chunk.size), C.byref(nb), C.byref(rec)))
+        self._rec = rec
+        if rec.thrown_append:
+            _raise_thrown(rec.thrown_append, rec.msg_id)
+        n = int(nb.value)
+        if n == 0:
+            return []
+        out = np.empty(n, dtype=np.uint8)
+        self._ctx.check(lib.sdz_inflater_read(h, out.ctypes.data, n))
+        new = out.tobytes()
+        return [new[i:i + OUTPUT_BUFSIZE] for i in range(0, n, OUTPUT_BUFSIZE)]
 
     def finish(self) -> InflateResult:
         if self._rec is None:
             return InflateResult(False, False, "unchecked", "unchecked", "", None)
-        return _record_to_result(self._rec, self._view)
+        rec = N.Result()
+        self._ctx.check(self._ctx.lib.sdz_inflater_finish(self._h, C.byref(rec)))
+        name = np.zeros(max(1, int(rec.name_len)), dtype=np.uint8)
+        if rec.name_len:
+            self._ctx.check(self._ctx.lib.sdz_inflater_input(self._h, int(rec.name_off), int(rec.name_len), name.ctypes.data))
+        r = InflateResult(bool(rec.success), bool(rec.complete), _CHECK[rec.checksum_state], _CHECK[rec.size_state],
+                          bytes(name[:int(rec.name_len)]).decode("latin-1") if rec.name_len else "",
+                          None if rec.mtime == 0 else datetime.datetime.fromtimestamp(rec.mtime, tz=datetime.timezone.utc))
+        self.record = rec
+        return r
+
+    def close(self):
+        if self._h is not None:
+            self._ctx.lib.sdz_inflater_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -546,37 +546,104 @@ def test_large_stream_slices_shorter_than_the_window():
 
 
 @pytest.mark.gpu
+def _append_events(make, parts, thrown_of):
+    """[(chunk lengths, bytes) per append() ..., ('throw', thrown, msg_id)] - the sequence ends at the first throw"""
+    inf = make()
+    ev = []
+    for p in parts:
+        try:
+            chunks = inf.append(p)
+            ev.append(([len(x) for x in chunks], b"".join(bytes(x) for x in chunks)))
+        except Exception as e:                      # noqa: BLE001 - both twins raise their own classes
+            ev.append(("throw",) + thrown_of(e))
+            return ev, None
+    return ev, inf.finish()
+
+
+def _compare_streaming(s, parts, raw=False, dictionary=None):
+    """device Inflater vs the oracle twin of class Inflater on the same append() sequence: chunk shapes and bytes of every
+    call, what the reference throws (and at which call), and the finish() record.  Returns True when the reference threw."""
+    state = {"unchecked": 0, "match": 1, "mismatch": 2}
+    oev, orr = _append_events(lambda: O.Inflater(raw=raw, dictionary=dictionary), parts,
+                              lambda e: (e.thrown, e.msg_id if e.thrown == 4 else 0))
+    gev, grr = _append_events(lambda: sdzlib.Inflater(raw=raw, dictionary=dictionary), parts, lambda e: (e.thrown, e.msg_id))
+    assert len(gev) == len(oev), ([len(p) for p in parts], gev[-1][:1], oev[-1][:1])
+    for k, (ge, oe) in enumerate(zip(gev, oev)):
+        assert ge[0] == oe[0], ("append #%d" % k, [len(p) for p in parts], ge[:1] if ge[0] != "throw" else ge, oe[:1] if oe[0] != "throw" else oe)
+        assert ge == oe, ("append #%d: bytes / codes differ" % k, [len(p) for p in parts])
+    if orr is None:
+        return True
+    assert (grr.success, grr.complete, state[grr.checksum], state[grr.fileSize]) == \
+           (bool(orr.success), bool(orr.complete), orr.checksum_state, orr.size_state), [len(p) for p in parts]
+    assert grr.fileName == orr.file_name
+    return False
+
+
 def test_inflater_append_split_points():
-    """Inflater.append() over 2-4 chunks cut at random byte positions.  Wherever the reference
-    itself survives the split (the oracle twin of class Inflater does not throw), the device path returns the same
-    <= 16 KiB chunk shapes per append(), the same bytes and the same finish() record.  Splits that land in one of the
-    reference's non-resumable states (inside a dynamic block header, Q3, and the cases that follow from it) make the
-    reference throw or spin; the device path re-decodes the bytes received so far and is not affected - those
-    splits are counted, not compared (documented divergence)."""
+    """Inflater.append() over 2-4 chunks cut at random byte positions, six kinds of streams, ALL 240 splits
+    compared with the oracle twin of class Inflater - including the splits where the reference breaks: a boundary inside a
+    dynamic block header makes the next append() throw "inflate error: " (Q3), a boundary inside stored data ends the
+    stored block there and the rest is parsed as block headers (Q2), and whatever follows from that."""
     import random
     rnd = random.Random(7)
     cases = []
     for kind, n, cont in ((K.TEXT, 40000, K.ZLIB), (K.TEXT, 70000, K.GZIP_NAME), (K.BINARY, 50000, K.RAW), (K.RUNS, 60000, K.ZLIB),
                           (K.RANDOM, 30000, K.GZIP), (K.TINY, 150, K.ZLIB)):
         cases.append((cont, bytes(K.compress(K.generate(kind, 99, n), 6, cont))))
-    state = {"unchecked": 0, "match": 1, "mismatch": 2}
-    compared = skipped = 0
+    threw = total = 0
     for cont, s in cases:
-        for _ in range(20):
+        for _ in range(40):
             cuts = sorted(rnd.randrange(1, len(s)) for _ in range(rnd.choice((1, 1, 2, 3))))
             parts = [s[a:b] for a, b in zip([0] + cuts, cuts + [len(s)])]
-            o = O.Inflater(raw=cont == K.RAW)
-            try:
-                oshape = [[len(x) for x in o.append(p)] for p in parts]
-            except O.OracleThrow:
-                skipped += 1
-                continue
-            g = sdzlib.Inflater(raw=cont == K.RAW)
-            gchunks = [g.append(p) for p in parts]
-            assert [[len(x) for x in c] for c in gchunks] == oshape, (cont, cuts)
-            orr, grr = o.finish(), g.finish()
-            assert (grr.success, grr.complete, state[grr.checksum], state[grr.fileSize]) == \
-                   (bool(orr.success), bool(orr.complete), orr.checksum_state, orr.size_state), (cont, cuts)
-            assert grr.fileName == orr.file_name
-            compared += 1
-    assert compared >= 80 and skipped < compared
+            threw += _compare_streaming(s, parts, raw=cont == K.RAW)
+            total += 1
+    assert total == 240 and 10 <= threw <= 120, (total, threw)
+
+
+def test_inflater_boundary_inside_every_header_state():
+    """cuts at EVERY byte of the first 400 bytes of a dynamic-block stream (container header, TYPE, TABLE, BTREE, DTREE, first
+    symbols) and at every byte around the second block header and the trailer: the Q3 window is hit exactly where the
+    reference has it"""
+    s = bytes(K.compress(K.generate(K.TEXT, 5, 90000), 6, K.GZIP_NAME))
+    threw = 0
+    for c in list(range(1, 400)) + list(range(len(s) - 24, len(s))):
+        threw += _compare_streaming(s, [s[:c], s[c:]])
+    assert threw > 20
+    # and three-way cuts with a tiny middle part (the reference's input frontier within a few bytes of both ends)
+    rnd = random.Random(21)
+    for _ in range(60):
+        a = rnd.randrange(1, len(s) - 40)
+        b = a + rnd.randrange(1, 12)
+        _compare_streaming(s, [s[:a], s[a:b], s[b:]])
+
+
+def test_inflater_many_small_appends():
+    """carried state over hundreds of append() calls: 1-byte appends of a small stream, 1-300 byte appends of a 70 KB
+    one, a preset-dictionary stream in pieces, stored blocks cut at their edges"""
+    rnd = random.Random(3)
+    tiny = bytes(K.compress(K.generate(K.TINY, 1, 120), 6, K.ZLIB))
+    _compare_streaming(tiny, [tiny[i:i + 1] for i in range(len(tiny))])
+    fixed = zlib.compress(b"hello hello hello hello, streaming world" * 3, 9)
+    _compare_streaming(fixed, [fixed[i:i + 1] for i in range(len(fixed))])
+    for kind, cont, n in ((K.TEXT, K.ZLIB, 70000), (K.BINARY, K.GZIP, 40000), (K.RUNS, K.RAW, 70000)):
+        s = bytes(K.compress(K.generate(kind, 17, n), 6, cont))
+        parts, o = [], 0
+        while o < len(s):
+            m = rnd.randrange(1, 300)
+            parts.append(s[o:o + m])
+            o += m
+        _compare_streaming(s, parts, raw=cont == K.RAW)
+    dic = bytes(K.generate(K.TEXT, 4242, 470))
+    s = bytes(K.compress(K.generate(K.TEXT, 8, 50000), 6, K.ZLIB_DICT, dic, O.adler32(dic)))
+    for cuts in ((3,), (5, 6), (1, 2, 3, 4, 5, 6, 7), (2000, 9000)):
+        parts = [s[a:b] for a, b in zip((0,) + cuts, cuts + (len(s),))]
+        _compare_streaming(s, parts, dictionary=dic)
+    # stored blocks: boundaries at the LEN / NLEN words, inside the data, exactly at a block's end
+    plain = os.urandom(20000)
+    co = zlib.compressobj(0, zlib.DEFLATED, 15)
+    st = co.compress(plain) + co.flush()
+    for c in (2, 3, 4, 5, 6, 7, 8, 100, 16383 + 7, 16383 + 8, len(st) - 5, len(st) - 4, len(st) - 1):
+        _compare_streaming(st, [st[:c], st[c:]])
+    # bytes after the end of the stream arriving in a later append(): the reference spins (Q4)
+    z = zlib.compress(b"abc" * 100)
+    assert _compare_streaming(z + b"x", [z, b"x"])

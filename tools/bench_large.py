@@ -72,8 +72,8 @@ def cpu_baseline(a):
             "sample": "first %d MiB of the same plaintext as one gzip stream, oracle C port" % cm}
 
 
-def single_gpu(a, stream, crc, n_out):
-    ctx = sdzlib.default_context()
+def single_gpu(a, stream, crc, n_out, ctx=None):
+    ctx = ctx or sdzlib.default_context()
     lib = ctx.lib
     h_in = lib.sdz_host_alloc(len(stream) + 1024)
     h_out = lib.sdz_host_alloc(n_out + 64)
@@ -105,20 +105,21 @@ def single_gpu(a, stream, crc, n_out):
         if it >= a.warmup:
             dtimes.append(dt)
     assert res.success and res.out_len == n_out
+    lib.sdz_device_free(ctx.h, d_in); lib.sdz_device_free(ctx.h, d_out)
+    lib.sdz_host_free(h_in); lib.sdz_host_free(h_out)
     return {"value": round(n_out / min(dtimes) / 1e9, 2), "ms_per_step": round(min(dtimes) * 1e3, 2),
             "e2e": {"value": round(n_out / min(times) / 1e9, 2), "unit": "GB/s", "ms_per_step": round(min(times) * 1e3, 2),
                     "h2d_bytes_per_step": len(stream), "d2h_bytes_per_step": n_out},
             "blocks": int(res.n_blocks), "gpu_launches": (ctx.launch_count() - launches0) // a.steps}
 
 
-def multi_gpu(a, stream, crc, n_out):
+def multi_gpu(a, stream, crc, n_out, ctx=None):
+    """every rank calls this inside an initialised NCCL process group; rank 0 gets the result dict"""
     import torch
     import torch.distributed as dist
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
-    ctx = sdzlib.default_context(local)
+    ctx = ctx or sdzlib.default_context(local)
     comm = LG.TorchComm(dev)
     d_in = torch.zeros(len(stream) + 1024, dtype=torch.uint8, device=dev)
     d_in[:len(stream)] = torch.from_numpy(np.frombuffer(stream, dtype=np.uint8)).to(dev)
@@ -154,7 +155,6 @@ def multi_gpu(a, stream, crc, n_out):
            "blocks": int(rec.n_blocks), "gpu_launches": int(launches.item()) // a.steps,
            "slices": [n for _, n in parts]}
     dist.barrier()
-    dist.destroy_process_group()
     return out if rank == 0 else None
 
 
@@ -174,7 +174,16 @@ def main():
     stream, crc = make_stream(a.mib, a.level)
     gen_s = time.time() - t0
     n_out = a.mib << 20
-    r = single_gpu(a, stream, crc, n_out) if world == 1 else multi_gpu(a, stream, crc, n_out)
+    if world == 1:
+        r = single_gpu(a, stream, crc, n_out)
+    else:
+        import torch
+        import torch.distributed as dist
+        local = int(os.environ.get("LOCAL_RANK", 0))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        r = multi_gpu(a, stream, crc, n_out)
+        dist.destroy_process_group()
     if r is None:
         return
     line = {

@@ -22,7 +22,7 @@ for name in args:
     for k in knobs:
         env[k.split("=")[0]] = k.split("=")[1]
     name = ",".join([name] + knobs)
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--no-checksums", "--no-e2e", "--cpu-sample", "0",
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--no-checksums", "--no-e2e", "--no-extras", "--cpu-sample", "0",
                         "--streams", streams, "--steps", "5", "--warmup", "3"], env=env, capture_output=True, text=True)
     line = p.stdout.strip().splitlines()[-1] if p.stdout.strip() else ""
     try:

@@ -6,8 +6,8 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 TAG=${1:-r02}
 export SDZ_CORPUS_CACHE=/tmp/sdzcorpus
-SHORT="python bench.py --steps 1 --warmup 3 --no-e2e --no-checksums --cpu-sample 0"
+SHORT="python bench.py --steps 1 --warmup 3 --no-e2e --no-checksums --no-extras --cpu-sample 0"
 $SHORT > gpurun_out/${TAG}_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'huff_tokens|lz_resolve' -s 12 -c 4 -o gpurun_out/${TAG}_full $SHORT > gpurun_out/${TAG}_ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"${KREGEX:-huff_tokens|lz_resolve}" -s ${KSKIP:-12} -c ${KCOUNT:-4} -o gpurun_out/${TAG}_full $SHORT > gpurun_out/${TAG}_ncu2.log 2>&1
 tail -5 gpurun_out/${TAG}_ncu2.log
 ls -la gpurun_out

@@ -10,7 +10,7 @@ tail -3 gpurun_out/${TAG}_pytest.log
 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
 tail -c 3000 gpurun_out/${TAG}_bench.json
 export SDZ_CORPUS_CACHE=/tmp/sdzcorpus
-SHORT="python bench.py --steps 1 --warmup 3 --no-e2e --no-checksums --cpu-sample 0"
+SHORT="python bench.py --steps 1 --warmup 3 --no-e2e --no-checksums --no-extras --cpu-sample 0"
 $SHORT > gpurun_out/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv $SHORT > gpurun_out/${TAG}_ncu1.log 2>&1
 $SHORT > gpurun_out/${TAG}_plain2.log 2>&1 &&
