@@ -123,6 +123,26 @@ int sdz_crc32_chain(sdz_ctx* ctx, const uint8_t* p, const uint64_t* seg_len, uin
 int sdz_checksum_batch(sdz_ctx* ctx, const uint8_t* const* bufs, const uint64_t* lens, const uint8_t* kind,
                        const int32_t* seeds, uint64_t n, int32_t* out);
 
+/* ---------------------------------------------------------------- Deflater support
+ * The compressor stays on the CPU; the device supplies what `Deflater` computes over its SOURCE data - checksum =
+ * adler32(chunk, 1) for "deflate", crc32(chunk, 0) for "gzip" (src/sd-deflate.ts:185-190), one launch for the batch - and
+ * writes the reference's containers around raw deflate payloads: zlib 78 01 (78 20 + DICTID when dict_adler != 0,
+ * src/sd-deflate.ts:98-116), gzip 1f 8b 08 FLG MTIME 00 ff [FNAME] (:118-152), trailers Adler-32 BE / CRC-32 + ISIZE LE
+ * (:154-165).  One source buffer == one Deflater.append(), so Q1 applies per buffer exactly as in the reference. */
+enum sdz_wrap_format { SDZ_WRAP_RAW = 0, SDZ_WRAP_DEFLATE = 1, SDZ_WRAP_GZIP = 2 };
+typedef struct sdz_wrap_in {
+    const uint8_t* payload;  uint64_t payload_len;   /* raw deflate data produced by the compressor        */
+    const uint8_t* source;   uint64_t source_len;    /* the data that was compressed                       */
+    const char*    file_name;                        /* gzip FNAME (Latin-1, NUL-terminated) or NULL       */
+    uint32_t       mtime;                            /* gzip MTIME (the reference uses Date.now() / 1000)   */
+    int32_t        dict_adler;                       /* adler32(dictionary) or 0 (src/sd-deflate.ts:88)     */
+    uint8_t        format;                           /* enum sdz_wrap_format                               */
+    uint8_t        reserved[7];
+} sdz_wrap_in;
+int sdz_deflate_wrap_sizes(const sdz_wrap_in* in, uint64_t n, uint64_t* out_len);
+int sdz_deflate_wrap_batch(sdz_ctx* ctx, const sdz_wrap_in* in, uint64_t n, uint8_t* out_arena, const uint64_t* out_off,
+                           uint64_t* out_len);
+
 /* ---------------------------------------------------------------- batched inflate */
 
 /* one input buffer == one `new Inflater(options)` fed with a single append() */

@@ -45,6 +45,17 @@ constexpr uint32_t NTOK_HANDED_OVER = 0xffffffffu;
 #ifndef SDZ_FA_RING
 #define SDZ_FA_RING 8
 #endif
+#ifndef SDZ_CACHE_HINTS
+#define SDZ_CACHE_HINTS 1              // L2 policies: compressed input and tokens evict_first (read / written once), output evict_last (the window)
+#endif
+// -DSDZ_CHECKED: every global / shared address the two fast-path kernels form is checked against the region it must stay in
+// (trap on violation -> the call fails with a CUDA error).  compute-sanitizer is closed on the GPU pool
+// (profiles/r02j_compute_sanitizer_closed.log); the GPU test suite is run once per change against this build instead.
+#ifdef SDZ_CHECKED
+#define SDZ_CHECK(cond) do { if (!(cond)) __trap(); } while (0)
+#else
+#define SDZ_CHECK(cond) do { } while (0)
+#endif
 #ifndef SDZ_FA_DEFER
 #define SDZ_FA_DEFER 4u               // the general single-symbol decoder runs every n-th group of four symbols (power of two)
 #endif
@@ -117,8 +128,12 @@ struct FastParams {
 // input bits per symbol are left to the general decoder (extremely repetitive data)
 __device__ __host__ __forceinline__ uint64_t token_cap(uint32_t in_len, uint32_t out_cap)
 {
-    uint64_t c = 2ull * in_len;
-    if (c > out_cap) c = out_cap;
+    // Slots, not symbols: a lane that meets a rare symbol leaves the rest of its group of four empty (and, while it waits
+    // for the general decoder, whole groups).  Fixed-Huffman blocks (every literal is longer than the 7-bit root) and
+    // run-heavy data need up to four slots per symbol; they are short streams, so the allowance is additive.
+    uint64_t c = 2ull * in_len + 4096;
+    if (c > 8ull * in_len) c = 8ull * in_len;
+    if (c > 4ull * out_cap) c = 4ull * out_cap;
     return (c + 32 + 3) & ~3ull;
 }
 
@@ -348,6 +363,30 @@ __device__ __forceinline__ void cp_async16_if(uint32_t dst_smem, const void* src
                  "l"(src_gmem), "r"((uint32_t)pred)
                  : "memory");
 }
+// the same with an L2 eviction policy (createpolicy): the compressed input is read exactly once
+__device__ __forceinline__ void cp_async16_if(uint32_t dst_smem, const void* src_gmem, bool pred, uint64_t policy)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %3;\n\t}" ::"r"(dst_smem),
+                 "l"(src_gmem), "r"((uint32_t)pred), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void stg_v4_hint(void* p, uint4 v, uint64_t policy)
+{
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(policy)
+                 : "memory");
+}
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
 {
     uint16_t r;
@@ -369,6 +408,9 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
     uint16_t* const wscr = reinterpret_cast<uint16_t*>(smem_raw + 32 * sizeof(LaneSmem));     // sorted_l | sorted_d | lens | aux
     uint16_t* const my_sorted = P.sorted_l + ((size_t)blockIdx.x * 32 + lane) * SORTED_L;
     const uint32_t ring_l = smem_addr(smem_raw + 32 * sizeof(LaneSmem) + SCRATCH_U16 * 2) + lane * (uint32_t)FA_RING_STRIDE;
+#if SDZ_CACHE_HINTS
+    const uint64_t pol_in = l2_policy_evict_first();
+#endif
 
     // ---- lane state
     int state = LS_FETCH;
@@ -414,9 +456,18 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                 int32_t stored = 0, isize = 0;
                 if (ok) {
                     if (C.raw) {
-                        // the reference looks up a symbol only when its table's root width is available;
-                        // nothing follows the final end-of-block code of a raw stream
-                        ok = lbits == 9 && eob_len <= 9 && total_bits - (consumed - (uint64_t)eob_len) >= 9;
+                        // The reference looks up a symbol only when its table's index width is available, and
+                        // nothing follows the final end-of-block code of a raw stream: replay that one lookup with the
+                        // reference's rule (slow_lookup: root width, then the width of the sub-table a longer code sits
+                        // in).  When it succeeds every earlier symbol had at least as many bits behind it (its own code plus
+                        // >= lbits more; distance roots are at most 6 bits wide, hence lbits >= 6).
+                        const uint64_t eob_start = consumed - (uint64_t)eob_len;
+                        const uint8_t* pb = src + (eob_start >> 3);                  // (SDZ_IN_PAD bytes are readable past the stream)
+                        uint64_t v = 0;
+                        for (int k = 0; k < 8; k++) v |= (uint64_t)pb[k] << (8 * k);
+                        const uint64_t A = total_bits - eob_start;
+                        const uint32_t r = slow_lookup(L->cnt_l, my_sorted, lbits, g_l, (uint32_t)(v >> (eob_start & 7)), (int)(A < 64 ? A : 64));
+                        ok = lbits >= 6 && (r >> 28) == (uint32_t)R_OK && (r & 0xffffu) == 256u && ((r >> 16) & 0xffu) == (uint32_t)eob_len;
                     } else {
                         const uint32_t nbytes = C.is_gzip ? 8u : 4u;
                         ok = tp + nbytes <= in_len;
@@ -634,7 +685,11 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                 if (fill) ci = (wp + 1u) >> 2;
                 #pragma unroll
                 for (int k = 0; k < FA_RING_CHUNKS; k++) {
+#if SDZ_CACHE_HINTS
+                    cp_async16_if(ring_l + ((ci & (FA_RING_CHUNKS - 1u)) << 4), reinterpret_cast<const uint8_t*>(wbase) + (size_t)ci * 16u, fill, pol_in);
+#else
                     cp_async16_if(ring_l + ((ci & (FA_RING_CHUNKS - 1u)) << 4), reinterpret_cast<const uint8_t*>(wbase) + (size_t)ci * 16u, fill);
+#endif
                     ci += fill ? 1u : 0u;
                 }
                 cp_async_commit();
@@ -806,7 +861,11 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                 #pragma unroll
                 for (int k = 0; k < 2; k++) {
                     const bool need = live && 4u * ci <= wp + (4u * FA_RING_CHUNKS - 3u);
+#if SDZ_CACHE_HINTS
+                    cp_async16_if(ring_l + ((ci & (FA_RING_CHUNKS - 1u)) << 4), reinterpret_cast<const uint8_t*>(wbase) + (size_t)ci * 16u, need, pol_in);
+#else
                     cp_async16_if(ring_l + ((ci & (FA_RING_CHUNKS - 1u)) << 4), reinterpret_cast<const uint8_t*>(wbase) + (size_t)ci * 16u, need);
+#endif
                     ci += need ? 1u : 0u;
                 }
                 cp_async_commit();
@@ -814,7 +873,12 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                 if (live) {
                     if (early != 0u || pos > cap || wp > lim_wp + 1u || ntok + 4u > cap_tok) ev = 2;
                     else if ((tk0 | tk1 | tk2 | tk3) != 0u) {
+                        SDZ_CHECK(ntok + 4u <= cap_tok && ((reinterpret_cast<uintptr_t>(tokp + ntok) & 15u) == 0u) && wp <= lim_wp + 1u);
+#if SDZ_CACHE_HINTS
+                        stg_v4_hint(tokp + ntok, make_uint4(tk0, tk1, tk2, tk3), pol_in);     // written once, read once by phase B
+#else
                         *reinterpret_cast<uint4*>(tokp + ntok) = make_uint4(tk0, tk1, tk2, tk3);
+#endif
                         ntok += 4u;
                     }
                 }
@@ -986,6 +1050,9 @@ __global__ void __launch_bounds__(32 * B2_WARPS, SDZ_B2_MINBLOCKS) lz_resolve2_k
     __shared__ __align__(16) uint8_t ring_all[B2_WARPS][B2_RING + 16];
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t ring = smem_addr(ring_all[threadIdx.x >> 5]);
+#if SDZ_CACHE_HINTS
+    const uint64_t pol_out = l2_policy_evict_last();
+#endif
     for (;;) {
         unsigned long long idx = 0;
         if (lane == 0) idx = atomicAdd(P.counter_b, 1ull);
@@ -998,6 +1065,9 @@ __global__ void __launch_bounds__(32 * B2_WARPS, SDZ_B2_MINBLOCKS) lz_resolve2_k
         uint8_t* const out = P.I.out + P.I.out_off[idx];
         const uint32_t gb = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u);   // g-coordinate of the stream's first byte
         uint8_t* const outg = out - gb;                                 // g-coordinate 0: a 16-byte aligned address
+#ifdef SDZ_CHECKED
+        const uint32_t chk_cap = P.I.out_cap ? P.I.out_cap[idx] : 0xfffffff0u;
+#endif
         uint32_t pos = gb;                                              // write frontier (uniform)
         uint32_t flushed = 0;                                           // bytes below are in global memory; multiple of 16
         __syncwarp();                                                   // the previous stream's ring reads are over
@@ -1033,6 +1103,8 @@ __global__ void __launch_bounds__(32 * B2_WARPS, SDZ_B2_MINBLOCKS) lz_resolve2_k
                     const bool third = o + len > 16u;
                     uint2 w0 = make_uint2(0u, 0u), w1 = w0, w2 = w0;
                     if (simple) {
+                        SDZ_CHECK(src >= gb && src + len <= pos && dst + len <= gb + chk_cap && (from_ring || a + (third ? 24u : 16u) <= flushed));
+                        SDZ_CHECK(!from_ring || pos - a <= B2_HIST + 8u);
                         if (from_ring) {
                             w0 = lds_v2(ring + (a & (B2_RING - 1u)));
                             w1 = lds_v2(ring + ((a + 8u) & (B2_RING - 1u)));
@@ -1077,6 +1149,7 @@ __global__ void __launch_bounds__(32 * B2_WARPS, SDZ_B2_MINBLOCKS) lz_resolve2_k
                             // dist >= 32: bytes at or after h_dst were written by earlier rounds of this loop;
                             // dist < 32: replicate the dist bytes before the match
                             const uint32_t q = h_src + (h_dist < 32u ? i % h_dist : i);
+                            SDZ_CHECK(h_src >= gb && q < h_dst + i && h_dst + h_len <= gb + chk_cap && (q < flushed || h_dst + i - q < B2_RING - 16u));
                             const uint32_t v = q >= flushed ? lds_u8(ring + (q & (B2_RING - 1u))) : (uint32_t)outg[q];
                             sts_u8(ring + ((h_dst + i) & (B2_RING - 1u)), v);
                         }
@@ -1089,7 +1162,12 @@ __global__ void __launch_bounds__(32 * B2_WARPS, SDZ_B2_MINBLOCKS) lz_resolve2_k
                 const uint32_t upto = pos & ~15u;
                 for (uint32_t g = flushed + lane * 16u; g < upto; g += 512u) {
                     const uint4 v = lds_v4(ring + (g & (B2_RING - 1u)));
+                    SDZ_CHECK(g + 16u <= pos && pos <= gb + chk_cap && pos - flushed <= B2_SUB + 16u);
+#if SDZ_CACHE_HINTS
+                    if (g >= gb) stg_v4_hint(outg + g, v, pol_out);    // the next 32 KiB of this stream read from here
+#else
                     if (g >= gb) *reinterpret_cast<uint4*>(outg + g) = v;
+#endif
                     else {                                              // the vector that holds the stream's first byte
                         const uint32_t w[4] = { v.x, v.y, v.z, v.w };
                         #pragma unroll

@@ -1436,6 +1436,79 @@ int sdz_inflater_finish(sdz_inflater* s, sdz_result* res)
 
 }  // extern "C"
 
+// ---------------------------------------------------------------------------- Deflater wrappers
+//
+// The compressor itself stays on the CPU (out of scope); what the device contributes to `Deflater` is the checksum of
+// the SOURCE data (src/sd-deflate.ts:185-190) - one launch for the whole batch - and with it the container around each
+// raw deflate payload: zlib header 78 01 (78 20 + DICTID with a preset dictionary, src/sd-deflate.ts:98-116), gzip
+// header with MTIME, XFL = 0, OS = 0xff and optional FNAME (:118-152), trailer Adler-32 big-endian / CRC-32 + ISIZE
+// little-endian (:154-165).
+
+extern "C" {
+
+static uint64_t wrap_size(const sdz_wrap_in& w)
+{
+    if (w.format == SDZ_WRAP_RAW) return w.payload_len;
+    if (w.format == SDZ_WRAP_DEFLATE) return 2 + (w.dict_adler ? 4 : 0) + w.payload_len + 4;
+    const size_t nl = w.file_name && w.file_name[0] ? strlen(w.file_name) + 1 : 0;
+    return 10 + nl + w.payload_len + 8;
+}
+
+int sdz_deflate_wrap_sizes(const sdz_wrap_in* in, uint64_t n, uint64_t* out_len)
+{
+    if ((n && !in) || (n && !out_len)) return SDZ_E_ARG;
+    for (uint64_t i = 0; i < n; i++) {
+        if (in[i].format > SDZ_WRAP_GZIP || (in[i].payload_len && !in[i].payload) || (in[i].source_len && !in[i].source)) return SDZ_E_ARG;
+        out_len[i] = wrap_size(in[i]);
+    }
+    return SDZ_OK;
+}
+
+int sdz_deflate_wrap_batch(sdz_ctx* ctx, const sdz_wrap_in* in, uint64_t n, uint8_t* out_arena, const uint64_t* out_off, uint64_t* out_len)
+{
+    if (!ctx || (n && (!in || !out_arena || !out_off))) return SDZ_E_ARG;
+    if (n == 0) return SDZ_OK;
+    std::vector<const uint8_t*> bufs(n);
+    std::vector<uint64_t> lens(n);
+    std::vector<uint8_t> kind(n);
+    std::vector<int32_t> sums(n);
+    for (uint64_t i = 0; i < n; i++) {
+        if (in[i].format > SDZ_WRAP_GZIP || (in[i].payload_len && !in[i].payload) || (in[i].source_len && !in[i].source)) return SDZ_E_ARG;
+        bufs[i] = in[i].source; lens[i] = in[i].format == SDZ_WRAP_RAW ? 0 : in[i].source_len;
+        kind[i] = in[i].format == SDZ_WRAP_GZIP ? 1 : 0;
+    }
+    // one append() per source: checksum = adler32(chunk, 1) / crc32(chunk, 0), the reference's own functions (Q1 included)
+    int rc = sdz_checksum_batch(ctx, bufs.data(), lens.data(), kind.data(), nullptr, n, sums.data());
+    if (rc) return rc;
+    for (uint64_t i = 0; i < n; i++) {
+        const sdz_wrap_in& w = in[i];
+        uint8_t* o = out_arena + out_off[i];
+        size_t p = 0;
+        if (w.format == SDZ_WRAP_DEFLATE) {
+            o[p++] = 0x78; o[p++] = w.dict_adler ? 0x20 : 0x01;
+            if (w.dict_adler) { const uint32_t d = (uint32_t)w.dict_adler; o[p++] = (uint8_t)(d >> 24); o[p++] = (uint8_t)(d >> 16); o[p++] = (uint8_t)(d >> 8); o[p++] = (uint8_t)d; }
+        } else if (w.format == SDZ_WRAP_GZIP) {
+            const bool named = w.file_name && w.file_name[0];
+            o[p++] = 0x1f; o[p++] = 0x8b; o[p++] = 8; o[p++] = named ? 0x08 : 0x00;
+            for (int j = 0; j < 4; j++) o[p++] = (uint8_t)(w.mtime >> (8 * j));
+            o[p++] = 0; o[p++] = 0xff;
+            if (named) { const size_t nl = strlen(w.file_name) + 1; memcpy(o + p, w.file_name, nl); p += nl; }
+        }
+        if (w.payload_len) memcpy(o + p, w.payload, w.payload_len);
+        p += w.payload_len;
+        const uint32_t c = (uint32_t)sums[i];
+        if (w.format == SDZ_WRAP_DEFLATE) { o[p++] = (uint8_t)(c >> 24); o[p++] = (uint8_t)(c >> 16); o[p++] = (uint8_t)(c >> 8); o[p++] = (uint8_t)c; }
+        else if (w.format == SDZ_WRAP_GZIP) {
+            for (int j = 0; j < 4; j++) o[p++] = (uint8_t)(c >> (8 * j));
+            for (int j = 0; j < 4; j++) o[p++] = (uint8_t)((uint32_t)w.source_len >> (8 * j));
+        }
+        if (out_len) out_len[i] = p;
+    }
+    return SDZ_OK;
+}
+
+}  // extern "C"
+
 // ---------------------------------------------------------------------------- one large stream
 //
 // The work is organised as phases of a session (sdz_large_*), so that the SAME code serves one GPU

@@ -17,6 +17,7 @@ EXPORTS = [
     "sdz_ctx_create", "sdz_ctx_create_multi", "sdz_ctx_device_count", "sdz_last_partition", "sdz_host_alloc_near", "sdz_ctx_numa_node", "sdz_ctx_destroy", "sdz_last_error", "sdz_version", "sdz_launch_count", "sdz_last_timing", "sdz_last_phase_timing", "sdz_last_fast_stats", "sdz_debug_table_totals",
     "sdz_host_alloc", "sdz_host_free", "sdz_device_alloc", "sdz_device_free", "sdz_memcpy_h2d", "sdz_memcpy_d2h",
     "sdz_adler32", "sdz_crc32", "sdz_adler32_chain", "sdz_crc32_chain", "sdz_checksum_batch",
+    "sdz_deflate_wrap_sizes", "sdz_deflate_wrap_batch",
     "sdz_inflater_create", "sdz_inflater_append", "sdz_inflater_read", "sdz_inflater_finish", "sdz_inflater_input", "sdz_inflater_destroy",
     "sdz_inflate_batch", "sdz_inflate_sizes", "sdz_inflate_batch_device", "sdz_inflate_large", "sdz_sync",
     "sdz_large_open", "sdz_large_close", "sdz_large_index", "sdz_large_plan", "sdz_large_range", "sdz_large_decode",
@@ -52,6 +53,13 @@ class In(C.Structure):
     """struct sdz_in"""
     _fields_ = [("data", C.c_void_p), ("len", C.c_uint64), ("dict", C.c_void_p), ("dict_len", C.c_uint32),
                 ("mode", C.c_uint8), ("reserved", C.c_uint8 * 3)]
+
+
+class WrapIn(C.Structure):
+    """struct sdz_wrap_in"""
+    _fields_ = [("payload", C.c_void_p), ("payload_len", C.c_uint64), ("source", C.c_void_p), ("source_len", C.c_uint64),
+                ("file_name", C.c_char_p), ("mtime", C.c_uint32), ("dict_adler", C.c_int32), ("format", C.c_uint8),
+                ("reserved", C.c_uint8 * 7)]
 
 
 class BatchDev(C.Structure):
@@ -113,6 +121,8 @@ def load():
         for f in (L.sdz_adler32_chain, L.sdz_crc32_chain):
             f.argtypes = [vp, vp, vp, u64, i32, C.c_int, vp, C.POINTER(i32)]
         L.sdz_checksum_batch.argtypes = [vp, vp, vp, vp, vp, u64, vp]
+        L.sdz_deflate_wrap_sizes.argtypes = [vp, u64, vp]
+        L.sdz_deflate_wrap_batch.argtypes = [vp, vp, u64, vp, vp, vp]
         L.sdz_inflater_create.argtypes = [vp, C.c_int, vp, u32, C.POINTER(vp)]
         L.sdz_inflater_append.argtypes = [vp, vp, u64, C.POINTER(u64), C.POINTER(Result)]
         L.sdz_inflater_read.argtypes = [vp, vp, u64]

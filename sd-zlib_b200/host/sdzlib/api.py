@@ -107,6 +107,46 @@ def checksum_batch(buffers, kinds, seeds=None, ctx=None):
     return [int(x) for x in out[:n]]
 
 
+def deflate_wrap_batch(payloads, sources, format="deflate", file_names=None, dictionaries=None, mtime=None, ctx=None):
+    """What `Deflater` puts around its raw deflate output (src/sd-deflate.ts:98-165), for a batch: the source checksums
+    are computed on the device in one launch, headers / trailers are the reference's.  The compressor itself is not
+    part of this package (out of scope) - `payloads` come from the caller's deflate."""
+    import time as _time
+    ctx = ctx or N.default_context()
+    fmt = {"raw": 0, "deflate": 1, "gzip": 2}
+    if format not in fmt:
+        raise ValueError("container must be one of `raw`, `deflate`, `gzip`")       # RangeError in JS
+    n = len(payloads)
+    pv = [_as_u8(p, "data must be an ArrayBuffer or buffer view") for p in payloads]
+    sv = [_as_u8(p, "data must be an ArrayBuffer or buffer view") for p in sources]
+    ins = (N.WrapIn * max(n, 1))()
+    t = int(_time.time()) if mtime is None else int(mtime)
+    names = []
+    for i in range(n):
+        ins[i].payload = pv[i].ctypes.data if pv[i].size else None
+        ins[i].payload_len = int(pv[i].size)
+        ins[i].source = sv[i].ctypes.data if sv[i].size else None
+        ins[i].source_len = int(sv[i].size)
+        ins[i].format = fmt[format]
+        ins[i].mtime = t & 0xFFFFFFFF
+        name = (file_names[i] if file_names else None) or ""
+        if name and format == "gzip":               # src/sd-deflate.ts:126-131: code points above 0xff become "_"
+            names.append(bytes(ord(c) if ord(c) <= 0xff else 95 for c in name))
+            ins[i].file_name = names[-1]
+        d = dictionaries[i] if dictionaries else None
+        if d is not None:
+            if format != "deflate":
+                raise TypeError("Can only provide a dictionary for `deflate` containers.")
+            ins[i].dict_adler = adler32(d, ctx=ctx)
+    sizes = np.zeros(max(n, 1), dtype=np.uint64)
+    ctx.check(ctx.lib.sdz_deflate_wrap_sizes(ins, n, sizes.ctypes.data))
+    off = np.zeros(max(n, 1), dtype=np.uint64)
+    off[1:] = np.cumsum(sizes[:-1])
+    arena = np.empty(max(int(sizes[:n].sum()), 1), dtype=np.uint8)
+    ctx.check(ctx.lib.sdz_deflate_wrap_batch(ctx.h, ins, n, arena.ctypes.data, off.ctypes.data, None))
+    return [arena[int(off[i]):int(off[i]) + int(sizes[i])].tobytes() for i in range(n)]
+
+
 def mergeBuffers(buffers: Sequence[bytes]) -> bytes:
     """src/common.ts:116-126"""
     return b"".join(bytes(b) for b in buffers)

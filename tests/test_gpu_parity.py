@@ -647,3 +647,37 @@ def test_inflater_many_small_appends():
     # bytes after the end of the stream arriving in a later append(): the reference spins (Q4)
     z = zlib.compress(b"abc" * 100)
     assert _compare_streaming(z + b"x", [z, b"x"])
+
+
+def test_deflate_wrap_batch_matches_reference_containers():
+    """the containers `Deflater` writes (src/sd-deflate.ts:98-165) around raw deflate payloads, with the source
+    checksums computed on the device in one launch.  Byte-identical to the reference-format streams of the corpus tool
+    (which reproduces the reference's own fixture, tests/test_corpus_tool.py), and the result inflates back through the
+    drop-in API with checksum / fileSize "match" - including a source whose length is a multiple of 5552 (Q1: the
+    reference's Deflater and Inflater agree with each other, not with zlib)."""
+    plains = [K.generate(K.TEXT, 300 + i, n).tobytes() for i, n in enumerate((1, 100, 5552, 11104, 40000, 65536, 70001))]
+    raws = [K.compress(p, 6, K.RAW) for p in plains]
+    z = sdzlib.deflate_wrap_batch(raws, plains, "deflate")
+    g = sdzlib.deflate_wrap_batch(raws, plains, "gzip", file_names=["stream.bin"] * len(plains), mtime=0x5d211b5e)
+    g0 = sdzlib.deflate_wrap_batch(raws, plains, "gzip", mtime=0x5d211b5e)
+    r = sdzlib.deflate_wrap_batch(raws, plains, "raw")
+    for i, p in enumerate(plains):
+        assert r[i] == raws[i]
+        assert g[i] == K.compress(p, 6, K.GZIP_NAME) and g0[i] == K.compress(p, 6, K.GZIP)
+        if len(p) % 5552:
+            assert z[i] == K.compress(p, 6, K.ZLIB)
+        else:                                                   # Q1: the trailer holds the REFERENCE's adler32 of the source
+            assert z[i][:-4] == K.compress(p, 6, K.ZLIB)[:-4]
+            assert int.from_bytes(z[i][-4:], "big", signed=True) == O.adler32(p) != zlib.adler32(p)
+    for streams in (z, g):
+        for i, o in enumerate(sdzlib.inflateBatch(streams)):
+            assert o["data"] == plains[i] and o["error"] is None
+            # a zlib stream of 5552 / 11104 bytes is "mismatch" in the reference even from its own Deflater? No: the Inflater
+            # checksums the same <= 16 KiB chunk with the same function, so both sides carry the same Q1 value
+            assert o["result"].checksum == "match", (i, len(plains[i]))
+    assert all(o["result"].fileName == "stream.bin" and o["result"].fileSize == "match" for o in sdzlib.inflateBatch(g))
+    dic = bytes(K.generate(K.TEXT, 4242, 470))
+    p = plains[4]
+    zd = sdzlib.deflate_wrap_batch([raw_deflate(p, 6, -15, dic)], [p], "deflate", dictionaries=[dic])[0]
+    assert zd[:2] == b"\x78\x20" and int.from_bytes(zd[2:6], "big", signed=True) == O.adler32(dic)
+    assert sdzlib.inflate(zd, dic) == p
