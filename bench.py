@@ -243,7 +243,7 @@ def bench_checksums(ctx, torch, peak):
     return out, verify, buf
 
 
-def build_mixed_batch(n, threads, first_index):
+def build_mixed_batch(n, threads, first_index, reps=1):
     """cfg4 at bench size: 6 corpus kinds x levels 1/6/9 x gzip / gzip+FNAME / zlib / raw, plus zlib streams with a
     preset dictionary; incompressible data stays <= 49,151 B per stream.  Streams of different kinds are
     interleaved.  Returns dict(arena, off, ln, mode, cap, dict_arena, dict_off, dict_len, dict_adler, plain_bytes)."""
@@ -283,8 +283,13 @@ def build_mixed_batch(n, threads, first_index):
     mode = np.array([s[2] | (0x80 if s[3] else 0) for s in streams], dtype=np.uint8)
     dlen = np.array([len(dic) if s[3] else 0 for s in streams], dtype=np.uint32)
     dadl = np.array([dictid if s[3] else 0 for s in streams], dtype=np.int32)
+    if reps > 1:                                     # multi-rank runs share the host cores: fewer distinct streams, tiled
+        one = arena.size - 1024
+        arena = np.concatenate([arena[:one]] * reps + [np.zeros(1024, dtype=np.uint8)])
+        off = np.concatenate([off + np.uint64(r * one) for r in range(reps)])
+        ln, cap, mode, dlen, dadl = (np.tile(x, reps) for x in (ln, cap, mode, dlen, dadl))
     return {"arena": arena, "off": off, "ln": ln, "mode": mode, "cap": cap, "dict": np.frombuffer(dic + b"\0" * 42, dtype=np.uint8),
-            "dict_len": dlen, "dict_adler": dadl, "plain_bytes": int(sum(s[1] for s in streams)), "dictionary": dic}
+            "dict_len": dlen, "dict_adler": dadl, "plain_bytes": int(sum(s[1] for s in streams)) * reps, "dictionary": dic}
 
 
 class DeviceBatch:
@@ -396,7 +401,7 @@ def main():
                     continue
                 c2, s2, l2, _ = make_corpus(nd8, 700000 + rank * nd8, my_cores, kind, level)
                 matrix_in.append((kname, level, pack(c2, s2, l2, n // nd8)))
-        mixed = build_mixed_batch(n, my_cores, 800000 + rank * n)
+        mixed = build_mixed_batch(n // reps, my_cores, 800000 + rank * n, reps)
         if args.large_mib:
             from tools import bench_large as BL
             large = BL.make_stream(args.large_mib, LEVEL)

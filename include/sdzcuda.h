@@ -266,6 +266,10 @@ int  sdz_large_finish(sdz_large* L, int32_t running_checksum, sdz_result* res);
 int  sdz_large_is_gzip(sdz_large* L);
 /* crc32(A || B) from crc32(A), crc32(B), len(B) - host arithmetic, no device needed */
 int32_t sdz_crc32_combine(int32_t crc_a, int32_t crc_b, uint64_t len_b);
+/* adler32(A || B) from adler32(A), adler32(B) and len(B) with the STANDARD arithmetic (B seeded with 1) - what the sharded
+ * running checksum of a zlib / raw stream is joined with; the reference's defect can only touch the final
+ * <= 16 KiB chunk, which is checksummed as one sdz_adler32 call seeded with the combined value (sdzlib/large.py) */
+int32_t sdz_adler32_combine(int32_t adler_a, int32_t adler_b, uint64_t len_b);
 int sdz_sync(sdz_ctx* ctx);
 
 #ifdef __cplusplus

@@ -53,6 +53,8 @@ struct sdz_ctx {
     bool large_cache_full = false;
     void* h_stage = nullptr;           // pinned
     size_t h_stage_cap = 0;
+    void* h_out = nullptr;             // pinned landing zone of the decoded bytes when the caller's arena is pageable: the
+    size_t h_out_cap = 0;              // device -> host copy stays asynchronous, host threads move the bytes on
     void* h_res = nullptr;             // pinned landing zone of the result records (a copy into the caller's pageable
     size_t h_res_cap = 0;              // array would block the host thread and serialise the pipeline)
     unsigned long long* d_counter = nullptr;   // [0..3] lane 0 / checksums / large-stream path, [4 + 2 l ..] lane l
@@ -79,6 +81,7 @@ struct sdz_ctx {
     bool fast_timed = false;
     const unsigned long long* last_fb_count = nullptr;   // device counter of the most recent fast-path launch
     uint64_t last_fast_n = 0;
+    bool h2d_first = false;            // SDZ_H2D_FIRST=1: the pipelined host path sends every input before it fetches any output
     bool poison = false;               // SDZ_POISON=1 (tests): fill the device output arena with 0xA5 before every decode
     // multi-device context (sdz_ctx_create_multi): one child context per entry of the device list; this object then only
     // partitions batches (inflate_multi) and owns no streams of its own.  numa_node: host memory node next to the device
@@ -321,6 +324,28 @@ int launch_finalize(sdz_ctx* ctx, const uint8_t* d_out, sdz_result* d_res, uint6
 // Two-phase fast path: token offsets -> phase A (Huffman -> tokens) -> phase B (tokens -> bytes) -> the general
 // decoder for the streams phase A handed over.  `tok_total`: size of the token arena when the caller knows it
 // (host path: computed from the host copies of in_len / out_cap), 0 = read it back from the device.
+// Grow every device buffer a sub-batch of `n` streams / `tok_total` token slots will need on compute lane `lane` BEFORE the
+// pipeline starts: cudaMalloc / cudaFree synchronise the device, and a first call that grows its buffers between
+// sub-batches stalls every stream in flight (round 1: 730 ms at sub-batch 4 of the first call).
+int reserve_lane(sdz_ctx* ctx, int lane, uint64_t n, uint64_t tok_total, bool fast)
+{
+    int rc;
+    {
+        const int threads = ctx->block_threads, groups = threads / ctx->group;
+        // (upper bound of the persistent grid of inflate_kernel: 16 blocks per SM is more than its shared memory allows)
+        const uint64_t grid = std::min<uint64_t>((n + groups - 1) / groups, (uint64_t)ctx->sm_count * 16);
+        DevBuf& scratch = lane ? ctx->lane_scratch[lane] : ctx->d_misc;
+        if ((rc = grow(ctx, scratch, (size_t)grid * groups * sdz::SCRATCH_U16 * sizeof(uint16_t)))) return rc;
+    }
+    if (!fast) return SDZ_OK;
+    const size_t off_list = 256 + (n + 1) * 8 + (n * 4 + 7) / 8 * 8;
+    if ((rc = grow(ctx, ctx->fast_meta[lane], off_list + n * 4))) return rc;
+    if ((rc = grow(ctx, ctx->fast_tok[lane], tok_total * 4 + 64))) return rc;
+    const uint64_t grid_a = std::min<uint64_t>((n + 31) / 32, (uint64_t)ctx->sm_count * 8);
+    if ((rc = grow(ctx, ctx->fast_sorted[lane], (size_t)grid_a * 32 * sdz::SORTED_L * sizeof(uint16_t)))) return rc;
+    return SDZ_OK;
+}
+
 int launch_fast(sdz_ctx* ctx, const sdz::InflateParams& P, uint64_t tok_total, bool timed)
 {
     const uint64_t n = P.n;
@@ -441,12 +466,13 @@ void parallel_copy(const std::vector<std::pair<uint8_t*, std::pair<const uint8_t
     }
     std::atomic<size_t> next{ 0 };
     std::vector<std::thread> th;
+    const size_t step = std::max<size_t>(1, std::min<size_t>(256, jobs.size() / (nt * 8)));
     for (unsigned t = 0; t < nt; t++)
         th.emplace_back([&] {
             for (;;) {
-                size_t lo = next.fetch_add(256);
+                size_t lo = next.fetch_add(step);
                 if (lo >= jobs.size()) break;
-                size_t hi = std::min(jobs.size(), lo + 256);
+                size_t hi = std::min(jobs.size(), lo + step);
                 for (size_t i = lo; i < hi; i++) memcpy(jobs[i].first, jobs[i].second.first, jobs[i].second.second);
             }
         });
@@ -534,6 +560,7 @@ int sdz_ctx_create(int device, uint32_t flags, sdz_ctx** out)
     if (const char* t = getenv("SDZ_BLOCK")) { int v = atoi(t); if (v == 32 || v == 64 || v == 128) ctx->block_threads = v; }
     if (ctx->block_threads < ctx->group) ctx->block_threads = ctx->group;
     if (const char* z = getenv("SDZ_POISON")) ctx->poison = atoi(z) != 0;
+    if (const char* z = getenv("SDZ_H2D_FIRST")) ctx->h2d_first = atoi(z) != 0;
     int rc = upload_tables(ctx);
     if (rc) return fail(rc);
     *out = ctx;
@@ -597,6 +624,7 @@ void sdz_ctx_destroy(sdz_ctx* ctx)
     }
     pinned_free(ctx->h_stage);
     pinned_free(ctx->h_res);
+    pinned_free(ctx->h_out);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
     for (auto& e : ctx->ev)
         if (e) cudaEventDestroy(e);
@@ -1114,6 +1142,37 @@ static int inflate_host(sdz_ctx* ctx, const sdz_in* in, uint64_t n, uint8_t* out
         if (cudaPointerGetAttributes(&attr, ubase) != cudaSuccess || attr.type != cudaMemoryTypeHost) { direct = false; cudaGetLastError(); }
     } else direct = false;
     const size_t data_end = in_off[n - 1] + in_len[n - 1];
+    // pageable output arena (what an N-API caller hands over): a device -> host copy straight into it would be staged by
+    // the driver, synchronously and at a fraction of the link rate.  The bytes land in a pinned zone instead, sub-batch by
+    // sub-batch, and host threads move each sub-batch on while the next one is in flight.
+    bool out_staged = false;
+    if (!sizes_only && dense && K > 1) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, out_arena + out_lo) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered) { out_staged = true; cudaGetLastError(); }
+        if (out_staged) {
+            if (ctx->h_out_cap < out_hi - out_lo) {
+                pinned_free(ctx->h_out);
+                ctx->h_out_cap = 0;
+                ctx->h_out = pinned_alloc(out_hi - out_lo, ctx->numa_node);
+                if (ctx->h_out) ctx->h_out_cap = out_hi - out_lo;
+                else out_staged = false;                                  // no pinned memory left: the plain copy still works
+            }
+        }
+    }
+    // every buffer the sub-batches will need, before anything is in flight
+    {
+        uint64_t n_max[sdz_ctx::N_LANES] = { 0 }, tok_max[sdz_ctx::N_LANES] = { 0 };
+        for (uint64_t c = 0; c < K; c++) {
+            const int l = (int)(c % n_lanes);
+            uint64_t tt = 0;
+            if (!sizes_only && ctx->fast)
+                for (uint64_t i = cut[c]; i < cut[c + 1]; i++) tt += sdz::token_cap(in_len[i], d_out_cap[i]);
+            n_max[l] = std::max(n_max[l], cut[c + 1] - cut[c]);
+            tok_max[l] = std::max(tok_max[l], tt);
+        }
+        for (int l = 0; l < n_lanes; l++)
+            if ((rc = reserve_lane(ctx, l, n_max[l], tok_max[l], !sizes_only && ctx->fast))) return rc;
+    }
 
     if (ctx->poison && !sizes_only) {
         // stale bytes of an earlier call must never be able to stand in for bytes a kernel failed to write
@@ -1130,6 +1189,21 @@ static int inflate_host(sdz_ctx* ctx, const sdz_in* in, uint64_t n, uint8_t* out
     }
     const auto t_host0 = std::chrono::steady_clock::now();
     CK(cudaMemcpyAsync(ctx->d_meta.p, hm, meta_bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
+    // records and bytes of sub-batch c go home once its kernels are done
+    auto enqueue_d2h = [&](uint64_t c) -> int {
+        const uint64_t lo = cut[c], hi = cut[c + 1];
+        if (lo == hi) return SDZ_OK;
+        CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->pipe_ev[2 * c + 1], 0));
+        CK(cudaMemcpyAsync(rdst + lo, (sdz_result*)ctx->d_res.p + lo, (hi - lo) * sizeof(sdz_result), cudaMemcpyDeviceToHost, ctx->s_d2h));
+        if (!sizes_only && dense) {
+            const uint64_t o_lo = d_out_off[lo], o_hi = d_out_off[hi - 1] + d_out_cap[hi - 1];
+            uint8_t* land = out_staged ? (uint8_t*)ctx->h_out : out_arena + out_lo;
+            CK(cudaMemcpyAsync(land + o_lo, (uint8_t*)ctx->d_out.p + o_lo, o_hi - o_lo, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            if (out_staged) CK(cudaEventRecord(ctx->pipe_ev[2 * c], ctx->s_d2h));      // (the input-landed event of c has been waited on)
+        }
+        if (trace_pipe) cudaEventRecord(tev[3 * c + 2], ctx->s_d2h);
+        return SDZ_OK;
+    };
     for (uint64_t c = 0; c < K; c++) {
         const uint64_t lo = cut[c], hi = cut[c + 1];
         if (lo == hi) continue;
@@ -1160,13 +1234,29 @@ static int inflate_host(sdz_ctx* ctx, const sdz_in* in, uint64_t n, uint8_t* out
         if (rc) return rc;
         CK(cudaEventRecord(ctx->pipe_ev[2 * c + 1], lane_st));
         if (trace_pipe) cudaEventRecord(tev[3 * c + 1], lane_st);
-        CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->pipe_ev[2 * c + 1], 0));
-        CK(cudaMemcpyAsync(rdst + lo, (sdz_result*)ctx->d_res.p + lo, (hi - lo) * sizeof(sdz_result), cudaMemcpyDeviceToHost, ctx->s_d2h));
-        if (!sizes_only && dense) {
+        if (!ctx->h2d_first) { if ((rc = enqueue_d2h(c))) return rc; }
+    }
+    if (ctx->h2d_first) {
+        // SDZ_H2D_FIRST=1: no device -> host copy starts before the last input has landed.  On hosts whose memory system
+        // sustains less with both directions active than with one (profiles/r02n_8gpu_summary.md: 8 GPUs on one socket,
+        // ~100 GB/s mixed against 168 GB/s device -> host alone) the two phases are faster one after the other.
+        CK(cudaEventRecord(ctx->ev[3], ctx->s_h2d));
+        CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev[3], 0));
+        for (uint64_t c = 0; c < K; c++)
+            if ((rc = enqueue_d2h(c))) return rc;
+    }
+    if (out_staged) {
+        for (uint64_t c = 0; c < K; c++) {
+            const uint64_t lo = cut[c], hi = cut[c + 1];
+            if (lo == hi) continue;
+            CK(cudaEventSynchronize(ctx->pipe_ev[2 * c]));
             const uint64_t o_lo = d_out_off[lo], o_hi = d_out_off[hi - 1] + d_out_cap[hi - 1];
-            CK(cudaMemcpyAsync(out_arena + out_lo + o_lo, (uint8_t*)ctx->d_out.p + o_lo, o_hi - o_lo, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            std::vector<std::pair<uint8_t*, std::pair<const uint8_t*, size_t>>> jobs;
+            const size_t piece = 1u << 20;
+            for (uint64_t o = o_lo; o < o_hi; o += piece)
+                jobs.push_back({ out_arena + out_lo + o, { (const uint8_t*)ctx->h_out + o, (size_t)std::min<uint64_t>(piece, o_hi - o) } });
+            parallel_copy(jobs);
         }
-        if (trace_pipe) cudaEventRecord(tev[3 * c + 2], ctx->s_d2h);
     }
     const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
     CK(cudaStreamSynchronize(ctx->s_d2h));
@@ -2073,6 +2163,24 @@ extern "C" int sdz_large_is_gzip(sdz_large* L) { return L && L->is_gzip; }
 
 // crc32(A || B) from crc32(A), crc32(B) and len(B): multiplication by x^(8 len2) modulo the CRC polynomial
 // (reflected), the same GF(2) arithmetic the device kernels use for their partials.  Pure host code.
+// adler32(A || B) from adler32(A), adler32(B) (standard arithmetic, B seeded with 1) and len(B): the sums are linear in
+// the bytes, so B's contribution is shifted by len(B) * (a of A) and the two initial 1s are taken out once
+extern "C" int32_t sdz_adler32_combine(int32_t adler1, int32_t adler2, uint64_t len2)
+{
+    const uint32_t BASE = 65521u;
+    const uint32_t a1 = (uint32_t)adler1, a2 = (uint32_t)adler2;
+    const uint32_t rem = (uint32_t)(len2 % BASE);
+    uint32_t sum1 = a1 & 0xffffu;
+    uint32_t sum2 = (uint32_t)(((uint64_t)rem * sum1) % BASE);
+    sum1 += (a2 & 0xffffu) + BASE - 1u;
+    sum2 += (a1 >> 16) + (a2 >> 16) + BASE - rem;
+    if (sum1 >= BASE) sum1 -= BASE;
+    if (sum1 >= BASE) sum1 -= BASE;
+    if (sum2 >= (BASE << 1)) sum2 -= (BASE << 1);
+    if (sum2 >= BASE) sum2 -= BASE;
+    return (int32_t)(sum1 | (sum2 << 16));
+}
+
 extern "C" int32_t sdz_crc32_combine(int32_t crc1, int32_t crc2, uint64_t len2)
 {
     // x^(8 * len2) by square-and-multiply over the bits of len2 (x2n[k] = x^(2^k), k >= 3 for bytes)

@@ -21,7 +21,7 @@ EXPORTS = [
     "sdz_inflater_create", "sdz_inflater_append", "sdz_inflater_read", "sdz_inflater_finish", "sdz_inflater_input", "sdz_inflater_destroy",
     "sdz_inflate_batch", "sdz_inflate_sizes", "sdz_inflate_batch_device", "sdz_inflate_large", "sdz_sync",
     "sdz_large_open", "sdz_large_close", "sdz_large_index", "sdz_large_plan", "sdz_large_range", "sdz_large_decode",
-    "sdz_large_windows", "sdz_large_resolve", "sdz_large_finish", "sdz_large_is_gzip", "sdz_crc32_combine",
+    "sdz_large_windows", "sdz_large_resolve", "sdz_large_finish", "sdz_large_is_gzip", "sdz_crc32_combine", "sdz_adler32_combine",
 ]
 
 
@@ -147,6 +147,8 @@ def load():
         L.sdz_large_is_gzip.argtypes = [vp]
         L.sdz_crc32_combine.argtypes = [i32, i32, u64]
         L.sdz_crc32_combine.restype = i32
+        L.sdz_adler32_combine.argtypes = [i32, i32, u64]
+        L.sdz_adler32_combine.restype = i32
         _lib = L
         return L
 

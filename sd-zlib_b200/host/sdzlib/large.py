@@ -46,6 +46,14 @@ def crc32_combine(crc_a, crc_b, len_b):
     return int(N.load().sdz_crc32_combine(int(crc_a), int(crc_b), int(len_b)))
 
 
+def adler32_combine(adler_a, adler_b, len_b):
+    """adler32(A || B) from adler32(A), adler32(B) (both with the STANDARD arithmetic, B seeded with 1) and len(B)."""
+    return int(N.load().sdz_adler32_combine(int(adler_a), int(adler_b), int(len_b)))
+
+
+OUTBUF = 16384                              # src/zstream.ts:11
+
+
 class CudaBackend:
     """The phases of one rank, on one device, through the C ABI.  `stream_ptr` is a DEVICE pointer to the whole
     compressed stream (16-byte aligned, readable for 1 KiB past its end)."""
@@ -105,6 +113,30 @@ class CudaBackend:
         self.ctx.check(self.lib.sdz_crc32(self.ctx.h, ptr, int(n), 0, 1, C.byref(out)))
         return out.value
 
+    def adler32_std(self, ptr, n):
+        """STANDARD adler32 (seed 1) of n bytes in HBM.  The reference's function differs from it only for a single
+        call whose length is a non-zero multiple of 5552, so such a slice is checksummed as two calls."""
+        if n == 0:
+            return 1
+        segs = np.array([n - 1, 1] if n % 5552 == 0 else [n], dtype=np.uint64)
+        vals = np.zeros(len(segs), dtype=np.int32)
+        last = C.c_int32()
+        self.ctx.check(self.lib.sdz_adler32_chain(self.ctx.h, ptr, segs.ctypes.data, len(segs), 1, 1, vals.ctypes.data, C.byref(last)))
+        return last.value
+
+    def adler32_ref(self, data, seed):
+        """the reference's adler32(chunk, seed) of a small host buffer (one call: Q1 applies)"""
+        buf = np.ascontiguousarray(data, dtype=np.uint8)
+        out = C.c_int32()
+        self.ctx.check(self.lib.sdz_adler32(self.ctx.h, buf.ctypes.data if buf.size else None, int(buf.size), int(seed), 0, C.byref(out)))
+        return out.value
+
+    def read(self, ptr, n):
+        buf = np.empty(max(n, 1), dtype=np.uint8)
+        if n:
+            self.ctx.check(self.lib.sdz_memcpy_d2h(self.ctx.h, buf.ctypes.data, ptr, int(n)))
+        return buf[:n]
+
     def finish(self, running):
         r = N.Result()
         self._check(self.lib.sdz_large_finish(self.h, int(running), C.byref(r)))
@@ -142,13 +174,9 @@ def run_rank(backend, comm, rank, world, alloc):
     """The protocol above for one rank.  `alloc(nbytes)` returns (object to keep alive, device/host pointer) for
     the rank's output slice with WIN bytes of headroom BEFORE and 64 bytes after it.
     Returns (keepalive, pointer to the slice, lo, hi, finish() record)."""
-    if not backend.is_gzip():
-        # the running adler32 of zlib / raw streams is chained over the reference's 16 KiB chunks (SURVEY Q1); only the
-        # single-GPU path reproduces that chain
-        raise NeedsSequentialDecoder()
     mine = backend.index(rank, world)
     everyone = comm.allgather_index(mine)
-    backend.plan(*merge_index(everyone))
+    total, _ = backend.plan(*merge_index(everyone))
     lo, hi = backend.range(rank, world)
     keep, base = alloc(WIN + (hi - lo) + 64)
     out_ptr = base + WIN
@@ -160,10 +188,37 @@ def run_rank(backend, comm, rank, world, alloc):
         # the last 32 KiB before `hi`; a slice shorter than the window forwards part of what it received
         comm.send_window(rank + 1, keep, out_ptr + (hi - lo) - WIN)
     backend.resolve()
-    crc = backend.crc32(out_ptr, hi - lo) if hi > lo else 0
-    parts = comm.allgather_crc((crc, hi - lo))
-    rec = backend.finish(combine_crcs(parts))
+    if backend.is_gzip():
+        crc = backend.crc32(out_ptr, hi - lo) if hi > lo else 0
+        parts = comm.allgather_crc((crc, hi - lo))
+        rec = backend.finish(combine_crcs(parts))
+    else:
+        rec = backend.finish(running_adler32(backend, comm, out_ptr, lo, hi, total))
     return keep, out_ptr, lo, hi, rec
+
+
+def running_adler32(backend, comm, out_ptr, lo, hi, total):
+    """Inflater.checksum of a zlib / raw stream whose output is sharded over the ranks.  append() chains
+    adler32 over its <= 16 KiB chunks (src/sd-inflate.ts:133-149); every chunk but the last is exactly 16,384 bytes, where
+    the reference's adler32 IS the standard one, so all bytes before the final chunk combine associatively: each rank
+    sends (standard adler32 of its part, length), joined with adler32_combine in rank order.  Only the final chunk
+    (total mod 16,384 bytes, or 16,384) can hit the reference's defect (a call of 5552 or 11104 bytes, Q1): its bytes
+    (<= 16 KiB, possibly from two ranks) are gathered and checksummed as ONE reference call seeded with the rest."""
+    if total == 0:
+        return 0                                            # no chunk was ever produced (SURVEY Q8)
+    last_len = total % OUTBUF or OUTBUF
+    tail_lo = total - last_len
+    pre_n = max(0, min(hi, tail_lo) - lo)                   # my bytes before the final chunk
+    mine = backend.adler32_std(out_ptr, pre_n)
+    seed = 1
+    for a, n in comm.allgather_crc((mine, pre_n)):
+        if n:
+            seed = adler32_combine(seed, a, n)
+    t_lo, t_hi = max(lo, tail_lo), hi                       # my part of the final chunk
+    piece = backend.read(out_ptr + (t_lo - lo), t_hi - t_lo) if t_hi > t_lo else np.empty(0, dtype=np.uint8)
+    chunk = np.concatenate(comm.allgather_bytes(piece))
+    assert chunk.size == last_len
+    return backend.adler32_ref(chunk, seed)
 
 
 class TorchComm:
@@ -188,6 +243,9 @@ class TorchComm:
         bufs = [torch.empty(cap, dtype=torch.uint8, device=self.device) for _ in range(world)]
         dist.all_gather(bufs, mine, group=self.group)
         return [b[:s].cpu().numpy() for b, s in zip(bufs, sizes)]
+
+    def allgather_bytes(self, payload):
+        return self._allgather_bytes(np.ascontiguousarray(payload, dtype=np.uint8))
 
     def allgather_index(self, mine):
         blocks, ckpts = mine
@@ -247,8 +305,7 @@ def inflate_large_parts(view, n_parts, mode=MODE_SNIFF, ctx=None):
     ranks, bufs = [], []
     try:
         ranks = [CudaBackend(ctx, d_in, n, mode) for _ in range(n_parts)]
-        if not ranks[0].is_gzip():
-            raise NeedsSequentialDecoder()
+        gz = ranks[0].is_gzip()
         merged = merge_index([r.index(p, n_parts) for p, r in enumerate(ranks)])
         total = 0
         for r in ranks:
@@ -268,8 +325,29 @@ def inflate_large_parts(view, n_parts, mode=MODE_SNIFF, ctx=None):
             r.resolve()
             if hi > lo:
                 ctx.check(lib.sdz_memcpy_d2h(ctx.h, out[lo:hi].ctypes.data, base + WIN, hi - lo))
-            crcs.append((r.crc32(base + WIN, hi - lo) if hi > lo else 0, hi - lo))
-        rec = ranks[0].finish(combine_crcs(crcs))
+            if gz:
+                crcs.append((r.crc32(base + WIN, hi - lo) if hi > lo else 0, hi - lo))
+        if gz:
+            rec = ranks[0].finish(combine_crcs(crcs))
+        else:
+            # the same exchange as running_adler32(), all ranks played by this process
+            class _Loop:
+                def __init__(self):
+                    self.sums, self.pieces = [], []
+            loop = _Loop()
+            last_len = (total % OUTBUF or OUTBUF) if total else 0
+            tail_lo = total - last_len
+            for p, r in enumerate(ranks):
+                lo, hi = r.range(p, n_parts)
+                pre_n = max(0, min(hi, tail_lo) - lo)
+                loop.sums.append((r.adler32_std(bufs[p] + WIN, pre_n), pre_n))
+                t_lo = max(lo, tail_lo)
+                loop.pieces.append(r.read(bufs[p] + WIN + (t_lo - lo), hi - t_lo) if hi > t_lo else np.empty(0, dtype=np.uint8))
+            seed = 1
+            for a, n_ in loop.sums:
+                if n_:
+                    seed = adler32_combine(seed, a, n_)
+            rec = ranks[0].finish(ranks[0].adler32_ref(np.concatenate(loop.pieces), seed) if total else 0)
         return out, rec
     finally:
         for r in ranks:

@@ -541,11 +541,25 @@ def test_large_stream_slices_shorter_than_the_window():
     out, r = LG.inflate_large_parts(np.frombuffer(s, dtype=np.uint8), 6)
     assert np.array_equal(out, plain)
     assert r.success and r.checksum_state == 1 and r.size_state == 1
-    with pytest.raises(LG.NeedsSequentialDecoder):
-        LG.inflate_large_parts(np.frombuffer(zlib.compress(plain.tobytes(), 6), dtype=np.uint8), 2)   # zlib: single-GPU path only
 
 
-@pytest.mark.gpu
+@pytest.mark.parametrize("n_parts", [2, 3, 5])
+def test_large_stream_zlib_and_raw_over_several_parts(n_parts):
+    """zlib / raw streams on the multi-part protocol: the running Adler-32 is joined from per-part (adler32, length)
+    with adler32_combine, and the final <= 16 KiB chunk is one reference call - so a stream whose output ends with a
+    5552- or 11104-byte chunk is reported "mismatch" exactly like the reference reports it."""
+    from sdzlib import large as LG
+    for total in (6 << 20, (6 << 20) + 5552, (5 << 20) + 11104, (3 << 20) + 16384 * 3 + 1, 16384 + 11104):
+        plain = _large_plain(K.TEXT, (total >> 20) + 1, 9300)[:total]
+        for s in (zlib.compress(plain.tobytes(), 6), raw_deflate(plain.tobytes(), 6)):
+            out, r = LG.inflate_large_parts(np.frombuffer(s, dtype=np.uint8), n_parts)
+            assert np.array_equal(out, plain)
+            _, exp = O.inflate_oneshot(s)
+            assert r.observable() == exp.observable(), (total, n_parts)
+            if s[0] == 0x78:
+                assert r.checksum_state == (2 if total % 16384 in (5552, 11104) else 1)
+
+
 def _append_events(make, parts, thrown_of):
     """[(chunk lengths, bytes) per append() ..., ('throw', thrown, msg_id)] - the sequence ends at the first throw"""
     inf = make()

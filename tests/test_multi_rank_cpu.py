@@ -90,11 +90,28 @@ class _StandInBackend:
     records in its slice of the compressed bits; decode() refuses to produce the right bytes unless the protocol
     delivered the full index, and windows() checks that the 32 KiB before the slice arrived from the left."""
 
-    def __init__(self, plain, rank, world):
-        self.plain, self.rank, self.world = plain, rank, world
+    def __init__(self, plain, rank, world, gz=True):
+        self.plain, self.rank, self.world, self.gz = plain, rank, world, gz
 
     def is_gzip(self):
-        return True
+        return self.gz
+
+    # zlib / raw streams: the three local operations of sdzlib.large.running_adler32()
+    def adler32_std(self, ptr, n):
+        import zlib
+        buf = np.empty(max(n, 1), dtype=np.uint8)
+        C.memmove(buf.ctypes.data, ptr, n)
+        v = zlib.adler32(buf[:n].tobytes())
+        return v - (1 << 32) if v & 0x80000000 else v
+
+    def adler32_ref(self, data, seed):
+        from oracle import oracle as O
+        return O.adler32(np.ascontiguousarray(data, dtype=np.uint8).tobytes(), seed)
+
+    def read(self, ptr, n):
+        buf = np.empty(max(n, 1), dtype=np.uint8)
+        C.memmove(buf.ctypes.data, ptr, n)
+        return buf[:n]
 
     def index(self, part, n_parts):
         from sdzlib import large as LG
@@ -145,7 +162,7 @@ class _StandInBackend:
         return running
 
 
-def _large_worker(rank, world, port, n_bytes, out_q):
+def _large_worker(rank, world, port, n_bytes, out_q, gz=True):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "sd-zlib_b200", "host"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -153,7 +170,7 @@ def _large_worker(rank, world, port, n_bytes, out_q):
     from sdzlib import large as LG
     plain = np.random.default_rng(5).integers(0, 256, n_bytes, dtype=np.uint8)
     comm = LG.TorchComm(torch.device("cpu"))
-    keep, ptr, lo, hi, rec = LG.run_rank(_StandInBackend(plain, rank, world), comm, rank, world, LG.torch_alloc(torch.device("cpu")))
+    keep, ptr, lo, hi, rec = LG.run_rank(_StandInBackend(plain, rank, world, gz), comm, rank, world, LG.torch_alloc(torch.device("cpu")))
     got = np.empty(hi - lo, dtype=np.uint8)
     C.memmove(got.ctypes.data, ptr, hi - lo)
     assert np.array_equal(got, plain[lo:hi])
@@ -184,3 +201,33 @@ def test_large_stream_rank_protocol(world, n_bytes):
     assert [g[1] for g in got] == [n_bytes * r // world for r in range(world)]
     assert got[-1][2] == n_bytes
     assert all(g[3] == exp for g in got)                                  # every rank assembled the whole-stream CRC
+
+
+@pytest.mark.parametrize("world,n_bytes", [(2, 16384 * 9 + 5552), (3, 16384 + 11104), (3, 16384 * 4)])
+def test_large_stream_adler_over_ranks(world, n_bytes):
+    """zlib / raw streams: every rank ends up with the reference's chunk-chained Adler-32 (Q1 on a final chunk of 5552 or
+    11104 bytes), joined from per-rank (standard adler32, length) pairs + the gathered final chunk.  (3, 27488): the
+    final chunk straddles two ranks."""
+    from oracle import oracle as O
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_large_worker, args=(r, world, port, n_bytes, q, False)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    plain = np.random.default_rng(5).integers(0, 256, n_bytes, dtype=np.uint8).tobytes()
+    exp = 1
+    for o in range(0, n_bytes, 16384):                              # what append() computes (src/sd-inflate.ts:133-149)
+        exp = O.adler32(plain[o:o + 16384], exp)
+    assert all(g[3] == exp for g in got)
+    if n_bytes % 16384 in (5552, 11104):
+        import zlib
+        std = zlib.adler32(plain)
+        assert exp != (std - (1 << 32) if std & 0x80000000 else std)      # the defect is really in play
