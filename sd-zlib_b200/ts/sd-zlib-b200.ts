@@ -14,6 +14,9 @@ const native = createRequire(import.meta.url)("./sdz_napi.node") as {
 	inflateSizes(bufs: Uint8Array[], dicts: (Uint8Array | undefined)[], modes: Uint8Array): Float64Array;
 	inflateBatch(bufs: Uint8Array[], dicts: (Uint8Array | undefined)[], modes: Uint8Array, out: Uint8Array,
 		outOff: BigUint64Array, outCap: BigUint64Array, records: Uint8Array): number;
+	inflaterNew(raw: boolean, dict: Uint8Array | undefined): unknown;
+	inflaterAppend(handle: unknown, chunk: Uint8Array, record: Uint8Array): Uint8Array;
+	inflaterFinish(handle: unknown, record: Uint8Array): Uint8Array;
 };
 
 export interface InflaterOptions { raw?: boolean; dictionary?: BufferSource; }
@@ -113,10 +116,11 @@ export function inflate(data: BufferSource, dictionary?: BufferSource): Uint8Arr
 	return item.data;
 }
 
-/** class Inflater - src/sd-inflate.ts:54-180 (round-1 streaming model: see sdzlib/api.py) */
+/** class Inflater - src/sd-inflate.ts:54-180 over a device session (sdz_inflater_*, include/sdzcuda.h): every append()
+ *  decodes only its own chunk; the reference's behaviour at chunk boundaries (Q2 / Q3 / Q4) is reproduced */
 export class Inflater {
 	private raw: boolean; private dict: Uint8Array | undefined;
-	private parts: Uint8Array[] = []; private emitted = 0; private last: Rec | undefined;
+	private handle: unknown; private rec = new Uint8Array(RECORD); private used = false;
 	constructor(options?: InflaterOptions) {
 		const raw = options?.raw;
 		if (raw !== undefined && raw !== true && raw !== false) throw new TypeError("options.raw must be undefined or true or false");
@@ -131,18 +135,20 @@ export class Inflater {
 		const chunk = u8(data);
 		if (!(chunk instanceof Uint8Array)) throw new TypeError("data must be an ArrayBuffer or buffer view");
 		if (chunk.length === 0) return [];
-		this.parts.push(chunk.slice());
-		const all = mergeBuffers(this.parts);
-		const { arena, records } = runBatch([all], [this.dict], new Uint8Array([this.raw ? Mode.Raw : Mode.Inflater]));
-		const r = parseRecord(new DataView(records.buffer, 0, RECORD), all);
-		this.last = r;
+		this.handle ??= native.inflaterNew(this.raw, this.dict);
+		const fresh: Uint8Array = native.inflaterAppend(this.handle, chunk, this.rec);
+		this.used = true;
+		const r = parseRecord(new DataView(this.rec.buffer, 0, RECORD), new Uint8Array(0));
 		if (r.thrownAppend) throw errorOf(r.thrownAppend, r.msg);
 		const out: Uint8Array[] = [];
-		for (let o = this.emitted; o < r.outLen; o += OUTPUT_BUFSIZE) out.push(arena.slice(o, Math.min(r.outLen, o + OUTPUT_BUFSIZE)));
-		this.emitted = r.outLen;
+		// every append() starts with an empty 16 KiB buffer (src/sd-inflate.ts:101-103): these are the reference's chunk shapes
+		for (let o = 0; o < fresh.length; o += OUTPUT_BUFSIZE) out.push(fresh.slice(o, Math.min(fresh.length, o + OUTPUT_BUFSIZE)));
 		return out;
 	}
 	finish(): InflateResult {
-		return this.last?.result ?? { success: false, complete: false, checksum: "unchecked", fileSize: "unchecked", fileName: "", modDate: undefined };
+		if (!this.used) return { success: false, complete: false, checksum: "unchecked", fileSize: "unchecked", fileName: "", modDate: undefined };
+		const name: Uint8Array = native.inflaterFinish(this.handle, this.rec);
+		const r = parseRecord(new DataView(this.rec.buffer, 0, RECORD), new Uint8Array(0));
+		return { ...r.result, fileName: String.fromCharCode(...name) };
 	}
 }

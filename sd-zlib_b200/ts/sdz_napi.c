@@ -24,11 +24,22 @@
 
 static sdz_ctx* g_ctx;
 
+/* SDZ_DEVICES=0,1,2,...: a multi-device context - sdz_inflate_batch partitions every batch per stream over the listed
+ * B200s (include/sdzcuda.h, sdz_ctx_create_multi); one entry or SDZ_DEVICE=n: a single device */
 static sdz_ctx* ctx_or_throw(napi_env env)
 {
     if (!g_ctx) {
-        int device = getenv("SDZ_DEVICE") ? atoi(getenv("SDZ_DEVICE")) : 0;
-        int rc = sdz_ctx_create(device, 0, &g_ctx);
+        int devices[64], ndev = 0, rc;
+        const char* list = getenv("SDZ_DEVICES");
+        if (list) {
+            while (*list && ndev < 64) {
+                devices[ndev++] = atoi(list);
+                while (*list && *list != ',') list++;
+                if (*list == ',') list++;
+            }
+        }
+        if (ndev > 1) rc = sdz_ctx_create_multi(devices, ndev, 0, &g_ctx);
+        else rc = sdz_ctx_create(ndev == 1 ? devices[0] : (getenv("SDZ_DEVICE") ? atoi(getenv("SDZ_DEVICE")) : 0), 0, &g_ctx);
         if (rc != SDZ_OK) { napi_throw_error(env, NULL, "sdzcuda: no usable B200 (sm_100a) device"); return NULL; }
     }
     return g_ctx;
@@ -136,6 +147,68 @@ static napi_value js_inflate_batch(napi_env env, napi_callback_info info)
     return out;
 }
 
+/* ---- class Inflater over several append() calls: one sdz_inflater per JS object (an external wrapped by the facade)
+ *   inflaterNew(raw: boolean, dict: Uint8Array | undefined): External
+ *   inflaterAppend(h, chunk: Uint8Array, record: Uint8Array /* 72 bytes * /): Uint8Array   (the bytes this call produced)
+ *   inflaterFinish(h, record: Uint8Array): Uint8Array                                      (the gzip FNAME bytes)        */
+static void inflater_gc(napi_env env, void* data, void* hint) { (void)env; (void)hint; sdz_inflater_destroy((sdz_inflater*)data); }
+
+static napi_value js_inflater_new(napi_env env, napi_callback_info info)
+{
+    size_t argc = 2;
+    napi_value argv[2], out;
+    napi_get_cb_info(env, info, &argc, argv, NULL, NULL);
+    bool raw = false;
+    napi_get_value_bool(env, argv[0], &raw);
+    uint8_t* dp = NULL; size_t dl = 0;
+    const int has_dict = u8_arg(env, argv[1], &dp, &dl);
+    sdz_ctx* ctx = ctx_or_throw(env);
+    if (!ctx) return NULL;
+    sdz_inflater* h = NULL;
+    int rc = sdz_inflater_create(ctx, raw, has_dict ? (dl ? dp : (const uint8_t*)"") : NULL, (uint32_t)dl, &h);
+    if (rc != SDZ_OK) { napi_throw_error(env, NULL, sdz_last_error(ctx)); return NULL; }
+    napi_create_external(env, h, inflater_gc, NULL, &out);
+    return out;
+}
+
+static napi_value js_inflater_append(napi_env env, napi_callback_info info)
+{
+    size_t argc = 3;
+    napi_value argv[3], ab, out;
+    napi_get_cb_info(env, info, &argc, argv, NULL, NULL);
+    sdz_inflater* h = NULL;
+    napi_get_value_external(env, argv[0], (void**)&h);
+    uint8_t *p, *rec; size_t n, rec_n;
+    if (!u8_arg(env, argv[1], &p, &n)) { napi_throw_type_error(env, NULL, "data must be an ArrayBuffer or buffer view"); return NULL; }
+    if (!u8_arg(env, argv[2], &rec, &rec_n) || rec_n < sizeof(sdz_result)) { napi_throw_type_error(env, NULL, "bad record buffer"); return NULL; }
+    uint64_t fresh = 0;
+    int rc = sdz_inflater_append(h, p, n, &fresh, (sdz_result*)rec);
+    if (rc != SDZ_OK) { napi_throw_error(env, NULL, sdz_last_error(g_ctx)); return NULL; }
+    void* dst;
+    napi_create_arraybuffer(env, (size_t)fresh, &dst, &ab);
+    if (fresh && sdz_inflater_read(h, (uint8_t*)dst, fresh) != SDZ_OK) { napi_throw_error(env, NULL, sdz_last_error(g_ctx)); return NULL; }
+    napi_create_typedarray(env, napi_uint8_array, (size_t)fresh, ab, 0, &out);
+    return out;
+}
+
+static napi_value js_inflater_finish(napi_env env, napi_callback_info info)
+{
+    size_t argc = 2;
+    napi_value argv[2], ab, out;
+    napi_get_cb_info(env, info, &argc, argv, NULL, NULL);
+    sdz_inflater* h = NULL;
+    napi_get_value_external(env, argv[0], (void**)&h);
+    uint8_t* rec; size_t rec_n;
+    if (!u8_arg(env, argv[1], &rec, &rec_n) || rec_n < sizeof(sdz_result)) { napi_throw_type_error(env, NULL, "bad record buffer"); return NULL; }
+    sdz_result* r = (sdz_result*)rec;
+    sdz_inflater_finish(h, r);
+    void* dst;
+    napi_create_arraybuffer(env, r->name_len, &dst, &ab);
+    if (r->name_len) sdz_inflater_input(h, r->name_off, r->name_len, (uint8_t*)dst);
+    napi_create_typedarray(env, napi_uint8_array, r->name_len, ab, 0, &out);
+    return out;
+}
+
 static napi_value init(napi_env env, napi_value exports)
 {
     napi_property_descriptor props[] = {
@@ -143,6 +216,9 @@ static napi_value init(napi_env env, napi_value exports)
         { "crc32", NULL, js_crc32, NULL, NULL, NULL, napi_default, NULL },
         { "inflateSizes", NULL, js_inflate_sizes, NULL, NULL, NULL, napi_default, NULL },
         { "inflateBatch", NULL, js_inflate_batch, NULL, NULL, NULL, napi_default, NULL },
+        { "inflaterNew", NULL, js_inflater_new, NULL, NULL, NULL, napi_default, NULL },
+        { "inflaterAppend", NULL, js_inflater_append, NULL, NULL, NULL, napi_default, NULL },
+        { "inflaterFinish", NULL, js_inflater_finish, NULL, NULL, NULL, napi_default, NULL },
     };
     napi_define_properties(env, exports, sizeof props / sizeof props[0], props);
     return exports;
