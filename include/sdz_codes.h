@@ -46,6 +46,14 @@ enum sdz_msg {
     SDZ_MSG_EMPTY_DIST_TREE,          /* src/inftree.ts:372                     */
     SDZ_MSG_BAD_DIST_CODE,            /* src/infcodes.ts:215,:500               */
     SDZ_MSG_BAD_LITLEN_CODE,          /* src/infcodes.ts:266,:417               */
+    /* SDZ_PARITY_SPEC only: zlib 1.3's texts for what the reference accepts, or words differently */
+    SDZ_MSG_DIST_TOO_FAR,             /* zlib inflate.c / inffast.c              */
+    SDZ_MSG_MISSING_EOB,
+    SDZ_MSG_BAD_CODE_LENGTHS_SET,
+    SDZ_MSG_BAD_LITLEN_SET,
+    SDZ_MSG_BAD_DIST_SET,
+    SDZ_MSG_BAD_GZIP_FLAGS,
+    SDZ_MSG_BAD_HEADER_CRC,
     SDZ_MSG__COUNT
 };
 
@@ -100,6 +108,13 @@ static const char* const sdz_msg_text[SDZ_MSG__COUNT] = {
     "empty distance tree with lengths",
     "invalid distance code",
     "invalid literal/length code",
+    "invalid distance too far back",
+    "invalid code -- missing end-of-block",
+    "invalid code lengths set",
+    "invalid literal/lengths set",
+    "invalid distances set",
+    "unknown header flags set",
+    "header crc mismatch",
 };
 
 static const char* const sdz_thrown_text[SDZ_THROW__COUNT] = {

@@ -45,7 +45,12 @@ enum sdz_err {
 
 /* sdz_inflate_batch flags */
 #define SDZ_PARITY_REFERENCE 0u   /* default: identical to @stardazed/zlib, quirks included  */
-#define SDZ_PARITY_SPEC      1u   /* RFC-strict behaviour (not implemented yet)              */
+#define SDZ_PARITY_SPEC      1u   /* RFC 1950/1951/1952 as zlib 1.3 implements them: stored blocks of any size (no Q2), FEXTRA
+                                     parsed (Q5), distances before the start of the output rejected (Q6), zlib's Huffman acceptance
+                                     rules and texts (Q9; no MANY limit, Q10), standard Adler-32 (Q1), unsigned ISIZE (Q13),
+                                     32,768-byte dictionaries (Q14), symbols decoded as soon as their own bits are there (Q15),
+                                     bytes after the end ignored (Q4).  sdz_inflate_batch / _sizes / _batch_device only;
+                                     streams go through the general decoder (the two-phase fast path is reference-exact only) */
 
 typedef struct sdz_ctx sdz_ctx;
 

@@ -72,10 +72,10 @@ struct AdlerCall {
         b = (b + (uint64_t)L * a + W) % ADLER_BASE;
         a = (uint32_t)(((uint64_t)a + S) % ADLER_BASE);
     }
-    __device__ __forceinline__ uint32_t end() const
+    __device__ __forceinline__ uint32_t end(bool standard = false) const
     {
         if (!any) return a | (b0 << 16);                                // empty buffer: seed recombined (:104)
-        uint32_t hi = all_full ? (sq & 0xffffu) : (uint32_t)b;          // Q1: no `sum2 %= BASE` without a tail
+        uint32_t hi = (all_full && !standard) ? (sq & 0xffffu) : (uint32_t)b;   // Q1: no `sum2 %= BASE` without a tail
         return a | (hi << 16);
     }
 };
@@ -113,7 +113,8 @@ __device__ __forceinline__ void adler_unit_sums(const uint8_t* p, uint32_t L, ui
 }
 
 // Adler-32 of one adler32(buf, seed) call evaluated by a warp (all lanes return the value)
-__device__ __forceinline__ uint32_t adler_call_warp(const uint8_t* p, uint64_t n, uint32_t seed, uint32_t lane)
+// (standard = true: RFC 1950, without the reference's Q1 defect)
+__device__ __forceinline__ uint32_t adler_call_warp(const uint8_t* p, uint64_t n, uint32_t seed, uint32_t lane, bool standard = false)
 {
     AdlerCall st;
     st.begin(seed);
@@ -124,7 +125,7 @@ __device__ __forceinline__ uint32_t adler_call_warp(const uint8_t* p, uint64_t n
         uint32_t W = (uint32_t)((uint64_t)L * S - T);
         st.unit(S, W, L);
     }
-    return st.end();
+    return st.end(standard);
 }
 
 // raw CRC register update over bytes, slice-by-1 with a shared-memory table

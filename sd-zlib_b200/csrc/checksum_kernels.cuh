@@ -13,8 +13,45 @@ namespace sdz {
 // One warp per stream (dynamic scheduling).  The reference checksums every <= 16 KiB chunk
 // append() emits, chaining the seed (src/sd-inflate.ts:137-146); with single-buffer input
 // all chunks but the last are exactly 16384 bytes, so chunk k = bytes [16384 k, 16384 (k+1)).
+// SDZ_PARITY_SPEC: the record as zlib 1.3 would settle it (RFC 1950 / 1952): standard Adler-32 over the whole output (no Q1,
+// so the 16 KiB chunking is invisible), a stored checksum / ISIZE of zero is still checked, both compared as unsigned
+// 32-bit values (no Q13), and an empty stream has the checksum of nothing (1 / 0) rather than none.
+__device__ __forceinline__ void finalize_spec(const uint32_t* tab, const uint8_t* out, sdz_result* R, uint32_t lane)
+{
+    if (R->thrown_inflate != 0) return;
+    const uint32_t thrown = R->thrown_append;
+    const uint64_t len = R->out_len;
+    const uint32_t stored = (uint32_t)R->stored_checksum, isize = (uint32_t)R->stored_isize;
+    const bool complete = R->complete != 0;
+    const int container = R->container;
+    uint32_t running = container == SDZ_GZIP ? 0u : 1u;
+    if (!thrown && len > 0) {
+        const uint8_t* p = out + R->out_off;
+        if (container == SDZ_GZIP) running = crc_call_warp(tab, p, len, 0u, lane);
+        else running = adler_call_warp(p, len, 1u, lane, true);
+    }
+    if (lane == 0) {
+        const bool have = !thrown;
+        int cks = SDZ_UNCHECKED, fsz = SDZ_UNCHECKED;
+        if (complete && container != SDZ_RAW) cks = stored == running ? SDZ_MATCH : SDZ_MISMATCH;
+        if (complete && container == SDZ_GZIP) fsz = isize == (uint32_t)len ? SDZ_MATCH : SDZ_MISMATCH;
+        const int success = complete && !thrown && cks != SDZ_MISMATCH && fsz != SDZ_MISMATCH;
+        R->running_checksum = have ? (int32_t)running : 0;
+        R->have_running = have ? 1 : 0;
+        R->checksum_state = (uint8_t)cks;
+        R->size_state = (uint8_t)fsz;
+        R->success = (uint8_t)success;
+        int ti = SDZ_THROW_NONE;
+        if (thrown) ti = (int)thrown;
+        else if (!complete) ti = SDZ_THROW_UNEXPECTED_EOF;
+        else if (cks == SDZ_MISMATCH) ti = SDZ_THROW_INTEGRITY;
+        else if (fsz == SDZ_MISMATCH) ti = SDZ_THROW_SIZE_CHECK;
+        R->thrown_inflate = (uint8_t)ti;
+    }
+}
+
 __global__ void __launch_bounds__(256) finalize_streams_kernel(const uint8_t* out, sdz_result* res,
-                                                               unsigned long long n, unsigned long long* counter)
+                                                               unsigned long long n, unsigned long long* counter, uint32_t spec)
 {
     __shared__ uint32_t tab[1024];
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) tab[i] = (&g_crc_tab[0][0])[i];
@@ -26,6 +63,7 @@ __global__ void __launch_bounds__(256) finalize_streams_kernel(const uint8_t* ou
         idx = __shfl_sync(0xffffffffu, idx, 0);
         if (idx >= n) break;
         sdz_result* R = res + idx;
+        if (spec) { finalize_spec(tab, out, R, lane); continue; }
         if (R->thrown_inflate != 0) continue;            // inflate() rejected the call before decoding
         const uint32_t thrown = R->thrown_append;
         const uint64_t len = R->out_len;

@@ -121,6 +121,7 @@ struct InflateParams {
     // had (resume_out), and where to pick it up now that the input has grown (resume_in).  nullptr: plain one-shot decode.
     const sdz_resume* resume_in;
     sdz_resume* resume_out;
+    uint32_t spec;                     // SDZ_PARITY_SPEC: zlib 1.3's behaviour instead of the reference's (general decoder only)
 };
 
 // resume point inside a block (TM_INDEX): the symbol at bit `bit` produces output byte `pos` of task `task`
@@ -146,20 +147,20 @@ __device__ __constant__ uint8_t c_border[19] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 
 // :154, :289-313; src/infcodes.ts:547-573).  Only byte COUNTS flow through it.
 struct RingModel {
     int q, r, ao;                      // write, read, avail_out
-    __device__ __forceinline__ void init(int dict_used) { q = r = dict_used; ao = OUTBUF; }
-    __device__ __forceinline__ int room() const { return q < r ? r - q - 1 : WSIZE - q; }
-    __device__ __forceinline__ void flush()
+    __host__ __device__ __forceinline__ void init(int dict_used) { q = r = dict_used; ao = OUTBUF; }
+    __host__ __device__ __forceinline__ int room() const { return q < r ? r - q - 1 : WSIZE - q; }
+    __host__ __device__ __forceinline__ void flush()
     {
         int n = (r <= q ? q : WSIZE) - r;
-        n = min(n, ao); ao -= n; r += n;
+        n = n < ao ? n : ao; ao -= n; r += n;
         if (r == WSIZE) {
             r = 0;
             if (q == WSIZE) q = 0;
-            n = min(q - r, ao); ao -= n; r += n;
+            n = q - r < ao ? q - r : ao; ao -= n; r += n;
         }
     }
     // the "no room" dance; returns how many times proc() went back to append()
-    __device__ __forceinline__ int make_room()
+    __host__ __device__ __forceinline__ int make_room()
     {
         int returns = 0;
         for (;;) {
@@ -173,17 +174,17 @@ struct RingModel {
         }
         return returns;
     }
-    __device__ __forceinline__ void write(uint32_t n)
+    __host__ __device__ __forceinline__ void write(uint32_t n)
     {
         while (n) {
             int m = room();
             if (!m) { make_room(); m = room(); }
-            uint32_t t = min(n, (uint32_t)m);
+            uint32_t t = n < (uint32_t)m ? n : (uint32_t)m;
             q += (int)t; n -= t;
         }
     }
     // WASH / DRY: everything must leave the window before the block ends (src/infcodes.ts:626-639)
-    __device__ __forceinline__ void wash()
+    __host__ __device__ __forceinline__ void wash()
     {
         flush();
         while (r != q) { flush(); ao = OUTBUF; flush(); }
@@ -263,9 +264,9 @@ __device__ __noinline__ int ref_table_total(const uint16_t* cnt, int g, int pad,
 // (SURVEY Q15): a lookup happens only when the table's index width is available.
 // bits = next 32 bits of the stream (LSB first), A = bits left in the input (capped).
 // Returns status << 28 | index width needed << 24 | code_length << 16 | symbol; status = R_OK / R_STALL / R_ERROR.
-__device__ __noinline__ uint32_t slow_lookup(const uint16_t* cnt, const uint16_t* sorted, int l, int g, uint32_t bits, int A)
+__device__ __noinline__ uint32_t slow_lookup(const uint16_t* cnt, const uint16_t* sorted, int l, int g, uint32_t bits, int A, bool spec = false)
 {
-    if (A < l) return (uint32_t)R_STALL << 28;
+    if (A < l && !spec) return (uint32_t)R_STALL << 28;
     int ncodes = 0, y = 1;
     for (int k = 1; k <= g; k++) { ncodes += (int)cnt[k]; y <<= 1; y -= (int)cnt[k]; }
     const int pad = y;                                  // unused codes of length g
@@ -288,6 +289,11 @@ __device__ __noinline__ uint32_t slow_lookup(const uint16_t* cnt, const uint16_t
         index += count; first += count; first <<= 1; code <<= 1;
     }
     const uint32_t ok = ((uint32_t)klen << 16) | sym;
+    if (spec) {
+        // zlib decodes a symbol as soon as its own bits are in the buffer (no root-width lookahead)
+        if (found) return ok | ((uint32_t)klen << 24);
+        return (uint32_t)(A >= g ? R_ERROR : R_STALL) << 28;
+    }
     if (found && klen <= l) return ok | ((uint32_t)l << 24);
     if (!found && A >= g) return (uint32_t)R_ERROR << 28;   // every bit of the longest code is there: no such code
     // walk the reference's table levels
@@ -456,7 +462,7 @@ __device__ __forceinline__ void make_lut(uint32_t* aux, const uint8_t* lens, int
 // and messages (inflate_trees_dynamic, src/inftree.ts:333-379).  fixed: no checks.
 template <int G, class SM>
 __device__ __noinline__ TreeInfo build_tables(SM* S, uint16_t* gsorted, int nl, int nd, bool fixed, int glane, unsigned gmask,
-                                              uint16_t* long_l, int long_n)
+                                              uint16_t* long_l, int long_n, bool spec = false)
 {
     TreeInfo T;
     T.msg = SDZ_MSG_NONE; T.lbits = T.dbits = T.g_l = T.g_d = 0;
@@ -464,6 +470,15 @@ __device__ __noinline__ TreeInfo build_tables(SM* S, uint16_t* gsorted, int nl, 
     const uint8_t* lens = reinterpret_cast<const uint8_t*>(gsorted + SORTED_L + SORTED_D);
     uint32_t* aux = reinterpret_cast<uint32_t*>(gsorted + SORTED_L + SORTED_D + 160);
     int st = classify<G>(lens, nl, 9, S->cnt_l, aux, &T.lbits, &T.g_l, &pad_l, &nz_l, glane, gmask);
+    if (!fixed && spec) {
+        // zlib 1.3 (inflate.c, state LENLENS -> CODELENS -> tables): the end-of-block code must exist; sets may be
+        // incomplete only when their longest code is one bit; no distance code at all is fine until one is used; no arena
+        // limit
+        if (lens[256] == 0) { T.msg = SDZ_MSG_MISSING_EOB; return T; }
+        if (st == 1 || st == 2) { T.msg = SDZ_MSG_BAD_LITLEN_SET; return T; }
+        st = classify<G>(lens + nl, nd, 6, S->cnt_d, aux, &T.dbits, &T.g_d, &pad_d, &nz_d, glane, gmask);
+        if (st == 1 || st == 2) { T.msg = SDZ_MSG_BAD_DIST_SET; return T; }
+    } else
     if (!fixed) {
         // the lit/len and distance tables share an arena of MANY = 1400 entries; running out of
         // it is reported as DATA_ERROR, i.e. with the "oversubscribed" text
@@ -472,8 +487,8 @@ __device__ __noinline__ TreeInfo build_tables(SM* S, uint16_t* gsorted, int nl, 
         if (used > 1400) { T.msg = SDZ_MSG_OVERSUB_LITLEN_TREE; return T; }
         if (st == 2 || st == 3) { T.msg = SDZ_MSG_INCOMPLETE_LITLEN_TREE; return T; }
     }
-    st = classify<G>(lens + nl, nd, fixed ? 5 : 6, S->cnt_d, aux, &T.dbits, &T.g_d, &pad_d, &nz_d, glane, gmask);
-    if (!fixed) {
+    if (!(spec && !fixed)) st = classify<G>(lens + nl, nd, fixed ? 5 : 6, S->cnt_d, aux, &T.dbits, &T.g_d, &pad_d, &nz_d, glane, gmask);
+    if (!fixed && !spec) {
         if (st == 1) { T.msg = SDZ_MSG_OVERSUB_DIST_TREE; return T; }
         if (st != 3 && used + ref_table_total<G>(S->cnt_d, T.g_d, pad_d, T.dbits, glane, gmask) > 1400) {
             T.msg = SDZ_MSG_OVERSUB_DIST_TREE; return T;
@@ -496,10 +511,19 @@ __device__ __noinline__ TreeInfo build_tables(SM* S, uint16_t* gsorted, int nl, 
     return T;
 }
 
+// SDZ_PARITY_SPEC: zlib 1.3 words the tree errors differently (inflate.c: "invalid code lengths set" etc.)
+__device__ __forceinline__ int spec_msg(int m)
+{
+    if (m == SDZ_MSG_OVERSUB_BITS_TREE || m == SDZ_MSG_INCOMPLETE_BITS_TREE) return SDZ_MSG_BAD_CODE_LENGTHS_SET;
+    if (m == SDZ_MSG_OVERSUB_LITLEN_TREE || m == SDZ_MSG_INCOMPLETE_LITLEN_TREE) return SDZ_MSG_BAD_LITLEN_SET;
+    if (m == SDZ_MSG_OVERSUB_DIST_TREE || m == SDZ_MSG_INCOMPLETE_DIST_TREE) return SDZ_MSG_BAD_DIST_SET;
+    return m;
+}
+
 // code-length-code LUT for the dynamic header (inflate_trees_bits, src/inftree.ts:313-331).
 // cl[19] are the code-length-code lengths; blut[128] receives sym | len << 5.
 // Returns bb (index width, >= 1) or -msg on error.
-__device__ __noinline__ int build_bits_lut(const uint8_t* cl, uint8_t* blut, uint16_t* cnt, int glane, unsigned gmask)
+__device__ __noinline__ int build_bits_lut(const uint8_t* cl, uint8_t* blut, uint16_t* cnt, int glane, unsigned gmask, bool spec = false)
 {
     if (glane == 0) {
         for (int i = 0; i < 16; i++) cnt[i] = 0;
@@ -517,7 +541,7 @@ __device__ __noinline__ int build_bits_lut(const uint8_t* cl, uint8_t* blut, uin
     for (; j < g; j++, y <<= 1) { y -= (int)cnt[j]; if (y < 0) return -SDZ_MSG_OVERSUB_BITS_TREE; }
     y -= (int)cnt[g];
     if (y < 0) return -SDZ_MSG_OVERSUB_BITS_TREE;
-    if (y != 0 && g != 1) return -SDZ_MSG_INCOMPLETE_BITS_TREE;
+    if (y != 0 && (g != 1 || spec)) return -SDZ_MSG_INCOMPLETE_BITS_TREE;      // zlib: the code-length code must be complete
     if (glane == 0) {
         uint32_t code = 0;
         for (int k = 1; k <= g; k++) {
@@ -621,6 +645,7 @@ struct Decoder {
     uint64_t blk_hdr_bit, last_sym_bit;
     uint32_t ref_floor;
     bool resume_first, hdr_counted;
+    bool spec;                         // SDZ_PARITY_SPEC (include/sdzcuda.h)
 
     // ------------------------------------------------------------------ input staging
     __device__ __forceinline__ uint32_t load_word(uint32_t w)
@@ -791,6 +816,9 @@ struct Decoder {
     // `lit_now`: number of literals lane 0 stored earlier in THIS lockstep iteration (at pos - lit_now .. pos - 1).
     __device__ __forceinline__ int copy_match(uint32_t len, uint32_t dist, uint32_t lit_now)
     {
+        if constexpr (TM == TM_NONE) {
+            if (spec && dist > pos + (uint32_t)D) { msg = SDZ_MSG_DIST_TOO_FAR; return R_ERROR; }      // (the reference copies zeros)
+        }
         if (len > cap - pos) return R_OUTFULL;
         if (MARK && dist > pos) {
             // reaches before the piece: those symbols become markers (synchronous; group sync inside)
@@ -900,8 +928,8 @@ struct Decoder {
         }
         __syncwarp(gmask);
         uint8_t* blut = reinterpret_cast<uint8_t*>(S->lut_l);
-        int bb_bits = build_bits_lut(cl, blut, S->cnt_l, glane, gmask);
-        if (bb_bits < 0) { msg = -bb_bits; return R_ERROR; }
+        int bb_bits = build_bits_lut(cl, blut, S->cnt_l, glane, gmask, spec);
+        if (bb_bits < 0) { msg = spec ? spec_msg(-bb_bits) : -bb_bits; return R_ERROR; }
         int index = 0;
         uint32_t prev = 0;
         while (index < total) {
@@ -987,7 +1015,7 @@ struct Decoder {
         uint32_t e = S->lut_l[(uint32_t)bb & ((1u << RL) - 1u)];
         uint32_t n = e >> 12, p = e & 0xfff;
         if (tail || n == 0) {
-            uint32_t r = slow_lookup(S->cnt_l, gsorted, lbits, g_l, (uint32_t)bb, avail_bits());
+            uint32_t r = slow_lookup(S->cnt_l, gsorted, lbits, g_l, (uint32_t)bb, avail_bits(), spec);
             uint32_t st = r >> 28;
             if (st) { if (st == (uint32_t)R_ERROR) msg = SDZ_MSG_BAD_LITLEN_CODE; return (int)st; }
             n = (r >> 16) & 0xff;
@@ -1033,7 +1061,7 @@ struct Decoder {
         uint32_t dn = de >> 12;
         if (tail || dn == 0) {
             if (g_d == 0) { msg = SDZ_MSG_BAD_DIST_CODE; return R_ERROR; }
-            uint32_t r = slow_lookup(S->cnt_d, gsorted + SORTED_L, dbits, g_d, (uint32_t)bb, avail_bits());
+            uint32_t r = slow_lookup(S->cnt_d, gsorted + SORTED_L, dbits, g_d, (uint32_t)bb, avail_bits(), spec);
             uint32_t st = r >> 28;
             if (st) { if (st == (uint32_t)R_ERROR) msg = SDZ_MSG_BAD_DIST_CODE; return (int)st; }
             dn = (r >> 16) & 0xff;
@@ -1160,7 +1188,12 @@ struct Decoder {
         const uint32_t dist = 1u + ((de & 3u) << dx) + (((uint32_t)bb >> dn) & ((1u << dx) - 1u));
         const uint32_t dcons = ismatch ? dn + dx : 0u;
         bb >>= dcons; bc -= (int)dcons;
-        if (!STORE) { pos += len; return R_OK; }
+        if (!STORE) {
+            if constexpr (TM == TM_NONE) {
+                if (spec && ismatch && dist > pos + (uint32_t)D) { msg = SDZ_MSG_DIST_TOO_FAR; return R_ERROR; }
+            }
+            pos += len; return R_OK;
+        }
         // ---- copy (byte units; a marker symbol is two bytes)
         constexpr uint32_t E = MARK ? 2u : 1u;
         const uint32_t bpos = pos * E, blen = len * E, bdist = dist * E;
@@ -1220,7 +1253,10 @@ struct Decoder {
             if (n_in == 0) { stall_kind = ST_STORED; r = R_STALL; break; }
             if (ring.room() == 0) {
                 int returns = ring.make_room();
-                if (returns) { left = 0; break; }      // `left` is a local of proc(): lost on return
+                // `left` is a local of proc(): lost on return.  Block tasks of the large-stream path start with
+                // an empty window model, so they take the whole block; sdz_large_plan replays the real window over the chain
+                // of blocks and sends streams in which the reference would have lost `left` to the sequential decoder.
+                if (returns && !spec && TM == TM_NONE) { left = 0; break; }
             }
             uint32_t t = min(min(left, n_in), (uint32_t)ring.room());
             ring.q += (int)t;
@@ -1262,6 +1298,7 @@ struct Decoder {
         ref_F = ref_Fentry = ring_done = 0; blk_sym0_bit = 0; ref_on = ref_burst = ref_forced_slow = eob_emu = eob_fast = false;
         o_dst = o_meta = n_dst = n_meta = 0;
         is_gzip = false; method = 0; n_blocks = 0; mtime = 0; name_off = 0; name_len = 0; last = 0; raw = true;
+        spec = false;
         const uint64_t sb = P.task_bit[i];
         if ((sb >> 3) >= (uint64_t)in_len) { finish_task(P, R_STALL); return; }
         seek((uint32_t)(sb >> 3));
@@ -1323,6 +1360,7 @@ struct Decoder {
         o_dst = o_meta = n_dst = n_meta = 0;
         is_gzip = false; method = 0; n_blocks = 0; mtime = 0; name_off = 0; name_len = 0; last = 0;
         blk_hdr_bit = last_sym_bit = 0; ref_floor = 0; resume_first = false; hdr_counted = false; resume_bit = 0;
+        spec = TM == TM_NONE && P.spec != 0;
 
         int thrown = SDZ_THROW_NONE, thrown_inflate = 0, zstatus = SDZ_Z_OK;
         bool decode = true;
@@ -1357,6 +1395,78 @@ struct Decoder {
         if (in_len == 0) decode = false;                                // append() of an empty chunk returns []
 
         uint32_t hp = 0, end_byte = 0;
+        if (decode && !raw && spec) {
+            // SDZ_PARITY_SPEC: the container header as zlib 1.3 reads it (inflate.c, states HEAD .. DICTID)
+            int err = 0;
+            bool ok = false;
+            do {
+                if (in_len < 2) { hp = in_len; break; }
+                const uint32_t h0 = src[0], h1 = src[1];
+                hp = 2;
+                if (h0 == 0x1f && h1 == 0x8b) {
+                    is_gzip = true;
+                    if (in_len < 4) { hp = in_len; break; }
+                    method = (int)src[2];
+                    const uint32_t gflags = src[3];
+                    hp = 4;
+                    if (method != 8) { err = SDZ_MSG_BAD_METHOD; break; }
+                    if (gflags & 0xe0) { err = SDZ_MSG_BAD_GZIP_FLAGS; break; }
+                    if (in_len < 10) { hp = in_len; break; }
+                    mtime = (int32_t)((uint32_t)src[4] | ((uint32_t)src[5] << 8) | ((uint32_t)src[6] << 16) | ((uint32_t)src[7] << 24));
+                    hp = 10;
+                    bool trunc = false;
+                    if (gflags & 4) {                                   // RFC 1952: XLEN (little-endian) + that many bytes
+                        if (hp + 2 > in_len) { hp = in_len; break; }
+                        const uint32_t xlen = (uint32_t)src[hp] | ((uint32_t)src[hp + 1] << 8);
+                        hp += 2;
+                        if (hp + xlen > in_len) { hp = in_len; break; }
+                        hp += xlen;
+                    }
+                    if (gflags & 8) {
+                        name_off = hp;
+                        for (;;) { if (hp >= in_len) { trunc = true; break; } const uint32_t b = src[hp++]; if (b == 0) break; name_len++; }
+                        if (trunc) break;
+                    }
+                    if (gflags & 16) {
+                        for (;;) { if (hp >= in_len) { trunc = true; break; } const uint32_t b = src[hp++]; if (b == 0) break; }
+                        if (trunc) break;
+                    }
+                    if (gflags & 2) {                                   // FHCRC: low half of the CRC-32 of the header so far
+                        if (hp + 2 > in_len) { hp = in_len; break; }
+                        uint32_t c = 0xffffffffu;
+                        for (uint32_t k = 0; k < hp; k++) {
+                            c ^= src[k];
+                            for (int t = 0; t < 8; t++) c = (c >> 1) ^ (0xedb88320u & (0u - (c & 1u)));
+                        }
+                        c = ~c;
+                        const uint32_t want = (uint32_t)src[hp] | ((uint32_t)src[hp + 1] << 8);
+                        hp += 2;
+                        if ((c & 0xffffu) != want) { err = SDZ_MSG_BAD_HEADER_CRC; break; }
+                    }
+                } else {
+                    if (((h0 << 8) + h1) % 31 != 0) { err = SDZ_MSG_BAD_HEADER_CHECK; break; }
+                    method = (int)h0;
+                    if ((h0 & 0xf) != 8) { err = SDZ_MSG_BAD_METHOD; break; }
+                    if ((h0 >> 4) + 8 > 15) { err = SDZ_MSG_BAD_WINDOW; break; }
+                    if (h1 & 0x20) {
+                        if (hp + 4 > in_len) { hp = in_len; break; }
+                        int32_t dictid = (int32_t)(((uint32_t)src[hp] << 24) | ((uint32_t)src[hp + 1] << 16) |
+                                                   ((uint32_t)src[hp + 2] << 8) | src[hp + 3]);
+                        hp += 4;
+                        if (!has_dict) { thrown = SDZ_THROW_DICT_REQUIRED; zstatus = SDZ_Z_NEED_DICT; break; }
+                        if (P.dict_adler[i] != dictid) { thrown = SDZ_THROW_DICT_INVALID; zstatus = SDZ_Z_NEED_DICT; break; }
+                        uint32_t dl = P.dict_len[i];
+                        uint32_t used = dl >= (uint32_t)WSIZE ? (uint32_t)WSIZE : dl;      // (the reference keeps 32,767: SURVEY Q14)
+                        D = (int)used;
+                        dict_tail = P.dict + P.dict_off[i] + (dl - used);
+                        ring.init((int)min(used, (uint32_t)WSIZE - 1u));
+                    }
+                }
+                ok = true;
+            } while (0);
+            if (err) { msg = err; thrown = SDZ_THROW_INFLATE_ERROR; zstatus = SDZ_Z_DATA_ERROR; }
+            if (!ok) { decode = false; end_byte = thrown ? hp : in_len; }
+        } else
         if (decode && !raw) {
             int err = 0;
             bool ok = false;
@@ -1478,7 +1588,7 @@ struct Decoder {
             // again, and BTREE/DTREE cannot be re-entered -> STREAM_ERROR is thrown.
             if (stall_kind == ST_DYNHDR) {
                 ring.flush();
-                if (ring.ao == 0) { thrown = SDZ_THROW_INFLATE_ERROR; zstatus = SDZ_Z_STREAM_ERROR; msg = SDZ_MSG_NONE; }
+                if (ring.ao == 0 && !spec) { thrown = SDZ_THROW_INFLATE_ERROR; zstatus = SDZ_Z_STREAM_ERROR; msg = SDZ_MSG_NONE; }
                 else rk = SDZ_RESUME_BROKEN_Q3;
             } else if (stall_kind == ST_STORED) {
                 // `left` is gone when proc() is entered again: the stored block ends where the input ended
@@ -1513,7 +1623,7 @@ struct Decoder {
             }
             if (done) {
                 zstatus = SDZ_Z_STREAM_END;
-                if (tp < in_len) thrown = SDZ_THROW_HANG;   // bytes after the end: append() spins
+                if (tp < in_len && !spec) thrown = SDZ_THROW_HANG;   // bytes after the end: append() spins
             }
             rk = done ? SDZ_RESUME_DONE : SDZ_RESUME_AT_TRAILER;
             rk_bit = bit_pos();
@@ -1590,7 +1700,7 @@ struct Decoder {
             r = dynamic_header(&nl, &nd);
             if (r != R_OK) { finish_stream(P, r); return; }
         }
-        TreeInfo T = build_tables<G>(S, gsorted, nl, nd, type == 1, glane, gmask, long_l(), LONG_N);
+        TreeInfo T = build_tables<G>(S, gsorted, nl, nd, type == 1, glane, gmask, long_l(), LONG_N, spec);
         if (T.msg) { msg = T.msg; finish_stream(P, R_ERROR); return; }
         lbits = T.lbits; dbits = T.dbits; g_l = T.g_l; g_d = T.g_d;
         if (MARK && resume_bit) {                                       // continue in the middle of the block

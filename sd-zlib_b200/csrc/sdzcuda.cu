@@ -306,7 +306,7 @@ int launch_inflate(sdz_ctx* ctx, const sdz::InflateParams& P)
     }
 }
 
-int launch_finalize(sdz_ctx* ctx, const uint8_t* d_out, sdz_result* d_res, uint64_t n)
+int launch_finalize(sdz_ctx* ctx, const uint8_t* d_out, sdz_result* d_res, uint64_t n, bool spec = false)
 {
     if (n == 0) return SDZ_OK;
     const int lane = ctx->cur_lane;
@@ -315,7 +315,7 @@ int launch_finalize(sdz_ctx* ctx, const uint8_t* d_out, sdz_result* d_res, uint6
     CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
     unsigned long long warps = n;
     unsigned grid = (unsigned)std::min<unsigned long long>((warps + 7) / 8, (unsigned long long)ctx->sm_count * 8);
-    sdz::finalize_streams_kernel<<<grid, 256, 0, st>>>(d_out, d_res, n, counter);
+    sdz::finalize_streams_kernel<<<grid, 256, 0, st>>>(d_out, d_res, n, counter, spec ? 1u : 0u);
     ctx->launches++;
     CK(cudaGetLastError());
     return SDZ_OK;
@@ -433,7 +433,8 @@ int launch_fast(sdz_ctx* ctx, const sdz::InflateParams& P, uint64_t tok_total, b
     return SDZ_OK;
 }
 
-int run_batch_device(sdz_ctx* ctx, const sdz_batch_dev* b, bool sizes_only, bool first = true, bool last = true, uint64_t tok_total = 0)
+int run_batch_device(sdz_ctx* ctx, const sdz_batch_dev* b, bool sizes_only, bool first = true, bool last = true, uint64_t tok_total = 0,
+                     bool spec = false)
 {
     sdz::InflateParams P;
     memset(&P, 0, sizeof P);
@@ -441,14 +442,15 @@ int run_batch_device(sdz_ctx* ctx, const sdz_batch_dev* b, bool sizes_only, bool
     P.dict = b->d_dict; P.dict_off = b->d_dict_off; P.dict_len = b->d_dict_len; P.dict_adler = b->d_dict_adler;
     P.out = sizes_only ? nullptr : b->d_out; P.out_off = b->d_out_off; P.out_cap = b->d_out_cap;
     P.res = b->d_results; P.n = b->n; P.counter = ctx->d_counter; P.scratch = nullptr;
+    P.spec = spec ? 1u : 0u;                             // (the two-phase fast path is reference-exact only)
     cudaStream_t st = ctx->lane_stream[ctx->cur_lane];
     if (first) CK(cudaEventRecord(ctx->ev[0], st));
     ctx->fast_timed = false;
-    int rc = sizes_only ? launch_inflate<false>(ctx, P) : (ctx->fast ? launch_fast(ctx, P, tok_total, first && last) : launch_inflate<true>(ctx, P));
+    int rc = sizes_only ? launch_inflate<false>(ctx, P) : (ctx->fast && !spec ? launch_fast(ctx, P, tok_total, first && last) : launch_inflate<true>(ctx, P));
     if (rc) return rc;
     if (last) CK(cudaEventRecord(ctx->ev[1], st));
     if (!sizes_only) {
-        rc = launch_finalize(ctx, b->d_out, b->d_results, b->n);
+        rc = launch_finalize(ctx, b->d_out, b->d_results, b->n, spec);
         if (rc) return rc;
     }
     if (last) CK(cudaEventRecord(ctx->ev[2], st));
@@ -928,9 +930,8 @@ int sdz_checksum_batch(sdz_ctx* ctx, const uint8_t* const* bufs, const uint64_t*
 int sdz_inflate_batch_device(sdz_ctx* ctx, const sdz_batch_dev* batch, uint32_t flags, int sync)
 {
     if (!ctx || !batch) return SDZ_E_ARG;
-    if (flags & SDZ_PARITY_SPEC) return SDZ_E_UNSUPPORTED;
     ENTER(ctx);
-    int rc = run_batch_device(ctx, batch, batch->d_out == nullptr);
+    int rc = run_batch_device(ctx, batch, batch->d_out == nullptr, true, true, 0, (flags & SDZ_PARITY_SPEC) != 0);
     if (rc) return rc;
     if (sync) CK(cudaStreamSynchronize(ctx->stream));
     return SDZ_OK;
@@ -996,7 +997,7 @@ static int inflate_host(sdz_ctx* ctx, const sdz_in* in, uint64_t n, uint8_t* out
                         const uint64_t* out_cap, sdz_result* results, uint64_t* out_len, uint32_t flags, bool sizes_only)
 {
     if (!ctx || (!in && n)) return SDZ_E_ARG;
-    if (flags & SDZ_PARITY_SPEC) return SDZ_E_UNSUPPORTED;
+    const bool spec = (flags & SDZ_PARITY_SPEC) != 0;
     if (!sizes_only && (!results || (n && (!out_arena || !out_off || !out_cap)))) return SDZ_E_ARG;
     if (n == 0) return SDZ_OK;
     if (!ctx->peers.empty()) return inflate_multi(ctx, in, n, out_arena, out_off, out_cap, results, out_len, flags, sizes_only);
@@ -1069,8 +1070,14 @@ static int inflate_host(sdz_ctx* ctx, const sdz_in* in, uint64_t n, uint8_t* out
             if (!(mode[i] & 0x80)) continue;
             uint64_t dl = dict_len[i];
             int32_t v = 1;
-            rc = checksum_chain(ctx, false, d_in + in_total + dict_off[i], &dl, 1, 1, 1, nullptr, &v);
-            if (rc) return rc;
+            if (spec) {                                  // RFC 1950 Adler-32 (no Q1)
+                uint32_t a = 1, b2 = 0;
+                for (uint64_t k = 0; k < dl; k++) { a = (a + in[i].dict[k]) % 65521u; b2 = (b2 + a) % 65521u; }
+                v = (int32_t)((b2 << 16) | a);
+            } else {
+                rc = checksum_chain(ctx, false, d_in + in_total + dict_off[i], &dl, 1, 1, 1, nullptr, &v);
+                if (rc) return rc;
+            }
             m_dict_adler[i] = v;
         }
     } else {
@@ -1160,18 +1167,19 @@ static int inflate_host(sdz_ctx* ctx, const sdz_in* in, uint64_t n, uint8_t* out
         }
     }
     // every buffer the sub-batches will need, before anything is in flight
+    const bool use_fast = ctx->fast && !spec;
     {
         uint64_t n_max[sdz_ctx::N_LANES] = { 0 }, tok_max[sdz_ctx::N_LANES] = { 0 };
         for (uint64_t c = 0; c < K; c++) {
             const int l = (int)(c % n_lanes);
             uint64_t tt = 0;
-            if (!sizes_only && ctx->fast)
+            if (!sizes_only && use_fast)
                 for (uint64_t i = cut[c]; i < cut[c + 1]; i++) tt += sdz::token_cap(in_len[i], d_out_cap[i]);
             n_max[l] = std::max(n_max[l], cut[c + 1] - cut[c]);
             tok_max[l] = std::max(tok_max[l], tt);
         }
         for (int l = 0; l < n_lanes; l++)
-            if ((rc = reserve_lane(ctx, l, n_max[l], tok_max[l], !sizes_only && ctx->fast))) return rc;
+            if ((rc = reserve_lane(ctx, l, n_max[l], tok_max[l], !sizes_only && use_fast))) return rc;
     }
 
     if (ctx->poison && !sizes_only) {
@@ -1227,9 +1235,9 @@ static int inflate_host(sdz_ctx* ctx, const sdz_in* in, uint64_t n, uint8_t* out
         bc.d_out_cap += lo; bc.d_dict_adler += lo; bc.d_mode += lo; bc.d_results += lo;
         bc.n = hi - lo;
         uint64_t tok_total = 0;                          // token arena of this sub-batch (the device computes the same sum)
-        if (!sizes_only && ctx->fast)
+        if (!sizes_only && use_fast)
             for (uint64_t i = lo; i < hi; i++) tok_total += sdz::token_cap(in_len[i], d_out_cap[i]);
-        rc = run_batch_device(ctx, &bc, sizes_only, c == 0, c == K - 1, tok_total);
+        rc = run_batch_device(ctx, &bc, sizes_only, c == 0, c == K - 1, tok_total, spec);
         ctx->cur_lane = 0;
         if (rc) return rc;
         CK(cudaEventRecord(ctx->pipe_ev[2 * c + 1], lane_st));
@@ -1915,6 +1923,32 @@ extern "C" int sdz_large_index(sdz_large* L, uint32_t part, uint32_t n_parts, co
     return SDZ_OK;
 }
 
+// A stored block at bit `cur`?  Reads its header (3 bits, padding to the byte boundary, LEN, NLEN) from the stream and
+// fills `blk`; false when the block is of another type (or the stream ends inside the header: the kernel's business).
+static bool large_stored_header(sdz_large* L, uint64_t cur, sdz_large_block& blk)
+{
+    uint8_t h[6] = { 0 };
+    const uint64_t b0 = cur >> 3;
+    const uint64_t have = L->len > b0 ? std::min<uint64_t>(6, L->len - b0) : 0;
+    if (have < 5) return false;
+    if (L->on_device) { if (cudaMemcpy(h, L->data + b0, have, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return false; } }
+    else memcpy(h, L->data + b0, have);
+    const uint32_t t3 = (((uint32_t)h[0] | ((uint32_t)h[1] << 8)) >> (cur & 7)) & 7u;
+    if ((t3 >> 1) != 0) return false;
+    const uint64_t lb = (cur + 3 + 7) >> 3;                                // LEN starts on the next byte boundary
+    if (lb + 4 > L->len || lb - b0 + 4 > have) return false;
+    const uint8_t* q = h + (lb - b0);
+    const uint32_t len = (uint32_t)q[0] | ((uint32_t)q[1] << 8), nlen = (uint32_t)q[2] | ((uint32_t)q[3] << 8);
+    memset(&blk, 0, sizeof blk);
+    blk.bit = cur;
+    blk.btype = 0;
+    blk.last = (uint8_t)(t3 & 1u);
+    blk.ok = (uint8_t)(((~nlen) & 0xffffu) == len && lb + 4 + len <= L->len);      // else: damaged / truncated -> exact path
+    blk.out_len = len;
+    blk.end_bit = (lb + 4 + len) * 8;
+    return true;
+}
+
 // The chain of real blocks from the first one (false candidates are never reached), cut into pieces at the resume
 // points.  `blocks` / `ckpts`: the index of ALL parts, in any order.
 extern "C" int sdz_large_plan(sdz_large* L, const sdz_large_block* blocks, uint64_t n_blocks, const sdz_large_ckpt* ckpts, uint64_t n_ckpts,
@@ -1932,9 +1966,19 @@ extern "C" int sdz_large_plan(sdz_large* L, const sdz_large_block* blocks, uint6
     if (!std::is_sorted(B.begin(), B.end(), b_less)) std::sort(B.begin(), B.end(), b_less);
     if (!std::is_sorted(C.begin(), C.end(), c_less)) std::sort(C.begin(), C.end(), c_less);
     L->t_bit.clear(); L->t_resume.clear(); L->t_off.clear(); L->t_limit.clear();
-    uint64_t cur = L->first_bit, total = 0, nb = 0, n_single = 0;
+    uint64_t cur = L->first_bit, total = 0, nb = 0, n_single = 0, n_stored = 0;
     bool finished = false;
     int rc;
+    // The reference's window / output-buffer bookkeeping, replayed over the chain (byte counts only, as in the kernels):
+    // it decides whether a stored block is copied whole or loses its remaining length.  Blocks that end within
+    // the last 16 bytes of the input end through the reference's input-frontier rules (step_general), which the plan
+    // does not model: a non-empty stored block after one of those goes to the sequential decoder.
+    sdz::RingModel ring;
+    ring.init(0);
+    bool ring_exact = true;
+    // blocks the header search does not index are measured one kernel launch at a time: a long chain of them
+    // (Z_FIXED, tiny flushes) is the sequential decoder's
+    constexpr uint64_t MAX_SINGLE = 4096;
     for (uint64_t guard = 0; guard < (1ull << 26); guard++) {
         auto it = std::lower_bound(B.begin(), B.end(), cur, [](const sdz_large_block& a, uint64_t v) { return a.bit < v; });
         sdz_large_block blk;
@@ -1947,8 +1991,12 @@ extern "C" int sdz_large_plan(sdz_large* L, const sdz_large_block* blocks, uint6
             auto hi = std::upper_bound(lo, C.end(), cur, [](uint64_t v, const sdz_large_ckpt& a) { return v < a.block_bit; });
             c = C.data() + (lo - C.begin());
             nc = (size_t)(hi - lo);
+        } else if (large_stored_header(L, cur, blk)) {
+            // a stored block: its extent is in its header (src/infblocks.ts:238-271)
+            n_stored++;
         } else {
-            // a block the header search does not look for (stored / fixed): measure it on its own
+            // a block the header search does not look for (fixed): measure it on its own
+            if (n_single >= MAX_SINGLE) return seq();
             std::vector<uint64_t> one{ cur };
             std::vector<sdz_result> r1;
             std::vector<sdz::Ckpt> k1;
@@ -1961,10 +2009,22 @@ extern "C" int sdz_large_plan(sdz_large* L, const sdz_large_block* blocks, uint6
             nc = own.size();
         }
         if (!blk.ok) return seq();                                          // truncated or damaged: exact sequential path
-        // a stored block's copy depends on where the reference's 16 KiB output chunks fall,
-        // which only the sequential decoder tracks
-        if (blk.btype == 0) return seq();
         if (blk.out_len >= (1ull << 32)) return seq();
+        if (blk.btype == 0) {
+            // a stored block's copy depends on where the reference's 16 KiB output chunks fall
+            uint32_t left = (uint32_t)blk.out_len;
+            if (left && !ring_exact) return seq();
+            while (left) {
+                if (ring.room() == 0 && ring.make_room()) return seq();     // `left` is lost: what follows is not a block boundary
+                const uint32_t t = std::min<uint32_t>(left, (uint32_t)ring.room());
+                ring.q += (int)t;
+                left -= t;
+            }
+        } else {
+            ring.write((uint32_t)blk.out_len);                              // block_end() of the kernels
+            if (ring.room() >= 258) ring.flush(); else ring.wash();
+            if (blk.end_bit + 16 * 8 >= L->len * 8) ring_exact = false;
+        }
         uint64_t from = 0, resume = 0;
         for (size_t k = 0; k <= nc; k++) {
             const uint64_t to = k < nc ? c[k].pos : blk.out_len;
@@ -1999,7 +2059,7 @@ extern "C" int sdz_large_plan(sdz_large* L, const sdz_large_block* blocks, uint6
     L->planned = true;
     L->lap("chain walk");
     if (L->trace) fprintf(stderr, "[sdz_large] %llu candidates, %llu blocks (%llu measured singly), %llu pieces, %llu -> %llu bytes\n",
-                          (unsigned long long)n_blocks, (unsigned long long)nb, (unsigned long long)n_single, (unsigned long long)L->t_bit.size(),
+                          (unsigned long long)n_blocks, (unsigned long long)nb, (unsigned long long)(n_single + n_stored), (unsigned long long)L->t_bit.size(),
                           (unsigned long long)L->len, (unsigned long long)total);
     if (total_out) *total_out = total;
     if (n_pieces) *n_pieces = L->t_bit.size();

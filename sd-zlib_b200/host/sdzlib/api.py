@@ -18,6 +18,9 @@ _MSG = [
     "oversubscribed literal/length tree", "incomplete literal/length tree", "oversubscribed distance tree",
     "incomplete distance tree", "empty distance tree with lengths", "invalid distance code",
     "invalid literal/length code",
+    # SDZ_PARITY_SPEC only (zlib 1.3's texts)
+    "invalid distance too far back", "invalid code -- missing end-of-block", "invalid code lengths set",
+    "invalid literal/lengths set", "invalid distances set", "unknown header flags set", "header crc mismatch",
 ]
 _THROWN = [
     "", "inflate error: bad input", "Custom dictionary is not valid for this data",
@@ -193,8 +196,13 @@ def _raise_thrown(thrown, msg_id):
     raise (InflateError if thrown != 6 else InflateHang)(text, thrown, msg_id if thrown == 4 else 0)
 
 
-def inflate_batch_raw(views, dictionaries=None, modes=None, caps=None, ctx=None):
-    """One sdz_inflate_batch call.  Returns (out_arena: np.uint8[], out_off, records)."""
+PARITY_REFERENCE, PARITY_SPEC = 0, 1
+
+
+def inflate_batch_raw(views, dictionaries=None, modes=None, caps=None, ctx=None, flags=PARITY_REFERENCE):
+    """One sdz_inflate_batch call.  Returns (out_arena: np.uint8[], out_off, records).
+    flags = PARITY_SPEC: RFC 1950 / 1951 / 1952 behaviour as zlib 1.3 implements it instead of the reference's
+    (no Q1 / Q2 / Q3 / Q4 / Q5 / Q6 / Q9 / Q10 / Q13 / Q14 / Q15 emulation)."""
     ctx = ctx or N.default_context()
     n = len(views)
     ins = (N.In * max(n, 1))()
@@ -212,7 +220,7 @@ def inflate_batch_raw(views, dictionaries=None, modes=None, caps=None, ctx=None)
         ins[i].mode = MODE_SNIFF if modes is None else modes[i]
     if caps is None:
         sizes = np.zeros(max(n, 1), dtype=np.uint64)
-        ctx.check(ctx.lib.sdz_inflate_sizes(ctx.h, ins, n, sizes.ctypes.data, 0))
+        ctx.check(ctx.lib.sdz_inflate_sizes(ctx.h, ins, n, sizes.ctypes.data, flags))
         caps = sizes[:n]
     caps = np.ascontiguousarray(caps, dtype=np.uint64)
     slot = (caps + np.uint64(15)) & ~np.uint64(15)
@@ -222,12 +230,12 @@ def inflate_batch_raw(views, dictionaries=None, modes=None, caps=None, ctx=None)
     total = int(slot.sum()) if n else 0
     arena = np.empty(max(total, 1), dtype=np.uint8)
     res = (N.Result * max(n, 1))()
-    ctx.check(ctx.lib.sdz_inflate_batch(ctx.h, ins, n, arena.ctypes.data, off.ctypes.data, slot.ctypes.data, res, 0),
+    ctx.check(ctx.lib.sdz_inflate_batch(ctx.h, ins, n, arena.ctypes.data, off.ctypes.data, slot.ctypes.data, res, flags),
               allow=(N.SDZ_E_OUT_CAP,))
     return arena, off, res
 
 
-def inflateBatch(buffers, dictionaries=None, raw=None, ctx=None):
+def inflateBatch(buffers, dictionaries=None, raw=None, ctx=None, parity="reference"):
     """inflateBatch(buffers[]) - the one entry point added to the reference API.
 
     Each buffer is decoded exactly like `inflate(buffer, dictionary)` (container sniffing
@@ -239,7 +247,9 @@ def inflateBatch(buffers, dictionaries=None, raw=None, ctx=None):
     modes = None
     if raw is not None:
         modes = [MODE_SNIFF if r is None else (MODE_RAW if r else MODE_INFLATER) for r in raw]
-    arena, off, res = inflate_batch_raw(views, dictionaries, modes, None, ctx)
+    if parity not in ("reference", "spec"):
+        raise ValueError("parity must be `reference` or `spec`")
+    arena, off, res = inflate_batch_raw(views, dictionaries, modes, None, ctx, PARITY_SPEC if parity == "spec" else PARITY_REFERENCE)
     out = []
     for i, v in enumerate(views):
         r = res[i]

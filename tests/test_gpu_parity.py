@@ -502,6 +502,40 @@ def test_large_stream_kinds_levels_and_flush_points():
         _check_large(s, m)
 
 
+def test_large_stream_stored_blocks_stay_block_parallel():
+    """Sync-flush points (empty stored blocks, what pigz-style writers emit between chunks) and small stored blocks of
+    incompressible data: sdz_large_plan replays the reference's window bookkeeping over the chain of blocks, so these
+    streams stay on the block-parallel path; a stored block the reference itself cuts short still goes to the
+    sequential decoder, with the reference's (broken) record."""
+    p = _large_plain(K.TEXT, 8, 500).tobytes()
+    co = zlib.compressobj(6)
+    s = b""
+    for k in range(0, len(p), 1 << 20):
+        s += co.compress(p[k:k + (1 << 20)]) + co.flush(zlib.Z_SYNC_FLUSH)
+    s += co.flush()
+    ctx = sdzlib.default_context()
+    before = ctx.launch_count()
+    r = _check_large(s, O.MODE_SNIFF, np.frombuffer(p, dtype=np.uint8))
+    assert r.success and r.n_blocks > 100 and ctx.launch_count() - before >= 6
+    # incompressible pieces of 1 .. 12 KiB between text: stored blocks with data
+    co = zlib.compressobj(6, zlib.DEFLATED, 31)
+    s, plain = b"", b""
+    rng = random.Random(17)
+    for k in range(40):
+        t = p[k * 150000:(k + 1) * 150000]
+        noise = os.urandom(rng.choice((1, 100, 1000, 4000, 12000)))
+        s += co.compress(t) + co.flush(zlib.Z_SYNC_FLUSH) + co.compress(noise) + co.flush(zlib.Z_SYNC_FLUSH)
+        plain += t + noise
+    s += co.flush()
+    before = ctx.launch_count()
+    r = _check_large(s, O.MODE_SNIFF)
+    exp_bytes, exp = O.inflate_oneshot(s)
+    if exp.success:                                     # (every stored block survived the reference's Q2 rule)
+        assert ctx.launch_count() - before >= 6
+    # one large stored block in the middle: the reference loses its tail (Q2) - the oracle's record, whatever it is
+    _check_large(zlib.compress(p[:1500000] + os.urandom(60000) + p[1500000:3000000], 6), O.MODE_SNIFF)
+
+
 def test_large_stream_far_references_and_small_blocks():
     """Windows that span many tiny blocks (Z_FULL_FLUSH is avoided: it emits stored blocks; level-1 output
     of short period data has long chains of window references across block boundaries)."""
