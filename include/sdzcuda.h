@@ -230,9 +230,10 @@ void sdz_inflater_destroy(sdz_inflater* s);
  * block in parallel with 16-bit marker symbols for back-references into the unknown 32 KiB window,
  * propagates the windows in stream order and resolves the markers.  Same record as one
  * `new Inflater(opts).append(data); finish()` (src/sd-inflate.ts:54-180).  on_device != 0: `data` and
- * `out` are device pointers (data 4-byte aligned and readable for SDZ_IN_PAD bytes past its end, out
- * with 64 bytes of slack).  Streams the index cannot handle (preset dictionary, anything that is not a
- * complete well-formed stream) are handed to the ordinary one-group decoder, which is exact but slow.
+ * `out` are device pointers (data 16-byte aligned and readable for SDZ_IN_PAD bytes past its end, out
+ * with 64 bytes of slack).  Streams the index cannot handle (preset dictionary, FEXTRA, a stored block the
+ * reference cuts short, anything that is not a complete well-formed stream) are handed to the
+ * ordinary one-group decoder, which is exact but slow.
  * Returns SDZ_E_OUT_CAP (res->out_len = needed size) if out_cap is too small. */
 int sdz_inflate_large(sdz_ctx* ctx, const uint8_t* data, uint64_t len, uint8_t mode, int on_device,
                       uint8_t* out, uint64_t out_cap, sdz_result* res);

@@ -1061,24 +1061,45 @@ static int inflate_host(sdz_ctx* ctx, const sdz_in* in, uint64_t n, uint8_t* out
     memset(hs + in_bytes, 0, SDZ_IN_PAD);
 
     uint8_t* d_in = (uint8_t*)ctx->d_in.p;
-    // dictionaries first (small): their reference adler32 (incl. Q1) is evaluated on the device, one call each
+    // dictionaries first (small): their reference adler32 (incl. Q1) is evaluated on the device, all of them in ONE launch
+    // (one warp per dictionary, checksum_batch_kernel) and one round trip
     if (dict_bytes) {
-        for (uint64_t i = 0; i < n; i++)
-            if (dict_len[i]) memcpy(hs + in_total + dict_off[i], in[i].dict, dict_len[i]);
-        CK(cudaMemcpyAsync(d_in + in_total, hs + in_total, dict_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        std::vector<uint64_t> k_off, k_len;
+        std::vector<uint64_t> k_idx;
         for (uint64_t i = 0; i < n; i++) {
+            if (dict_len[i]) memcpy(hs + in_total + dict_off[i], in[i].dict, dict_len[i]);
             if (!(mode[i] & 0x80)) continue;
-            uint64_t dl = dict_len[i];
-            int32_t v = 1;
             if (spec) {                                  // RFC 1950 Adler-32 (no Q1)
                 uint32_t a = 1, b2 = 0;
-                for (uint64_t k = 0; k < dl; k++) { a = (a + in[i].dict[k]) % 65521u; b2 = (b2 + a) % 65521u; }
-                v = (int32_t)((b2 << 16) | a);
-            } else {
-                rc = checksum_chain(ctx, false, d_in + in_total + dict_off[i], &dl, 1, 1, 1, nullptr, &v);
-                if (rc) return rc;
+                for (uint64_t k = 0; k < dict_len[i]; k++) { a = (a + in[i].dict[k]) % 65521u; b2 = (b2 + a) % 65521u; }
+                m_dict_adler[i] = (int32_t)((b2 << 16) | a);
+                continue;
             }
-            m_dict_adler[i] = v;
+            k_idx.push_back(i); k_off.push_back(dict_off[i]); k_len.push_back(dict_len[i]);
+        }
+        CK(cudaMemcpyAsync(d_in + in_total, hs + in_total, dict_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        const uint64_t k = k_idx.size();
+        if (k) {
+            // device scratch: off[k] | len[k] | out[k] (i32) | kind[k] (u8, all zero = adler32)
+            const size_t need = k * 8 * 2 + align_up(k * 4, 8) + align_up(k, 8);
+            if ((rc = grow(ctx, ctx->d_part, need + 16))) return rc;
+            uint8_t* dp = (uint8_t*)ctx->d_part.p;
+            uint64_t* dk_off = (uint64_t*)dp;
+            uint64_t* dk_len = dk_off + k;
+            int32_t* dk_out = (int32_t*)(dk_len + k);
+            uint8_t* dk_kind = (uint8_t*)dk_out + align_up(k * 4, 8);
+            CK(cudaMemcpyAsync(dk_off, k_off.data(), k * 8, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(dk_len, k_len.data(), k * 8, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemsetAsync(dk_kind, 0, k, ctx->stream));
+            CK(cudaMemsetAsync(ctx->d_counter + 3, 0, sizeof(unsigned long long), ctx->stream));
+            const unsigned grid = (unsigned)std::min<uint64_t>((k + 7) / 8, (uint64_t)ctx->sm_count * 8);
+            sdz::checksum_batch_kernel<<<grid, 256, 0, ctx->stream>>>(d_in + in_total, dk_off, dk_len, dk_kind, nullptr, k, dk_out, ctx->d_counter + 3);
+            ctx->launches++;
+            CK(cudaGetLastError());
+            std::vector<int32_t> vals(k);
+            CK(cudaMemcpyAsync(vals.data(), dk_out, k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            for (uint64_t j = 0; j < k; j++) m_dict_adler[k_idx[j]] = vals[j];
         }
     } else {
         for (uint64_t i = 0; i < n; i++) if (mode[i] & 0x80) m_dict_adler[i] = 1;   // adler32 of an empty dictionary
@@ -1196,75 +1217,87 @@ static int inflate_host(sdz_ctx* ctx, const sdz_in* in, uint64_t n, uint8_t* out
         cudaEventRecord(tev[3 * K], ctx->s_h2d);
     }
     const auto t_host0 = std::chrono::steady_clock::now();
-    CK(cudaMemcpyAsync(ctx->d_meta.p, hm, meta_bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
-    // records and bytes of sub-batch c go home once its kernels are done
-    auto enqueue_d2h = [&](uint64_t c) -> int {
-        const uint64_t lo = cut[c], hi = cut[c + 1];
-        if (lo == hi) return SDZ_OK;
-        CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->pipe_ev[2 * c + 1], 0));
-        CK(cudaMemcpyAsync(rdst + lo, (sdz_result*)ctx->d_res.p + lo, (hi - lo) * sizeof(sdz_result), cudaMemcpyDeviceToHost, ctx->s_d2h));
-        if (!sizes_only && dense) {
-            const uint64_t o_lo = d_out_off[lo], o_hi = d_out_off[hi - 1] + d_out_cap[hi - 1];
-            uint8_t* land = out_staged ? (uint8_t*)ctx->h_out : out_arena + out_lo;
-            CK(cudaMemcpyAsync(land + o_lo, (uint8_t*)ctx->d_out.p + o_lo, o_hi - o_lo, cudaMemcpyDeviceToHost, ctx->s_d2h));
-            if (out_staged) CK(cudaEventRecord(ctx->pipe_ev[2 * c], ctx->s_d2h));      // (the input-landed event of c has been waited on)
-        }
-        if (trace_pipe) cudaEventRecord(tev[3 * c + 2], ctx->s_d2h);
-        return SDZ_OK;
-    };
-    for (uint64_t c = 0; c < K; c++) {
-        const uint64_t lo = cut[c], hi = cut[c + 1];
-        if (lo == hi) continue;
-        if (!direct) {
-            std::vector<std::pair<uint8_t*, std::pair<const uint8_t*, size_t>>> jobs;
-            jobs.reserve(hi - lo);
-            for (uint64_t i = lo; i < hi; i++)
-                if (in_len[i]) jobs.push_back({ hs + in_off[i], { in[i].data, in_len[i] } });
-            parallel_copy(jobs);
-        }
-        const size_t c_lo = in_off[lo], c_hi = (hi < n ? (size_t)in_off[hi] : (direct ? data_end : in_total));
-        if (c_hi > c_lo)
-            CK(cudaMemcpyAsync(d_in + c_lo, (direct ? ubase : hs) + c_lo, c_hi - c_lo, cudaMemcpyHostToDevice, ctx->s_h2d));
-        CK(cudaEventRecord(ctx->pipe_ev[2 * c], ctx->s_h2d));
-        if (trace_pipe) cudaEventRecord(tev[3 * c], ctx->s_h2d);
-        ctx->cur_lane = (int)(c % n_lanes);
-        cudaStream_t lane_st = ctx->lane_stream[ctx->cur_lane];
-        CK(cudaStreamWaitEvent(lane_st, ctx->pipe_ev[2 * c], 0));
-        sdz_batch_dev bc = b;
-        bc.d_in_off += lo; bc.d_dict_off += lo; bc.d_out_off += lo; bc.d_in_len += lo; bc.d_dict_len += lo;
-        bc.d_out_cap += lo; bc.d_dict_adler += lo; bc.d_mode += lo; bc.d_results += lo;
-        bc.n = hi - lo;
-        uint64_t tok_total = 0;                          // token arena of this sub-batch (the device computes the same sum)
-        if (!sizes_only && use_fast)
-            for (uint64_t i = lo; i < hi; i++) tok_total += sdz::token_cap(in_len[i], d_out_cap[i]);
-        rc = run_batch_device(ctx, &bc, sizes_only, c == 0, c == K - 1, tok_total, spec);
-        ctx->cur_lane = 0;
-        if (rc) return rc;
-        CK(cudaEventRecord(ctx->pipe_ev[2 * c + 1], lane_st));
-        if (trace_pipe) cudaEventRecord(tev[3 * c + 1], lane_st);
-        if (!ctx->h2d_first) { if ((rc = enqueue_d2h(c))) return rc; }
-    }
-    if (ctx->h2d_first) {
-        // SDZ_H2D_FIRST=1: no device -> host copy starts before the last input has landed.  On hosts whose memory system
-        // sustains less with both directions active than with one (profiles/r02n_8gpu_summary.md: 8 GPUs on one socket,
-        // ~100 GB/s mixed against 168 GB/s device -> host alone) the two phases are faster one after the other.
-        CK(cudaEventRecord(ctx->ev[3], ctx->s_h2d));
-        CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev[3], 0));
-        for (uint64_t c = 0; c < K; c++)
-            if ((rc = enqueue_d2h(c))) return rc;
-    }
-    if (out_staged) {
+    // (everything that enqueues work: on an error nothing may stay in flight - the copies read the caller's buffers and
+    //  write into them, and the next call may free the staging areas)
+    auto pipeline = [&]() -> int {
+        CK(cudaMemcpyAsync(ctx->d_meta.p, hm, meta_bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
+        // records and bytes of sub-batch c go home once its kernels are done
+        auto enqueue_d2h = [&](uint64_t c) -> int {
+            const uint64_t lo = cut[c], hi = cut[c + 1];
+            if (lo == hi) return SDZ_OK;
+            CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->pipe_ev[2 * c + 1], 0));
+            CK(cudaMemcpyAsync(rdst + lo, (sdz_result*)ctx->d_res.p + lo, (hi - lo) * sizeof(sdz_result), cudaMemcpyDeviceToHost, ctx->s_d2h));
+            if (!sizes_only && dense) {
+                const uint64_t o_lo = d_out_off[lo], o_hi = d_out_off[hi - 1] + d_out_cap[hi - 1];
+                uint8_t* land = out_staged ? (uint8_t*)ctx->h_out : out_arena + out_lo;
+                CK(cudaMemcpyAsync(land + o_lo, (uint8_t*)ctx->d_out.p + o_lo, o_hi - o_lo, cudaMemcpyDeviceToHost, ctx->s_d2h));
+                if (out_staged) CK(cudaEventRecord(ctx->pipe_ev[2 * c], ctx->s_d2h));      // (the input-landed event of c has been waited on)
+            }
+            if (trace_pipe) cudaEventRecord(tev[3 * c + 2], ctx->s_d2h);
+            return SDZ_OK;
+        };
         for (uint64_t c = 0; c < K; c++) {
             const uint64_t lo = cut[c], hi = cut[c + 1];
             if (lo == hi) continue;
-            CK(cudaEventSynchronize(ctx->pipe_ev[2 * c]));
-            const uint64_t o_lo = d_out_off[lo], o_hi = d_out_off[hi - 1] + d_out_cap[hi - 1];
-            std::vector<std::pair<uint8_t*, std::pair<const uint8_t*, size_t>>> jobs;
-            const size_t piece = 1u << 20;
-            for (uint64_t o = o_lo; o < o_hi; o += piece)
-                jobs.push_back({ out_arena + out_lo + o, { (const uint8_t*)ctx->h_out + o, (size_t)std::min<uint64_t>(piece, o_hi - o) } });
-            parallel_copy(jobs);
+            if (!direct) {
+                std::vector<std::pair<uint8_t*, std::pair<const uint8_t*, size_t>>> jobs;
+                jobs.reserve(hi - lo);
+                for (uint64_t i = lo; i < hi; i++)
+                    if (in_len[i]) jobs.push_back({ hs + in_off[i], { in[i].data, in_len[i] } });
+                parallel_copy(jobs);
+            }
+            const size_t c_lo = in_off[lo], c_hi = (hi < n ? (size_t)in_off[hi] : (direct ? data_end : in_total));
+            if (c_hi > c_lo)
+                CK(cudaMemcpyAsync(d_in + c_lo, (direct ? ubase : hs) + c_lo, c_hi - c_lo, cudaMemcpyHostToDevice, ctx->s_h2d));
+            CK(cudaEventRecord(ctx->pipe_ev[2 * c], ctx->s_h2d));
+            if (trace_pipe) cudaEventRecord(tev[3 * c], ctx->s_h2d);
+            ctx->cur_lane = (int)(c % n_lanes);
+            cudaStream_t lane_st = ctx->lane_stream[ctx->cur_lane];
+            CK(cudaStreamWaitEvent(lane_st, ctx->pipe_ev[2 * c], 0));
+            sdz_batch_dev bc = b;
+            bc.d_in_off += lo; bc.d_dict_off += lo; bc.d_out_off += lo; bc.d_in_len += lo; bc.d_dict_len += lo;
+            bc.d_out_cap += lo; bc.d_dict_adler += lo; bc.d_mode += lo; bc.d_results += lo;
+            bc.n = hi - lo;
+            uint64_t tok_total = 0;                          // token arena of this sub-batch (the device computes the same sum)
+            if (!sizes_only && use_fast)
+                for (uint64_t i = lo; i < hi; i++) tok_total += sdz::token_cap(in_len[i], d_out_cap[i]);
+            rc = run_batch_device(ctx, &bc, sizes_only, c == 0, c == K - 1, tok_total, spec);
+            ctx->cur_lane = 0;
+            if (rc) return rc;
+            CK(cudaEventRecord(ctx->pipe_ev[2 * c + 1], lane_st));
+            if (trace_pipe) cudaEventRecord(tev[3 * c + 1], lane_st);
+            if (!ctx->h2d_first) { if ((rc = enqueue_d2h(c))) return rc; }
         }
+        if (ctx->h2d_first) {
+            // SDZ_H2D_FIRST=1: no device -> host copy starts before the last input has landed.  On hosts whose memory system
+            // sustains less with both directions active than with one (profiles/r02n_8gpu_summary.md: 8 GPUs on one socket,
+            // ~100 GB/s mixed against 168 GB/s device -> host alone) the two phases are faster one after the other.
+            CK(cudaEventRecord(ctx->ev[3], ctx->s_h2d));
+            CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev[3], 0));
+            for (uint64_t c = 0; c < K; c++)
+                if ((rc = enqueue_d2h(c))) return rc;
+        }
+        if (out_staged) {
+            for (uint64_t c = 0; c < K; c++) {
+                const uint64_t lo = cut[c], hi = cut[c + 1];
+                if (lo == hi) continue;
+                CK(cudaEventSynchronize(ctx->pipe_ev[2 * c]));
+                const uint64_t o_lo = d_out_off[lo], o_hi = d_out_off[hi - 1] + d_out_cap[hi - 1];
+                std::vector<std::pair<uint8_t*, std::pair<const uint8_t*, size_t>>> jobs;
+                const size_t piece = 1u << 20;
+                for (uint64_t o = o_lo; o < o_hi; o += piece)
+                    jobs.push_back({ out_arena + out_lo + o, { (const uint8_t*)ctx->h_out + o, (size_t)std::min<uint64_t>(piece, o_hi - o) } });
+                parallel_copy(jobs);
+            }
+        }
+        return SDZ_OK;
+    };
+    if ((rc = pipeline())) {
+        cudaStreamSynchronize(ctx->s_h2d);
+        for (int l = 0; l < sdz_ctx::N_LANES; l++) { cudaStreamSynchronize(ctx->lane_stream[l]); cudaStreamSynchronize(ctx->fast_sb[l]); }
+        cudaStreamSynchronize(ctx->s_d2h);
+        cudaGetLastError();
+        return rc;
     }
     const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
     CK(cudaStreamSynchronize(ctx->s_d2h));
@@ -2273,8 +2306,10 @@ extern "C" int sdz_inflate_large(sdz_ctx* ctx, const uint8_t* data, uint64_t len
         int rc = inflate_host(ctx, &in1, 1, nullptr, nullptr, nullptr, nullptr, &need, 0, true);
         if (rc) return rc;
         if (need > out_cap) { res->out_len = need; return SDZ_E_OUT_CAP; }
+        // (an empty / rejected / immediately failing stream needs no output: the record is still the reference's)
+        uint8_t none[16];
         uint64_t off0 = 0, cap0 = need;
-        return inflate_host(ctx, &in1, 1, out, &off0, &cap0, res, nullptr, 0, false);
+        return inflate_host(ctx, &in1, 1, need ? out : none, &off0, &cap0, res, nullptr, 0, false);
     };
     auto done = [&](int rc) { if (L) sdz_large_close(L); return rc; };
 #define LARGE_STEP(call)                                          \
@@ -2325,8 +2360,8 @@ extern "C" int sdz_inflate_large(sdz_ctx* ctx, const uint8_t* data, uint64_t len
     L->lap("checksum");
     ctx->last_ms[0] = ms_keep[0]; ctx->last_ms[1] = ms_keep[1]; ctx->last_ms[2] = ms_keep[2];
     if (!on_device && total_out) {
-        CK(cudaMemcpyAsync(out, d_o, total_out, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        if (cudaMemcpyAsync(out, d_o, total_out, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = cudaGetErrorString(cudaGetLastError()); return done(SDZ_E_CUDA); }
     }
     L->lap("output copy");
     int rc = sdz_large_finish(L, running, res);
