@@ -122,6 +122,7 @@ struct FastParams {
     unsigned long long* counter_b;
     uint32_t first, count;
     uint16_t* sorted_l;                // 288 u16 per lane of the phase-A grid
+    const uint32_t* order;             // work item k of the batch is stream order[k]: longest compressed streams first
 };
 
 // token capacity of a stream: a token needs at least one output byte, and streams with fewer than four
@@ -138,13 +139,35 @@ __device__ __host__ __forceinline__ uint64_t token_cap(uint32_t in_len, uint32_t
 }
 
 // exclusive scan of the token capacities (one block; n is a few 10^4)
+// The kernel also orders the streams for phase A: a lane decodes its stream alone, so a launch lasts as long as its
+// slowest lane, and lanes that finish early take the next stream of the launch's range.  Work items are therefore handed
+// out longest compressed stream first (the decode time of a Huffman-coded stream follows its compressed size; 64 classes
+// of 1 KiB, a counting sort): expensive streams start together at the beginning of a launch and cheap ones fill the gaps
+// behind them.  Streams that did not shrink (compressed >= decompressed: stored blocks, which phase A hands over at
+// their first block header) go last.
+__device__ __forceinline__ uint32_t cost_class(uint32_t in_len, uint32_t out_cap)
+{
+    if (in_len >= out_cap) return 63u;
+    const uint32_t c = 62u - min(in_len >> 10, 62u);
+    return c;                                            // class 0 = the longest streams
+}
+
 __global__ void __launch_bounds__(1024) token_offsets_kernel(const uint32_t* in_len, const uint32_t* out_cap, unsigned long long n,
-                                                             uint64_t* tok_off)
+                                                             uint64_t* tok_off, uint32_t* order)
 {
     __shared__ uint64_t wsum[32];
     __shared__ uint64_t carry_s;
+    __shared__ uint32_t hist[64], cursor[64];
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry_s = 0;
+    if (threadIdx.x < 64) hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (unsigned long long i = threadIdx.x; i < n; i += 1024) atomicAdd(&hist[cost_class(in_len[i], out_cap ? out_cap[i] : 0xffffffffu)], 1u);
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t acc = 0; for (int k = 0; k < 64; k++) { cursor[k] = acc; acc += hist[k]; } }
+    __syncthreads();
+    for (unsigned long long i = threadIdx.x; i < n; i += 1024)
+        order[atomicAdd(&cursor[cost_class(in_len[i], out_cap ? out_cap[i] : 0xffffffffu)], 1u)] = (uint32_t)i;
     __syncthreads();
     for (unsigned long long base = 0; base < n; base += 1024) {
         const unsigned long long i = base + threadIdx.x;
@@ -516,7 +539,7 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
             }
             // LS_FETCH
             unsigned long long i = atomicAdd(P.counter_a, 1ull);
-            if (i < P.count) i += P.first;
+            if (i < P.count) i = P.order[P.first + i];
             else {
                 // out of streams: the lane idles through the lockstep loop on zeroed tables (every lookup is a "literal"
                 // of zero bits) with a full bit buffer, so it never loads and never consumes
@@ -911,7 +934,7 @@ __global__ void __launch_bounds__(256) lz_resolve_kernel(FastParams P)
         if (lane == 0) idx = atomicAdd(P.counter_b, 1ull);
         idx = __shfl_sync(FULL, idx, 0);
         if (idx >= P.count) break;
-        idx += P.first;
+        idx = P.order[P.first + idx];
         const uint32_t nt = P.ntok[idx];
         if (nt == NTOK_HANDED_OVER || nt == 0u) continue;
         const uint32_t* tk = P.tokens + P.tok_off[idx];
@@ -1058,7 +1081,7 @@ __global__ void __launch_bounds__(32 * B2_WARPS, SDZ_B2_MINBLOCKS) lz_resolve2_k
         if (lane == 0) idx = atomicAdd(P.counter_b, 1ull);
         idx = __shfl_sync(FULL, idx, 0);
         if (idx >= P.count) break;
-        idx += P.first;
+        idx = P.order[P.first + idx];
         const uint32_t nt = P.ntok[idx];
         if (nt == NTOK_HANDED_OVER || nt == 0u) continue;
         const uint32_t* tk = P.tokens + P.tok_off[idx];

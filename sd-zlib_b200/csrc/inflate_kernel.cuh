@@ -1265,8 +1265,29 @@ struct Decoder {
         if (copied > cap - pos) return R_OUTFULL;
         if (STORE) {
             const uint8_t* src = gsrc + start;
-            if (MARK) { uint16_t* dst = out16 + pos; for (uint32_t i = glane; i < copied; i += G) dst[i] = src[i]; }
-            else { uint8_t* dst = out + pos; for (uint32_t i = glane; i < copied; i += G) dst[i] = src[i]; }
+            // (eight independent loads in flight per lane: the plain loop waited for every byte before it stored it)
+            uint32_t i = glane;
+            if (MARK) {
+                uint16_t* dst = out16 + pos;
+                for (; i + 7u * G < copied; i += 8u * G) {
+                    uint8_t v[8];
+                    #pragma unroll
+                    for (int k = 0; k < 8; k++) v[k] = src[i + k * G];
+                    #pragma unroll
+                    for (int k = 0; k < 8; k++) dst[i + k * G] = v[k];
+                }
+                for (; i < copied; i += G) dst[i] = src[i];
+            } else {
+                uint8_t* dst = out + pos;
+                for (; i + 7u * G < copied; i += 8u * G) {
+                    uint8_t v[8];
+                    #pragma unroll
+                    for (int k = 0; k < 8; k++) v[k] = src[i + k * G];
+                    #pragma unroll
+                    for (int k = 0; k < 8; k++) dst[i + k * G] = v[k];
+                }
+                for (; i < copied; i += G) dst[i] = src[i];
+            }
         }
         pos += copied;
         seek(start + copied);

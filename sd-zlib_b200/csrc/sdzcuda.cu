@@ -339,7 +339,7 @@ int reserve_lane(sdz_ctx* ctx, int lane, uint64_t n, uint64_t tok_total, bool fa
     }
     if (!fast) return SDZ_OK;
     const size_t off_list = 256 + (n + 1) * 8 + (n * 4 + 7) / 8 * 8;
-    if ((rc = grow(ctx, ctx->fast_meta[lane], off_list + n * 4))) return rc;
+    if ((rc = grow(ctx, ctx->fast_meta[lane], off_list + align_up(n * 4, 8) + n * 4))) return rc;
     if ((rc = grow(ctx, ctx->fast_tok[lane], tok_total * 4 + 64))) return rc;
     const uint64_t grid_a = std::min<uint64_t>((n + 31) / 32, (uint64_t)ctx->sm_count * 8);
     if ((rc = grow(ctx, ctx->fast_sorted[lane], (size_t)grid_a * 32 * sdz::SORTED_L * sizeof(uint16_t)))) return rc;
@@ -354,13 +354,13 @@ int launch_fast(sdz_ctx* ctx, const sdz::InflateParams& P, uint64_t tok_total, b
     const int lane = ctx->cur_lane;
     cudaStream_t st = ctx->lane_stream[lane];
     int rc;
-    const size_t off_tokoff = 256, off_ntok = off_tokoff + (n + 1) * 8, off_list = off_ntok + align_up(n * 4, 8);
-    if ((rc = grow(ctx, ctx->fast_meta[lane], off_list + n * 4))) return rc;
+    const size_t off_tokoff = 256, off_ntok = off_tokoff + (n + 1) * 8, off_list = off_ntok + align_up(n * 4, 8), off_order = off_list + align_up(n * 4, 8);
+    if ((rc = grow(ctx, ctx->fast_meta[lane], off_order + n * 4))) return rc;
     uint8_t* fm = (uint8_t*)ctx->fast_meta[lane].p;
     unsigned long long* counters = (unsigned long long*)fm;
     uint64_t* tok_off = (uint64_t*)(fm + off_tokoff);
     CK(cudaMemsetAsync(counters, 0, 256, st));
-    sdz::token_offsets_kernel<<<1, 1024, 0, st>>>(P.in_len, P.out_cap, n, tok_off);
+    sdz::token_offsets_kernel<<<1, 1024, 0, st>>>(P.in_len, P.out_cap, n, tok_off, (uint32_t*)(fm + off_order));
     ctx->launches++;
     if (!tok_total) {
         CK(cudaMemcpyAsync(&tok_total, tok_off + n, 8, cudaMemcpyDeviceToHost, st));
@@ -385,6 +385,7 @@ int launch_fast(sdz_ctx* ctx, const sdz::InflateParams& P, uint64_t tok_total, b
     F.fb_list = (uint32_t*)(fm + off_list);
     F.fb_count = counters;
     F.sorted_l = (uint16_t*)ctx->fast_sorted[lane].p;
+    F.order = (const uint32_t*)(fm + off_order);
     // The batch is cut into chunks: phase A of chunk c + 1 (latency-bound, one warp per scheduler, all of the shared
     // memory) runs next to phase B of chunk c (issue-bound, no shared memory) on a second stream, so the two kernels
     // fill each other's idle issue slots on the same SMs.
