@@ -17,6 +17,7 @@ Extra keys of the same JSON line (each parity-checked against the oracle / zlib,
   matrix        device arm on text / binary corpora at levels 1 / 6 / 9 (north_star's measurement matrix)
   mixed_batch   BASELINE configs[3]: gzip + raw + zlib (+ preset dictionary), levels 1/6/9, stored / fixed /
                 dynamic blocks, 65,536 streams per GPU
+  dict_batch    65,536 zlib streams that all use a preset dictionary (InflaterOptions.dictionary)
   large_stream  BASELINE configs[4]: ONE gzip stream decoded block-parallel on all ranks (strong scaling)
   e2e_pageable  the e2e arm with separately allocated pageable inputs and a pageable output arena
                 (what an N-API caller hands over)
@@ -292,6 +293,44 @@ def build_mixed_batch(n, threads, first_index, reps=1):
             "dict_len": dlen, "dict_adler": dadl, "plain_bytes": int(sum(s[1] for s in streams)) * reps, "dictionary": dic}
 
 
+def build_dict_batch(n, n_distinct=2048):
+    """n zlib streams (30,000 bytes of text each, levels 1/6/9) that all name the same 470-byte preset dictionary
+    (`new Inflater({dictionary})`, src/sd-inflate.ts:54-80); n_distinct different streams, tiled.  Same dict layout as
+    build_mixed_batch()."""
+    from tools import corpus as K
+    from oracle import oracle as O
+    dic = bytes(K.generate(K.TEXT, 4242, 470))
+    dictid = O.adler32(dic)
+    ss = [np.frombuffer(K.compress(K.generate(K.TEXT, 90000 + i, 30000), (1, 6, 9)[i % 3], K.ZLIB_DICT, dic, dictid), dtype=np.uint8)
+          for i in range(min(n, n_distinct))]
+    ss = [ss[i % len(ss)] for i in range(n)]
+    ln = np.array([s.size for s in ss], dtype=np.uint32)
+    al = (ln.astype(np.uint64) + np.uint64(15)) & ~np.uint64(15)
+    off = np.zeros(n, dtype=np.uint64)
+    off[1:] = np.cumsum(al[:-1])
+    arena = np.zeros(int(al.sum()) + 1024, dtype=np.uint8)
+    for i, s in enumerate(ss):
+        arena[int(off[i]):int(off[i]) + s.size] = s
+    return {"arena": arena, "off": off, "ln": ln, "mode": np.full(n, 0x81, dtype=np.uint8), "cap": np.full(n, (30000 + 15) & ~15, dtype=np.uint32),
+            "dict": np.frombuffer(dic + b"\0" * 42, dtype=np.uint8), "dict_len": np.full(n, len(dic), dtype=np.uint32),
+            "dict_adler": np.full(n, dictid, dtype=np.int32), "plain_bytes": 30000 * n, "dictionary": dic}
+
+
+def check_sampled(N, O, m, dm, n, n_samples):
+    """record + bytes of n_samples evenly spaced streams of a device batch against the oracle"""
+    rm = dm.records(N)
+    ok, checked = True, 0
+    for i in range(0, n, max(1, n // n_samples)):
+        hd = bool(m["mode"][i] & 0x80)
+        exp, er = O.inflate_oneshot(m["arena"][int(m["off"][i]):int(m["off"][i]) + int(m["ln"][i])].tobytes(),
+                                    dictionary=m["dictionary"] if hd else None, mode=int(m["mode"][i] & 0x7f))
+        o0 = int(dm.ooff[i])
+        gotb = dm.d_out[o0:o0 + int(rm[i].out_len)].cpu().numpy().tobytes()
+        ok = ok and er.observable() == rm[i].observable() and (er.thrown_append or gotb == exp)
+        checked += 1
+    return rm, bool(ok), checked
+
+
 class DeviceBatch:
     """a batch resident in HBM + the sdz_batch_dev that describes it"""
 
@@ -515,17 +554,8 @@ def main():
         dm = DeviceBatch(torch, N, m["arena"], m["off"], m["ln"], m["mode"], m["cap"], m["dict"], m["dict_len"], m["dict_adler"])
         ms, kms, ph = time_device_batch(ctx, dm, 3, 2)
         fs = list(ctx.last_fast_stats())
-        rm = dm.records(N)
+        rm, ok, checked = check_sampled(N, O, m, dm, n, 256)
         produced = int(sum(int(rm[i].out_len) for i in range(n)))
-        ok, checked = True, 0
-        for i in range(0, n, max(1, n // 256)):
-            hd = bool(m["mode"][i] & 0x80)
-            exp, er = O.inflate_oneshot(m["arena"][int(m["off"][i]):int(m["off"][i]) + int(m["ln"][i])].tobytes(),
-                                        dictionary=m["dictionary"] if hd else None, mode=int(m["mode"][i] & 0x7f))
-            o0 = int(dm.ooff[i])
-            gotb = dm.d_out[o0:o0 + int(rm[i].out_len)].cpu().numpy().tobytes()
-            ok = ok and er.observable() == rm[i].observable() and (er.thrown_append or gotb == exp)
-            checked += 1
         cb = int(m["ln"].astype(np.uint64).sum())
         ms, kms = reduce_max(ms), reduce_max(kms)
         mixed_out = {"workload": "cfg4: gzip / gzip+FNAME / zlib / raw / zlib+dictionary, levels 1/6/9, text / binary / tiny (fixed) / incompressible (stored) / runs",
@@ -535,6 +565,24 @@ def main():
                      "parity_ok": bool(ok), "parity_scope": "%d sampled streams: record + bytes vs the oracle" % checked}
         del dm
         mixed = None
+        torch.cuda.empty_cache()
+
+    # ---- streams with a preset dictionary (InflaterOptions.dictionary): finished by the two-phase path since round 2
+    dict_out = None
+    if extras:
+        m = build_dict_batch(n)
+        dm = DeviceBatch(torch, N, m["arena"], m["off"], m["ln"], m["mode"], m["cap"], m["dict"], m["dict_len"], m["dict_adler"])
+        ms, kms, ph = time_device_batch(ctx, dm, 3, 2)
+        fs = list(ctx.last_fast_stats())
+        rm, ok, checked = check_sampled(N, O, m, dm, n, 64)
+        produced = int(sum(int(rm[i].out_len) for i in range(n)))
+        cb = int(m["ln"].astype(np.uint64).sum())
+        ms, kms = reduce_max(ms), reduce_max(kms)
+        dict_out = {"workload": "%d zlib streams x 30,000 B text, levels 1/6/9, all with FDICT + the caller's 470-byte preset dictionary" % n,
+                    "GB/s": round(reduce_sum(float(produced)) / (ms / 1000.0) / 1e9, 1), "ms": round(ms, 3), "kernel_ms": round(kms, 3),
+                    "frac": round((cb + produced) / (kms / 1000.0) / 1e9 / peak, 4), "fast_path_streams": fs,
+                    "phase_ms": [round(x, 3) for x in ph], "parity_ok": bool(ok), "parity_scope": "%d sampled streams: record + bytes vs the oracle" % checked}
+        del dm, m
         torch.cuda.empty_cache()
 
     # ---- cfg5: one large gzip stream on all ranks
@@ -676,10 +724,14 @@ def main():
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "device_ms_per_step": round(dev_ms, 3),
-            "phase_ms": {"huff_tokens": round(k_phase[0], 3), "lz_resolve": round(k_phase[1], 3), "general_decoder": round(k_phase[2], 3),
-                         "finalize": round(k_phase[3], 3), "fast_path_streams": fast_stats},
+            "phase_ms": {"huff_tokens": round(k_phase[0], 3), "lz_resolve": round(k_phase[1] + k_phase[2], 3), "general_decoder": round(k_phase[2], 3),
+                         "finalize": round(k_phase[3], 3), "fast_path_streams": fast_stats,
+                         "note": "huff_tokens = phase A of all chunks (phase B of the earlier chunks runs next to it); lz_resolve = what is left of "
+                                 "phase B after the last phase A; general_decoder = the hand-over run, queued behind the last phase A and running NEXT TO "
+                                 "that rest of phase B (it is part of lz_resolve's span; with an empty list it only waits for a free SM slot)"},
             "matrix": matrix,
             "mixed_batch": mixed_out,
+            "dict_batch": dict_out,
             "large_stream": large_out,
             "checksums": checks,
         }))

@@ -77,9 +77,10 @@ uint64_t sdz_launch_count(sdz_ctx* ctx);
 /* device time of the most recent call's kernels in milliseconds (CUDA events on the ctx
  * stream), split by phase: [0] inflate kernel, [1] checksum kernel, [2] whole device phase */
 int sdz_last_timing(sdz_ctx* ctx, float ms[3]);
-/* the same for the most recent batched inflate, by kernel: [0] phase A (Huffman decode -> tokens), [1] phase B
- * (tokens -> bytes), [2] the general decoder (streams handed over by phase A; the whole batch when the fast
- * path is off), [3] finalize (checksums + records), [4] all of it */
+/* the same for the most recent batched inflate, by kernel: [0] phase A (Huffman decode -> tokens; the earlier chunks'
+ * phase B runs next to it), [2] the general decoder over the streams phase A handed over (queued right behind the last
+ * phase A, running next to the last phase B; the whole batch when the fast path is off), [1] what phase B (tokens ->
+ * bytes) still needs after that, [3] finalize (checksums + records), [4] all of it.  [0] + [2] + [1] + [3] = [4]. */
 int sdz_last_phase_timing(sdz_ctx* ctx, float ms[5]);
 /* most recent fast-path launch (the last sub-batch of a pipelined call): out[0] = streams finished by the two-phase
  * path, out[1] = streams it handed to the general decoder */

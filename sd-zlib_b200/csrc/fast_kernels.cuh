@@ -123,6 +123,7 @@ struct FastParams {
     uint32_t first, count;
     uint16_t* sorted_l;                // 288 u16 per lane of the phase-A grid
     const uint32_t* order;             // work item k of the batch is stream order[k]: longest compressed streams first
+    uint32_t dict_ok;                  // phase B resolves sources inside a preset dictionary (lz_resolve2_kernel only)
 };
 
 // token capacity of a stream: a token needs at least one output byte, and streams with fewer than four
@@ -196,20 +197,36 @@ __global__ void __launch_bounds__(1024) token_offsets_kernel(const uint32_t* in_
 
 // ---------------------------------------------------------------------- phase A
 
+__device__ __forceinline__ uint32_t dict_len_of(const InflateParams& I, unsigned long long i)
+{
+    return (I.mode[i] & 0x80) && I.dict_len ? I.dict_len[i] : 0u;
+}
+__device__ __forceinline__ int32_t dict_adler_of(const InflateParams& I, unsigned long long i)
+{
+    return (I.mode[i] & 0x80) && I.dict_adler ? I.dict_adler[i] : 0;
+}
+
 // container header of a stream the fast path may finish (src/inflate.ts:142-401).  false: anything else
 // (errors, truncation, FDICT, FEXTRA ...) - the general decoder writes that record.
 struct Container {
     uint32_t hp;                       // first byte of the deflate data
     int32_t mtime;
     uint32_t name_off, name_len;
+    uint32_t dict_used;                // bytes of preset dictionary that sit before the output (FDICT accepted), else 0
     int method;
     bool raw, is_gzip;
 };
-__device__ __forceinline__ bool parse_container_clean(const uint8_t* src, uint32_t in_len, uint8_t mode_raw, Container& C)
+// `dict_len` / `dict_adler`: the dictionary the caller supplied (mode_raw & 0x80), as inflateSetDictionary would see it
+// (src/inflate.ts:465-491): a zlib stream with FDICT is finished here when the caller's dictionary is the one the stream
+// names (DICTID == the reference's adler32 of it) and is shorter than the window - then the reference's window simply
+// starts with those bytes.  32 KiB and more (the 32,767 rule), a missing or a wrong dictionary: general decoder.
+constexpr uint32_t FA_MAX_DICT = 32767;
+__device__ __forceinline__ bool parse_container_clean(const uint8_t* src, uint32_t in_len, uint8_t mode_raw, uint32_t dict_len, int32_t dict_adler,
+                                                      bool dict_ok, Container& C)
 {
     const int mode = mode_raw & 0x7f;
     const bool has_dict = (mode_raw & 0x80) != 0;
-    C.hp = 0; C.mtime = 0; C.name_off = 0; C.name_len = 0; C.method = 0; C.is_gzip = false;
+    C.hp = 0; C.mtime = 0; C.name_off = 0; C.name_len = 0; C.method = 0; C.is_gzip = false; C.dict_used = 0;
     C.raw = mode == SDZ_MODE_RAW;
     if (in_len == 0) return false;
     if (mode == SDZ_MODE_SNIFF) {                                       // inflate(): src/sd-inflate.ts:194-207
@@ -246,7 +263,13 @@ __device__ __forceinline__ bool parse_container_clean(const uint8_t* src, uint32
         if (gflags & 2) { if (hp + 2 > in_len) return false; hp += 2; }
     } else {
         if ((((uint32_t)C.method << 8) + b) % 31 != 0) return false;
-        if (b & 0x20) return false;                                     // FDICT: preset dictionary
+        if (b & 0x20) {                                                 // FDICT: preset dictionary (src/inflate.ts:196-230)
+            if (!has_dict || !dict_ok || dict_len > FA_MAX_DICT || hp + 4 > in_len) return false;
+            const int32_t dictid = (int32_t)(((uint32_t)src[hp] << 24) | ((uint32_t)src[hp + 1] << 16) | ((uint32_t)src[hp + 2] << 8) | (uint32_t)src[hp + 3]);
+            if (dictid != dict_adler) return false;
+            hp += 4;
+            C.dict_used = dict_len;
+        }
     }
     C.hp = hp;
     return true;
@@ -442,7 +465,7 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
     uint64_t bb = 0;
     int bc = 0;
     uint32_t nw = 0, wp = 0, lim_wp = 0, in_len = 0;
-    uint32_t pos = 0, cap = 0, ntok = 0, cap_tok = 0, n_blocks = 0;
+    uint32_t pos = 0, cap = 0, ntok = 0, cap_tok = 0, n_blocks = 0, dbias = 0;
     uint32_t* tokp = nullptr;
     int last = 0, eob_len = 0, lbits = 0, g_l = 0, g_d = 0;
     int nl = 0, nd = 0;
@@ -474,7 +497,7 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                 const uint64_t consumed = (uint64_t)wp * 32 - (uint64_t)bc, total_bits = (uint64_t)in_len * 8;
                 bool ok = consumed <= total_bits;
                 Container C;
-                ok = ok && parse_container_clean(src, in_len, P.I.mode[idx], C);
+                ok = ok && parse_container_clean(src, in_len, P.I.mode[idx], dict_len_of(P.I, idx), dict_adler_of(P.I, idx), P.dict_ok != 0u, C);
                 uint32_t tp = (uint32_t)((consumed + 7) >> 3);
                 int32_t stored = 0, isize = 0;
                 if (ok) {
@@ -509,7 +532,7 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                 if (ok) {
                     sdz_result R;
                     R.out_off = P.I.out_off ? P.I.out_off[idx] : 0;
-                    R.out_len = pos;
+                    R.out_len = pos - dbias;
                     R.total_in = tp;
                     R.zstatus = SDZ_Z_STREAM_END;
                     R.stored_checksum = stored;
@@ -553,10 +576,14 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
             const uint8_t* src = P.I.in + P.I.in_off[i];
             wbase = reinterpret_cast<const uint32_t*>(src);
             Container C;
-            if (!parse_container_clean(src, in_len, P.I.mode[i], C)) { state = LS_HANDOVER; continue; }
+            if (!parse_container_clean(src, in_len, P.I.mode[i], dict_len_of(P.I, i), dict_adler_of(P.I, i), P.dict_ok != 0u, C)) { state = LS_HANDOVER; continue; }
             lim_wp = (in_len + 3) / 4;
-            pos = 0;
+            // `pos` and `cap` count from the first byte of the dictionary: a distance is valid while it stays inside
+            // dictionary + output, which is the one compare the symbol loop makes (dist - 1 >= pos: SURVEY Q6)
+            dbias = C.dict_used;
+            pos = dbias;
             cap = P.I.out_cap ? P.I.out_cap[i] : 0xffffffffu;
+            cap = cap > 0xffffffffu - dbias ? 0xffffffffu : cap + dbias;
             ntok = 0;
             cap_tok = (uint32_t)(P.tok_off[i + 1] - P.tok_off[i]);
             tokp = P.tokens + P.tok_off[i];
@@ -1091,6 +1118,10 @@ __global__ void __launch_bounds__(32 * B2_WARPS, SDZ_B2_MINBLOCKS) lz_resolve2_k
 #ifdef SDZ_CHECKED
         const uint32_t chk_cap = P.I.out_cap ? P.I.out_cap[idx] : 0xfffffff0u;
 #endif
+        // preset dictionary: its last byte sits at stream position -1 (phase A only lets a distance reach back that far
+        // when the stream's FDICT header named the caller's dictionary)
+        const uint32_t dlen = dict_len_of(P.I, idx);
+        const uint8_t* const dend = dlen ? P.I.dict + P.I.dict_off[idx] + dlen : nullptr;
         uint32_t pos = gb;                                              // write frontier (uniform)
         uint32_t flushed = 0;                                           // bytes below are in global memory; multiple of 16
         __syncwarp();                                                   // the previous stream's ring reads are over
@@ -1117,7 +1148,7 @@ __global__ void __launch_bounds__(32 * B2_WARPS, SDZ_B2_MINBLOCKS) lz_resolve2_k
                 const bool match = mine && !lit;
                 // simple: the whole source lies before this step's bytes and the copy is one 16-byte piece
                 const uint32_t o = src & 7u, a = src - o;
-                const bool simple = match && len <= 16u && src + len <= pos && a >= gb;
+                const bool simple = match && len <= 16u && dist <= dst - gb && src + len <= pos && a >= gb;      // (dist > dst - gb: the source starts in the dictionary)
                 const bool hard = match && !simple;
                 if (mine && lit) sts_u8(rd, t);
                 // ---- parallel step: every simple match
@@ -1172,8 +1203,11 @@ __global__ void __launch_bounds__(32 * B2_WARPS, SDZ_B2_MINBLOCKS) lz_resolve2_k
                             // dist >= 32: bytes at or after h_dst were written by earlier rounds of this loop;
                             // dist < 32: replicate the dist bytes before the match
                             const uint32_t q = h_src + (h_dist < 32u ? i % h_dist : i);
-                            SDZ_CHECK(h_src >= gb && q < h_dst + i && h_dst + h_len <= gb + chk_cap && (q < flushed || h_dst + i - q < B2_RING - 16u));
-                            const uint32_t v = q >= flushed ? lds_u8(ring + (q & (B2_RING - 1u))) : (uint32_t)outg[q];
+                            // back = how far before the stream's first byte the source byte lies (> 0: a dictionary byte)
+                            const int32_t back = (int32_t)(gb - q);
+                            SDZ_CHECK((back > 0 ? (uint32_t)back <= dlen : q < h_dst + i) && h_dst + h_len <= gb + chk_cap &&
+                                      (back > 0 || q < flushed || h_dst + i - q < B2_RING - 16u));
+                            const uint32_t v = back > 0 ? (uint32_t)dend[-back] : (q >= flushed ? lds_u8(ring + (q & (B2_RING - 1u))) : (uint32_t)outg[q]);
                             sts_u8(ring + ((h_dst + i) & (B2_RING - 1u)), v);
                         }
                         __syncwarp();

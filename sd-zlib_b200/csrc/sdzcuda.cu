@@ -77,7 +77,7 @@ struct sdz_ctx {
     cudaStream_t fast_sb[N_LANES] = { nullptr, nullptr, nullptr };     // phase B streams
     cudaEvent_t fast_ev[N_LANES][MAX_FAST_CHUNKS + 1] = {};
     DevBuf fast_tok[N_LANES], fast_meta[N_LANES], fast_sorted[N_LANES];
-    cudaEvent_t ev_fast[4] = { nullptr, nullptr, nullptr, nullptr };   // before A, after A, after B, after the hand-over run
+    cudaEvent_t ev_fast[4] = { nullptr, nullptr, nullptr, nullptr };   // before A, after A, after B (joined), after the hand-over run (which overlaps B)
     bool fast_timed = false;
     const unsigned long long* last_fb_count = nullptr;   // device counter of the most recent fast-path launch
     uint64_t last_fast_n = 0;
@@ -386,6 +386,7 @@ int launch_fast(sdz_ctx* ctx, const sdz::InflateParams& P, uint64_t tok_total, b
     F.fb_count = counters;
     F.sorted_l = (uint16_t*)ctx->fast_sorted[lane].p;
     F.order = (const uint32_t*)(fm + off_order);
+    F.dict_ok = ctx->b_tokenwise ? 1u : 0u;
     // The batch is cut into chunks: phase A of chunk c + 1 (latency-bound, one warp per scheduler, all of the shared
     // memory) runs next to phase B of chunk c (issue-bound, no shared memory) on a second stream, so the two kernels
     // fill each other's idle issue slots on the same SMs.
@@ -407,6 +408,20 @@ int launch_fast(sdz_ctx* ctx, const sdz::InflateParams& P, uint64_t tok_total, b
         kern<<<ga, 32, smem, st>>>(F);
         CK(cudaEventRecord(ctx->fast_ev[lane][c], st));
         CK(cudaStreamWaitEvent(sb, ctx->fast_ev[lane][c], 0));
+        if (c == n_chunks - 1) {
+            // hand-over run: the general decoder over the list (its length is only known on the device).  The list is
+            // complete when the last phase A is, and the streams on it are none of phase B's, so the run is queued right
+            // behind phase A, AHEAD of the last phase B: its blocks take their share of the SMs first (an empty list costs
+            // nothing, its blocks leave at once) and phase B fills the rest - a handful of handed-over streams are decoded
+            // at the latency of ONE group (~ 0.4 ms per KiB of output), and that tail used to start after phase B.
+            if (timed) CK(cudaEventRecord(ctx->ev_fast[1], st));
+            sdz::InflateParams Q = P;
+            Q.list = F.fb_list;
+            Q.n_dev = F.fb_count;
+            rc = launch_inflate<true>(ctx, Q);
+            if (rc) return rc;
+            if (timed) CK(cudaEventRecord(ctx->ev_fast[3], st));
+        }
         if (ctx->b_tokenwise) {
             const unsigned gb = (unsigned)std::min<uint64_t>((hi - lo + sdz::B2_WARPS - 1) / sdz::B2_WARPS, (uint64_t)ctx->sm_count * ctx->b2_blocks_per_sm);
             sdz::lz_resolve2_kernel<<<gb, 32 * sdz::B2_WARPS, 0, sb>>>(F);
@@ -416,18 +431,10 @@ int launch_fast(sdz_ctx* ctx, const sdz::InflateParams& P, uint64_t tok_total, b
         }
         ctx->launches += 2;
     }
-    if (timed) CK(cudaEventRecord(ctx->ev_fast[1], st));
     CK(cudaEventRecord(ctx->fast_ev[lane][sdz_ctx::MAX_FAST_CHUNKS], sb));
+    CK(cudaGetLastError());
     CK(cudaStreamWaitEvent(st, ctx->fast_ev[lane][sdz_ctx::MAX_FAST_CHUNKS], 0));
     if (timed) CK(cudaEventRecord(ctx->ev_fast[2], st));
-    CK(cudaGetLastError());
-    // hand-over run: the general decoder over the list (its length is only known on the device)
-    sdz::InflateParams Q = P;
-    Q.list = F.fb_list;
-    Q.n_dev = F.fb_count;
-    rc = launch_inflate<true>(ctx, Q);
-    if (rc) return rc;
-    if (timed) CK(cudaEventRecord(ctx->ev_fast[3], st));
     ctx->fast_timed = timed;
     ctx->last_fb_count = F.fb_count;
     ctx->last_fast_n = n;
@@ -667,8 +674,8 @@ int sdz_last_phase_timing(sdz_ctx* ctx, float ms[5])
     for (int i = 0; i < 5; i++) ms[i] = 0.f;
     if (ctx->fast_timed) {
         CK(cudaEventElapsedTime(&ms[0], ctx->ev_fast[0], ctx->ev_fast[1]));
-        CK(cudaEventElapsedTime(&ms[1], ctx->ev_fast[1], ctx->ev_fast[2]));
-        CK(cudaEventElapsedTime(&ms[2], ctx->ev_fast[2], ctx->ev_fast[3]));
+        CK(cudaEventElapsedTime(&ms[2], ctx->ev_fast[1], ctx->ev_fast[3]));      // the hand-over run starts right behind phase A ...
+        CK(cudaEventElapsedTime(&ms[1], ctx->ev_fast[3], ctx->ev_fast[2]));      // ... and this is what phase B still needs after it
     } else {
         CK(cudaEventElapsedTime(&ms[2], ctx->ev[0], ctx->ev[1]));
     }

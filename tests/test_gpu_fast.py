@@ -119,3 +119,42 @@ def test_ragged_batch_fast(both):
         assert rf[i][0] == rg[i][0], i
         if rf[i][1].container != 0:
             assert rf[i][1].success == 1, i
+
+
+def _run_dict(ctx, streams, dicts):
+    views = [np.frombuffer(bytes(s), dtype=np.uint8) for s in streams]
+    dv = [None if d is None else np.frombuffer(bytes(d), dtype=np.uint8) for d in dicts]
+    arena, off, res = A.inflate_batch_raw(views, dv, [O.MODE_INFLATER] * len(views), None, ctx)
+    return [(bytes(arena[int(off[i]):int(off[i]) + int(res[i].out_len)]), res[i]) for i in range(len(views))]
+
+
+def test_preset_dictionary_streams_on_the_fast_path(both):
+    """zlib streams with FDICT whose dictionary the caller supplied are finished by the two-phase path (matches that start
+    in the dictionary, and matches that run from the dictionary into the output); a missing, wrong or >= 32 KiB dictionary
+    goes to the general decoder.  Fast path == general decoder == oracle everywhere."""
+    f, g = both
+    streams, dicts = [], []
+    for k, dl in enumerate((1, 2, 31, 470, 5552, 20000, 32767)):
+        dic = bytes(K.generate(K.TEXT, 3000 + k, dl))
+        did = O.adler32(dic)
+        for j in range(4):
+            # the plaintext starts with a piece of the dictionary's tail and goes on inside the dictionary's text: the first
+            # matches reach into the dictionary, some of them across its end
+            head = dic[-min(dl, 40 + 13 * j):] + dic[:min(dl, 300)]
+            plain = head + bytes(K.generate(K.TEXT, 3100 + 10 * k + j, 3000 + 9000 * j))
+            streams.append(K.compress(plain, (1, 6, 9, 6)[j], K.ZLIB_DICT, dic, did)); dicts.append(dic)
+    n_fast = len(streams)
+    dic = bytes(K.generate(K.TEXT, 3999, 470))
+    s0 = K.compress(dic[-100:] + bytes(K.generate(K.TEXT, 4000, 5000)), 6, K.ZLIB_DICT, dic, O.adler32(dic))
+    big = bytes(K.generate(K.TEXT, 4001, 32768))
+    streams += [s0, s0, K.compress(big[-500:] + bytes(K.generate(K.TEXT, 4002, 5000)), 6, K.ZLIB_DICT, big, O.adler32(big))]
+    dicts += [None, dic[:-1] + b"?", big]                                       # required / invalid / 32 KiB (Q14)
+    rf, rg = _run_dict(f, streams, dicts), _run_dict(g, streams, dicts)
+    done, handed = f.last_fast_stats()
+    assert (done, handed) == (n_fast, 3)
+    for i, s in enumerate(streams):
+        eb, er = O.inflate_oneshot(bytes(s), dictionary=dicts[i], mode=O.MODE_INFLATER)
+        assert rf[i][1].observable() == rg[i][1].observable() == er.observable(), i
+        if not er.thrown_append:
+            assert rf[i][0] == rg[i][0] == eb, i
+    assert all(rf[i][1].success == 1 for i in range(n_fast))
