@@ -467,7 +467,8 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
     uint32_t nw = 0, wp = 0, lim_wp = 0, in_len = 0;
     uint32_t pos = 0, cap = 0, ntok = 0, cap_tok = 0, n_blocks = 0, dbias = 0;
     uint32_t* tokp = nullptr;
-    int last = 0, eob_len = 0, lbits = 0, g_l = 0, g_d = 0;
+    int last = 0, eob_len = 0, lbits = 0, dbits = 0, g_l = 0, g_d = 0;
+    uint32_t ck_bit = 0;                                                // (mod 2^32) a symbol boundary of the current block: its first symbol, or the last data symbol the general decoder took
     int nl = 0, nd = 0;
     bool fixed = false;
     uint32_t ci = 0;                                                    // input ring: next 16-byte chunk to request
@@ -495,7 +496,7 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                 // plain complete stream
                 const uint8_t* src = reinterpret_cast<const uint8_t*>(wbase);
                 const uint64_t consumed = (uint64_t)wp * 32 - (uint64_t)bc, total_bits = (uint64_t)in_len * 8;
-                bool ok = consumed <= total_bits;
+                bool ok = consumed <= total_bits, stalled_eob = false;
                 Container C;
                 ok = ok && parse_container_clean(src, in_len, P.I.mode[idx], dict_len_of(P.I, idx), dict_adler_of(P.I, idx), P.dict_ok != 0u, C);
                 uint32_t tp = (uint32_t)((consumed + 7) >> 3);
@@ -514,6 +515,61 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                         const uint64_t A = total_bits - eob_start;
                         const uint32_t r = slow_lookup(L->cnt_l, my_sorted, lbits, g_l, (uint32_t)(v >> (eob_start & 7)), (int)(A < 64 ? A : 64));
                         ok = lbits >= 6 && (r >> 28) == (uint32_t)R_OK && (r & 0xffffu) == 256u && ((r >> 16) & 0xffu) == (uint32_t)eob_len;
+                        if (!ok && lbits >= 6 && (r >> 28) == (uint32_t)R_STALL) {
+                            // The reference cannot look the final end-of-block code up: it returns with everything before it
+                            // decoded and waits for input that never comes (Z_OK, complete = false - about one raw stream in
+                            // 250).  That record is written here when the LAST DATA SYMBOL passes the same rule at each of its
+                            // lookups (its extra bits are its own; every symbol before it has at least lbits >= dbits bits
+                            // behind its codes, and a sub-table is never wider than its root): walk from the checkpoint to the
+                            // end-of-block code to find that symbol.  Anything else: general decoder.
+                            uint64_t q = consumed - (uint64_t)((uint32_t)consumed - ck_bit), qs = 0;
+                            uint32_t pn = 0, pxb = 0, pdn = 0, pdx = 0;
+                            bool pmatch = false, walked = false, bad = q > eob_start;
+                            for (int it2 = 0; it2 < 8192 && !bad && q < eob_start; it2++) {
+                                const uint8_t* pq = src + (q >> 3);
+                                uint64_t u = 0;
+                                for (int k = 0; k < 8; k++) u |= (uint64_t)pq[k] << (8 * k);
+                                u >>= (q & 7);
+                                uint32_t e2 = L->lut_l[(uint32_t)u & ((1u << FA_RL) - 1u)], n2, x2 = 0;
+                                bool m2 = false;
+                                if (e2 == E_LONG) {
+                                    const uint32_t r2 = canon_long(L->cnt_l, my_sorted, FA_RL, g_l, L->start, (uint32_t)u, L->long_l, 32);
+                                    const uint32_t sy = r2 & 0xffffu;
+                                    n2 = r2 >> 16;
+                                    if (r2 == 0u || sy == 256u || sy > 285u) { bad = true; break; }
+                                    if (sy > 256u) { const uint32_t i2 = sy - 257u; m2 = true; x2 = i2 < 8 ? 0 : (i2 == 28 ? 0 : (i2 >> 2) - 1); }
+                                } else if (e2 < 0x1000u) { bad = true; break; }
+                                else { n2 = e2 >> 12; x2 = (e2 >> 8) & 7u; m2 = (e2 & 0x800u) != 0u; }
+                                uint32_t dn2 = 0, dx2 = 0;
+                                if (m2) {
+                                    const uint32_t u2 = (uint32_t)(u >> (n2 + x2));
+                                    const uint32_t de2 = L->lut_d[u2 & ((1u << FA_RD) - 1u)];
+                                    if (de2 < 0x1000u) {
+                                        const uint32_t r2 = (de2 == E_LONG && g_d > FA_RD) ? canon_long(L->cnt_d, L->sorted_d, FA_RD, g_d, L->start + 2, u2) : 0u;
+                                        const uint32_t ds = r2 & 0xffffu;
+                                        if (r2 == 0u || ds > 29u) { bad = true; break; }
+                                        dn2 = r2 >> 16; dx2 = ds < 4 ? 0u : (ds >> 1) - 1u;
+                                    } else { dn2 = de2 >> 12; dx2 = (de2 >> 8) & 15u; }
+                                }
+                                qs = q; pn = n2; pxb = x2; pdn = dn2; pdx = dx2; pmatch = m2; walked = true;
+                                q += n2 + x2 + dn2 + dx2;
+                            }
+                            if (!bad && walked && q == eob_start) {
+                                const uint8_t* pq = src + (qs >> 3);
+                                uint64_t u = 0;
+                                for (int k = 0; k < 8; k++) u |= (uint64_t)pq[k] << (8 * k);
+                                u >>= (qs & 7);
+                                const uint64_t AP = total_bits - qs;
+                                const uint32_t r1 = slow_lookup(L->cnt_l, my_sorted, lbits, g_l, (uint32_t)u, (int)(AP < 64 ? AP : 64));
+                                bool pass = (r1 >> 28) == (uint32_t)R_OK && ((r1 >> 16) & 0xffu) == pn;
+                                if (pass && pmatch) {
+                                    const uint64_t AD = AP - pn - pxb;
+                                    const uint32_t r2 = slow_lookup(L->cnt_d, L->sorted_d, dbits, g_d, (uint32_t)(u >> (pn + pxb)), (int)(AD < 64 ? AD : 64));
+                                    pass = g_d > 0 && (r2 >> 28) == (uint32_t)R_OK && ((r2 >> 16) & 0xffu) == pdn && AD >= (uint64_t)(pdn + pdx);
+                                }
+                                if (pass) { ok = true; stalled_eob = true; }
+                            }
+                        }
                     } else {
                         const uint32_t nbytes = C.is_gzip ? 8u : 4u;
                         ok = tp + nbytes <= in_len;
@@ -534,7 +590,7 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                     R.out_off = P.I.out_off ? P.I.out_off[idx] : 0;
                     R.out_len = pos - dbias;
                     R.total_in = tp;
-                    R.zstatus = SDZ_Z_STREAM_END;
+                    R.zstatus = stalled_eob ? SDZ_Z_OK : SDZ_Z_STREAM_END;
                     R.stored_checksum = stored;
                     R.running_checksum = 0;
                     R.stored_isize = isize;
@@ -546,7 +602,7 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                     R.thrown_append = SDZ_THROW_NONE;
                     R.thrown_inflate = 0;
                     R.container = (uint8_t)(C.is_gzip ? SDZ_GZIP : (C.method == 0 ? SDZ_RAW : SDZ_ZLIB));
-                    R.complete = 1;
+                    R.complete = stalled_eob ? 0 : 1;
                     R.checksum_state = R.size_state = R.success = R.have_running = 0;
                     for (int k = 0; k < 7; k++) R.reserved[k] = 0;
                     P.I.res[idx] = R;
@@ -704,7 +760,7 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                 __syncwarp();
                 if ((int)lane == who) {
                     if (TI.msg != SDZ_MSG_NONE) state = LS_HANDOVER;    // the general decoder reproduces the message
-                    else { lbits = TI.lbits; g_l = TI.g_l; g_d = TI.g_d; state = LS_CODES; fresh = true; pending = false; }
+                    else { lbits = TI.lbits; dbits = TI.dbits; g_l = TI.g_l; g_d = TI.g_d; state = LS_CODES; fresh = true; pending = false; }
                 }
             }
         }
@@ -732,6 +788,7 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
             // lanes that come from a block header: the ring takes over at word wp + 1 (nw already holds word wp)
             {
                 const bool fill = live && fresh;
+                if (fill) ck_bit = wp * 32u - (uint32_t)bc;             // the block's first symbol
                 if (fill) ci = (wp + 1u) >> 2;
                 #pragma unroll
                 for (int k = 0; k < FA_RING_CHUNKS; k++) {
@@ -852,6 +909,7 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                             bc += 32; wp++;
                             nw = lds_u32(ring_l + ((wp & (4u * FA_RING_CHUNKS - 1u)) << 2));
                         }
+                        const uint32_t sym_bit = wp * 32u - (uint32_t)bc;
                         const uint32_t lo = (uint32_t)bb;
                         uint32_t e = L->lut_l[lo & ((1u << FA_RL) - 1u)];
                         if (e == E_LONG) {
@@ -873,6 +931,7 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                                 ev = 1;
                             } else ev = 2;                              // invalid literal/length code
                         } else {
+                            ck_bit = sym_bit;                           // (a data symbol: where LS_FINISH may start its look at the stream's last symbols)
                             const uint32_t n = e >> 12, xb = (e >> 8) & 7u;
                             const bool ismatch = (e & 0x800u) != 0u;
                             const uint32_t lenf = (e & 0xffu) + ((lo >> n) & ((1u << xb) - 1u));
@@ -1148,7 +1207,8 @@ __global__ void __launch_bounds__(32 * B2_WARPS, SDZ_B2_MINBLOCKS) lz_resolve2_k
                 const bool match = mine && !lit;
                 // simple: the whole source lies before this step's bytes and the copy is one 16-byte piece
                 const uint32_t o = src & 7u, a = src - o;
-                const bool simple = match && len <= 16u && dist <= dst - gb && src + len <= pos && a >= gb;      // (dist > dst - gb: the source starts in the dictionary)
+                bool simple = match && len <= 16u && src + len <= pos && a >= gb;
+                if (dlen) simple = simple && dist <= dst - gb;          // (dist > dst - gb: the source starts in the dictionary; `src` has wrapped)
                 const bool hard = match && !simple;
                 if (mine && lit) sts_u8(rd, t);
                 // ---- parallel step: every simple match
@@ -1197,17 +1257,30 @@ __global__ void __launch_bounds__(32 * B2_WARPS, SDZ_B2_MINBLOCKS) lz_resolve2_k
                     hm &= hm - 1;
                     const uint32_t h_dst = __shfl_sync(FULL, dst, k), h_len = __shfl_sync(FULL, len, k), h_dist = __shfl_sync(FULL, dist, k);
                     const uint32_t h_src = h_dst - h_dist;
+                    if (h_dist > h_dst - gb) {
+                        // the source starts in the preset dictionary (and may run on into the stream's first bytes)
+                        for (uint32_t c = 0; c < h_len; c += 32u) {
+                            const uint32_t i = c + lane;
+                            if (i < h_len) {
+                                const uint32_t q = h_src + (h_dist < 32u ? i % h_dist : i);
+                                const int32_t back = (int32_t)(gb - q);   // > 0: that many bytes before the stream's first byte
+                                SDZ_CHECK((back > 0 ? (uint32_t)back <= dlen : q < h_dst + i) && h_dst + h_len <= gb + chk_cap &&
+                                          (back > 0 || q < flushed || h_dst + i - q < B2_RING - 16u));
+                                const uint32_t v = back > 0 ? (uint32_t)dend[-back] : (q >= flushed ? lds_u8(ring + (q & (B2_RING - 1u))) : (uint32_t)outg[q]);
+                                sts_u8(ring + ((h_dst + i) & (B2_RING - 1u)), v);
+                            }
+                            __syncwarp();
+                        }
+                        continue;
+                    }
                     for (uint32_t c = 0; c < h_len; c += 32u) {
                         const uint32_t i = c + lane;
                         if (i < h_len) {
                             // dist >= 32: bytes at or after h_dst were written by earlier rounds of this loop;
                             // dist < 32: replicate the dist bytes before the match
                             const uint32_t q = h_src + (h_dist < 32u ? i % h_dist : i);
-                            // back = how far before the stream's first byte the source byte lies (> 0: a dictionary byte)
-                            const int32_t back = (int32_t)(gb - q);
-                            SDZ_CHECK((back > 0 ? (uint32_t)back <= dlen : q < h_dst + i) && h_dst + h_len <= gb + chk_cap &&
-                                      (back > 0 || q < flushed || h_dst + i - q < B2_RING - 16u));
-                            const uint32_t v = back > 0 ? (uint32_t)dend[-back] : (q >= flushed ? lds_u8(ring + (q & (B2_RING - 1u))) : (uint32_t)outg[q]);
+                            SDZ_CHECK(h_src >= gb && q < h_dst + i && h_dst + h_len <= gb + chk_cap && (q < flushed || h_dst + i - q < B2_RING - 16u));
+                            const uint32_t v = q >= flushed ? lds_u8(ring + (q & (B2_RING - 1u))) : (uint32_t)outg[q];
                             sts_u8(ring + ((h_dst + i) & (B2_RING - 1u)), v);
                         }
                         __syncwarp();
