@@ -1153,6 +1153,9 @@ __device__ __forceinline__ uint2 ldg_v2(const uint8_t* p)
     return r;
 }
 
+// DICT: the batch has a dictionary arena (some streams may carry a preset dictionary); batches without one run the
+// kernel without the three places that look at it.
+template <bool DICT>
 __global__ void __launch_bounds__(32 * B2_WARPS, SDZ_B2_MINBLOCKS) lz_resolve2_kernel(FastParams P)
 {
     constexpr unsigned FULL = 0xffffffffu;
@@ -1179,7 +1182,7 @@ __global__ void __launch_bounds__(32 * B2_WARPS, SDZ_B2_MINBLOCKS) lz_resolve2_k
 #endif
         // preset dictionary: its last byte sits at stream position -1 (phase A only lets a distance reach back that far
         // when the stream's FDICT header named the caller's dictionary)
-        const uint32_t dlen = dict_len_of(P.I, idx);
+        const uint32_t dlen = DICT ? dict_len_of(P.I, idx) : 0u;
         const uint8_t* const dend = dlen ? P.I.dict + P.I.dict_off[idx] + dlen : nullptr;
         uint32_t pos = gb;                                              // write frontier (uniform)
         uint32_t flushed = 0;                                           // bytes below are in global memory; multiple of 16
@@ -1208,7 +1211,7 @@ __global__ void __launch_bounds__(32 * B2_WARPS, SDZ_B2_MINBLOCKS) lz_resolve2_k
                 // simple: the whole source lies before this step's bytes and the copy is one 16-byte piece
                 const uint32_t o = src & 7u, a = src - o;
                 bool simple = match && len <= 16u && src + len <= pos && a >= gb;
-                if (dlen) simple = simple && dist <= dst - gb;          // (dist > dst - gb: the source starts in the dictionary; `src` has wrapped)
+                if (DICT && dlen) simple = simple && dist <= dst - gb;  // (dist > dst - gb: the source starts in the dictionary; `src` has wrapped)
                 const bool hard = match && !simple;
                 if (mine && lit) sts_u8(rd, t);
                 // ---- parallel step: every simple match
@@ -1257,7 +1260,7 @@ __global__ void __launch_bounds__(32 * B2_WARPS, SDZ_B2_MINBLOCKS) lz_resolve2_k
                     hm &= hm - 1;
                     const uint32_t h_dst = __shfl_sync(FULL, dst, k), h_len = __shfl_sync(FULL, len, k), h_dist = __shfl_sync(FULL, dist, k);
                     const uint32_t h_src = h_dst - h_dist;
-                    if (h_dist > h_dst - gb) {
+                    if (DICT && h_dist > h_dst - gb) {
                         // the source starts in the preset dictionary (and may run on into the stream's first bytes)
                         for (uint32_t c = 0; c < h_len; c += 32u) {
                             const uint32_t i = c + lane;

@@ -386,7 +386,7 @@ int launch_fast(sdz_ctx* ctx, const sdz::InflateParams& P, uint64_t tok_total, b
     F.fb_count = counters;
     F.sorted_l = (uint16_t*)ctx->fast_sorted[lane].p;
     F.order = (const uint32_t*)(fm + off_order);
-    F.dict_ok = ctx->b_tokenwise ? 1u : 0u;
+    F.dict_ok = ctx->b_tokenwise && P.dict ? 1u : 0u;
     // The batch is cut into chunks: phase A of chunk c + 1 (latency-bound, one warp per scheduler, all of the shared
     // memory) runs next to phase B of chunk c (issue-bound, no shared memory) on a second stream, so the two kernels
     // fill each other's idle issue slots on the same SMs.
@@ -424,7 +424,8 @@ int launch_fast(sdz_ctx* ctx, const sdz::InflateParams& P, uint64_t tok_total, b
         }
         if (ctx->b_tokenwise) {
             const unsigned gb = (unsigned)std::min<uint64_t>((hi - lo + sdz::B2_WARPS - 1) / sdz::B2_WARPS, (uint64_t)ctx->sm_count * ctx->b2_blocks_per_sm);
-            sdz::lz_resolve2_kernel<<<gb, 32 * sdz::B2_WARPS, 0, sb>>>(F);
+            if (P.dict) sdz::lz_resolve2_kernel<true><<<gb, 32 * sdz::B2_WARPS, 0, sb>>>(F);
+            else sdz::lz_resolve2_kernel<false><<<gb, 32 * sdz::B2_WARPS, 0, sb>>>(F);
         } else {
             const unsigned gb = (unsigned)std::min<uint64_t>((hi - lo + 7) / 8, (uint64_t)ctx->sm_count * ctx->b_blocks_per_sm);
             sdz::lz_resolve_kernel<<<gb, 256, 0, sb>>>(F);
