@@ -433,6 +433,12 @@ __device__ __forceinline__ void stg_v4_hint(void* p, uint4 v, uint64_t policy)
     asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(policy)
                  : "memory");
 }
+__device__ __forceinline__ void stg_v4_hint_if(void* p, uint4 v, uint64_t policy, bool pred)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %6, 0;\n\t@q st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;\n\t}" ::"l"(p), "r"(v.x),
+                 "r"(v.y), "r"(v.z), "r"(v.w), "l"(policy), "r"((uint32_t)pred)
+                 : "memory");
+}
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
 {
     uint16_t r;
@@ -900,7 +906,7 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                 pending = su < 4u;
                 const unsigned pend = __ballot_sync(FULL, pending);
                 it++;
-                if (pend != 0u && ((it & (SDZ_FA_DEFER - 1u)) == 0u || __popc(pend) >= 8)) {
+                if ((pend != 0u) & (((it & (SDZ_FA_DEFER - 1u)) == 0u) | (__popc(pend) >= 8))) {       // (one branch, not three)
                     if (pending) {
                         pending = false;
                         uint32_t tslow = 0u;
@@ -979,17 +985,18 @@ __global__ void __launch_bounds__(32) huff_tokens_kernel(FastParams P)
                 }
                 cp_async_commit();
                 asm volatile("cp.async.wait_group " SDZ_STR(SDZ_FA_RING_WAIT) ";" ::: "memory");
-                if (live) {
-                    if (early != 0u || pos > cap || wp > lim_wp + 1u || ntok + 4u > cap_tok) ev = 2;
-                    else if ((tk0 | tk1 | tk2 | tk3) != 0u) {
-                        SDZ_CHECK(ntok + 4u <= cap_tok && ((reinterpret_cast<uintptr_t>(tokp + ntok) & 15u) == 0u) && wp <= lim_wp + 1u);
+                // (no branches: a taken or not-taken branch costs a latency-bound warp ~20 cycles, and these were three per group)
+                {
+                    const bool bad = live & ((early != 0u) | (pos > cap) | (wp > lim_wp + 1u) | (ntok + 4u > cap_tok));
+                    const bool put = live & !bad & ((tk0 | tk1 | tk2 | tk3) != 0u);
+                    SDZ_CHECK(!put || (ntok + 4u <= cap_tok && ((reinterpret_cast<uintptr_t>(tokp + ntok) & 15u) == 0u) && wp <= lim_wp + 1u));
 #if SDZ_CACHE_HINTS
-                        stg_v4_hint(tokp + ntok, make_uint4(tk0, tk1, tk2, tk3), pol_in);     // written once, read once by phase B
+                    stg_v4_hint_if(tokp + ntok, make_uint4(tk0, tk1, tk2, tk3), pol_in, put);     // written once, read once by phase B
 #else
-                        *reinterpret_cast<uint4*>(tokp + ntok) = make_uint4(tk0, tk1, tk2, tk3);
+                    if (put) *reinterpret_cast<uint4*>(tokp + ntok) = make_uint4(tk0, tk1, tk2, tk3);
 #endif
-                        ntok += 4u;
-                    }
+                    ntok += put ? 4u : 0u;
+                    ev = bad ? 2 : ev;
                 }
                 if (__any_sync(FULL, ev != 0)) break;
             }
