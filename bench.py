@@ -619,6 +619,25 @@ def main():
         o_off = (np.arange(n, dtype=np.uint64) * np.uint64(STREAM_BYTES))
         o_cap = np.full(n, STREAM_BYTES, dtype=np.uint64)
         hres = (N.Result * n)()
+        # Ceiling of this arm on THIS box: the call has to bring out_bytes back over the link, so it cannot beat the rate of a
+        # plain pinned device -> host copy (1 GiB, best of 3; all ranks copy at the same time, as they do in the timed call)
+        probe = min(1 << 30, out_bytes)
+        d_probe = lib.sdz_device_alloc(ctx.h, probe)
+        d2h_gbs = h2d_gbs = 0.0
+        if d_probe:
+            for fn, which in ((lib.sdz_memcpy_h2d, "h2d"), (lib.sdz_memcpy_d2h, "d2h")):
+                best = 1e9
+                for _ in range(3):
+                    if world > 1:
+                        dist.barrier()
+                    t0 = time.perf_counter()
+                    ctx.check(fn(ctx.h, d_probe, h_out, probe) if which == "h2d" else fn(ctx.h, h_out, d_probe, probe))
+                    best = min(best, time.perf_counter() - t0)
+                if which == "h2d":
+                    h2d_gbs = probe / best / 1e9
+                else:
+                    d2h_gbs = probe / best / 1e9
+            lib.sdz_device_free(ctx.h, d_probe)
         times = []
         for it in range(1 + args.e2e_steps):
             if world > 1:
@@ -633,10 +652,16 @@ def main():
         first = (C.c_uint8 * STREAM_BYTES).from_address(h_out)
         exp0, _ = O.inflate_oneshot(arena[int(off[0]):int(off[0]) + int(ln[0])].tobytes())
         ok = ok and bytes(first) == exp0
+        sum_d2h, sum_h2d = reduce_sum(d2h_gbs), reduce_sum(h2d_gbs)
         e2e = {"value": round(all_out / (e_ms / 1000.0) / 1e9, 3), "unit": "GB/s", "ms_per_step": round(e_ms, 2),
                "h2d_bytes_per_step": int(arena.size + n * 41), "d2h_bytes_per_step": int(out_bytes + n * C.sizeof(N.Result)),
                "parity_ok": bool(ok), "numa_node": int(lib.sdz_ctx_numa_node(ctx.h)),
+               "link_d2h_gbs": round(sum_d2h, 1), "link_h2d_gbs": round(sum_h2d, 1),
+               "ceiling_gbs": round(sum_d2h * all_out / (world * float(out_bytes + n * C.sizeof(N.Result))), 1) if sum_d2h > 0 else None,
+               "ceiling": "decompressed GB/s if the device -> host bytes of the call moved at the measured pinned-copy rate of this box (sum over ranks, all copying at once) and nothing else took time",
                "api": "sdz_inflate_batch: host pointers into one pinned arena (zero-copy DMA), 4,096-stream sub-batches pipelined over copy streams and 3 compute lanes"}
+        if e2e["ceiling_gbs"]:
+            e2e["frac_of_ceiling"] = round(e2e["value"] / e2e["ceiling_gbs"], 3)
         lib.sdz_host_free(h_in); lib.sdz_host_free(h_out)
         if extras:
             # what an N-API caller hands over: one pageable allocation per input buffer, a pageable output arena
