@@ -10,20 +10,20 @@
 //            tables of src/inftree.ts:95-299 as shared-memory LUTs per lane).  Every symbol becomes one
 //            32-bit token (literal byte, or length + distance) in HBM; four tokens leave a lane as one
 //            16-byte store.  No window, no copies.
-//   phase B  lz_resolve_kernel    ONE WARP per stream: 32 tokens at a time, a warp scan of their lengths
-//            gives the output offsets, then the bytes are produced 32 per step with lane = output byte:
-//            the token that covers a byte is found with one REDUX + POPC, its source byte is read from
-//            the stream's own earlier output (or taken from the token), bytes whose source lies in the
-//            same 32-byte row are resolved by pointer jumping over shuffles, and the row leaves the warp
-//            as ONE coalesced 32-byte store (src/infcodes.ts:160-207 is what this replaces).
+//   phase B  lz_resolve2_kernel   ONE WARP per stream, lane = TOKEN (src/infcodes.ts:160-207 is what it replaces): 32
+//            tokens per step, a warp scan of their lengths gives the output offsets; the bytes are assembled in a
+//            1 KiB shared-memory ring per warp and leave it as coalesced 16-byte vector stores (see the comment at
+//            the kernel).  lz_resolve_kernel is its first, byte-centric version (lane = output byte; SDZ_B2=0).
 //
-// Phase A decodes optimistically and validates at the end of the stream; it only finishes streams whose
-// record is the plain "decoded completely" one: container header without preset dictionary / FEXTRA,
-// fixed and dynamic blocks whose trees the reference accepts (complete codes, table arena within MANY,
-// SURVEY Q9 / Q10), no distance reaching before the start of the output (Q6), the whole trailer present
-// and nothing after it (Q4), and - raw streams - enough lookahead for the reference's final lookups (Q15).
-// EVERYTHING else (stored blocks with their Q2 rule, errors, truncation, dictionaries, slots that are too
-// small ...) is handed, whole stream, to the general decoder inflate_kernel<4> through a device-side list,
+// Phase A decodes optimistically and validates at the end of the stream; it only finishes streams whose record it
+// can write with certainty: container header without FEXTRA (a preset dictionary only when the FDICT header names the
+// dictionary the caller supplied and it is shorter than the window: SURVEY Q14), fixed and dynamic blocks whose trees the
+// reference accepts (complete codes, table arena within MANY), no distance reaching before the start of
+// the window (Q6), the whole trailer present and nothing after it (Q4), and - raw streams - the reference's lookahead
+// rule replayed on the final end-of-block lookup and, when that one stalls, on the last data symbol (Q15: the stream is
+// then complete = false with all data delivered).
+// EVERYTHING else (stored blocks with their Q2 rule, errors, truncation, missing / wrong / 32 KiB dictionaries, slots that
+// are too small ...) is handed, whole stream, to the general decoder inflate_kernel<4> through a device-side list,
 // so records stay bit-exact with the reference in every case.  There is no CPU path.
 #pragma once
 #include "inflate_kernel.cuh"
