@@ -199,3 +199,27 @@ def test_error_messages():
         assert r.thrown_append == O.THROW_INFLATE_ERROR and O.MSG_TEXT[r.msg_id] == msg, (data, r.observable())
     out, r = O.inflate_oneshot(b"x")
     assert r.thrown_inflate == O.THROW_TOO_SMALL
+
+
+def test_q15_raw_stream_final_end_of_block_needs_lookahead():
+    """the reference looks a code up only when its table's index width is in the bit buffer, and nothing
+    follows the end-of-block code of a raw stream.  A stream whose last code is shorter than that width therefore never
+    completes: every data byte is delivered, z stays Z_OK, finish() says complete = false and inflate() throws
+    "Unexpected EOF" - while zlib decodes the same bytes to the end.  (The GPU fast path writes this record itself:
+    tests/test_gpu_fast.py::test_raw_streams_the_reference_leaves_incomplete_stay_on_the_fast_path.)"""
+    import zlib
+    from tools import corpus as K
+    seen = 0
+    for i in range(600):
+        plain = K.generate(K.TEXT if i % 2 else K.BINARY, 20000 + i, 200 + (i * 37) % 900)
+        s = K.compress(plain, (1, 6, 9)[i % 3], K.RAW)
+        out, r = O.inflate_oneshot(bytes(s), mode=O.MODE_RAW)
+        assert zlib.decompress(bytes(s), -15) == bytes(plain)
+        if r.complete:
+            assert r.zstatus == 1 and r.success == 1 and out == bytes(plain)
+            continue
+        seen += 1
+        assert out == bytes(plain) and r.out_len == len(plain)          # all data delivered ...
+        assert r.zstatus == 0 and r.total_in == len(s) and r.thrown_append == 0 and r.success == 0
+        assert r.thrown_inflate == O.THROW_UNEXPECTED_EOF                  # ... but inflate() throws
+    assert seen >= 3
